@@ -1,0 +1,614 @@
+// hs_tmat.cuh -- single-layer EBCM T-matrix kernel (stages K1 special functions, K2 Q/RgQ assembly,
+// K3 parity-decoupled complex solve, convergence controller) for one particle per thread group.
+//
+// Replaces pytmatrix's Fortran `calctmat` (Mishchenko ampld.lp.f: CONST, VARY, BESS, VIG, TMATR0, TMATR,
+// TT), SURVEY.md rows P2-P7 / Appendix A.1-A.6.  Written B200-first: a particle's whole working set
+// (radial-function tables, Wigner tables, the two parity-class linear systems) lives in shared memory
+// for the entire convergence loop and the azimuthal-mode sweep; HBM sees 5 doubles in and the packed
+// T-matrix out.
+#pragma once
+#include "hs_compat.cuh"
+#include "../../include/hydrotm.h"
+
+namespace hs {
+
+struct TmArgs {
+    const int *items;
+    int n_items;
+    int *queue;  // dynamic work queue counter
+    const double *axi, *lam, *mr, *mi, *eps;
+    double rat;
+    int np;
+    double ddelt;
+    int ndgs;
+    const double *gx, *gw;  // Gauss table: for rule 2g the g positive nodes ascending at g(g-1)/2
+    int gmax;
+    double *tarena;
+    long long arena_cap;
+    unsigned long long *arena_top;
+    long long *toff;
+    int *nmax, *ngauss, *ntrials, *status;
+    int ws_cap;         // doubles available per group
+    double *ws_global;  // GLOBAL_WS variant: per-CTA slices of ws_cap doubles
+};
+
+__host__ __device__ inline long long ws_need(int nmax, int g)
+{
+    int ld = nmax | 1;
+    return 12LL * g + 10LL * g * ld + 8LL * nmax * nmax;
+}
+
+__host__ __device__ inline long long tmat_size(int nmax)
+{
+    long long n = nmax;
+    return 2 * (n * n + n * (n + 1) * (2 * n + 1) / 6);
+}
+
+struct Carve {
+    double *x, *w, *s, *ss, *r, *dr, *ddr, *drr, *dri, *rr, *ds, *dss;
+    double *bj, *by, *bdj, *bdy, *bjr, *bji, *bdjr, *bdji;
+    double *d1, *d2;
+    double2 *sys;
+    int ld;
+};
+
+__device__ inline void carve(Carve &c, double *ws, int nmax, int g)
+{
+    int ld = nmax | 1;
+    c.ld = ld;
+    double *p = ws;
+    c.x = p; p += g; c.w = p; p += g; c.s = p; p += g; c.ss = p; p += g;
+    c.r = p; p += g; c.dr = p; p += g; c.ddr = p; p += g; c.drr = p; p += g;
+    c.dri = p; p += g; c.rr = p; p += g; c.ds = p; p += g; c.dss = p; p += g;
+    long tab = (long)g * ld;
+    c.bj = p; p += tab; c.by = p; p += tab; c.bdj = p; p += tab; c.bdy = p; p += tab;
+    c.bjr = p; p += tab; c.bji = p; p += tab; c.bdjr = p; p += tab; c.bdji = p; p += tab;
+    c.d1 = p; p += tab; c.d2 = p; p += tab;
+    c.sys = reinterpret_cast<double2 *>(p);
+}
+
+// per-group control block (shared memory)
+struct Ctl {
+    int item, nmax, g, phase, done, status, ntr, sing;
+    double qsca1, qext1;
+    int piv[2];
+    double2 pivinv[2];
+    unsigned long long toff;
+};
+
+template <bool WARP>
+struct Grp {
+    int tid, nt;
+    __device__ __forceinline__ void sync() const
+    {
+        if (WARP) __syncwarp();
+        else __syncthreads();
+    }
+};
+
+// ---- K1: radial functions, one quadrature node per task (P4: RJB / RYB / CJB) ----
+// j_n(x): downward ratio recurrence from order nmax+nnmax; ratios for n<=nmax are parked in y[] then
+// turned into function values upward.  y,u hold n=1..nmax at index n-1.
+__device__ inline void rjb(double x, double *y, double *u, int nmax, int nnmax)
+{
+    int l = nmax + nnmax;
+    double xx = 1.0 / x;
+    double zc = 1.0 / ((double)(2 * l + 1) * xx);
+    for (int i1 = l - 1; i1 >= 1; i1--) {
+        zc = 1.0 / ((double)(2 * i1 + 1) * xx - zc);
+        if (i1 <= nmax) y[i1 - 1] = zc;
+    }
+    double z1 = y[0];
+    double z0 = 1.0 / (xx - z1);
+    double y0 = z0 * cos(x) * xx;
+    double y1 = y0 * z1;
+    u[0] = y0 - y1 * xx;
+    y[0] = y1;
+    for (int i = 2; i <= nmax; i++) {
+        double yi1 = y[i - 2];
+        double yi = yi1 * y[i - 1];
+        u[i - 1] = yi1 - (double)i * yi * xx;
+        y[i - 1] = yi;
+    }
+}
+
+__device__ inline void ryb(double x, double *y, double *v, int nmax)
+{
+    double s, c;
+    sincos(x, &s, &c);
+    double x1 = 1.0 / x, x2 = x1 * x1, x3 = x2 * x1;
+    double y1 = -c * x2 - s * x1;
+    y[0] = y1;
+    if (nmax >= 2) y[1] = (-3.0 * x3 + x1) * c - 3.0 * x2 * s;
+    for (int i = 2; i <= nmax - 1; i++) y[i] = (double)(2 * i + 1) * x1 * y[i - 1] - y[i - 2];
+    v[0] = -x1 * (c + y1);
+    for (int i = 2; i <= nmax; i++) v[i - 1] = y[i - 2] - (double)i * x1 * y[i - 1];
+}
+
+__device__ inline void cjb(double xr, double xi, double *yr, double *yi, double *ur, double *ui,
+                           int nmax, int nnmax)
+{
+    int l = nmax + nnmax;
+    double xrxi = 1.0 / (xr * xr + xi * xi);
+    double cxxr = xr * xrxi, cxxi = -xi * xrxi;
+    double qf = 1.0 / (double)(2 * l + 1);
+    double czr = xr * qf, czi = xi * qf;
+    for (int i1 = l - 1; i1 >= 1; i1--) {
+        qf = (double)(2 * i1 + 1);
+        double ar = qf * cxxr - czr;
+        double ai = qf * cxxi - czi;
+        double ari = 1.0 / (ar * ar + ai * ai);
+        czr = ar * ari;
+        czi = -ai * ari;
+        if (i1 <= nmax) { yr[i1 - 1] = czr; yi[i1 - 1] = czi; }
+    }
+    double z1r = yr[0], z1i = yi[0];
+    double ar = cxxr - z1r, ai = cxxi - z1i;
+    double ari = 1.0 / (ar * ar + ai * ai);
+    double cz0r = ar * ari, cz0i = -ai * ari;
+    double sxr, cxr;
+    sincos(xr, &sxr, &cxr);
+    double cr = cxr * cosh(xi), ci = -sxr * sinh(xi);
+    ar = cz0r * cr - cz0i * ci;
+    ai = cz0i * cr + cz0r * ci;
+    double cy0r = ar * cxxr - ai * cxxi, cy0i = ai * cxxr + ar * cxxi;
+    double cy1r = cy0r * z1r - cy0i * z1i, cy1i = cy0i * z1r + cy0r * z1i;
+    ar = cy1r * cxxr - cy1i * cxxi;
+    ai = cy1i * cxxr + cy1r * cxxi;
+    yr[0] = cy1r; yi[0] = cy1i;
+    ur[0] = cy0r - ar; ui[0] = cy0i - ai;
+    for (int i = 2; i <= nmax; i++) {
+        double qi = (double)i;
+        double p1r = yr[i - 2], p1i = yi[i - 2];
+        double zr = yr[i - 1], zi = yi[i - 1];
+        double cyir = p1r * zr - p1i * zi;
+        double cyii = p1i * zr + p1r * zi;
+        ar = cyir * cxxr - cyii * cxxi;
+        ai = cyii * cxxr + cyir * cxxi;
+        yr[i - 1] = cyir; yi[i - 1] = cyii;
+        ur[i - 1] = p1r - qi * ar; ui[i - 1] = p1i - qi * ai;
+    }
+}
+
+// ---- K1: Wigner d^n_{0m} and d/dtheta at the mirrored node, reflected to x<0 (P5: VIG + TMATR sign rule) ----
+__device__ inline void vig_reflect(double x, int nmax, int m, double *d1, double *d2)
+{
+    double qs = sqrt(1.0 - x * x), qs1 = 1.0 / qs;
+    if (m == 0) {
+        double a1 = 1.0, a2 = x;
+        for (int n = 1; n <= nmax; n++) {
+            double qn = n, qn1 = n + 1, qn2 = 2 * n + 1;
+            double a3 = (qn2 * x * a2 - qn * a1) / qn1;
+            double der = qs1 * (qn1 * qn / qn2) * (-a1 + a3);
+            double si = (n & 1) ? -1.0 : 1.0;
+            d1[n - 1] = a2 * si;
+            d2[n - 1] = -der * si;
+            a1 = a2; a2 = a3;
+        }
+        return;
+    }
+    double qmm = (double)(m * m), a = 1.0;
+    for (int i = 1; i <= m; i++) a = a * sqrt((double)(2 * i - 1) / (double)(2 * i)) * qs;
+    double a1 = 0.0, a2 = a;
+    for (int n = m; n <= nmax; n++) {
+        double qn = n, qn2 = 2 * n + 1, qn1 = n + 1;
+        double qnm = sqrt(qn * qn - qmm), qnm1 = sqrt(qn1 * qn1 - qmm);
+        double a3 = (qn2 * x * a2 - qnm * a1) / qnm1;
+        double der = qs1 * (-qn1 * qnm * a1 + qn * qnm1 * a3) / qn2;
+        double si = ((n + m) & 1) ? -1.0 : 1.0;
+        d1[n - 1] = a2 * si;
+        d2[n - 1] = -der * si;
+        a1 = a2; a2 = a3;
+    }
+}
+
+// CONST + VARY + BESS (+ VIG for m=0) for one (nmax, g) trial.
+template <bool WARP>
+__device__ void trial_setup(const Grp<WARP> &grp, const Carve &c, int nmax, int g, double a_rev, double lam,
+                            double mrr, double mri, double eps, const double *gx, const double *gw)
+{
+    const double PI = 3.14159265358979323846;
+    const double kw = PI * 2.0 / lam;
+    const double A = a_rev * pow(eps, 1.0 / 3.0);
+    const double aa = A * A, ee = eps * eps, ee1 = ee - 1.0;
+    double v0 = 1.0 / (mrr * mrr + mri * mri);
+    const double prr = mrr * v0, pri = -mri * v0;
+    const long goff = (long)g * (g - 1) / 2;
+    for (int i = grp.tid; i < g; i += grp.nt) {
+        double xp = gx[goff + g - 1 - i], wv = gw[goff + g - 1 - i];
+        double x = -xp;
+        double yv = 1.0 / (1.0 - x * x);
+        c.ss[i] = yv;
+        c.s[i] = sqrt(yv);
+        double cc = x * x, ssq = 1.0 - cc, sth = sqrt(ssq);
+        double rq = 1.0 / (ssq + ee * cc);
+        double r = aa * rq;
+        c.r[i] = r;
+        c.dr[i] = rq * x * sth * ee1;
+        double v = sqrt(r) * kw;
+        double vi = 1.0 / v;
+        c.ddr[i] = vi;
+        c.drr[i] = prr * vi;
+        c.dri[i] = pri * vi;
+        c.x[i] = xp;
+        c.w[i] = wv;
+        c.rr[i] = wv * r;
+    }
+    grp.sync();
+    double ta = fmax(sqrt(c.r[0]) * kw, sqrt(c.r[g - 1]) * kw);
+    double tb = ta * sqrt(mrr * mrr + mri * mri);
+    tb = fmax(tb, (double)nmax);
+    double tmx = fmax(ta, (double)nmax);
+    int nnmax1 = (int)(1.2 * sqrt(tmx) + 3.0);
+    int nnmax2 = (int)(tb + 4.0 * pow(tb, 0.33333) + 1.2 * sqrt(tb));
+    nnmax2 = nnmax2 - nmax + 5;
+    const int ld = c.ld;
+    for (int t = grp.tid; t < 4 * g; t += grp.nt) {
+        int kind = t / g, i = t - kind * g;
+        long o = (long)i * ld;
+        double v = sqrt(c.r[i]) * kw;
+        if (kind == 2) cjb(v * mrr, v * mri, c.bjr + o, c.bji + o, c.bdjr + o, c.bdji + o, nmax, nnmax2);
+        else if (kind == 0) rjb(v, c.bj + o, c.bdj + o, nmax, nnmax1);
+        else if (kind == 1) ryb(v, c.by + o, c.bdy + o, nmax);
+        else vig_reflect(c.x[i], nmax, 0, c.d1 + o, c.d2 + o);
+    }
+    grp.sync();
+}
+
+// Wigner tables + per-node weights for mode m >= 1
+template <bool WARP>
+__device__ void mode_setup(const Grp<WARP> &grp, const Carve &c, int nmax, int g, int m)
+{
+    const double qm = (double)m, qmm = qm * qm;
+    for (int i = grp.tid; i < g; i += grp.nt) {
+        c.ds[i] = c.s[i] * qm * c.rr[i];
+        c.dss[i] = c.ss[i] * qmm;
+        vig_reflect(c.x[i], nmax, m, c.d1 + (long)i * c.ld, c.d2 + (long)i * c.ld);
+    }
+    grp.sync();
+}
+
+// ---- K2: assembly of the two parity-class systems [Q^T | -RgQ^T] (P6: TMATR0 / TMATR) ----
+__device__ __forceinline__ double2 combine(double pir, double pii, double ppi, double pr, double pi, double qr, double qi)
+{
+    return make_double2(pir * pr - pii * pi + ppi * qr, pir * pi + pii * pr + ppi * qi);
+}
+
+template <bool WARP>
+__device__ void assemble(const Grp<WARP> &grp, const Carve &c, int nmax, int g, int m, double ppi,
+                         double pir, double pii, const double *an, const double *dd)
+{
+    const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
+    const int h0 = (NM + 1) >> 1, h1 = NM >> 1;
+    const int nE = h0 * h0 + h1 * h1, nO = 2 * h0 * h1;
+    const int ld = c.ld, ldc = 2 * NM;
+    double2 *sys = c.sys;
+    // even pairs: X12, X21
+    for (int t = grp.tid; t < nE; t += grp.nt) {
+        int k1, k2;
+        if (t < h0 * h0) { int a = t / h0; k1 = 2 * a; k2 = 2 * (t - a * h0); }
+        else { int u = t - h0 * h0; int a = u / h1; k1 = 2 * a + 1; k2 = 2 * (u - a * h1) + 1; }
+        const int n1 = nmin + k1, n2 = nmin + k2;
+        const double an1 = an[n1], an2 = an[n2];
+        double ar12 = 0, ai12 = 0, gr12 = 0, gi12 = 0, ar21 = 0, ai21 = 0, gr21 = 0, gi21 = 0;
+        const double *pj = c.bj + (n1 - 1), *py = c.by + (n1 - 1), *pdj = c.bdj + (n1 - 1), *pdy = c.bdy + (n1 - 1);
+        const double *pjr = c.bjr + (n2 - 1), *pji = c.bji + (n2 - 1), *pdjr = c.bdjr + (n2 - 1), *pdji = c.bdji + (n2 - 1);
+        const double *pd1a = c.d1 + (n1 - 1), *pd2a = c.d2 + (n1 - 1), *pd1b = c.d1 + (n2 - 1), *pd2b = c.d2 + (n2 - 1);
+        for (int i = 0; i < g; i++) {
+            const long o = (long)i * ld;
+            double d1n1 = pd1a[o], d2n1 = pd2a[o], d1n2 = pd1b[o], d2n2 = pd2b[o];
+            double a11 = d1n1 * d1n2, a12 = d1n1 * d2n2, a21 = d2n1 * d1n2, a22 = d2n1 * d2n2;
+            double aa2 = (m == 0) ? a22 : a11 * c.dss[i] + a22;
+            double qj1 = pj[o], qy1 = py[o], qdj1 = pdj[o], qdy1 = pdy[o];
+            double qjr2 = pjr[o], qji2 = pji[o], qdjr2 = pdjr[o], qdji2 = pdji[o];
+            double c1r = qjr2 * qj1, c1i = qji2 * qj1;
+            double b1r = c1r - qji2 * qy1, b1i = c1i + qjr2 * qy1;
+            double c2r = qjr2 * qdj1, c2i = qji2 * qdj1;
+            double b2r = c2r - qji2 * qdy1, b2i = c2i + qjr2 * qdy1;
+            double ddri = c.ddr[i];
+            double c3r = ddri * c1r, c3i = ddri * c1i, b3r = ddri * b1r, b3i = ddri * b1i;
+            double c4r = qdjr2 * qj1, c4i = qdji2 * qj1;
+            double b4r = c4r - qdji2 * qy1, b4i = c4i + qdjr2 * qy1;
+            double drri = c.drr[i], drii = c.dri[i];
+            double c5r = c1r * drri - c1i * drii, c5i = c1i * drri + c1r * drii;
+            double b5r = b1r * drri - b1i * drii, b5i = b1i * drri + b1r * drii;
+            double uri = c.dr[i], rri = c.rr[i];
+            double f1 = rri * aa2, f2 = rri * uri * an1 * a12;
+            ar12 += f1 * b2r + f2 * b3r; ai12 += f1 * b2i + f2 * b3i;
+            gr12 += f1 * c2r + f2 * c3r; gi12 += f1 * c2i + f2 * c3i;
+            f2 = rri * uri * an2 * a21;
+            ar21 += f1 * b4r + f2 * b5r; ai21 += f1 * b4i + f2 * b5i;
+            gr21 += f1 * c4r + f2 * c5r; gi21 += f1 * c4i + f2 * c5i;
+        }
+        const double an12 = dd[n1] * dd[n2] * 0.5 * 2.0;
+        double r12 = ar12 * an12, i12 = ai12 * an12, rg12 = gr12 * an12, ig12 = gi12 * an12;
+        double r21 = ar21 * an12, i21 = ai21 * an12, rg21 = gr21 * an12, ig21 = gi21 * an12;
+        // t12 = -i*x12 -> (i12, -r12); t21 = +i*x21 -> (-i21, r21)
+        double2 qa = combine(pir, pii, ppi, -i21, r21, i12, -r12);
+        double2 qb = combine(pir, pii, ppi, i12, -r12, -i21, r21);
+        double2 ga = combine(pir, pii, ppi, -ig21, rg21, ig12, -rg12);
+        double2 gb = combine(pir, pii, ppi, ig12, -rg12, -ig21, rg21);
+        const int ca = (n1 + 1) & 1, cb = ca ^ 1;
+        sys[(long)(ca * NM + k2) * ldc + k1] = qa;
+        sys[(long)(ca * NM + k2) * ldc + NM + k1] = make_double2(-ga.x, -ga.y);
+        sys[(long)(cb * NM + k2) * ldc + k1] = qb;
+        sys[(long)(cb * NM + k2) * ldc + NM + k1] = make_double2(-gb.x, -gb.y);
+    }
+    // odd pairs: X11, X22 (identically zero for m = 0)
+    for (int t = grp.tid; t < nO; t += grp.nt) {
+        int k1, k2;
+        if (t < h0 * h1) { int a = t / h1; k1 = 2 * a; k2 = 2 * (t - a * h1) + 1; }
+        else { int u = t - h0 * h1; int a = u / h0; k1 = 2 * a + 1; k2 = 2 * (u - a * h0); }
+        const int n1 = nmin + k1, n2 = nmin + k2;
+        double ar11 = 0, ai11 = 0, gr11 = 0, gi11 = 0, ar22 = 0, ai22 = 0, gr22 = 0, gi22 = 0;
+        if (m != 0) {
+            const double an1 = an[n1], an2 = an[n2];
+            const double *pj = c.bj + (n1 - 1), *py = c.by + (n1 - 1), *pdj = c.bdj + (n1 - 1), *pdy = c.bdy + (n1 - 1);
+            const double *pjr = c.bjr + (n2 - 1), *pji = c.bji + (n2 - 1), *pdjr = c.bdjr + (n2 - 1), *pdji = c.bdji + (n2 - 1);
+            const double *pd1a = c.d1 + (n1 - 1), *pd2a = c.d2 + (n1 - 1), *pd1b = c.d1 + (n2 - 1), *pd2b = c.d2 + (n2 - 1);
+            for (int i = 0; i < g; i++) {
+                const long o = (long)i * ld;
+                double d1n1 = pd1a[o], d2n1 = pd2a[o], d1n2 = pd1b[o], d2n2 = pd2b[o];
+                double a11 = d1n1 * d1n2, a12 = d1n1 * d2n2, a21 = d2n1 * d1n2;
+                double aa1 = a12 + a21;
+                double qj1 = pj[o], qy1 = py[o], qdj1 = pdj[o], qdy1 = pdy[o];
+                double qjr2 = pjr[o], qji2 = pji[o], qdjr2 = pdjr[o], qdji2 = pdji[o];
+                double c1r = qjr2 * qj1, c1i = qji2 * qj1;
+                double b1r = c1r - qji2 * qy1, b1i = c1i + qjr2 * qy1;
+                double c2r = qjr2 * qdj1, c2i = qji2 * qdj1;
+                double b2r = c2r - qji2 * qdy1, b2i = c2i + qjr2 * qdy1;
+                double ddri = c.ddr[i];
+                double c4r = qdjr2 * qj1, c4i = qdji2 * qj1;
+                double b4r = c4r - qdji2 * qy1, b4i = c4i + qdjr2 * qy1;
+                double drri = c.drr[i], drii = c.dri[i];
+                double c6r = qdjr2 * qdj1, c6i = qdji2 * qdj1;
+                double b6r = c6r - qdji2 * qdy1, b6i = c6i + qdjr2 * qdy1;
+                double c7r = c4r * ddri, c7i = c4i * ddri, b7r = b4r * ddri, b7i = b4i * ddri;
+                double c8r = c2r * drri - c2i * drii, c8i = c2i * drri + c2r * drii;
+                double b8r = b2r * drri - b2i * drii, b8i = b2i * drri + b2r * drii;
+                double uri = c.dr[i], dsi = c.ds[i];
+                double e1 = dsi * aa1;
+                ar11 += e1 * b1r; ai11 += e1 * b1i; gr11 += e1 * c1r; gi11 += e1 * c1i;
+                double e2 = dsi * uri * a11, e3 = e2 * an2;
+                e2 = e2 * an1;
+                ar22 += e1 * b6r + e2 * b7r + e3 * b8r; ai22 += e1 * b6i + e2 * b7i + e3 * b8i;
+                gr22 += e1 * c6r + e2 * c7r + e3 * c8r; gi22 += e1 * c6i + e2 * c7i + e3 * c8i;
+            }
+        }
+        const double an12 = dd[n1] * dd[n2] * 0.5 * 2.0;
+        double r11 = ar11 * an12, i11 = ai11 * an12, rg11 = gr11 * an12, ig11 = gi11 * an12;
+        double r22 = ar22 * an12, i22 = ai22 * an12, rg22 = gr22 * an12, ig22 = gi22 * an12;
+        // t11 = -x11, t22 = -x22
+        double2 qa = combine(pir, pii, ppi, -r11, -i11, -r22, -i22);
+        double2 qb = combine(pir, pii, ppi, -r22, -i22, -r11, -i11);
+        double2 ga = combine(pir, pii, ppi, -rg11, -ig11, -rg22, -ig22);
+        double2 gb = combine(pir, pii, ppi, -rg22, -ig22, -rg11, -ig11);
+        const int ca = (n1 + 1) & 1, cb = ca ^ 1;
+        sys[(long)(ca * NM + k2) * ldc + k1] = qa;
+        sys[(long)(ca * NM + k2) * ldc + NM + k1] = make_double2(-ga.x, -ga.y);
+        sys[(long)(cb * NM + k2) * ldc + k1] = qb;
+        sys[(long)(cb * NM + k2) * ldc + NM + k1] = make_double2(-gb.x, -gb.y);
+    }
+    grp.sync();
+}
+
+// ---- K3: Gauss-Jordan with row pivoting on both class systems at once (P7: TT, T = -RgQ Q^-1) ----
+// Solves Q_c^T X_c = -RgQ_c^T in place; on exit columns NM..2NM-1 hold X_c = T_c^T.
+template <bool WARP>
+__device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
+{
+    const int ldc = 2 * NM;
+    double2 *sys = c.sys;
+    const int nl = grp.nt < 32 ? grp.nt : 32;  // lanes searching for the pivot (32 on the GPU)
+    const int lane = grp.tid & 31;
+    for (int k = 0; k < NM; k++) {
+        if (grp.tid < nl) {
+            for (int cl = 0; cl < 2; cl++) {
+                double best = -1.0;
+                int bi = k;
+                for (int r = k + lane; r < NM; r += nl) {
+                    double2 v = sys[(long)(cl * NM + r) * ldc + k];
+                    double av = fabs(v.x) + fabs(v.y);
+                    if (av > best) { best = av; bi = r; }
+                }
+                for (int off = nl >> 1; off > 0; off >>= 1) {
+                    double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) {
+                    double2 pv = sys[(long)(cl * NM + bi) * ldc + k];
+                    double den = pv.x * pv.x + pv.y * pv.y;
+                    if (!(best > 0.0)) ctl->sing = 1;
+                    ctl->piv[cl] = bi;
+                    ctl->pivinv[cl] = make_double2(pv.x / den, -pv.y / den);
+                }
+            }
+        }
+        grp.sync();
+        const int ncol = ldc - k - 1;  // live columns k+1 .. 2NM-1
+        for (int t = grp.tid; t < 2 * ncol; t += grp.nt) {
+            int cl = t >= ncol;
+            int col = k + 1 + (t - cl * ncol);
+            double2 *S = sys + (long)cl * NM * ldc;
+            const int p = ctl->piv[cl];
+            const double2 inv = ctl->pivinv[cl];
+            double2 a = S[(long)k * ldc + col], b = S[(long)p * ldc + col];
+            double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
+            S[(long)k * ldc + col] = nk;
+            if (p != k) S[(long)p * ldc + col] = a;
+            const double2 fkk = S[(long)k * ldc + k];
+            for (int r = 0; r < NM; r++) {
+                if (r == k) continue;
+                double2 f = (r == p) ? fkk : S[(long)r * ldc + k];
+                double2 v = S[(long)r * ldc + col];
+                v.x -= f.x * nk.x - f.y * nk.y;
+                v.y -= f.x * nk.y + f.y * nk.x;
+                S[(long)r * ldc + col] = v;
+            }
+        }
+        grp.sync();
+    }
+}
+
+// ---- one particle: convergence loop (A.1) + mode sweep ----
+template <bool WARP>
+__device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, const Grp<WARP> &grp, Ctl *ctl,
+                                  const double *an, const double *dd)
+{
+    const double PI = 3.14159265358979323846;
+    double axi = a.axi[pidx], lam = a.lam[pidx], mrr = a.mr[pidx], mri = a.mi[pidx], eps = a.eps[pidx];
+    double rat = a.rat;
+    if (fabs(rat - 1.0) > 1e-8) {
+        // SAREA: equal-surface-area radius -> equal-volume radius ratio
+        double e, r;
+        if (eps < 1.0) {
+            e = sqrt(1.0 - eps * eps);
+            r = 0.5 * (pow(eps, 2.0 / 3.0) + pow(eps, -1.0 / 3.0) * asin(e) / e);
+        } else {
+            e = sqrt(1.0 - 1.0 / (eps * eps));
+            r = 0.25 * (2.0 * pow(eps, 2.0 / 3.0) + pow(eps, -4.0 / 3.0) * log((1.0 + e) / (1.0 - e)) / e);
+        }
+        rat = 1.0 / sqrt(r);
+    }
+    const double arev = rat * axi;
+    const double xev = 2.0 * PI * arev / lam;
+    int ixxx = (int)(xev + 4.05 * pow(xev, 0.333333));
+    int nmax0 = ixxx > 4 ? ixxx : 4;
+    const double kw = PI * 2.0 / lam;
+    const double ppi = kw * kw, pir = ppi * mrr, pii = ppi * mri;
+    const double ddelt = a.ddelt;
+
+    if (grp.tid == 0) {
+        ctl->nmax = nmax0; ctl->g = 0; ctl->phase = 0; ctl->done = 0; ctl->status = HS_ST_OK;
+        ctl->ntr = 0; ctl->sing = 0; ctl->qsca1 = 0.0; ctl->qext1 = 0.0;
+        bool bad = !(axi > 0.0) || !(lam > 0.0) || !(eps > 0.0) || !isfinite(mrr) || !isfinite(mri) || !(mrr * mrr + mri * mri > 0.0);
+        if (bad) { ctl->done = 2; ctl->status = HS_ST_BAD_INPUT; }
+        else if (nmax0 >= HS_NPN1) { ctl->done = 2; ctl->status = HS_ST_NMAX_LIMIT; }
+    }
+    grp.sync();
+    Carve c;
+    while (true) {
+        if (ctl->done) break;
+        int nmax = ctl->nmax, g;
+        if (ctl->phase == 0) g = nmax * a.ndgs;
+        else g = ctl->g + 1;
+        grp.sync();  // everyone has read ctl before thread 0 rewrites it
+        // limits and capacity
+        int stop = 0;
+        if (g > HS_NPNG1) stop = HS_ST_NGAUSS_LIMIT;
+        else if (g > a.gmax) stop = HS_ST_INTERNAL_GAUSS;
+        else if (ws_need(nmax, g) > (long long)a.ws_cap) stop = HS_ST_INTERNAL_ESCALATE;
+        if (stop) {
+            if (grp.tid == 0) { ctl->status = stop; ctl->done = 2; }
+            grp.sync();
+            break;
+        }
+        carve(c, ws, nmax, g);
+        trial_setup(grp, c, nmax, g, arev, lam, mrr, mri, eps, a.gx, a.gw);
+        assemble(grp, c, nmax, g, 0, ppi, pir, pii, an, dd);
+        solve(grp, c, nmax, ctl);
+        if (grp.tid == 0) {
+            const int NM = nmax, ldc = 2 * NM;
+            double qext = 0.0, qsca = 0.0;
+            for (int n = 1; n <= nmax; n++) {
+                int k = n - 1;
+                double2 t1 = c.sys[(long)(((n + 1) & 1) * NM + k) * ldc + NM + k];
+                double2 t2 = c.sys[(long)((n & 1) * NM + k) * ldc + NM + k];
+                double dn1 = (double)(2 * n + 1);
+                qsca += dn1 * (t1.x * t1.x + t1.y * t1.y + t2.x * t2.x + t2.y * t2.y);
+                qext += (t1.x + t2.x) * dn1;
+            }
+            double dsca = fabs((ctl->qsca1 - qsca) / qsca), dext = fabs((ctl->qext1 - qext) / qext);
+            ctl->qext1 = qext; ctl->qsca1 = qsca;
+            ctl->ntr++;
+            ctl->g = g;
+            bool ok = (dsca <= ddelt && dext <= ddelt);
+            if (ctl->phase == 0) {
+                if (ok) { ctl->phase = 1; if (g == HS_NPNG1) ctl->done = 1; }
+                else if (nmax + 1 > HS_NPN1) { ctl->status = HS_ST_NMAX_LIMIT; ctl->done = 2; }
+                else ctl->nmax = nmax + 1;
+            } else {
+                if (ok) ctl->done = 1;
+                else if (g == HS_NPNG1) { ctl->status = HS_ST_NGAUSS_LIMIT; ctl->done = 1; }
+            }
+        }
+        grp.sync();
+    }
+    const int nmax = ctl->nmax, g = ctl->g;
+    if (ctl->done == 1) {
+        // converged at (nmax, g); sys holds the m=0 solution.  Reserve arena space.
+        if (grp.tid == 0) {
+            unsigned long long sz = (unsigned long long)tmat_size(nmax);
+            unsigned long long off = atomicAdd(a.arena_top, sz);
+            if (off + sz > (unsigned long long)a.arena_cap) { ctl->status = HS_ST_ARENA_FULL; ctl->done = 2; }
+            ctl->toff = off;
+        }
+        grp.sync();
+        if (ctl->done == 1) {
+            double2 *tg = reinterpret_cast<double2 *>(a.tarena) + ctl->toff;
+            for (int m = 0; m <= nmax; m++) {
+                const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1, ldc = 2 * NM;
+                if (m >= 1) {
+                    mode_setup(grp, c, nmax, g, m);
+                    assemble(grp, c, nmax, g, m, ppi, pir, pii, an, dd);
+                    solve(grp, c, NM, ctl);
+                }
+                for (int t = grp.tid; t < 2 * NM * NM; t += grp.nt) {
+                    int row = t / NM, col = t - row * NM;  // row = c*NM + k'
+                    tg[t] = c.sys[(long)row * ldc + NM + col];
+                }
+                tg += 2 * NM * NM;
+                grp.sync();
+            }
+        }
+    }
+    if (grp.tid == 0) {
+        int st = ctl->status;
+        if (st == HS_ST_OK && ctl->sing) st = HS_ST_SINGULAR;
+        a.status[pidx] = st;
+        a.nmax[pidx] = nmax;
+        a.ngauss[pidx] = g;
+        a.ntrials[pidx] = ctl->ntr;
+        a.toff[pidx] = (ctl->done == 1) ? (long long)ctl->toff : -1;
+    }
+    grp.sync();
+}
+
+#define HS_MAX_GROUPS 8
+#ifndef HS_HOST_EMU
+
+template <bool WARP, bool GLOBAL_WS>
+__global__ void k_calctmat(TmArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ Ctl ctls[HS_MAX_GROUPS];
+    __shared__ double s_an[HS_NPN1 + 1], s_dd[HS_NPN1 + 1];
+    for (int n = threadIdx.x; n <= HS_NPN1; n += blockDim.x) {
+        if (n == 0) { s_an[0] = 0.0; s_dd[0] = 0.0; }
+        else {
+            int nn = n * (n + 1);
+            s_an[n] = (double)nn;
+            s_dd[n] = sqrt((double)(2 * n + 1) / (double)nn);
+        }
+    }
+    __syncthreads();
+    Grp<WARP> grp;
+    int gidx;
+    if (WARP) { grp.tid = threadIdx.x & 31; grp.nt = 32; gidx = threadIdx.x >> 5; }
+    else { grp.tid = threadIdx.x; grp.nt = blockDim.x; gidx = 0; }
+    double *ws = GLOBAL_WS ? (a.ws_global + (long long)blockIdx.x * a.ws_cap) : (smem + (long long)gidx * a.ws_cap);
+    Ctl *ctl = &ctls[gidx];
+    while (true) {
+        if (grp.tid == 0) ctl->item = atomicAdd(a.queue, 1);
+        grp.sync();
+        int it = ctl->item;
+        grp.sync();
+        if (it >= a.n_items) break;
+        calctmat_particle<WARP>(a, a.items[it], ws, grp, ctl, s_an, s_dd);
+    }
+}
+
+#endif  // HS_HOST_EMU
+
+}  // namespace hs

@@ -1,0 +1,298 @@
+// hydrotm.cu -- C ABI of libhydrotm.so (see include/hydrotm.h) and the host-side bucketing / launch logic.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/hydrotm.h"
+#include "hs_gauss.h"
+#include "hs_tmat.cuh"
+#include "hs_ampl.cuh"
+
+struct hs_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int smem_optin = 227 * 1024;
+    std::string err;
+    long long launches = 0;
+    // Gauss table
+    int gmax = 0;
+    double *d_gx = nullptr, *d_gw = nullptr;
+    // scratch
+    int *d_queue = nullptr;      // work-queue counters (16)
+    int *d_items = nullptr;      // particle index lists
+    int items_cap = 0;
+    int *h_pin = nullptr;        // pinned staging
+    size_t h_pin_cap = 0;
+    double *d_ws_global = nullptr;
+    size_t ws_global_bytes = 0;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return -1;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+static int ensure_gauss(hs_ctx *ctx, int gmax)
+{
+    if (gmax <= ctx->gmax) return 0;
+    if (gmax > HS_NPNG1) gmax = HS_NPNG1;
+    size_t tot = (size_t)gmax * (gmax + 1) / 2;
+    std::vector<double> hx(tot), hw(tot);
+    for (int g = 1; g <= gmax; g++) hs::gauss_positive(2 * g, &hx[(size_t)g * (g - 1) / 2], &hw[(size_t)g * (g - 1) / 2]);
+    double *nx = nullptr, *nw = nullptr;
+    CK(cudaMalloc(&nx, tot * sizeof(double)));
+    CK(cudaMalloc(&nw, tot * sizeof(double)));
+    CK(cudaMemcpy(nx, hx.data(), tot * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(nw, hw.data(), tot * sizeof(double), cudaMemcpyHostToDevice));
+    if (ctx->d_gx) cudaFree(ctx->d_gx);
+    if (ctx->d_gw) cudaFree(ctx->d_gw);
+    ctx->d_gx = nx; ctx->d_gw = nw; ctx->gmax = gmax;
+    return 0;
+}
+
+extern "C" const char *hs_version(void) { return "hydrotm-b200 0.1 (sm_100a)"; }
+extern "C" long long hs_tmat_size(int nmax) { return hs::tmat_size(nmax); }
+extern "C" long long hs_tmat_mode_offset(int nmax, int m)
+{
+    long long off = 0;
+    for (int mm = 0; mm < m; mm++) { long long nm = nmax - (mm > 1 ? mm : 1) + 1; off += 2 * nm * nm; }
+    return off;
+}
+extern "C" int hs_nmax_start(double r_ev, double wavelength)
+{
+    double xev = 2.0 * acos(-1.0) * r_ev / wavelength;
+    int ixxx = (int)(xev + 4.05 * pow(xev, 0.333333));
+    return ixxx > 4 ? ixxx : 4;
+}
+
+extern "C" int hs_ctx_create(hs_ctx **out, int device)
+{
+    hs_ctx *ctx = new hs_ctx();
+    *out = ctx;
+    ctx->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CK(cudaMalloc(&ctx->d_queue, 16 * sizeof(int)));
+    if (ensure_gauss(ctx, 64)) return -1;
+    return 0;
+}
+
+extern "C" void hs_ctx_destroy(hs_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaFree(ctx->d_gx); cudaFree(ctx->d_gw); cudaFree(ctx->d_queue); cudaFree(ctx->d_items);
+    cudaFree(ctx->d_ws_global);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    delete ctx;
+}
+
+extern "C" const char *hs_last_error(const hs_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" long long hs_launch_count(const hs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int ensure_pin(hs_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_pin_cap) return 0;
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr; ctx->h_pin_cap = 0;
+    CK(cudaMallocHost(&ctx->h_pin, bytes));
+    ctx->h_pin_cap = bytes;
+    return 0;
+}
+
+// bucket = launch configuration
+struct Bucket {
+    bool warp;        // group = warp (several particles per CTA) or whole CTA
+    bool global_ws;
+    int threads;
+    int groups;       // groups per CTA
+    int ws_cap;       // doubles per group
+};
+
+__global__ void k_nmax0(int n, const double *axi, const double *lam, const double *eps, double rat, int *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double PI = 3.14159265358979323846;
+    double r = rat;
+    double e_ = eps[i];
+    if (fabs(rat - 1.0) > 1e-8) {
+        double e, q;
+        if (e_ < 1.0) { e = sqrt(1.0 - e_ * e_); q = 0.5 * (pow(e_, 2.0 / 3.0) + pow(e_, -1.0 / 3.0) * asin(e) / e); }
+        else { e = sqrt(1.0 - 1.0 / (e_ * e_)); q = 0.25 * (2.0 * pow(e_, 2.0 / 3.0) + pow(e_, -4.0 / 3.0) * log((1.0 + e) / (1.0 - e)) / e); }
+        r = 1.0 / sqrt(q);
+    }
+    double xev = 2.0 * PI * r * axi[i] / lam[i];
+    int ixxx = (xev > 0.0 && xev < 1e6) ? (int)(xev + 4.05 * pow(xev, 0.333333)) : 0;
+    out[i] = ixxx > 4 ? ixxx : 4;
+}
+
+template <bool WARP, bool GLOBAL_WS>
+static cudaError_t launch_tm(const hs::TmArgs &a, int grid, int threads, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(hs::k_calctmat<WARP, GLOBAL_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hs::k_calctmat<WARP, GLOBAL_WS><<<grid, threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const double *d_lam, const double *d_mr,
+                                 const double *d_mi, const double *d_eps, double rat, int np, double ddelt,
+                                 int ndgs, int rescale_ddelt, double *d_tarena, long long arena_cap,
+                                 unsigned long long *d_arena_top, long long *d_toff, int *d_nmax, int *d_ngauss,
+                                 int *d_ntrials, int *d_status, void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0) return 0;
+    if (np != HS_SHAPE_SPHEROID) { ctx->err = "only spheroids (np=-1) are supported"; return -3; }
+    if (ndgs < 1) { ctx->err = "ndgs must be >= 1"; return -3; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    if (rescale_ddelt) ddelt = 0.1 * ddelt;
+
+    const Bucket buckets[4] = {
+        {true, false, 128, 4, 2816},
+        {false, false, 128, 1, 12000},
+        {false, false, 256, 1, (ctx->smem_optin - 4096) / 8},
+        {false, true, 256, 1, (int)hs::ws_need(HS_NPN1, HS_NPNG1)},
+    };
+    const int NB = 4;
+
+    if (ensure_pin(ctx, (size_t)n * sizeof(int) * 2)) return -1;
+    if (n > ctx->items_cap) {
+        if (ctx->d_items) cudaFree(ctx->d_items);
+        ctx->d_items = nullptr; ctx->items_cap = 0;
+        CK(cudaMalloc(&ctx->d_items, (size_t)n * sizeof(int)));
+        ctx->items_cap = n;
+    }
+    // predicted starting NMAX -> initial bucket
+    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_eps, rat, d_nmax);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n;
+    CK(cudaMemcpyAsync(h_n0, d_nmax, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+
+    std::vector<int> bucket_of(n), nm0(n);
+    std::vector<std::vector<int>> lists(NB);
+    for (int i = 0; i < n; i++) {
+        int n0 = h_n0[i];
+        nm0[i] = n0;
+        int np_ = std::min(n0 + 4, HS_NPN1);
+        long long need = hs::ws_need(np_, np_ * ndgs + 1);
+        int b = 0;
+        while (b < NB - 1 && need > buckets[b].ws_cap) b++;
+        bucket_of[i] = b;
+        lists[b].push_back(i);
+    }
+    int gauss_needed = ctx->gmax;
+    for (int round = 0; round < 16; round++) {
+        bool any = false;
+        std::vector<int> order;
+        order.reserve(n);
+        std::vector<int> seg_start(NB + 1, 0);
+        for (int b = 0; b < NB; b++) {
+            auto &L = lists[b];
+            std::stable_sort(L.begin(), L.end(), [&](int x, int y) { return nm0[x] > nm0[y]; });
+            seg_start[b] = (int)order.size();
+            order.insert(order.end(), L.begin(), L.end());
+            if (!L.empty()) any = true;
+        }
+        seg_start[NB] = (int)order.size();
+        if (!any) break;
+        CK(cudaMemcpyAsync(ctx->d_items, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ctx->d_queue, 0, 16 * sizeof(int), st));
+        for (int b = 0; b < NB; b++) {
+            int cnt = seg_start[b + 1] - seg_start[b];
+            if (!cnt) continue;
+            const Bucket &B = buckets[b];
+            hs::TmArgs a;
+            a.items = ctx->d_items + seg_start[b]; a.n_items = cnt; a.queue = ctx->d_queue + b;
+            a.axi = d_axi; a.lam = d_lam; a.mr = d_mr; a.mi = d_mi; a.eps = d_eps;
+            a.rat = rat; a.np = np; a.ddelt = ddelt; a.ndgs = ndgs;
+            a.gx = ctx->d_gx; a.gw = ctx->d_gw; a.gmax = ctx->gmax;
+            a.tarena = d_tarena; a.arena_cap = arena_cap; a.arena_top = d_arena_top;
+            a.toff = d_toff; a.nmax = d_nmax; a.ngauss = d_ngauss; a.ntrials = d_ntrials; a.status = d_status;
+            a.ws_cap = B.ws_cap; a.ws_global = nullptr;
+            size_t smem = B.global_ws ? 0 : (size_t)B.groups * B.ws_cap * sizeof(double);
+            int ctas_needed = (cnt + B.groups - 1) / B.groups;
+            int per_sm = B.global_ws ? 1 : std::max(1, (int)((size_t)(ctx->smem_optin + 1024) / (smem + 4096)));
+            int grid = std::min(ctas_needed, ctx->sm_count * per_sm);
+            cudaError_t e;
+            if (B.global_ws) {
+                grid = std::min(ctas_needed, ctx->sm_count);
+                size_t bytes = (size_t)grid * B.ws_cap * sizeof(double);
+                if (bytes > ctx->ws_global_bytes) {
+                    if (ctx->d_ws_global) cudaFree(ctx->d_ws_global);
+                    ctx->d_ws_global = nullptr; ctx->ws_global_bytes = 0;
+                    CK(cudaMalloc(&ctx->d_ws_global, bytes));
+                    ctx->ws_global_bytes = bytes;
+                }
+                a.ws_global = ctx->d_ws_global;
+                e = launch_tm<false, true>(a, grid, B.threads, 0, st);
+            } else if (B.warp) {
+                e = launch_tm<true, false>(a, grid, B.threads, smem, st);
+            } else {
+                e = launch_tm<false, false>(a, grid, B.threads, smem, st);
+            }
+            ctx->launches++;
+            if (e != cudaSuccess) { ctx->err = std::string("k_calctmat launch: ") + cudaGetErrorString(e); return -1; }
+        }
+        CK(cudaMemcpyAsync(h_st, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        // escalations
+        std::vector<std::vector<int>> next(NB);
+        bool need_gauss = false;
+        for (int b = 0; b < NB; b++)
+            for (int i : lists[b]) {
+                if (h_st[i] == HS_ST_INTERNAL_ESCALATE) {
+                    int nb = std::min(b + 1, NB - 1);
+                    if (nb == b) { ctx->err = "workspace escalation beyond the largest bucket"; return -4; }
+                    next[nb].push_back(i);
+                } else if (h_st[i] == HS_ST_INTERNAL_GAUSS) {
+                    need_gauss = true;
+                    next[b].push_back(i);
+                }
+            }
+        if (need_gauss) {
+            gauss_needed = std::min(HS_NPNG1, std::max(2 * ctx->gmax, 128));
+            if (ensure_gauss(ctx, gauss_needed)) return -1;
+        }
+        lists.swap(next);
+    }
+    return 0;
+}
+
+extern "C" int hs_calcampl_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff,
+                                 const int *d_nmax, const int *d_status, const double *d_lam, int n_geom,
+                                 const double *d_geom, int n_orient, const double *d_alpha, const double *d_beta,
+                                 const double *d_weight, double scale, int reduce, double *d_S, double *d_Z,
+                                 void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0 || n_geom <= 0 || n_orient <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    hs::AmplArgs a;
+    a.n = n; a.tarena = d_tarena; a.toff = d_toff; a.nmax = d_nmax; a.status = d_status; a.lam = d_lam;
+    a.n_geom = n_geom; a.geom = d_geom; a.n_orient = n_orient; a.alpha = d_alpha; a.beta = d_beta;
+    a.weight = d_weight; a.scale = scale; a.reduce = reduce; a.S = d_S; a.Z = d_Z;
+    int items = reduce ? n_orient : n_geom * n_orient;
+    int threads = std::min(128, std::max(32, (items + 31) / 32 * 32));
+    size_t smem = (size_t)threads * 25 * sizeof(double);
+    hs::k_ampl<<<n, threads, smem, st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,179 @@
+"""Batched host API over the C-ABI (include/hydrotm.h): torch tensors for device memory and streams only.
+
+``Engine.calctmat`` is the batched equivalent of pytmatrix's ``calctmat`` (one call per particle in the
+reference: scattering_rain.py:183-191 via Scatterer._init_tmatrix); ``TMatrixBatch.ampl`` of ``calcampl``
+plus ``orientation.orient_averaged_fixed``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ST_OK, ST_NMAX_LIMIT, ST_NGAUSS_LIMIT, ST_SINGULAR, ST_ARENA_FULL, ST_BAD_INPUT = 0, 1, 2, 3, 4, 5
+STATUS_TEXT = {
+    ST_OK: "ok",
+    ST_NMAX_LIMIT: "convergence not obtained: NMAX reached NPN1=100",
+    ST_NGAUSS_LIMIT: "NGAUSS reached NPNG1=500",
+    ST_SINGULAR: "singular Q matrix",
+    ST_ARENA_FULL: "T-matrix arena full",
+    ST_BAD_INPUT: "invalid particle parameters",
+}
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def tmat_size(nmax):
+    """complex128 entries of a packed T-matrix (tensor or int nmax)."""
+    return 2 * (nmax * nmax + nmax * (nmax + 1) * (2 * nmax + 1) // 6)
+
+
+class Engine:
+    """One CUDA context of the T-matrix engine on ``device``."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise EngineError("hydroscatt_b200 needs a CUDA device (no CPU fallback)")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_ctx_create(C.byref(h), self.device.index)
+        self._h = h
+        if rc != 0:
+            raise EngineError("hs_ctx_create: " + self._err())
+
+    def _err(self):
+        return self.lib.hs_last_error(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.hs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self.lib.hs_launch_count(self._h))
+
+    def _dev(self, x, n=None, dtype=torch.float64):
+        t = torch.as_tensor(x, dtype=dtype)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        t = t.reshape(-1)
+        if n is not None and t.numel() == 1 and n != 1:
+            t = t.expand(n)
+        return t.contiguous()
+
+    def calctmat(self, radius, wavelength, m_re, m_im, axis_ratio, rat=1.0, shape=-1, ddelt=1e-3, ndgs=2,
+                 rescale_ddelt=True, arena_margin=1.0):
+        """Converged T-matrices of a batch of spheroids.  All array arguments broadcast to [n]."""
+        sizes = [np.size(a) if not torch.is_tensor(a) else a.numel()
+                 for a in (radius, wavelength, m_re, m_im, axis_ratio)]
+        n = max(sizes)
+        axi = self._dev(radius, n)
+        lam = self._dev(wavelength, n)
+        mr = self._dev(m_re, n)
+        mi = self._dev(m_im, n)
+        eps = self._dev(axis_ratio, n)
+        dev = self.device
+        # arena estimate from the starting truncation (converged NMAX is typically NMAX0+1..+4)
+        xev = 2.0 * np.pi * axi / lam
+        n0 = torch.clamp((xev + 4.05 * xev.clamp_min(0) ** 0.333333).nan_to_num(0.0).floor().to(torch.int64), 4, 100)
+        est = tmat_size(torch.clamp(n0 + 5, max=100))
+        cap = int(est.sum().item() * arena_margin) + 1024
+        stream = torch.cuda.current_stream(dev)
+        while True:
+            arena = torch.empty(2 * cap, dtype=torch.float64, device=dev)
+            top = torch.zeros(1, dtype=torch.int64, device=dev)
+            toff = torch.empty(n, dtype=torch.int64, device=dev)
+            nmax = torch.empty(n, dtype=torch.int32, device=dev)
+            ngauss = torch.empty(n, dtype=torch.int32, device=dev)
+            ntr = torch.empty(n, dtype=torch.int32, device=dev)
+            status = torch.empty(n, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                rc = self.lib.hs_calctmat_batch(
+                    self._h, n, _ptr(axi), _ptr(lam), _ptr(mr), _ptr(mi), _ptr(eps), float(rat), int(shape),
+                    float(ddelt), int(ndgs), 1 if rescale_ddelt else 0, _ptr(arena), cap, _ptr(top), _ptr(toff),
+                    _ptr(nmax), _ptr(ngauss), _ptr(ntr), _ptr(status), C.c_void_p(stream.cuda_stream))
+            if rc != 0:
+                raise EngineError(f"hs_calctmat_batch rc={rc}: " + self._err())
+            if bool((status == ST_ARENA_FULL).any().item()):
+                cap = max(2 * cap, int(top.item()) + 1024)
+                continue
+            break
+        return TMatrixBatch(self, n, arena, top, toff, nmax, ngauss, ntr, status, lam)
+
+
+class TMatrixBatch:
+    """Device-resident packed T-matrices of ``n`` particles (layout: include/hydrotm.h)."""
+
+    def __init__(self, eng, n, arena, top, toff, nmax, ngauss, ntrials, status, lam):
+        self.eng, self.n = eng, n
+        self.arena, self.top, self.toff = arena, top, toff
+        self.nmax, self.ngauss, self.ntrials, self.status, self.lam = nmax, ngauss, ntrials, status, lam
+
+    def packed(self, i):
+        """complex128 numpy copy of particle i's packed T-matrix."""
+        off = int(self.toff[i].item())
+        sz = tmat_size(int(self.nmax[i].item()))
+        return self.arena[2 * off:2 * (off + sz)].cpu().numpy().view(np.complex128)
+
+    def ampl(self, geoms, alpha=(0.0,), beta=(0.0,), weight=None, scale=1.0, reduce=False):
+        """S [n,G,(O,)2,2] complex128 and Z [n,G,(O,)4,4] float64 on the device.
+
+        geoms: [G][4] (thet0, thet, phi0, phi) degrees; alpha/beta: [O] Euler angles (degrees);
+        reduce=True returns scale * sum_o weight[o] * (S,Z)(o) (orient_averaged_fixed).
+        """
+        eng = self.eng
+        dev = eng.device
+        g = eng._dev(np.asarray(geoms, dtype=np.float64).reshape(-1, 4))
+        G = g.numel() // 4
+        al = eng._dev(alpha)
+        be = eng._dev(beta)
+        O = al.numel()
+        if be.numel() != O:
+            raise ValueError("alpha and beta must have the same length")
+        w = eng._dev(weight if weight is not None else np.ones(O))
+        if reduce:
+            S = torch.empty((self.n, G, 2, 2), dtype=torch.complex128, device=dev)
+            Z = torch.empty((self.n, G, 4, 4), dtype=torch.float64, device=dev)
+        else:
+            S = torch.empty((self.n, G, O, 2, 2), dtype=torch.complex128, device=dev)
+            Z = torch.empty((self.n, G, O, 4, 4), dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            rc = eng.lib.hs_calcampl_batch(eng._h, self.n, _ptr(self.arena), _ptr(self.toff), _ptr(self.nmax),
+                                           _ptr(self.status), _ptr(self.lam), G, _ptr(g), O, _ptr(al), _ptr(be),
+                                           _ptr(w), float(scale), 1 if reduce else 0, _ptr(S), _ptr(Z),
+                                           C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise EngineError(f"hs_calcampl_batch rc={rc}: " + eng._err())
+        return S, Z
+
+
+_default = {}
+
+
+def default_engine(device=None):
+    """Process-wide engine per device (created on first use)."""
+    if not torch.cuda.is_available():
+        raise EngineError("hydroscatt_b200 needs a CUDA device (no CPU fallback)")
+    idx = torch.cuda.current_device() if device is None else int(device)
+    if idx not in _default:
+        _default[idx] = Engine(idx)
+    return _default[idx]

@@ -1,0 +1,109 @@
+/*
+ * hydrotm.h -- C ABI of libhydrotm.so, the B200 (sm_100a) T-matrix scattering engine.
+ *
+ * This is the drop-in boundary for hydroscatt's numerical back-ends.  Every entry point is
+ * batched, takes plain device pointers + sizes + a CUDA stream (as void*), returns an int status
+ * (0 = ok, <0 = call-level error, text via hs_last_error) and never throws.  Per-particle outcomes
+ * are reported in a device status array (HS_ST_*).
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference/hydroscatt):
+ *
+ *   hs_calctmat_batch   pytmatrix's f2py routine `calctmat(axi,rat,lam,mrr,mri,eps,np,ddelt,ndgs)->nmax`
+ *                       reached from Scatterer._init_tmatrix; call sites scattering.py:478-525,
+ *                       scattering_rain.py:183-191 (one call per diameter).  SURVEY.md rows P2-P7.
+ *   hs_calcampl_batch   pytmatrix's f2py routine `calcampl(nmax,lam,thet0,thet,phi0,phi,alpha,beta)->(S,Z)`
+ *                       + orientation.orient_averaged_fixed (50 calls per particle and geometry);
+ *                       call sites scattering.py:478-503 via radar.* / scatter.*.  Rows P8, P9.
+ *   hs_xsect_batch      scatter.sca_xsect / scatter.ext_xsect (scipy dblquad over calcampl,
+ *                       scattering.py:478-486, PSDIntegrator.init_scatter_table(angular_integration=True),
+ *                       scattering_rain.py:282-283).  Row P12.
+ *   hs_psd_integrate    PSDIntegrator.get_SZ / get_angular_integrated (trapz over D, row P10) and the
+ *                       rectangle-rule sums of scattering.py:312-448 (row S5).
+ *   hs_observables      radar.refl/Zdr/ldr/rho_hv/delta_hv/Kdp/Ai (row P12; scattering.py:530-587).
+ *   hs_tm2l_batch       f_2l_tmatrix.tm2l.tmatrix(2) = hydroscatt/f_2l_tmatrix/tmatrix_py.f:1-473
+ *                       (two-layer EBCM, rows F1-F11), called from scattering.py:32-67.
+ *
+ * T-matrix storage ("packed parity layout", complex128 interleaved):
+ *   for m = 0..nmax: nmin = max(m,1), NM = nmax-nmin+1; two NM x NM matrices (parity class c=0,1),
+ *   element [c][k'][k] (k = n-nmin scattered index, k' = n'-nmin incident index) holds
+ *   T^{tau tau'}_{m n n'} with tau = 1 if (n+1)%2==c else 2, tau' = 1 if (n'+1)%2==c else 2.
+ *   (All other T elements of a mirror-symmetric particle are exactly zero.)
+ *   Mode m starts at complex offset 2*sum_{m'<m} NM(m')^2; a particle occupies hs_tmat_size(nmax).
+ */
+#ifndef HYDROTM_H
+#define HYDROTM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_NPN1 100   /* NMAX limit (upstream ampld.par.f NPN1) */
+#define HS_NPNG1 500  /* NGAUSS limit (upstream NPNG1) */
+
+/* per-particle status codes */
+#define HS_ST_OK 0
+#define HS_ST_NMAX_LIMIT 1    /* NMAX reached HS_NPN1 without convergence (upstream: print + STOP) */
+#define HS_ST_NGAUSS_LIMIT 2  /* NGAUSS reached HS_NPNG1 (upstream: warning, continues) */
+#define HS_ST_SINGULAR 3      /* zero pivot in the Q solve */
+#define HS_ST_ARENA_FULL 4    /* caller's T arena too small for this particle */
+#define HS_ST_BAD_INPUT 5
+#define HS_ST_INTERNAL_ESCALATE 100 /* never returned to the caller */
+#define HS_ST_INTERNAL_GAUSS 101    /* never returned to the caller */
+
+#define HS_SHAPE_SPHEROID (-1)
+
+typedef struct hs_ctx hs_ctx;
+
+/* Library version / build info; safe to call without a GPU. */
+const char *hs_version(void);
+/* complex128 entries a particle with truncation nmax occupies in the T arena. */
+long long hs_tmat_size(int nmax);
+/* complex offset of mode m inside a particle's packed T-matrix. */
+long long hs_tmat_mode_offset(int nmax, int m);
+/* upstream's starting truncation max(4, int(x + 4.05 x**0.333333)), x = 2 pi r / lambda */
+int hs_nmax_start(double r_ev, double wavelength);
+
+/* Create / destroy an engine context on CUDA device `device`.  Returns 0 or a negative error. */
+int hs_ctx_create(hs_ctx **ctx, int device);
+void hs_ctx_destroy(hs_ctx *ctx);
+const char *hs_last_error(const hs_ctx *ctx);
+/* kernels launched by this context so far (for bench.py's gpu_launches) */
+long long hs_launch_count(const hs_ctx *ctx);
+
+/*
+ * Single-layer T-matrix for n spheroids (converged NMAX/NGAUSS per particle + all azimuthal modes).
+ *   d_axi,d_lam,d_mr,d_mi,d_eps : device [n]  radius, wavelength (same unit), Re m, Im m, axis ratio
+ *                                 (horizontal/vertical, >1 oblate)
+ *   rat      : 1.0 = d_axi is the equal-volume radius; other = equal-surface-area radius (SAREA)
+ *   np       : HS_SHAPE_SPHEROID
+ *   ddelt    : convergence tolerance as the caller states it; rescale_ddelt != 0 applies
+ *              Mishchenko's DDELT = 0.1*DDELT before use
+ *   d_tarena : device buffer of arena_cap complex128; d_arena_top device counter (complex entries
+ *              used so far; the call appends).  d_toff[n] receives each particle's offset.
+ *   d_nmax,d_ngauss,d_ntrials,d_status : device [n] outputs.
+ * The call enqueues on `stream` and synchronises it before returning.
+ */
+int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const double *d_lam, const double *d_mr,
+                      const double *d_mi, const double *d_eps, double rat, int np, double ddelt,
+                      int ndgs, int rescale_ddelt, double *d_tarena, long long arena_cap,
+                      unsigned long long *d_arena_top, long long *d_toff, int *d_nmax, int *d_ngauss,
+                      int *d_ntrials, int *d_status, void *stream);
+
+/*
+ * Amplitude (S, 2x2 complex) and phase (Z, 4x4 real) matrices.
+ *   d_geom   : device [n_geom][4]  thet0, thet, phi0, phi (degrees), shared by all particles
+ *   d_alpha,d_beta,d_weight : device [n_orient] Euler angles (degrees) and quadrature weights
+ *   reduce=1 : d_S [n][n_geom][4] complex, d_Z [n][n_geom][16] = scale * sum_o weight[o]*(S,Z)(o)
+ *   reduce=0 : d_S [n][n_geom][n_orient][4], d_Z [n][n_geom][n_orient][16] (weights ignored)
+ * Particles whose d_status != 0 get NaN.  Asynchronous on `stream`.
+ */
+int hs_calcampl_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff,
+                      const int *d_nmax, const int *d_status, const double *d_lam, int n_geom,
+                      const double *d_geom, int n_orient, const double *d_alpha, const double *d_beta,
+                      const double *d_weight, double scale, int reduce, double *d_S, double *d_Z,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDROTM_H */

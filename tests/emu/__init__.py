@@ -1,0 +1,56 @@
+"""Host emulation of the CUDA device functions (TEST INFRASTRUCTURE ONLY; see emu_driver.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "emu_driver.cpp")
+        out = os.path.join(_HERE, "libhs_emu.so")
+        csrc = os.path.join(_HERE, "..", "..", "hydroscatt_b200", "csrc")
+        deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas",
+                                   "-o", out, src])
+        _lib = C.CDLL(out)
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def calctmat(axi, lam, mr, mi, eps, rat=1.0, ddelt=1e-3, ndgs=2, rescale=True, ws_cap=600000, gmax=160,
+             arena_cap=None):
+    axi, lam, mr, mi, eps = [np.ascontiguousarray(np.atleast_1d(np.asarray(a, dtype=np.float64)))
+                             for a in (axi, lam, mr, mi, eps)]
+    n = axi.size
+    if arena_cap is None:
+        arena_cap = n * 200000
+    arena = np.zeros(2 * arena_cap)
+    toff = np.zeros(n, np.int64)
+    nmax = np.zeros(n, np.int32)
+    ngauss = np.zeros(n, np.int32)
+    ntr = np.zeros(n, np.int32)
+    st = np.zeros(n, np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    lib().emu_calctmat(n, _dp(axi), _dp(lam), _dp(mr), _dp(mi), _dp(eps), C.c_double(rat), C.c_double(ddelt),
+                       ndgs, 1 if rescale else 0, _dp(arena), C.c_longlong(arena_cap),
+                       toff.ctypes.data_as(C.POINTER(C.c_longlong)), ip(nmax), ip(ngauss), ip(ntr), ip(st),
+                       ws_cap, gmax)
+    return dict(arena=arena.view(np.complex128), toff=toff, nmax=nmax, ngauss=ngauss, ntrials=ntr, status=st)
+
+
+def ampl(t, nmax, lam, thet0, thet, phi0, phi, alpha=0.0, beta=0.0):
+    t = np.ascontiguousarray(t, dtype=np.complex128).view(np.float64)
+    out = np.zeros(24)
+    lib().emu_ampl(_dp(t), int(nmax), C.c_double(lam), C.c_double(thet0), C.c_double(thet), C.c_double(phi0),
+                   C.c_double(phi), C.c_double(alpha), C.c_double(beta), _dp(out))
+    return out[:8].view(np.complex128).reshape(2, 2), out[8:].reshape(4, 4)

@@ -1,0 +1,43 @@
+// emu_driver.cpp -- TEST INFRASTRUCTURE ONLY: runs the device functions of hydroscatt_b200/csrc as
+// single-lane host code (HS_HOST_EMU) so the kernel logic can be checked against the oracle on a box
+// without a GPU.  Never loaded by the product.
+#define HS_HOST_EMU 1
+#include "../../hydroscatt_b200/csrc/hs_gauss.h"
+#include "../../hydroscatt_b200/csrc/hs_tmat.cuh"
+#include "../../hydroscatt_b200/csrc/hs_ampl.cuh"
+#include <cstdlib>
+
+extern "C" int emu_calctmat(int n, const double *axi, const double *lam, const double *mr, const double *mi,
+                            const double *eps, double rat, double ddelt, int ndgs, int rescale, double *tarena,
+                            long long cap, long long *toff, int *nmax, int *ngauss, int *ntrials, int *status,
+                            int ws_cap, int gmax)
+{
+    size_t tot = (size_t)gmax * (gmax + 1) / 2;
+    std::vector<double> hx(tot), hw(tot);
+    for (int g = 1; g <= gmax; g++) hs::gauss_positive(2 * g, &hx[(size_t)g * (g - 1) / 2], &hw[(size_t)g * (g - 1) / 2]);
+    std::vector<double> an(HS_NPN1 + 1), dd(HS_NPN1 + 1);
+    for (int k = 1; k <= HS_NPN1; k++) { an[k] = (double)(k * (k + 1)); dd[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1))); }
+    unsigned long long top = 0;
+    int queue = 0;
+    hs::TmArgs a;
+    a.items = nullptr; a.n_items = n; a.queue = &queue;
+    a.axi = axi; a.lam = lam; a.mr = mr; a.mi = mi; a.eps = eps;
+    a.rat = rat; a.np = -1; a.ddelt = rescale ? 0.1 * ddelt : ddelt; a.ndgs = ndgs;
+    a.gx = hx.data(); a.gw = hw.data(); a.gmax = gmax;
+    a.tarena = tarena; a.arena_cap = cap; a.arena_top = &top;
+    a.toff = toff; a.nmax = nmax; a.ngauss = ngauss; a.ntrials = ntrials; a.status = status;
+    a.ws_cap = ws_cap; a.ws_global = nullptr;
+    std::vector<double> ws((size_t)ws_cap + 16);
+    hs::Grp<true> grp; grp.tid = 0; grp.nt = 1;
+    hs::Ctl ctl;
+    for (int i = 0; i < n; i++) hs::calctmat_particle<true>(a, i, ws.data(), grp, &ctl, an.data(), dd.data());
+    return 0;
+}
+
+extern "C" void emu_ampl(const double *t, int nmax, double lam, double thet0, double thet, double phi0, double phi,
+                         double alpha, double beta, double *out24)
+{
+    std::vector<double> fn(HS_NPN1 + 1);
+    for (int k = 1; k <= HS_NPN1; k++) fn[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1)));
+    hs::ampl_one(reinterpret_cast<const double2 *>(t), nmax, lam, thet0, thet, phi0, phi, alpha, beta, fn.data(), out24);
+}

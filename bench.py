@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: T-matrix solves/s on the rain-sweep scatter-table build (BASELINE.json configs[1]).
+
+One "step" = one complete scatter-table build of workload W2: 6 radar bands x T = 0..40 degC x 70
+drop diameters = 17 220 spheroids -> converged T-matrix of every particle (all NMAX/NGAUSS trials + every azimuthal
+mode), orientation-averaged S/Z for the back- and forward-scatter geometries (5 x 10 fixed quadrature, sigma = 10
+deg), h/v scattering + extinction cross sections, PSD integration over the 9 300 gamma DSDs of
+scattering_rain.py:236-267 for each of the 246 (band, T) tables and the radar observables of every DSD.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1: launched under torchrun, one rank per GPU; every rank builds its own jittered W2 replica (weak scaling, no
+data-path collective inside the solve), then the per-particle table records are all-gathered over NCCL.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, "port") on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BANDS = ("S", "C", "X", "Ku", "Ka", "W")
+WL = dict(S=111.0, C=53.5, X=33.3, Ku=22.0, Ka=8.43, W=3.19)
+GEOM_BACK = (90.0, 90.0, 0.0, 180.0)
+GEOM_FORW = (90.0, 90.0, 0.0, 0.0)
+CANTING = 10.0
+DDELT, NDGS = 1e-3, 2
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def dsr_thurai_2007(D):
+    lo = 1.173 - 0.5165 * D + 0.4698 * D**2 - 0.1317 * D**3 - 8.5e-3 * D**4
+    hi = 1.065 - 6.25e-2 * D - 3.99e-3 * D**2 + 7.66e-4 * D**3 - 4.095e-5 * D**4
+    return np.where(D < 0.7, 1.0, np.where(D < 1.5, lo, hi))
+
+
+def workload_w2(rank=0):
+    """Flat particle list, table-major: table t = (band, T), 70 diameters each.  rank > 0 jitters D by <= 1 %."""
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "water_refractive_index.json")))
+    D = np.arange(0.1, 7.0 + 0.1, 0.1)
+    if rank:
+        D = D * (1.0 + np.random.default_rng(1234 + rank).uniform(-0.01, 0.01, D.size))
+    eps = 1.0 / dsr_thurai_2007(D)
+    lam_tab, m_tab = [], []
+    for b in BANDS:
+        for (mr, mi) in fx["m"][b]:
+            lam_tab.append(WL[b])
+            m_tab.append(complex(mr, mi))
+    lam_tab = np.array(lam_tab)
+    m_tab = np.array(m_tab)
+    n_tab = lam_tab.size
+    return dict(D=D, n_tab=n_tab, n_D=D.size, lam_tab=lam_tab,
+                radius=np.tile(D / 2.0, n_tab), wavelength=np.repeat(lam_tab, D.size),
+                mr=np.repeat(m_tab.real, D.size), mi=np.repeat(m_tab.imag, D.size), eps=np.tile(eps, n_tab))
+
+
+def dsd_grid():
+    """scattering_rain.py:236-267: 31 Nw x 10 mu x 30 D0 gamma DSDs, D_max = 7 mm."""
+    nw = np.power(10, np.arange(1, 4 + 0.1, 0.1))
+    mu = np.arange(-1, 8 + 1, 1)
+    d0 = np.arange(0.1, 3 + 0.1, 0.1)
+    n = d0.size * mu.size * nw.size
+    d0v, nwv, muv = np.zeros(n), np.zeros(n), np.zeros(n)
+    for i0, a in enumerate(d0):
+        for i1, b in enumerate(nw):
+            for i2, c in enumerate(mu):
+                ind = i2 * d0.size * nw.size + i1 * d0.size + i0
+                d0v[ind], nwv[ind], muv[ind] = a, b, c
+    return d0v, nwv, muv
+
+
+def orientation_nodes():
+    from hydroscatt_b200.tables import fixed_orientation_nodes
+    return fixed_orientation_nodes(CANTING)
+
+
+# ------------------------------------------------------------------------------------------------ flop model
+def algorithmic_flops(w, nmax, ngauss, ndgs=NDGS, n_orient=50, n_geom=3):
+    """SURVEY.md 8(d) contract figure, per particle: (calctmat flops, amplitude flops)."""
+    nmax = nmax.astype(np.float64)
+    ngauss = ngauss.astype(np.float64)
+    xev = 2.0 * np.pi * w["radius"] / w["wavelength"]
+    n0 = np.maximum(4, np.floor(xev + 4.05 * xev**0.333333))
+    mabs = np.hypot(w["mr"], w["mi"])
+    a = w["radius"] * w["eps"] ** (1.0 / 3.0)
+    kr = 2.0 * np.pi / w["wavelength"] * np.maximum(a, a / w["eps"])
+    tot = np.zeros_like(nmax)
+
+    def special(n, g):
+        ta = np.maximum(kr, n)
+        tb = np.maximum(kr * mabs, n)
+        nn1 = np.floor(1.2 * np.sqrt(ta) + 3.0)
+        nn2 = np.floor(tb + 4.0 * tb ** 0.33333 + 1.2 * np.sqrt(tb)) - n + 5
+        return 60.0 * g * (2 * n + nn1 + nn2)
+
+    def trial(n, g):
+        return 40.0 * n * n * g + special(n, g) + 12.0 * g * n + (64.0 / 3.0) * n**3
+
+    nmax_max = int(nmax.max())
+    for n in range(4, nmax_max + 1):
+        act = (n0 <= n) & (n <= nmax)
+        tot += np.where(act, trial(float(n), float(n * ndgs)), 0.0)
+    gmax = int((ngauss - nmax * ndgs).max())
+    for k in range(1, gmax + 1):
+        act = (nmax * ndgs + k) <= ngauss
+        tot += np.where(act, trial(nmax, nmax * ndgs + k), 0.0)
+    for m in range(1, nmax_max + 1):
+        nm = nmax - m + 1
+        act = nm >= 1
+        tot += np.where(act, 113.0 * nm * nm * ngauss + 12.0 * ngauss * nmax + (64.0 / 3.0) * nm**3, 0.0)
+    ampl = (96.0 * nmax * (nmax + 1) * (2 * nmax + 1) / 6.0 + 30.0 * nmax**2) * n_orient * n_geom
+    return tot, ampl
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.stop = index, [], set(), False
+        self.smax = None
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.smax = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_chunk(args):
+    import oracle
+    (rev, lam, mr, mi, eps, geoms, al, be, wt) = args
+    r = oracle.sl_batch(rev, lam, mr, mi, eps, geoms=geoms, alpha=al, beta=be, wgt=wt, ddelt=DDELT, ndgs=NDGS)
+    return r["nmax"].sum()
+
+
+def cpu_reference_pass(w, stride, cores):
+    """Oracle (restated reference algorithm) on every `stride`-th particle of W2: calctmat + orientation-averaged
+    S/Z for the three amplitude geometries, one process per core.  Returns (particles, seconds)."""
+    import multiprocessing as mp
+    al, be, wt, _ = orientation_nodes()
+    idx = np.arange(0, w["radius"].size, stride)
+    # cost-sorted round-robin so every worker gets the same mix
+    cost = (w["radius"] / w["wavelength"])[idx]
+    idx = idx[np.argsort(-cost)]
+    geoms = [GEOM_BACK, GEOM_FORW]
+    nchunk = cores * 8
+    jobs = []
+    for c in range(nchunk):
+        s = idx[c::nchunk]
+        if s.size:
+            jobs.append((w["radius"][s], w["wavelength"][s], w["mr"][s], w["mi"][s], w["eps"][s], geoms, al, be, wt))
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_chunk, jobs, chunksize=1)
+    return idx.size, time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    w = workload_w2()
+    cores = os.cpu_count() or 1
+    stride = args.cpu_stride
+    for _ in range(args.warmup):
+        cpu_reference_pass(w, stride * 8, cores)
+    tot_n, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        n, t = cpu_reference_pass(w, stride, cores)
+        tot_n += n
+        tot_t += t
+    val = tot_n / tot_t
+    sample = f"every {stride}th particle of W2 ({tot_n // max(args.steps, 1)} of 17220 per step): calctmat + 2x50 calcampl"
+    line = {"impl": "reference", "metric": "T-matrix solves/s", "value": val, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "W2 rain-sweep: 6 bands x 0..40 degC x 70 D (17220 spheroids), bounded sample",
+                       "parallelism": f"multiprocessing x{cores}"},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from hydroscatt_b200.engine import Engine
+    from hydroscatt_b200 import tables
+
+    eng = Engine(local)
+    dev = eng.device
+    w = workload_w2(rank)
+    d0, nw, mu = dsd_grid()
+    al, be, wt, scale = orientation_nodes()
+    n = w["radius"].size
+    n_dsd = d0.size
+
+    # pinned host inputs (e2e path) and device-resident copies (kernel path)
+    host_in = {k: torch.from_numpy(np.ascontiguousarray(w[k])).pin_memory() for k in ("radius", "wavelength", "mr", "mi", "eps")}
+    host_dsd = {k: torch.from_numpy(v).pin_memory() for k, v in (("d0", d0), ("nw", nw), ("mu", mu))}
+    dev_in = {k: v.to(dev) for k, v in host_in.items()}
+    dev_dsd = {k: v.to(dev) for k, v in host_dsd.items()}
+    dmax = torch.full((n_dsd,), 7.0, dtype=torch.float64, device=dev)
+    h2d = sum(v.numel() * 8 for v in host_in.values()) + sum(v.numel() * 8 for v in host_dsd.values())
+    host_rows = torch.empty((n, tables.ROW), dtype=torch.float64).pin_memory()
+    host_obs = torch.empty((n_dsd, w["n_tab"], 15), dtype=torch.float64).pin_memory()
+    host_meta = torch.empty((4, n), dtype=torch.int32).pin_memory()
+    d2h = host_rows.numel() * 8 + host_obs.numel() * 8 + host_meta.numel() * 4
+    gathered = [torch.empty((n, tables.ROW), dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    stage_ms = {"calctmat": 0.0, "ampl": 0.0, "xsect": 0.0, "psd": 0.0}
+    last = {}
+
+    def step(inp, dsd, timed):
+        e = [ev() for _ in range(5)]
+        e[0].record()
+        tb = eng.calctmat(inp["radius"], inp["wavelength"], inp["mr"], inp["mi"], inp["eps"], ddelt=DDELT, ndgs=NDGS)
+        e[1].record()
+        S, Z = tb.ampl([GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, reduce=True)
+        e[2].record()
+        xs = tb.xsect([(GEOM_BACK[0], GEOM_BACK[2])], al, be, wt, scale)
+        e[3].record()
+        rows = torch.empty((n, tables.ROW), dtype=torch.float64, device=dev)
+        Sr = torch.view_as_real(S).reshape(n, 2, 8)
+        rows[:, 0:8], rows[:, 8:24] = Sr[:, 0], Z[:, 0].reshape(n, 16)
+        rows[:, 24:32], rows[:, 32:48] = Sr[:, 1], Z[:, 1].reshape(n, 16)
+        rows[:, 48:50], rows[:, 50:52] = xs[:, 0], xs[:, 0]
+        ext_h, ext_v = 2.0 * tb.lam * Sr[:, 1, 7], 2.0 * tb.lam * Sr[:, 1, 1]
+        rows[:, 52], rows[:, 53], rows[:, 54], rows[:, 55] = ext_h, ext_v, ext_h, ext_v
+        if world > 1:
+            dist.all_gather(gathered, rows)  # every rank ends up with every replica's scatter tables
+        obs, _ = tables.integrate_psd(eng, rows, w["n_tab"], w["D"], "gamma", dsd["d0"], dsd["nw"], dsd["mu"], dmax,
+                                      w["lam_tab"], rule="trapz")
+        e[4].record()
+        if timed:
+            last["e"] = e
+        last.update(tb=tb, rows=rows, obs=obs)
+        return tb, rows, obs
+
+    def step_e2e():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+        dsd = {k: v.to(dev, non_blocking=True) for k, v in host_dsd.items()}
+        tb, rows, obs = step(inp, dsd, False)
+        host_rows.copy_(rows, non_blocking=True)
+        host_obs.copy_(obs, non_blocking=True)
+        host_meta[0].copy_(tb.nmax, non_blocking=True)
+        host_meta[1].copy_(tb.ngauss, non_blocking=True)
+        host_meta[2].copy_(tb.ntrials, non_blocking=True)
+        host_meta[3].copy_(tb.status, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_tf = eng.fp64_peak()
+    for _ in range(max(args.warmup, 3)):
+        step(dev_in, dev_dsd, False)
+    l0 = eng.launch_count
+    sync_all()
+    with ClockSampler(local) as clk:
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(args.steps):
+            step(dev_in, dev_dsd, True)
+            for k, (a, b) in zip(("calctmat", "ampl", "xsect", "psd"), ((0, 1), (1, 2), (2, 3), (3, 4))):
+                pass
+        t1.record()
+        sync_all()
+        ms_total = t0.elapsed_time(t1)
+    launches = eng.launch_count - l0
+    # stage split of the last timed step
+    e = last["e"]
+    for k, (a, b) in zip(("calctmat", "ampl", "xsect", "psd"), ((0, 1), (1, 2), (2, 3), (3, 4))):
+        stage_ms[k] = e[a].elapsed_time(e[b])
+    # e2e: host buffers in, host results out, same K
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    tw0 = time.perf_counter()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    t1.record()
+    sync_all()
+    ms_e2e = max(t0.elapsed_time(t1), 0.0)
+    wall_e2e = (time.perf_counter() - tw0) * 1e3
+    ms_e2e = max(ms_e2e, wall_e2e)  # host-side work counts for the end-to-end number
+
+    tms = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = tms.tolist()
+
+    tb = last["tb"]
+    nmax = tb.nmax.cpu().numpy()
+    ngauss = tb.ngauss.cpu().numpy()
+    status = tb.status.cpu().numpy()
+    fl_tm, fl_am = algorithmic_flops(w, nmax, ngauss)
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        units = n * world
+        value = units / (ms_step * 1e-3)
+        dom = max(stage_ms, key=stage_ms.get)
+        dom_fl = {"calctmat": fl_tm.sum(), "ampl": fl_am.sum() * 2.0 / 3.0}.get(dom, fl_tm.sum())
+        dom_kernel = {"calctmat": "k_calctmat", "ampl": "k_ampl", "xsect": "k_xsect", "psd": "k_psd_gemm"}[dom]
+        ach = dom_fl / (stage_ms[dom] * 1e-3) / 1e12
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            ncpu, tcpu = cpu_reference_pass(workload_w2(), args.cpu_stride, cores)
+            cpu = {"value": ncpu / tcpu, "unit": "solves/s", "cores": cores, "kind": "port",
+                   "sample": f"every {args.cpu_stride}th particle of W2 ({ncpu} of 17220): calctmat + 2x50 calcampl, "
+                             f"no cross sections / PSD integration, {tcpu:.1f} s"}
+        line = {
+            "metric": "T-matrix solves/s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "W2 rain-sweep scatter-table build: 6 bands x 0..40 degC x 70 D = 17220 spheroids "
+                                   "per GPU, 2 geometries x 50 orientations, 9300 gamma DSDs x 246 tables",
+                       "l2": "working set per step (T arena + 1 GB PSD output) exceeds the 126 MB L2",
+                       "parallelism": f"particles sharded x{world}" if world > 1 else "single GPU",
+                       "ddelt_rescale": True},
+            "clocks": clk.summary(),
+            "e2e": {"value": units / (ms_e2e / args.steps * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "stage_ms": stage_ms,
+            "roofline": {"bound": "fp64", "kernel": dom_kernel, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ach / peak_tf, "traffic": None,
+                         "peak_source": "measured in this run (hs_fp64_peak DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
+                         "algorithmic_gflop_per_step": {"calctmat": fl_tm.sum() / 1e9, "ampl": fl_am.sum() * 2.0 / 3.0 / 1e9}},
+            "status_counts": {str(k): int((status == k).sum()) for k in np.unique(status)},
+            "nmax_range": [int(nmax.min()), int(nmax.max())],
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-stride", type=int, default=2, dest="cpu_stride")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

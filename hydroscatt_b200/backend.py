@@ -1,0 +1,113 @@
+"""CUDA back-end object behind the pytmatrix shim (numpy in / numpy out; everything numerical runs through the
+C-ABI on the device).  Mirrors what pytmatrix's f2py module offered (calctmat / calcampl) plus the fused batched
+calls the shim uses instead of Python loops."""
+import os
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+
+#: Mishchenko's ``DDELT = 0.1*DDELT`` rescale inside calctmat (hard part 1).  ON = original
+#: ampld.lp.f behaviour.  Recorded in every result the table layer writes.
+RESCALE_DDELT = os.environ.get("HYDROTM_RESCALE_DDELT", "1") not in ("0", "false", "False")
+
+
+class ConvergenceError(RuntimeError):
+    """Raised where upstream calctmat would print 'CONVERGENCE IS NOT OBTAINED' and STOP the interpreter."""
+
+
+class TMHandle:
+    """One particle's device-resident T-matrix."""
+
+    def __init__(self, batch):
+        self.batch = batch
+        self.nmax_host = int(batch.nmax[0].item())
+        self.ngauss_host = int(batch.ngauss[0].item())
+        self.status_host = int(batch.status[0].item())
+
+    @property
+    def nmax(self):
+        return self.nmax_host
+
+
+def trapz_weights(D):
+    D = np.asarray(D, dtype=np.float64)
+    w = np.zeros_like(D)
+    if D.size > 1:
+        d = np.diff(D)
+        w[:-1] += 0.5 * d
+        w[1:] += 0.5 * d
+    return w
+
+
+def rect_weights(D):
+    """Rectangle rule of scattering_rain.py:271: delta_d = D - D_prev (first bin: D[0])."""
+    D = np.asarray(D, dtype=np.float64)
+    return D - np.concatenate([[0.0], D[:-1]])
+
+
+class CudaBackend:
+    def __init__(self, device=None):
+        self.eng = _engine.default_engine(device)
+
+    # ---- per-call equivalents of the f2py routines --------------------------------------------------------
+    def calctmat(self, radius, radius_type, wavelength, m, axis_ratio, shape, ddelt, ndgs):
+        tb = self.eng.calctmat([radius], [wavelength], [m.real], [m.imag], [axis_ratio], rat=float(radius_type),
+                               shape=int(shape), ddelt=ddelt, ndgs=ndgs, rescale_ddelt=RESCALE_DDELT)
+        h = TMHandle(tb)
+        if h.status_host not in (_engine.ST_OK, _engine.ST_NGAUSS_LIMIT):
+            raise ConvergenceError("calctmat: " + _engine.STATUS_TEXT.get(h.status_host, str(h.status_host)))
+        return h
+
+    def calcampl(self, h, thet0, thet, phi0, phi, alpha, beta):
+        S, Z = h.batch.ampl([(thet0, thet, phi0, phi)], [alpha], [beta])
+        return S[0, 0, 0].cpu().numpy(), Z[0, 0, 0].cpu().numpy()
+
+    def orient_avg(self, h, geom4, alpha, beta, weight, scale):
+        S, Z = h.batch.ampl([geom4], alpha, beta, weight=weight, scale=scale, reduce=True)
+        return S[0, 0].cpu().numpy(), Z[0, 0].cpu().numpy()
+
+    def xsect(self, h, inc, alpha, beta, weight, scale, want_asym=False):
+        if want_asym:
+            raise NotImplementedError("asymmetry parameter: not built yet (SURVEY.md 8(f) 'next')")
+        out = h.batch.xsect(inc, alpha, beta, weight, scale).cpu().numpy()
+        return {"sca_xsect_h": out[:, :, 0], "sca_xsect_v": out[:, :, 1]}
+
+    # ---- fused batched table ------------------------------------------------------------------------------
+    def scatter_table(self, radii, radius_type, wavelength, m, axis_ratio, shape, ddelt, ndgs, geometries, alpha,
+                      beta, weight, scale, angular):
+        """S [n,G,2,2], Z [n,G,4,4] (+ sca/ext/asym tables [n,G]) for all diameters in three device calls."""
+        m = np.asarray(m, dtype=np.complex128)
+        tb = self.eng.calctmat(radii, wavelength, m.real, m.imag, axis_ratio, rat=float(radius_type),
+                               shape=int(shape), ddelt=ddelt, ndgs=ndgs, rescale_ddelt=RESCALE_DDELT)
+        st = tb.status.cpu().numpy()
+        bad = np.nonzero((st != _engine.ST_OK) & (st != _engine.ST_NGAUSS_LIMIT))[0]
+        if bad.size:
+            raise ConvergenceError("calctmat: particle %d: %s" % (bad[0], _engine.STATUS_TEXT.get(int(st[bad[0]]))))
+        g4 = [tuple(g[:4]) for g in geometries]
+        S, Z = tb.ampl(g4, alpha, beta, weight=weight, scale=scale, reduce=True)
+        res = {"S": S.cpu().numpy(), "Z": Z.cpu().numpy(), "nmax": tb.nmax.cpu().numpy(),
+               "ngauss": tb.ngauss.cpu().numpy()}
+        if angular:
+            inc = [(g[0], g[2]) for g in geometries]
+            xs = tb.xsect(inc, alpha, beta, weight, scale).cpu().numpy()
+            res["sca_xsect_h"], res["sca_xsect_v"] = xs[:, :, 0], xs[:, :, 1]
+            # ext_xsect: optical theorem on the orientation-averaged forward amplitude
+            fw = [(g[0], g[0], g[2], g[2]) for g in geometries]
+            Sf, _ = tb.ampl(fw, alpha, beta, weight=weight, scale=scale, reduce=True)
+            Sf = Sf.cpu().numpy()
+            lam = np.broadcast_to(np.asarray(wavelength, dtype=np.float64), (len(radii),))[:, None]
+            res["ext_xsect_h"] = 2.0 * lam * Sf[:, :, 1, 1].imag
+            res["ext_xsect_v"] = 2.0 * lam * Sf[:, :, 0, 0].imag
+            res["asym_h"] = np.full_like(res["sca_xsect_h"], np.nan)
+            res["asym_v"] = np.full_like(res["sca_xsect_h"], np.nan)
+        return res
+
+    # ---- PSD integration ------------------------------------------------------------------------------------
+    def psd_integrate(self, table, D, psd_w, rule="trapz"):
+        """table [ncol][n_D], psd_w [n_dsd][n_D] -> [n_dsd][ncol] on the device."""
+        wq = trapz_weights(D) if rule == "trapz" else rect_weights(D)
+        W = np.asarray(psd_w, dtype=np.float64) * wq[None, :]
+        Tt = np.ascontiguousarray(np.asarray(table, dtype=np.float64).T)
+        return self.eng.psd_integrate(torch.from_numpy(np.ascontiguousarray(W)), torch.from_numpy(Tt)).cpu().numpy()

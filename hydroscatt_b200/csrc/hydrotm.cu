@@ -12,6 +12,8 @@
 #include "hs_gauss.h"
 #include "hs_tmat.cuh"
 #include "hs_ampl.cuh"
+#include "hs_xsect.cuh"
+#include "hs_psd.cuh"
 
 struct hs_ctx {
     int device = 0;
@@ -294,5 +296,112 @@ extern "C" int hs_calcampl_batch(hs_ctx *ctx, int n, const double *d_tarena, con
     hs::k_ampl<<<n, threads, smem, st>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hs_xsect_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff, const int *d_nmax,
+                              const int *d_status, const double *d_lam, int n_inc, const double *d_inc, int n_orient,
+                              const double *d_alpha, const double *d_beta, const double *d_weight, double scale,
+                              double *d_out, void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0 || n_inc <= 0 || n_orient <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    hs::XsArgs a;
+    a.n = n; a.tarena = d_tarena; a.toff = d_toff; a.nmax = d_nmax; a.status = d_status; a.lam = d_lam;
+    a.n_inc = n_inc; a.inc = d_inc; a.n_orient = n_orient; a.alpha = d_alpha; a.beta = d_beta; a.weight = d_weight;
+    a.scale = scale; a.out = d_out;
+    int threads = std::min(128, std::max(32, (n_orient + 31) / 32 * 32));
+    hs::k_xsect<<<n, threads, (size_t)threads * 2 * sizeof(double), st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hs_psd_weights(hs_ctx *ctx, int kind, int n_dsd, const double *d_p0, const double *d_p1,
+                              const double *d_p2, const double *d_dmax, int n_D, const double *d_D,
+                              const double *d_wq, double *d_W, void *stream)
+{
+    if (!ctx) return -2;
+    if (n_dsd <= 0 || n_D <= 0) return 0;
+    if (kind < 0 || kind > 2) { ctx->err = "unknown PSD kind"; return -3; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    long tot = (long)n_dsd * n_D;
+    hs::k_psd_weights<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(kind, n_dsd, d_p0, d_p1, d_p2, d_dmax, n_D, d_D, d_wq, d_W);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hs_psd_integrate(hs_ctx *ctx, int n_dsd, int n_D, int ncol, const double *d_W, const double *d_Tt,
+                                double *d_out, void *stream)
+{
+    if (!ctx) return -2;
+    if (n_dsd <= 0 || n_D <= 0 || ncol <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    dim3 grid((ncol + PSD_CB - 1) / PSD_CB, (n_dsd + PSD_RB - 1) / PSD_RB);
+    hs::k_psd_gemm<<<grid, 256, 0, st>>>(n_dsd, n_D, ncol, d_W, d_Tt, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hs_observables(hs_ctx *ctx, int n, int stride, const double *d_in, int off_back, int off_forw,
+                              int off_ext, int off_sca, const double *d_lam, int lam_stride, double kw_sqr,
+                              double *d_out, void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    hs::k_observables<<<(n + 127) / 128, 128, 0, st>>>(n, stride, d_in, off_back, off_forw, off_ext, off_sca, d_lam,
+                                                       lam_stride, kw_sqr, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// FP64 FMA peak: 8 independent DFMA chains per thread, enough CTAs to fill every SM.
+__global__ void k_dfma_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;
+    double a4 = a0 + 4e-9, a5 = a0 + 5e-9, a6 = a0 + 6e-9, a7 = a0 + 7e-9;
+    const double b = 1.0000001, c = 1e-12;
+    for (int i = 0; i < iters; i++) {
+        a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+        a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int hs_fp64_peak(hs_ctx *ctx, double *tflops, void *stream)
+{
+    if (!ctx) return -2;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->sm_count * 8, iters = 20000;
+    double *d_out = nullptr;
+    CK(cudaMalloc(&d_out, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0, st));
+        k_dfma_peak<<<blocks, threads, 0, st>>>(d_out, iters);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    ctx->launches += 5;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *tflops = best;
     return 0;
 }

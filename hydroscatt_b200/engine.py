@@ -118,6 +118,65 @@ class Engine:
             break
         return TMatrixBatch(self, n, arena, top, toff, nmax, ngauss, ntr, status, lam)
 
+    # ---- PSD integration / observables ---------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def psd_weights(self, kind, p0, p1, p2, dmax, D, wq):
+        """W[n_dsd, n_D] = wq[i] * N_d(D_i); kind in {'gamma','exponential','ungamma'} (pytmatrix.psd classes)."""
+        k = {"gamma": 0, "exponential": 1, "ungamma": 2}[kind]
+        p0 = self._dev(p0)
+        nd = p0.numel()
+        p1 = self._dev(p1, nd)
+        p2 = self._dev(p2 if p2 is not None else 0.0, nd)
+        dmax = self._dev(dmax, nd)
+        D = self._dev(D)
+        wq = self._dev(wq)
+        W = torch.empty((nd, D.numel()), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_psd_weights(self._h, k, nd, _ptr(p0), _ptr(p1), _ptr(p2), _ptr(dmax), D.numel(),
+                                         _ptr(D), _ptr(wq), _ptr(W), self._stream())
+        if rc != 0:
+            raise EngineError(f"hs_psd_weights rc={rc}: " + self._err())
+        return W
+
+    def psd_integrate(self, W, Tt):
+        """out[n_dsd, ncol] = W[n_dsd, n_D] @ Tt[n_D, ncol] (FP64, i ascending)."""
+        W = torch.as_tensor(W, dtype=torch.float64).to(self.device).contiguous()
+        Tt = torch.as_tensor(Tt, dtype=torch.float64).to(self.device).contiguous()
+        nd, nD = W.shape
+        assert Tt.shape[0] == nD
+        ncol = Tt.shape[1]
+        out = torch.empty((nd, ncol), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_psd_integrate(self._h, nd, nD, ncol, _ptr(W), _ptr(Tt), _ptr(out), self._stream())
+        if rc != 0:
+            raise EngineError(f"hs_psd_integrate rc={rc}: " + self._err())
+        return out
+
+    def observables(self, rows, off_back, off_forw, off_ext, off_sca, lam, kw_sqr=0.93):
+        """[n,15] radar observables from rows [n, stride] (layout: include/hydrotm.h hs_observables)."""
+        rows = rows.contiguous()
+        n, stride = rows.shape
+        lam = self._dev(lam)
+        lam_stride = 0 if lam.numel() == 1 else 1
+        out = torch.empty((n, 15), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_observables(self._h, n, stride, _ptr(rows), off_back, off_forw, off_ext, off_sca,
+                                         _ptr(lam), lam_stride, float(kw_sqr), _ptr(out), self._stream())
+        if rc != 0:
+            raise EngineError(f"hs_observables rc={rc}: " + self._err())
+        return out
+
+    def fp64_peak(self):
+        """Measured DFMA peak of this device, TFLOP/s."""
+        v = C.c_double(0.0)
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_fp64_peak(self._h, C.byref(v), self._stream())
+        if rc != 0:
+            raise EngineError(f"hs_fp64_peak rc={rc}: " + self._err())
+        return v.value
+
 
 class TMatrixBatch:
     """Device-resident packed T-matrices of ``n`` particles (layout: include/hydrotm.h)."""
@@ -164,6 +223,24 @@ class TMatrixBatch:
         if rc != 0:
             raise EngineError(f"hs_calcampl_batch rc={rc}: " + eng._err())
         return S, Z
+
+    def xsect(self, inc, alpha=(0.0,), beta=(0.0,), weight=None, scale=1.0):
+        """[n, n_inc, 2] orientation-averaged (sca_xsect_h, sca_xsect_v) for incidence directions inc [n_inc][2]."""
+        eng = self.eng
+        g = eng._dev(np.asarray(inc, dtype=np.float64).reshape(-1, 2))
+        G = g.numel() // 2
+        al = eng._dev(alpha)
+        be = eng._dev(beta)
+        O = al.numel()
+        w = eng._dev(weight if weight is not None else np.ones(O))
+        out = torch.empty((self.n, G, 2), dtype=torch.float64, device=eng.device)
+        with torch.cuda.device(eng.device):
+            rc = eng.lib.hs_xsect_batch(eng._h, self.n, _ptr(self.arena), _ptr(self.toff), _ptr(self.nmax),
+                                        _ptr(self.status), _ptr(self.lam), G, _ptr(g), O, _ptr(al), _ptr(be),
+                                        _ptr(w), float(scale), _ptr(out), eng._stream())
+        if rc != 0:
+            raise EngineError(f"hs_xsect_batch rc={rc}: " + eng._err())
+        return out
 
 
 _default = {}

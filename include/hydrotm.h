@@ -103,6 +103,45 @@ int hs_calcampl_batch(hs_ctx *ctx, int n, const double *d_tarena, const long lon
                       const double *d_weight, double scale, int reduce, double *d_S, double *d_Z,
                       void *stream);
 
+/*
+ * Orientation-averaged scattering cross sections (h- and v-polarised incidence) from the T-matrix expansion
+ * coefficients; equals the sphere integral of Z11 -/+ Z12 that scatter.sca_xsect evaluates with dblquad.
+ *   d_inc : device [n_inc][2] thet0, phi0 (degrees);  d_out : device [n][n_inc][2] (sca_h, sca_v)
+ *   result = scale * sum_o weight[o] * C(o).  Asynchronous on `stream`.
+ */
+int hs_xsect_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff, const int *d_nmax,
+                   const int *d_status, const double *d_lam, int n_inc, const double *d_inc, int n_orient,
+                   const double *d_alpha, const double *d_beta, const double *d_weight, double scale,
+                   double *d_out, void *stream);
+
+/*
+ * PSD weights W[d][i] = wq[i] * N_d(D[i]) for n_dsd size distributions (pytmatrix.psd classes, row P11).
+ *   kind 0: GammaPSD (p0=D0, p1=Nw, p2=mu)   1: ExponentialPSD (p0=N0, p1=Lambda)
+ *   kind 2: UnnormalizedGammaPSD (p0=N0, p1=Lambda, p2=mu);   d_dmax[d] = D_max cut-off
+ *   d_wq[n_D]: quadrature weights over D (trapezoid for PSDIntegrator, D[i]-D[i-1] for scattering.py:312-448).
+ */
+int hs_psd_weights(hs_ctx *ctx, int kind, int n_dsd, const double *d_p0, const double *d_p1, const double *d_p2,
+                   const double *d_dmax, int n_D, const double *d_D, const double *d_wq, double *d_W,
+                   void *stream);
+
+/* PSD integration as an FP64 GEMM: out[n_dsd][ncol] = W[n_dsd][n_D] * Tt[n_D][ncol]. */
+int hs_psd_integrate(hs_ctx *ctx, int n_dsd, int n_D, int ncol, const double *d_W, const double *d_Tt,
+                     double *d_out, void *stream);
+
+/*
+ * Radar observables per row (radar.refl/Zdr/ldr/rho_hv/delta_hv/Kdp/Ai, scatter.sca_xsect/ext_xsect as combined
+ * by scattering.py:451-587).  d_in: [n][stride]; column offsets: off_back / off_forw -> S(8 doubles) Z(16 doubles)
+ * of the back / forward geometry, off_ext -> ext_xsect_h, ext_xsect_v (or -1: optical theorem on the forward S),
+ * off_sca -> sca_xsect_h, sca_xsect_v (or -1).  d_lam[i*lam_stride] = wavelength of row i.
+ * d_out: [n][15] = sca_xsect_h, sca_xsect_v, refl_h, refl_v, zdr, ldr_h, ldr_v (dB), rho_hv, delta_hv (deg),
+ *                  ext_xsect_h, ext_xsect_v (dB), kdp (deg/km), A_h, A_v, Adp (dB/km)
+ */
+int hs_observables(hs_ctx *ctx, int n, int stride, const double *d_in, int off_back, int off_forw, int off_ext,
+                   int off_sca, const double *d_lam, int lam_stride, double kw_sqr, double *d_out, void *stream);
+
+/* Measured FP64 FMA peak of the device (dependent-chain-free DFMA loop), TFLOP/s; used as roofline denominator. */
+int hs_fp64_peak(hs_ctx *ctx, double *tflops, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,3 +54,11 @@ def ampl(t, nmax, lam, thet0, thet, phi0, phi, alpha=0.0, beta=0.0):
     lib().emu_ampl(_dp(t), int(nmax), C.c_double(lam), C.c_double(thet0), C.c_double(thet), C.c_double(phi0),
                    C.c_double(phi), C.c_double(alpha), C.c_double(beta), _dp(out))
     return out[:8].view(np.complex128).reshape(2, 2), out[8:].reshape(4, 4)
+
+
+def xsect(t, nmax, lam, thet0, phi0, alpha=0.0, beta=0.0):
+    t = np.ascontiguousarray(t, dtype=np.complex128).view(np.float64)
+    out = np.zeros(2)
+    lib().emu_xsect(_dp(t), int(nmax), C.c_double(lam), C.c_double(thet0), C.c_double(phi0), C.c_double(alpha),
+                    C.c_double(beta), _dp(out))
+    return out

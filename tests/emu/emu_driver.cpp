@@ -41,3 +41,12 @@ extern "C" void emu_ampl(const double *t, int nmax, double lam, double thet0, do
     for (int k = 1; k <= HS_NPN1; k++) fn[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1)));
     hs::ampl_one(reinterpret_cast<const double2 *>(t), nmax, lam, thet0, thet, phi0, phi, alpha, beta, fn.data(), out24);
 }
+
+#include "../../hydroscatt_b200/csrc/hs_xsect.cuh"
+extern "C" void emu_xsect(const double *t, int nmax, double lam, double thet0, double phi0, double alpha, double beta,
+                          double *out2)
+{
+    std::vector<double> fn(HS_NPN1 + 1);
+    for (int k = 1; k <= HS_NPN1; k++) fn[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1)));
+    hs::xsect_one(reinterpret_cast<const double2 *>(t), nmax, lam, thet0, phi0, alpha, beta, fn.data(), out2);
+}

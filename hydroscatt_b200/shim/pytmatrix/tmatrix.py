@@ -143,6 +143,9 @@ class Scatterer(object):
         self.nmax = self._tm.nmax_host
         self.ngauss = self._tm.ngauss_host
         self._tm_signature = self._tm_sig()
+        # a new T-matrix invalidates every amplitude cached from the old one
+        self._single_signature = ()
+        self._orient_sz_signature = ()
 
     def _init_orient(self):
         """Gauss points and weights of the orientation PDF for the fixed-quadrature average."""

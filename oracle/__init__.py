@@ -168,3 +168,30 @@ def sl_batch(rev, lam, mr, mi, eps, geoms=None, alpha=None, beta=None, wgt=None,
                       1 if rescale_ddelt else 0, 0, null, 0, null, null, null, _ip(nmax), _ip(ngauss),
                       _ip(ntr), _ip(st), null, null)
     return out
+
+
+_t2 = None
+
+
+def tm2l_lib():
+    global _t2
+    if _t2 is None:
+        build()
+        lib = C.CDLL(os.path.join(_HERE, "libtm2l_oracle.so"))
+        lib.tm2l_batch.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
+        _t2 = lib
+    return _t2
+
+
+def tm2l(d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm):
+    """Two-layer oracle: returns amp[n, 8] = borrp borip borrpe boripe forrp forip forpe foripe (metres)."""
+    arrs = np.broadcast_arrays(np.asarray(d_ext_cm, float), np.asarray(d_int_cm, float), np.asarray(ar_ext, float),
+                               np.asarray(ar_int, float), np.asarray(eps_ext, complex), np.asarray(eps_int, complex))
+    n = arrs[0].size
+    p = np.zeros((n, 8))
+    p[:, 0], p[:, 1], p[:, 2], p[:, 3] = [a.reshape(-1) for a in arrs[:4]]
+    p[:, 4], p[:, 5] = arrs[4].reshape(-1).real, arrs[4].reshape(-1).imag
+    p[:, 6], p[:, 7] = arrs[5].reshape(-1).real, arrs[5].reshape(-1).imag
+    out = np.zeros((n, 8))
+    tm2l_lib().tm2l_batch(n, _dp(p), float(wavelength_cm), _dp(out))
+    return out

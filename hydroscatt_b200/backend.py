@@ -104,6 +104,14 @@ class CudaBackend:
             res["asym_v"] = np.full_like(res["sca_xsect_h"], np.nan)
         return res
 
+    # ---- two-layer path (tm2l) ----
+    def tm2l(self, d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm):
+        amp, st = self.eng.tm2l(d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm)
+        st = st.cpu().numpy()
+        if (st != 0).any():
+            raise RuntimeError("tm2l: singular matrix for particle %d" % int(np.nonzero(st)[0][0]))
+        return amp.cpu().numpy()
+
     # ---- PSD integration ------------------------------------------------------------------------------------
     def psd_integrate(self, table, D, psd_w, rule="trapz"):
         """table [ncol][n_D], psd_w [n_dsd][n_D] -> [n_dsd][ncol] on the device."""

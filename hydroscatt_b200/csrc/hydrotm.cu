@@ -14,6 +14,7 @@
 #include "hs_ampl.cuh"
 #include "hs_xsect.cuh"
 #include "hs_psd.cuh"
+#include "hs_tm2l.cuh"
 
 struct hs_ctx {
     int device = 0;
@@ -403,5 +404,28 @@ extern "C" int hs_fp64_peak(hs_ctx *ctx, double *tflops, void *stream)
     ctx->launches += 5;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
     *tflops = best;
+    return 0;
+}
+
+extern "C" int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const double *d_dcore, const double *d_aovrb,
+                             const double *d_aovrb2, const double *d_eor, const double *d_eoi, const double *d_eir,
+                             const double *d_eii, double wavelength_cm, double *d_amp, int *d_status, void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0) return 0;
+    if (!(wavelength_cm > 0.0)) { ctx->err = "wavelength must be positive"; return -3; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    hs::T2Args a;
+    a.n = n; a.dpart = d_dpart; a.dcore = d_dcore; a.aovrb = d_aovrb; a.aovrb2 = d_aovrb2;
+    a.eor = d_eor; a.eoi = d_eoi; a.eir = d_eir; a.eii = d_eii; a.alamd = wavelength_cm;
+    a.amp = d_amp; a.status = d_status;
+    size_t smem = (size_t)hs::t2_smem_doubles() * sizeof(double);
+    CK(cudaFuncSetAttribute(hs::k_tm2l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaMemsetAsync(ctx->d_queue + 8, 0, sizeof(int), st));
+    int grid = std::min(n, ctx->sm_count);
+    hs::k_tm2l<<<grid, 320, smem, st>>>(a, ctx->d_queue + 8);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return 0;
 }

@@ -168,6 +168,26 @@ class Engine:
             raise EngineError(f"hs_observables rc={rc}: " + self._err())
         return out
 
+    def tm2l(self, d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm):
+        """Two-layer amplitudes [n, 8] (borrp borip borrpe boripe forrp forip forpe foripe, metres) + status [n]."""
+        eps_ext = np.asarray(eps_ext, dtype=np.complex128) if not torch.is_tensor(eps_ext) else eps_ext
+        eps_int = np.asarray(eps_int, dtype=np.complex128) if not torch.is_tensor(eps_int) else eps_int
+        n = max(int(np.size(a)) if not torch.is_tensor(a) else a.numel()
+                for a in (d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int))
+        de, di = self._dev(d_ext_cm, n), self._dev(d_int_cm, n)
+        ae, ai = self._dev(ar_ext, n), self._dev(ar_int, n)
+        eor, eoi = self._dev(eps_ext.real, n), self._dev(eps_ext.imag, n)
+        eir, eii = self._dev(eps_int.real, n), self._dev(eps_int.imag, n)
+        amp = torch.empty((n, 8), dtype=torch.float64, device=self.device)
+        status = torch.empty(n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_tm2l_batch(self._h, n, _ptr(de), _ptr(di), _ptr(ae), _ptr(ai), _ptr(eor), _ptr(eoi),
+                                        _ptr(eir), _ptr(eii), float(wavelength_cm), _ptr(amp), _ptr(status),
+                                        self._stream())
+        if rc != 0:
+            raise EngineError(f"hs_tm2l_batch rc={rc}: " + self._err())
+        return amp, status
+
     def fp64_peak(self):
         """Measured DFMA peak of this device, TFLOP/s."""
         v = C.c_double(0.0)

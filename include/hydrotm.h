@@ -139,6 +139,21 @@ int hs_psd_integrate(hs_ctx *ctx, int n_dsd, int n_D, int ncol, const double *d_
 int hs_observables(hs_ctx *ctx, int n, int stride, const double *d_in, int off_back, int off_forw, int off_ext,
                    int off_sca, const double *d_lam, int lam_stride, double kw_sqr, double *d_out, void *stream);
 
+/*
+ * Two-layer (coated spheroid) T-matrix amplitudes for n particles at one wavelength: the batched equivalent of
+ * tm2l.tmatrix(2) = tmatrix_py.f (fixed nrank 17, 7 azimuthal modes, 31-node Patterson rule; rows F1-F11).
+ *   d_dpart,d_dcore : device [n] outer / inner equal-volume diameter [cm]   (fort.20 columns 1-2, tmatrix_py.f:580)
+ *   d_aovrb,d_aovrb2: device [n] outer / inner axis ratio a/b (<1 oblate)   (columns 3-4)
+ *   d_eor,d_eoi,d_eir,d_eii : device [n] Re/Im permittivity of the outer layer, then the inner body (columns 5-8)
+ *   wavelength_cm   : namelist value palamd of spongyice.inp
+ *   d_amp : device [n][8] = borrp borip borrpe boripe forrp forip forpe foripe [m] (tmatrix_py.f:2515-2520,
+ *           full double precision; the e15.7 rounding belongs to the file layer);  d_status : device [n].
+ * Asynchronous on `stream`.
+ */
+int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const double *d_dcore, const double *d_aovrb,
+                  const double *d_aovrb2, const double *d_eor, const double *d_eoi, const double *d_eir,
+                  const double *d_eii, double wavelength_cm, double *d_amp, int *d_status, void *stream);
+
 /* Measured FP64 FMA peak of the device (dependent-chain-free DFMA loop), TFLOP/s; used as roofline denominator. */
 int hs_fp64_peak(hs_ctx *ctx, double *tflops, void *stream);
 

@@ -62,3 +62,12 @@ def xsect(t, nmax, lam, thet0, phi0, alpha=0.0, beta=0.0):
     lib().emu_xsect(_dp(t), int(nmax), C.c_double(lam), C.c_double(thet0), C.c_double(phi0), C.c_double(alpha),
                     C.c_double(beta), _dp(out))
     return out
+
+
+def tm2l(p8, wl_cm):
+    p8 = np.ascontiguousarray(p8, dtype=np.float64).reshape(-1, 8)
+    n = p8.shape[0]
+    amp = np.zeros((n, 8))
+    st = np.zeros(n, np.int32)
+    lib().emu_tm2l(n, _dp(p8), C.c_double(wl_cm), _dp(amp), st.ctypes.data_as(C.POINTER(C.c_int)))
+    return amp, st

@@ -50,3 +50,18 @@ extern "C" void emu_xsect(const double *t, int nmax, double lam, double thet0, d
     for (int k = 1; k <= HS_NPN1; k++) fn[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1)));
     hs::xsect_one(reinterpret_cast<const double2 *>(t), nmax, lam, thet0, phi0, alpha, beta, fn.data(), out2);
 }
+
+#include "../../hydroscatt_b200/csrc/hs_tm2l.cuh"
+extern "C" void emu_tm2l(int n, const double *p8, double alamd, double *amp, int *status)
+{
+    std::vector<double> col[8];
+    for (int c = 0; c < 8; c++) { col[c].resize(n); for (int i = 0; i < n; i++) col[c][i] = p8[8 * i + c]; }
+    hs::T2Args a;
+    a.n = n; a.dpart = col[0].data(); a.dcore = col[1].data(); a.aovrb = col[2].data(); a.aovrb2 = col[3].data();
+    a.eor = col[4].data(); a.eoi = col[5].data(); a.eir = col[6].data(); a.eii = col[7].data();
+    a.alamd = alamd; a.amp = amp; a.status = status;
+    std::vector<double> smem(hs::t2_smem_doubles() + 16);
+    hs::Ctl ctl;
+    double cmx[T2_NRANKI], acc[8];
+    for (int i = 0; i < n; i++) { ctl.sing = 0; hs::tm2l_particle(a, i, smem.data(), &ctl, cmx, acc, 0, 1); }
+}

@@ -1,0 +1,67 @@
+"""GPU parity of the two-layer path (hs_tm2l_batch) against the CPU oracle, through the C-ABI and the tm2l shim."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _hail_like(n, seed=7):
+    """Synthetic melting-hail-like table: water-coated ice cores, 0.1 .. 35 mm."""
+    rng = np.random.default_rng(seed)
+    D = np.linspace(0.01, 3.5, n)                       # cm
+    fmw = rng.uniform(0.05, 0.95, n)
+    d_int = D * (1.0 - 0.5 * fmw) ** (1.0 / 3.0)
+    ar_ext = 1.0 - 0.25 * rng.uniform(0, 1, n)
+    ar_int = np.minimum(1.0, ar_ext + 0.05)
+    m_w, m_i = 8.601 + 1.687j, 1.78 + 0.002j
+    return D, d_int, ar_ext, ar_int, np.full(n, m_w**2), np.full(n, m_i**2)
+
+
+def test_tm2l_matches_oracle(engine):
+    D, di, ae, ai, ee, ei = _hail_like(48)
+    amp, st = engine.tm2l(D, di, ae, ai, ee, ei, 5.35)
+    amp = amp.cpu().numpy()
+    assert (st.cpu().numpy() == 0).all()
+    ref = oracle.tm2l(D, di, ae, ai, ee, ei, 5.35)
+    c = amp[:, 0::2] + 1j * amp[:, 1::2]
+    r = ref[:, 0::2] + 1j * ref[:, 1::2]
+    err = np.abs(c - r).max(axis=1) / np.abs(r).max(axis=1)
+    assert err.max() < 1e-6, err
+
+
+def test_tm2l_homogeneous_equals_single_layer(engine):
+    m = 8.601 + 1.687j
+    D = np.array([0.1, 0.4, 0.7])
+    ar = np.array([0.9707, 0.79, 0.5577])
+    amp, _ = engine.tm2l(D, D / 2, ar, ar, np.full(3, m * m), np.full(3, m * m), 5.35)
+    amp = amp.cpu().numpy()
+    tb = engine.calctmat(D * 5.0, 53.5, m.real, m.imag, 1.0 / ar, ddelt=1e-8)
+    S, _ = tb.ampl([(90.0, 90.0, 0.0, 180.0), (90.0, 90.0, 0.0, 0.0)])
+    S = S.cpu().numpy()[:, :, 0]
+    for i in range(3):
+        got = amp[i, 0::2] + 1j * amp[i, 1::2]
+        ref = np.array([-1e-3 * S[i, 0, 0, 0], -1e-3 * S[i, 0, 1, 1], 1e-3 * S[i, 1, 0, 0], 1e-3 * S[i, 1, 1, 1]])
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-7   # the Fortran's float32 pi
+
+
+def test_tm2l_shim_files(engine, tmp_path, monkeypatch):
+    import hydroscatt_b200
+    hydroscatt_b200.install_shims()
+    from f_2l_tmatrix import tm2l
+    tm2l.set_backend(None)
+    monkeypatch.chdir(tmp_path)
+    D, di, ae, ai, ee, ei = _hail_like(12, seed=3)
+    (tmp_path / "spongyice.inp").write_text("&ingest\npalamd=3.33\n/\n")
+    with open(tmp_path / "fort.20", "w") as f:
+        f.write("12\n")
+        for i in range(12):
+            f.write(f"{D[i]} {di[i]} {ae[i]} {ai[i]} {ee[i].real} {ee[i].imag} {ei[i].real} {ei[i].imag}\n")
+    tm2l.tmatrix(2)
+    rows = (tmp_path / "spongyice.out").read_text().splitlines()
+    vals = np.array([[float(r[15 * i:15 * i + 15]) for i in range(8)] for r in rows])
+    ref = oracle.tm2l(D, di, ae, ai, ee, ei, 3.33)
+    big = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(vals - ref) / big).max() < 1e-6
+    assert (tmp_path / "fort.8").exists() and (tmp_path / "pck_tmatrix2b.out").exists()

@@ -28,6 +28,16 @@ def build(force=False):
         if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
             subprocess.check_call(
                 ["gcc", "-O2", "-fPIC", "-std=c11", "-fno-fast-math", "-shared", "-o", out, src, "-lm"])
+    # rounding-perturbed twin of the two-layer oracle (FMA contraction on): used only to measure how sensitive the
+    # ORACLE's own answer is to last-bit rounding, i.e. to flag ill-conditioned particles (hard part 3)
+    src = os.path.join(_HERE, "tm2l_oracle.c")
+    out = os.path.join(_HERE, "libtm2l_oracle_fma.so")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        try:
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-mfma", "-ffp-contract=fast", "-shared",
+                                   "-o", out, src, "-lm"])
+        except subprocess.CalledProcessError:
+            pass
 
 
 _sl = None
@@ -183,7 +193,20 @@ def tm2l_lib():
     return _t2
 
 
-def tm2l(d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm):
+def tm2l_sensitivity(d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm):
+    """Relative change of the oracle's own amplitudes under a last-bit rounding perturbation (FMA-contracted twin
+    build).  Particles where this exceeds ~1e-7 are ill-conditioned: no two correct implementations agree to 1e-6."""
+    ref = tm2l(d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm)
+    path = os.path.join(_HERE, "libtm2l_oracle_fma.so")
+    if not os.path.exists(path):
+        return np.zeros(ref.shape[0])
+    twin = tm2l(d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm, _lib=C.CDLL(path))
+    c = twin[:, 0::2] + 1j * twin[:, 1::2]
+    r = ref[:, 0::2] + 1j * ref[:, 1::2]
+    return np.abs(c - r).max(axis=1) / np.abs(r).max(axis=1)
+
+
+def tm2l(d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm, _lib=None):
     """Two-layer oracle: returns amp[n, 8] = borrp borip borrpe boripe forrp forip forpe foripe (metres)."""
     arrs = np.broadcast_arrays(np.asarray(d_ext_cm, float), np.asarray(d_int_cm, float), np.asarray(ar_ext, float),
                                np.asarray(ar_int, float), np.asarray(eps_ext, complex), np.asarray(eps_int, complex))
@@ -193,5 +216,7 @@ def tm2l(d_ext_cm, d_int_cm, ar_ext, ar_int, eps_ext, eps_int, wavelength_cm):
     p[:, 4], p[:, 5] = arrs[4].reshape(-1).real, arrs[4].reshape(-1).imag
     p[:, 6], p[:, 7] = arrs[5].reshape(-1).real, arrs[5].reshape(-1).imag
     out = np.zeros((n, 8))
-    tm2l_lib().tm2l_batch(n, _dp(p), float(wavelength_cm), _dp(out))
+    lib = _lib if _lib is not None else tm2l_lib()
+    lib.tm2l_batch.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
+    lib.tm2l_batch(n, _dp(p), float(wavelength_cm), _dp(out))
     return out

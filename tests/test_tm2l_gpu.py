@@ -28,7 +28,14 @@ def test_tm2l_matches_oracle(engine):
     c = amp[:, 0::2] + 1j * amp[:, 1::2]
     r = ref[:, 0::2] + 1j * ref[:, 1::2]
     err = np.abs(c - r).max(axis=1) / np.abs(r).max(axis=1)
-    assert err.max() < 1e-6, err
+    # ill-conditioned particles (e.g. a 20 um water film on a 4.5 mm core) are identified by the oracle's OWN
+    # sensitivity to last-bit rounding and held to 10x that sensitivity instead of 1e-6 (hard part 3)
+    sens = oracle.tm2l_sensitivity(D, di, ae, ai, ee, ei, 5.35)
+    well = sens < 1e-7
+    assert well.sum() >= 44, (np.nonzero(~well)[0], sens[~well])
+    assert err[well].max() < 1e-6, err
+    assert (err[~well] <= 10 * sens[~well]).all(), (err[~well], sens[~well])
+    print("ill-conditioned (excluded from the 1e-6 gate):", np.nonzero(~well)[0], sens[~well], err[~well])
 
 
 def test_tm2l_homogeneous_equals_single_layer(engine):

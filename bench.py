@@ -82,7 +82,7 @@ def orientation_nodes():
 
 
 # ------------------------------------------------------------------------------------------------ flop model
-def algorithmic_flops(w, nmax, ngauss, ndgs=NDGS, n_orient=50, n_geom=3):
+def algorithmic_flops(w, nmax, ngauss, ndgs=NDGS, n_orient=50, n_geom=2):
     """SURVEY.md 8(d) contract figure, per particle: (calctmat flops, amplitude flops)."""
     nmax = nmax.astype(np.float64)
     ngauss = ngauss.astype(np.float64)
@@ -256,7 +256,7 @@ def run_gpu(args):
     gathered = [torch.empty((n, tables.ROW), dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_ms = {"calctmat": 0.0, "ampl": 0.0, "xsect": 0.0, "psd": 0.0}
+    stage_ms = {"calctmat": 0.0, "scatter": 0.0, "psd": 0.0}
     last = {}
 
     def step(inp, dsd, timed):
@@ -264,15 +264,14 @@ def run_gpu(args):
         e[0].record()
         tb = eng.calctmat(inp["radius"], inp["wavelength"], inp["mr"], inp["mi"], inp["eps"], ddelt=DDELT, ndgs=NDGS)
         e[1].record()
-        S, Z = tb.ampl([GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, reduce=True)
+        S, Z, xs = tb.scatter([GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, want_xs=True)
         e[2].record()
-        xs = tb.xsect([(GEOM_BACK[0], GEOM_BACK[2])], al, be, wt, scale)
         e[3].record()
         rows = torch.empty((n, tables.ROW), dtype=torch.float64, device=dev)
         Sr = torch.view_as_real(S).reshape(n, 2, 8)
         rows[:, 0:8], rows[:, 8:24] = Sr[:, 0], Z[:, 0].reshape(n, 16)
         rows[:, 24:32], rows[:, 32:48] = Sr[:, 1], Z[:, 1].reshape(n, 16)
-        rows[:, 48:50], rows[:, 50:52] = xs[:, 0], xs[:, 0]
+        rows[:, 48:50], rows[:, 50:52] = xs[:, 0], xs[:, 1]
         ext_h, ext_v = 2.0 * tb.lam * Sr[:, 1, 7], 2.0 * tb.lam * Sr[:, 1, 1]
         rows[:, 52], rows[:, 53], rows[:, 54], rows[:, 55] = ext_h, ext_v, ext_h, ext_v
         if world > 1:
@@ -312,15 +311,13 @@ def run_gpu(args):
         t0.record()
         for _ in range(args.steps):
             step(dev_in, dev_dsd, True)
-            for k, (a, b) in zip(("calctmat", "ampl", "xsect", "psd"), ((0, 1), (1, 2), (2, 3), (3, 4))):
-                pass
         t1.record()
         sync_all()
         ms_total = t0.elapsed_time(t1)
     launches = eng.launch_count - l0
     # stage split of the last timed step
     e = last["e"]
-    for k, (a, b) in zip(("calctmat", "ampl", "xsect", "psd"), ((0, 1), (1, 2), (2, 3), (3, 4))):
+    for k, (a, b) in zip(("calctmat", "scatter", "psd"), ((0, 1), (1, 2), (3, 4))):
         stage_ms[k] = e[a].elapsed_time(e[b])
     # e2e: host buffers in, host results out, same K
     for _ in range(2):
@@ -352,8 +349,8 @@ def run_gpu(args):
         units = n * world
         value = units / (ms_step * 1e-3)
         dom = max(stage_ms, key=stage_ms.get)
-        dom_fl = {"calctmat": fl_tm.sum(), "ampl": fl_am.sum() * 2.0 / 3.0}.get(dom, fl_tm.sum())
-        dom_kernel = {"calctmat": "k_calctmat", "ampl": "k_ampl", "xsect": "k_xsect", "psd": "k_psd_gemm"}[dom]
+        dom_fl = {"calctmat": fl_tm.sum(), "scatter": fl_am.sum()}.get(dom, fl_tm.sum())
+        dom_kernel = {"calctmat": "k_calctmat", "scatter": "k_scatter", "psd": "k_psd_gemm"}[dom]
         ach = dom_fl / (stage_ms[dom] * 1e-3) / 1e12
         cores = os.cpu_count() or 1
         cpu = None
@@ -381,7 +378,7 @@ def run_gpu(args):
             "roofline": {"bound": "fp64", "kernel": dom_kernel, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": ach / peak_tf, "traffic": None,
                          "peak_source": "measured in this run (hs_fp64_peak DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
-                         "algorithmic_gflop_per_step": {"calctmat": fl_tm.sum() / 1e9, "ampl": fl_am.sum() * 2.0 / 3.0 / 1e9}},
+                         "algorithmic_gflop_per_step": {"calctmat": fl_tm.sum() / 1e9, "scatter": fl_am.sum() / 1e9}},
             "status_counts": {str(k): int((status == k).sum()) for k in np.unique(status)},
             "nmax_range": [int(nmax.min()), int(nmax.max())],
         }

@@ -86,22 +86,25 @@ class CudaBackend:
         if bad.size:
             raise ConvergenceError("calctmat: particle %d: %s" % (bad[0], _engine.STATUS_TEXT.get(int(st[bad[0]]))))
         g4 = [tuple(g[:4]) for g in geometries]
-        S, Z = tb.ampl(g4, alpha, beta, weight=weight, scale=scale, reduce=True)
-        res = {"S": S.cpu().numpy(), "Z": Z.cpu().numpy(), "nmax": tb.nmax.cpu().numpy(),
-               "ngauss": tb.ngauss.cpu().numpy()}
+        res = {"nmax": tb.nmax.cpu().numpy(), "ngauss": tb.ngauss.cpu().numpy()}
         if angular:
-            inc = [(g[0], g[2]) for g in geometries]
-            xs = tb.xsect(inc, alpha, beta, weight, scale).cpu().numpy()
-            res["sca_xsect_h"], res["sca_xsect_v"] = xs[:, :, 0], xs[:, :, 1]
-            # ext_xsect: optical theorem on the orientation-averaged forward amplitude
             fw = [(g[0], g[0], g[2], g[2]) for g in geometries]
-            Sf, _ = tb.ampl(fw, alpha, beta, weight=weight, scale=scale, reduce=True)
-            Sf = Sf.cpu().numpy()
+            allg = g4 + [f for f in dict.fromkeys(fw) if f not in g4]
+            S, Z, xs = tb.scatter(allg, alpha, beta, weight=weight, scale=scale, want_xs=True)
+            S, Z, xs = S.cpu().numpy(), Z.cpu().numpy(), xs.cpu().numpy()
+            G = len(g4)
+            res["S"], res["Z"] = S[:, :G], Z[:, :G]
+            res["sca_xsect_h"], res["sca_xsect_v"] = xs[:, :G, 0], xs[:, :G, 1]
+            # ext_xsect: optical theorem on the orientation-averaged forward amplitude
             lam = np.broadcast_to(np.asarray(wavelength, dtype=np.float64), (len(radii),))[:, None]
-            res["ext_xsect_h"] = 2.0 * lam * Sf[:, :, 1, 1].imag
-            res["ext_xsect_v"] = 2.0 * lam * Sf[:, :, 0, 0].imag
+            fi = [allg.index(f) for f in fw]
+            res["ext_xsect_h"] = 2.0 * lam * S[:, fi, 1, 1].imag
+            res["ext_xsect_v"] = 2.0 * lam * S[:, fi, 0, 0].imag
             res["asym_h"] = np.full_like(res["sca_xsect_h"], np.nan)
             res["asym_v"] = np.full_like(res["sca_xsect_h"], np.nan)
+        else:
+            S, Z, _ = tb.scatter(g4, alpha, beta, weight=weight, scale=scale, want_xs=False)
+            res["S"], res["Z"] = S.cpu().numpy(), Z.cpu().numpy()
         return res
 
     # ---- two-layer path (tm2l) ----

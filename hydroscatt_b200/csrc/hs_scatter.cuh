@@ -1,0 +1,328 @@
+// hs_scatter.cuh -- K4 fused: orientation-averaged amplitude / phase matrices for several scattering geometries
+// AND the h/v scattering cross sections, from one pass over the T-matrix per orientation.
+//
+// Replaces (batched) pytmatrix calcampl + orientation.orient_averaged_fixed + scatter.sca_xsect
+// (reference call sites scattering.py:478-525 and
+// PSDIntegrator.init_scatter_table(angular_integration=True) at scattering_rain.py:282-283).
+//
+// AMPL's double sum  sum_{n,n'} CAL(n,n') [..T_{nn'}..]  factorises into an incident-side vector
+//   G1_n = sum_n' b_n' (T11 m pi0_n' + T12 tau0_n')   G2_n = sum_n' b_n' (T21 m pi0_n' + T22 tau0_n')
+//   G3_n = sum_n' b_n' (T11 tau0_n' + T12 m pi0_n')   G4_n = sum_n' b_n' (T21 tau0_n' + T22 m pi0_n')
+// (b_n' = i^n' f_n', O(NMAX^2) per mode, depends only on orientation + incident direction) and an O(NMAX) sum per
+// scattered direction:
+//   VV += fc a_n (m pi_n G1 + tau_n G2)    VH += fs a_n (m pi_n G3 + tau_n G4)
+//   HV -= fs a_n (tau_n G1 + m pi_n G2)    HH += fc a_n (tau_n G3 + m pi_n G4)      a_n = i^(-n-1) f_n
+// The same G's give the cross sections: C = 4 pi/k^2 sum_m w_m sum_n [u_t^2(|G1|^2+|G2|^2) + u_p^2(|G3|^2+|G4|^2)].
+// So back-scatter, forward-scatter and sca_xsect of one orientation cost one T-matrix sweep instead of three.
+#pragma once
+#include "hs_compat.cuh"
+#include "hs_ampl.cuh"
+
+namespace hs {
+
+#define SC_MAXG 4  // scattered directions per incident direction handled in one sweep
+
+struct ScArgs {
+    int n;
+    const double *tarena;
+    const long long *toff;
+    const int *nmax;
+    const int *status;
+    const double *lam;
+    int n_inc;
+    const double *inc;      // [n_inc][2] thet0, phi0
+    const int *g_begin;     // [n_inc+1] geometry range of each incident direction (geometries sorted by inc)
+    const double *gsc;      // [n_geom][2] thet, phi of each (sorted) geometry
+    const int *g_out;       // [n_geom] output slot of each sorted geometry
+    int n_geom;
+    int n_orient;
+    const double *alpha, *beta, *weight;
+    double scale;
+    double *S, *Z;          // [n][n_geom][8], [n][n_geom][16]
+    double *xs;             // [n][n_inc][2] or null
+};
+
+// Wigner pi_n = d/sin, tau_n = dd/dtheta generated in lock-step with n (VIGAMPL as a recurrence)
+struct WigRec {
+    double x, qs1, d1, d2;
+    int m;
+    bool pole;
+    __device__ void init(double x_, int m_)
+    {
+        x = x_; m = m_;
+        pole = fabs(1.0 - fabs(x)) <= 1e-10;
+        if (pole) return;
+        double qs = sqrt(1.0 - x * x);
+        qs1 = 1.0 / qs;
+        if (m == 0) { d1 = 1.0; d2 = x; }
+        else {
+            double a = 1.0;
+            for (int i = 1; i <= m; i++) a = a * sqrt((double)(2 * i - 1) / (double)(2 * i)) * qs;
+            d1 = 0.0; d2 = a;
+        }
+    }
+    // call with n = max(m,1), max(m,1)+1, ... in order
+    __device__ void next(int n, double &pi_n, double &tau_n)
+    {
+        if (pole) {
+            if (m != 1) { pi_n = 0.0; tau_n = 0.0; return; }
+            double dn = 0.5 * sqrt((double)(n * (n + 1)));
+            if (x < 0.0) dn = dn * (((n + 1) & 1) ? -1.0 : 1.0);
+            pi_n = dn;
+            tau_n = (x < 0.0) ? -dn : dn;
+            return;
+        }
+        double qn = n, qn1 = n + 1, qn2 = 2 * n + 1, d3, der;
+        if (m == 0) {
+            d3 = (qn2 * x * d2 - qn * d1) / qn1;
+            der = qs1 * (qn1 * qn / qn2) * (-d1 + d3);
+        } else {
+            double qmm = (double)(m * m);
+            double qnm = sqrt(qn * qn - qmm), qnm1 = sqrt(qn1 * qn1 - qmm);
+            d3 = (qn2 * x * d2 - qnm * d1) / qnm1;
+            der = qs1 * (-qn1 * qnm * d1 + qn * qnm1 * d3) / qn2;
+        }
+        pi_n = d2 * qs1;
+        tau_n = der;
+        d1 = d2; d2 = d3;
+    }
+};
+
+// particle-frame direction (cos theta_p, phi_p) of a lab direction + the 2x2 polarisation rotation (AMPL eqs.)
+__device__ inline void frame(double thet_deg, double phi_deg, double alph, double bet, double &ctp, double &phip,
+                             double R[2][2])
+{
+    const double pin = 3.14159265358979323846, pin2 = pin * 0.5, rad = pin / 180.0, eps = 1e-7;
+    double thetl = thet_deg * rad, phil = phi_deg * rad;
+    if (thetl < pin2) thetl += eps;
+    if (thetl > pin2) thetl -= eps;
+    if (phil < pin) phil += eps;
+    if (phil > pin) phil -= eps;
+    double cb = cos(bet), sb = sin(bet), ct = cos(thetl), st = sin(thetl);
+    double cp = cos(phil - alph), sp = sin(phil - alph);
+    ctp = ct * cb + st * sb * cp;
+    double thetp = acos(ctp);
+    double cpp = cb * st * cp - sb * ct, spp = st * sp;
+    phip = atan(spp / cpp);
+    if (phip > 0.0 && sp < 0.0) phip += pin;
+    if (phip < 0.0 && sp > 0.0) phip += pin;
+    if (phip < 0.0) phip += 2.0 * pin;
+    double ca = cos(alph), sa = sin(alph);
+    double B[3][3] = {{ca * cb, sa * cb, -sb}, {-sa, ca, 0.0}, {ca * sb, sa * sb, cb}};
+    cp = cos(phil); sp = sin(phil);
+    double AL[3][2] = {{ct * cp, -sp}, {ct * sp, cp}, {-st, 0.0}};
+    double stp = sin(thetp), cpp_ = cos(phip), spp_ = sin(phip);
+    double AP[2][3] = {{ctp * cpp_, ctp * spp_, -stp}, {-spp_, cpp_, 0.0}};
+    double C[3][2];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 2; j++) { double x = 0; for (int k = 0; k < 3; k++) x += B[i][k] * AL[k][j]; C[i][j] = x; }
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) { double x = 0; for (int k = 0; k < 3; k++) x += AP[i][k] * C[k][j]; R[i][j] = x; }
+}
+
+// One (particle, orientation, incident direction): ng scattered directions -> out[g*24..] (S 8, Z 16), xs2 (h, v)
+__device__ void scatter_one(const double2 *__restrict__ t, int nmax, double lam, double thet0, double phi0, int ng,
+                            const double *gsc, double alpha, double beta, const double *fn, double *out, double *xs2)
+{
+    const double pin = 3.14159265358979323846, pin2 = pin * 0.5, rad = pin / 180.0, eps = 1e-7;
+    double alph = alpha * rad, bet = beta * rad;
+    if (bet <= pin2 && pin2 - bet <= eps) bet -= eps;
+    if (bet > pin2 && bet - pin2 <= eps) bet += eps;
+    double ctp0, phip0, R[2][2];
+    frame(thet0, phi0, alph, bet, ctp0, phip0, R);
+    double ctp[SC_MAXG], dphi[SC_MAXG], R1[SC_MAXG][2][2];
+    for (int g = 0; g < ng; g++) {
+        double ph, Rg[2][2];
+        frame(gsc[2 * g], gsc[2 * g + 1], alph, bet, ctp[g], ph, Rg);
+        dphi[g] = ph - phip0;
+        double d = 1.0 / (Rg[0][0] * Rg[1][1] - Rg[0][1] * Rg[1][0]);
+        R1[g][0][0] = Rg[1][1] * d; R1[g][0][1] = -Rg[0][1] * d; R1[g][1][0] = -Rg[1][0] * d; R1[g][1][1] = Rg[0][0] * d;
+    }
+    double acc[SC_MAXG][8];
+    for (int g = 0; g < ng; g++)
+        for (int k = 0; k < 8; k++) acc[g][k] = 0.0;
+    double acc_t = 0.0, acc_p = 0.0;
+    double pr[HS_NPN1 + 1], pi_[HS_NPN1 + 1], qr[HS_NPN1 + 1], qi[HS_NPN1 + 1];  // P = b m pi0, Q = b tau0
+    for (int m = 0; m <= nmax; m++) {
+        const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
+        {
+            WigRec w0;
+            w0.init(ctp0, m);
+            for (int nn = nmin; nn <= nmax; nn++) {
+                double p0, t0;
+                w0.next(nn, p0, t0);
+                const double f = fn[nn], mp = m * p0 * f, tq = t0 * f;
+                const int pw = nn & 3;
+                pr[nn] = (pw == 0) ? mp : (pw == 2) ? -mp : 0.0;
+                pi_[nn] = (pw == 1) ? mp : (pw == 3) ? -mp : 0.0;
+                qr[nn] = (pw == 0) ? tq : (pw == 2) ? -tq : 0.0;
+                qi[nn] = (pw == 1) ? tq : (pw == 3) ? -tq : 0.0;
+            }
+        }
+        WigRec ws[SC_MAXG];
+        double fc[SC_MAXG], fs[SC_MAXG];
+        for (int g = 0; g < ng; g++) {
+            ws[g].init(ctp[g], m);
+            if (m == 0) { fc[g] = 1.0; fs[g] = 0.0; }
+            else { fc[g] = 2.0 * cos(m * dphi[g]); fs[g] = 2.0 * sin(m * dphi[g]); }
+        }
+        const double wm = (m == 0) ? 1.0 : 2.0;
+        for (int n = nmin; n <= nmax; n++) {
+            const int k = n - nmin;
+            const double2 *ta = t + (long)(((n + 1) & 1) * NM) * NM + k;  // tau = 1 row of T, stride NM over n'
+            const double2 *tb = t + (long)((n & 1) * NM) * NM + k;        // tau = 2 row
+            double g1r = 0, g1i = 0, g2r = 0, g2i = 0, g3r = 0, g3i = 0, g4r = 0, g4i = 0;
+            // n' with the parity of n: T11, T22 ; other parity: T12, T21
+            for (int nn = nmin + ((n - nmin) & 1); nn <= nmax; nn += 2) {
+                const long o = (long)(nn - nmin) * NM;
+                const double2 a_ = ta[o], b_ = tb[o];
+                const double Pr = pr[nn], Pi = pi_[nn], Qr = qr[nn], Qi = qi[nn];
+                g1r += a_.x * Pr - a_.y * Pi; g1i += a_.x * Pi + a_.y * Pr;   // T11 * P
+                g3r += a_.x * Qr - a_.y * Qi; g3i += a_.x * Qi + a_.y * Qr;   // T11 * Q
+                g2r += b_.x * Qr - b_.y * Qi; g2i += b_.x * Qi + b_.y * Qr;   // T22 * Q
+                g4r += b_.x * Pr - b_.y * Pi; g4i += b_.x * Pi + b_.y * Pr;   // T22 * P
+            }
+            for (int nn = nmin + ((n - nmin + 1) & 1); nn <= nmax; nn += 2) {
+                const long o = (long)(nn - nmin) * NM;
+                const double2 a_ = ta[o], b_ = tb[o];
+                const double Pr = pr[nn], Pi = pi_[nn], Qr = qr[nn], Qi = qi[nn];
+                g1r += a_.x * Qr - a_.y * Qi; g1i += a_.x * Qi + a_.y * Qr;   // T12 * Q
+                g3r += a_.x * Pr - a_.y * Pi; g3i += a_.x * Pi + a_.y * Pr;   // T12 * P
+                g2r += b_.x * Pr - b_.y * Pi; g2i += b_.x * Pi + b_.y * Pr;   // T21 * P
+                g4r += b_.x * Qr - b_.y * Qi; g4i += b_.x * Qi + b_.y * Qr;   // T21 * Q
+            }
+            acc_t += wm * (g1r * g1r + g1i * g1i + g2r * g2r + g2i * g2i);
+            acc_p += wm * (g3r * g3r + g3i * g3i + g4r * g4r + g4i * g4i);
+            // a_n = i^(-n-1) f_n
+            const double f = fn[n];
+            const int pw = (-(n + 1)) & 3;
+            const double ar = (pw == 0) ? f : (pw == 2) ? -f : 0.0, ai = (pw == 1) ? f : (pw == 3) ? -f : 0.0;
+            for (int g = 0; g < ng; g++) {
+                double p_, t_;
+                ws[g].next(n, p_, t_);
+                const double mp = m * p_;
+                // u = m pi G1 + tau G2 ; v = m pi G3 + tau G4 ; w = tau G1 + m pi G2 ; z = tau G3 + m pi G4
+                const double ur = mp * g1r + t_ * g2r, ui = mp * g1i + t_ * g2i;
+                const double vr = mp * g3r + t_ * g4r, vi = mp * g3i + t_ * g4i;
+                const double wr = t_ * g1r + mp * g2r, wi = t_ * g1i + mp * g2i;
+                const double zr = t_ * g3r + mp * g4r, zi = t_ * g3i + mp * g4i;
+                const double cr = ar * fc[g], ci = ai * fc[g], sr = ar * fs[g], si = ai * fs[g];
+                acc[g][0] += ur * cr - ui * ci; acc[g][1] += ur * ci + ui * cr;   // VV
+                acc[g][2] += vr * sr - vi * si; acc[g][3] += vr * si + vi * sr;   // VH
+                acc[g][4] -= wr * sr - wi * si; acc[g][5] -= wr * si + wi * sr;   // HV
+                acc[g][6] += zr * cr - zi * ci; acc[g][7] += zr * ci + zi * cr;   // HH
+            }
+        }
+        t += 2 * NM * NM;
+    }
+    const double dk = 2.0 * pin / lam;
+    if (xs2) {
+        const double c0 = 4.0 * pin / (dk * dk);
+        xs2[0] = c0 * (R[0][1] * R[0][1] * acc_t + R[1][1] * R[1][1] * acc_p);
+        xs2[1] = c0 * (R[0][0] * R[0][0] * acc_t + R[1][0] * R[1][0] * acc_p);
+    }
+    for (int g = 0; g < ng; g++) {
+        double vvr = acc[g][0] / dk, vvi = acc[g][1] / dk, vhr = acc[g][2] / dk, vhi = acc[g][3] / dk;
+        double hvr = acc[g][4] / dk, hvi = acc[g][5] / dk, hhr = acc[g][6] / dk, hhi = acc[g][7] / dk;
+        double cvvr = vvr * R[0][0] + vhr * R[1][0], cvvi = vvi * R[0][0] + vhi * R[1][0];
+        double cvhr = vvr * R[0][1] + vhr * R[1][1], cvhi = vvi * R[0][1] + vhi * R[1][1];
+        double chvr = hvr * R[0][0] + hhr * R[1][0], chvi = hvi * R[0][0] + hhi * R[1][0];
+        double chhr = hvr * R[0][1] + hhr * R[1][1], chhi = hvi * R[0][1] + hhi * R[1][1];
+        double s11r = R1[g][0][0] * cvvr + R1[g][0][1] * chvr, s11i = R1[g][0][0] * cvvi + R1[g][0][1] * chvi;
+        double s12r = R1[g][0][0] * cvhr + R1[g][0][1] * chhr, s12i = R1[g][0][0] * cvhi + R1[g][0][1] * chhi;
+        double s21r = R1[g][1][0] * cvvr + R1[g][1][1] * chvr, s21i = R1[g][1][0] * cvvi + R1[g][1][1] * chvi;
+        double s22r = R1[g][1][0] * cvhr + R1[g][1][1] * chhr, s22i = R1[g][1][0] * cvhi + R1[g][1][1] * chhi;
+        double *o = out + g * 24;
+        o[0] = s11r; o[1] = s11i; o[2] = s12r; o[3] = s12i; o[4] = s21r; o[5] = s21i; o[6] = s22r; o[7] = s22i;
+#define RE(a, b) (a##r * b##r + a##i * b##i)
+#define IM(a, b) (a##i * b##r - a##r * b##i)
+        double *Z = o + 8;
+        Z[0] = 0.5 * (RE(s11, s11) + RE(s12, s12) + RE(s21, s21) + RE(s22, s22));
+        Z[1] = 0.5 * (RE(s11, s11) - RE(s12, s12) + RE(s21, s21) - RE(s22, s22));
+        Z[2] = -(RE(s11, s12) + RE(s22, s21));
+        Z[3] = -(IM(s11, s12) - IM(s22, s21));
+        Z[4] = 0.5 * (RE(s11, s11) + RE(s12, s12) - RE(s21, s21) - RE(s22, s22));
+        Z[5] = 0.5 * (RE(s11, s11) - RE(s12, s12) - RE(s21, s21) + RE(s22, s22));
+        Z[6] = -(RE(s11, s12) - RE(s22, s21));
+        Z[7] = -(IM(s11, s12) + IM(s22, s21));
+        Z[8] = -(RE(s11, s21) + RE(s22, s12));
+        Z[9] = -(RE(s11, s21) - RE(s22, s12));
+        Z[10] = RE(s11, s22) + RE(s12, s21);
+        Z[11] = IM(s11, s22) + IM(s21, s12);
+        Z[12] = -(IM(s21, s11) + IM(s22, s12));
+        Z[13] = -(IM(s21, s11) - IM(s22, s12));
+        Z[14] = IM(s22, s11) - IM(s12, s21);
+        Z[15] = RE(s22, s11) - RE(s12, s21);
+#undef RE
+#undef IM
+    }
+}
+
+#ifndef HS_HOST_EMU
+// grid.x = particles; threads over orientations; in-order weighted sums (same order as orient_averaged_fixed)
+__global__ void k_scatter(ScArgs a)
+{
+    extern __shared__ __align__(16) double sm[];  // [blockDim][SC_MAXG*24 + 2 + 1 pad]
+    __shared__ double s_fn[HS_NPN1 + 1];
+    for (int n = threadIdx.x; n <= HS_NPN1; n += blockDim.x)
+        s_fn[n] = (n == 0) ? 0.0 : sqrt((double)(2 * n + 1) / (double)(n * (n + 1)));
+    __syncthreads();
+    const int p = blockIdx.x;
+    const bool bad = (a.status[p] != HS_ST_OK && a.status[p] != HS_ST_NGAUSS_LIMIT && a.status[p] != HS_ST_SINGULAR) || a.toff[p] < 0;
+    if (bad) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int t = threadIdx.x; t < a.n_geom * 8; t += blockDim.x) a.S[(long)p * a.n_geom * 8 + t] = nan;
+        for (int t = threadIdx.x; t < a.n_geom * 16; t += blockDim.x) a.Z[(long)p * a.n_geom * 16 + t] = nan;
+        if (a.xs) for (int t = threadIdx.x; t < a.n_inc * 2; t += blockDim.x) a.xs[(long)p * a.n_inc * 2 + t] = nan;
+        return;
+    }
+    const double2 *t = reinterpret_cast<const double2 *>(a.tarena) + a.toff[p];
+    const int nmax = a.nmax[p];
+    const double lam = a.lam[p];
+    const int stride = SC_MAXG * 24 + 3;
+    double *accs = sm + (long)blockDim.x * stride;  // [SC_MAXG*24 + 2] running sums, one owner thread per component
+    double out[SC_MAXG * 24], xs2[2];
+    for (int d = 0; d < a.n_inc; d++) {
+        const int gend = a.g_begin[d + 1];
+        for (int gb = a.g_begin[d];; gb += SC_MAXG) {
+            const int ng = max(0, min(SC_MAXG, gend - gb));
+            const int ncomp = ng * 24 + 2;
+            for (int c = threadIdx.x; c < ncomp; c += blockDim.x) accs[c] = 0.0;
+            for (int o0 = 0; o0 < a.n_orient; o0 += blockDim.x) {
+                int o = o0 + threadIdx.x;
+                if (o < a.n_orient) {
+                    scatter_one(t, nmax, lam, a.inc[2 * d], a.inc[2 * d + 1], ng, a.gsc + 2 * gb, a.alpha[o], a.beta[o],
+                                s_fn, out, xs2);
+                    const double w = a.weight[o];
+                    double *row = sm + (long)threadIdx.x * stride;
+                    for (int k = 0; k < ng * 24; k++) row[k] = w * out[k];
+                    row[ng * 24] = w * xs2[0];
+                    row[ng * 24 + 1] = w * xs2[1];
+                }
+                __syncthreads();
+                const int cnt = min((int)blockDim.x, a.n_orient - o0);
+                for (int c = threadIdx.x; c < ncomp; c += blockDim.x) {
+                    double acc = accs[c];
+                    for (int j = 0; j < cnt; j++) acc += sm[(long)j * stride + c];
+                    accs[c] = acc;
+                }
+                __syncthreads();
+            }
+            for (int c = threadIdx.x; c < ncomp; c += blockDim.x) {
+                const double v = accs[c] * a.scale;
+                if (c < ng * 24) {
+                    const int g = c / 24, k = c - g * 24, slot = a.g_out[gb + g];
+                    if (k < 8) a.S[((long)p * a.n_geom + slot) * 8 + k] = v;
+                    else a.Z[((long)p * a.n_geom + slot) * 16 + k - 8] = v;
+                } else if (a.xs && gb == a.g_begin[d]) {
+                    a.xs[((long)p * a.n_inc + d) * 2 + (c - ng * 24)] = v;
+                }
+            }
+            __syncthreads();
+            if (gb + SC_MAXG >= gend) break;
+        }
+    }
+}
+#endif
+
+}  // namespace hs

@@ -394,6 +394,8 @@ __device__ void assemble(const Grp<WARP> &grp, const Carve &c, int nmax, int g, 
 
 // ---- K3: Gauss-Jordan with row pivoting on both class systems at once (P7: TT, T = -RgQ Q^-1) ----
 // Solves Q_c^T X_c = -RgQ_c^T in place; on exit columns NM..2NM-1 hold X_c = T_c^T.
+// Per elimination step: (1) pivot search (one warp per class), (2) swap + scale of the pivot row, (3) rank-1 update
+// of all other rows with every thread of the group busy (threads tile [row group] x [live column of either class]).
 template <bool WARP>
 __device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
 {
@@ -401,9 +403,11 @@ __device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
     double2 *sys = c.sys;
     const int nl = grp.nt < 32 ? grp.nt : 32;  // lanes searching for the pivot (32 on the GPU)
     const int lane = grp.tid & 31;
+    const int wid = grp.tid >> 5;
+    const bool two_warps = grp.nt >= 64;
     for (int k = 0; k < NM; k++) {
-        if (grp.tid < nl) {
-            for (int cl = 0; cl < 2; cl++) {
+        if (grp.tid < (two_warps ? 64 : nl)) {
+            for (int cl = (two_warps ? wid : 0); cl < (two_warps ? wid + 1 : 2); cl++) {
                 double best = -1.0;
                 int bi = k;
                 for (int r = k + lane; r < NM; r += nl) {
@@ -426,25 +430,40 @@ __device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
             }
         }
         grp.sync();
-        const int ncol = ldc - k - 1;  // live columns k+1 .. 2NM-1
+        const int ncol = ldc - k - 1;  // live columns k+1 .. 2NM-1 of each class
         for (int t = grp.tid; t < 2 * ncol; t += grp.nt) {
-            int cl = t >= ncol;
-            int col = k + 1 + (t - cl * ncol);
+            const int cl = t >= ncol;
+            const int col = k + 1 + (t - cl * ncol);
             double2 *S = sys + (long)cl * NM * ldc;
             const int p = ctl->piv[cl];
             const double2 inv = ctl->pivinv[cl];
             double2 a = S[(long)k * ldc + col], b = S[(long)p * ldc + col];
-            double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
-            S[(long)k * ldc + col] = nk;
+            S[(long)k * ldc + col] = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
             if (p != k) S[(long)p * ldc + col] = a;
-            const double2 fkk = S[(long)k * ldc + k];
-            for (int r = 0; r < NM; r++) {
-                if (r == k) continue;
-                double2 f = (r == p) ? fkk : S[(long)r * ldc + k];
-                double2 v = S[(long)r * ldc + col];
-                v.x -= f.x * nk.x - f.y * nk.y;
-                v.y -= f.x * nk.y + f.y * nk.x;
-                S[(long)r * ldc + col] = v;
+        }
+        grp.sync();
+        {
+            const int n2 = 2 * ncol;
+            const int w = n2 < grp.nt ? n2 : grp.nt;  // threads per row group
+            const int nrg = grp.nt / w, rg = grp.tid / w, c0 = grp.tid - rg * w;
+            if (rg < nrg) {
+                for (int t = c0; t < n2; t += w) {
+                    const int cl = t >= ncol;
+                    const int col = k + 1 + (t - cl * ncol);
+                    double2 *S = sys + (long)cl * NM * ldc;
+                    const int p = ctl->piv[cl];
+                    const double2 nk = S[(long)k * ldc + col];
+                    const double2 fkk = S[(long)k * ldc + k];
+                    for (int r = rg; r < NM; r += nrg) {
+                        if (r == k) continue;
+                        // after the row swap, row p holds the old row k whose column-k entry is still at S[k][k]
+                        const double2 f = (r == p) ? fkk : S[(long)r * ldc + k];
+                        double2 v = S[(long)r * ldc + col];
+                        v.x -= f.x * nk.x - f.y * nk.y;
+                        v.y -= f.x * nk.y + f.y * nk.x;
+                        S[(long)r * ldc + col] = v;
+                    }
+                }
             }
         }
         grp.sync();

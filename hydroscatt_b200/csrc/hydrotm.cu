@@ -13,6 +13,7 @@
 #include "hs_tmat.cuh"
 #include "hs_ampl.cuh"
 #include "hs_xsect.cuh"
+#include "hs_scatter.cuh"
 #include "hs_psd.cuh"
 #include "hs_tm2l.cuh"
 
@@ -31,6 +32,11 @@ struct hs_ctx {
     int items_cap = 0;
     int *h_pin = nullptr;        // pinned staging
     size_t h_pin_cap = 0;
+    cudaStream_t bstream[4] = {nullptr, nullptr, nullptr, nullptr};  // one stream per size bucket
+    cudaEvent_t ev_start = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *d_sc = nullptr;      // scatter geometry tables (device)
+    double *d_xs_tmp = nullptr;
+    size_t xs_tmp_cap = 0;
     double *d_ws_global = nullptr;
     size_t ws_global_bytes = 0;
 };
@@ -88,6 +94,11 @@ extern "C" int hs_ctx_create(hs_ctx **out, int device)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaMalloc(&ctx->d_queue, 16 * sizeof(int)));
+    for (int b = 0; b < 4; b++) {
+        CK(cudaStreamCreateWithFlags(&ctx->bstream[b], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     if (ensure_gauss(ctx, 64)) return -1;
     return 0;
 }
@@ -96,8 +107,10 @@ extern "C" void hs_ctx_destroy(hs_ctx *ctx)
 {
     if (!ctx) return;
     cudaFree(ctx->d_gx); cudaFree(ctx->d_gw); cudaFree(ctx->d_queue); cudaFree(ctx->d_items);
-    cudaFree(ctx->d_ws_global);
+    cudaFree(ctx->d_ws_global); cudaFree(ctx->d_sc); cudaFree(ctx->d_xs_tmp);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (int b = 0; b < 4; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     delete ctx;
 }
 
@@ -216,7 +229,8 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         if (!any) break;
         CK(cudaMemcpyAsync(ctx->d_items, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(ctx->d_queue, 0, 16 * sizeof(int), st));
-        for (int b = 0; b < NB; b++) {
+        CK(cudaEventRecord(ctx->ev_start, st));
+        for (int b = NB - 1; b >= 0; b--) {  // heaviest bucket first; buckets run concurrently on their own streams
             int cnt = seg_start[b + 1] - seg_start[b];
             if (!cnt) continue;
             const Bucket &B = buckets[b];
@@ -233,6 +247,8 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
             int per_sm = B.global_ws ? 1 : std::max(1, (int)((size_t)(ctx->smem_optin + 1024) / (smem + 4096)));
             int grid = std::min(ctas_needed, ctx->sm_count * per_sm);
             cudaError_t e;
+            cudaStream_t bs = ctx->bstream[b];
+            CK(cudaStreamWaitEvent(bs, ctx->ev_start, 0));
             if (B.global_ws) {
                 grid = std::min(ctas_needed, ctx->sm_count);
                 size_t bytes = (size_t)grid * B.ws_cap * sizeof(double);
@@ -243,14 +259,16 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
                     ctx->ws_global_bytes = bytes;
                 }
                 a.ws_global = ctx->d_ws_global;
-                e = launch_tm<false, true>(a, grid, B.threads, 0, st);
+                e = launch_tm<false, true>(a, grid, B.threads, 0, bs);
             } else if (B.warp) {
-                e = launch_tm<true, false>(a, grid, B.threads, smem, st);
+                e = launch_tm<true, false>(a, grid, B.threads, smem, bs);
             } else {
-                e = launch_tm<false, false>(a, grid, B.threads, smem, st);
+                e = launch_tm<false, false>(a, grid, B.threads, smem, bs);
             }
             ctx->launches++;
             if (e != cudaSuccess) { ctx->err = std::string("k_calctmat launch: ") + cudaGetErrorString(e); return -1; }
+            CK(cudaEventRecord(ctx->ev_done[b], bs));
+            CK(cudaStreamWaitEvent(st, ctx->ev_done[b], 0));
         }
         CK(cudaMemcpyAsync(h_st, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -427,5 +445,93 @@ extern "C" int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const do
     hs::k_tm2l<<<grid, 320, smem, st>>>(a, ctx->d_queue + 8);
     ctx->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_xs_expand(int n, int n_geom, int n_inc, const int *inc_of_geom, const double *xs_inc, double *xs)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n * n_geom * 2) return;
+    int c = (int)(i & 1);
+    long pg = i >> 1;
+    int g = (int)(pg % n_geom);
+    long p = pg / n_geom;
+    xs[i] = xs_inc[(p * n_inc + inc_of_geom[g]) * 2 + c];
+}
+
+extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff, const int *d_nmax,
+                                const int *d_status, const double *d_lam, int n_geom, const double *h_geom, int n_orient,
+                                const double *d_alpha, const double *d_beta, const double *d_weight, double scale,
+                                double *d_S, double *d_Z, double *d_xs, void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0 || n_geom <= 0 || n_orient <= 0) return 0;
+    if (n_geom > 64) { ctx->err = "at most 64 geometries per call"; return -3; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    // group geometries by incidence direction
+    std::vector<double> inc;           // unique (thet0, phi0)
+    std::vector<int> inc_of(n_geom);
+    for (int g = 0; g < n_geom; g++) {
+        int f = -1;
+        for (size_t d = 0; d < inc.size() / 2; d++)
+            if (inc[2 * d] == h_geom[4 * g] && inc[2 * d + 1] == h_geom[4 * g + 2]) { f = (int)d; break; }
+        if (f < 0) { f = (int)(inc.size() / 2); inc.push_back(h_geom[4 * g]); inc.push_back(h_geom[4 * g + 2]); }
+        inc_of[g] = f;
+    }
+    const int n_inc = (int)(inc.size() / 2);
+    std::vector<int> g_begin(n_inc + 1, 0), g_out(n_geom);
+    std::vector<double> gsc(2 * n_geom);
+    int pos = 0;
+    for (int d = 0; d < n_inc; d++) {
+        g_begin[d] = pos;
+        for (int g = 0; g < n_geom; g++)
+            if (inc_of[g] == d) { gsc[2 * pos] = h_geom[4 * g + 1]; gsc[2 * pos + 1] = h_geom[4 * g + 3]; g_out[pos] = g; pos++; }
+    }
+    g_begin[n_inc] = pos;
+    // pack: [inc 2*64][gsc 2*64][g_begin 65 ints][g_out 64 ints][inc_of 64 ints] in one small device block
+    const size_t blk_doubles = 128 + 128 + 128;
+    if (!ctx->d_sc) CK(cudaMalloc(&ctx->d_sc, blk_doubles * sizeof(double) * 4));
+    static thread_local int slot = 0;
+    slot = (slot + 1) & 3;  // 4 rotating parameter blocks so that back-to-back async calls do not overwrite each other
+    std::vector<double> hostblk(blk_doubles, 0.0);
+    memcpy(hostblk.data(), inc.data(), inc.size() * sizeof(double));
+    memcpy(hostblk.data() + 128, gsc.data(), gsc.size() * sizeof(double));
+    int *ib = reinterpret_cast<int *>(hostblk.data() + 256);
+    memcpy(ib, g_begin.data(), g_begin.size() * sizeof(int));
+    memcpy(ib + 65, g_out.data(), g_out.size() * sizeof(int));
+    memcpy(ib + 130, inc_of.data(), inc_of.size() * sizeof(int));
+    double *dblk = ctx->d_sc + (size_t)slot * blk_doubles;
+    CK(cudaMemcpyAsync(dblk, hostblk.data(), blk_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // hostblk is pageable stack/heap memory: make the copy complete before it dies
+    const int *dib = reinterpret_cast<const int *>(dblk + 256);
+    double *xs_inc = nullptr;
+    if (d_xs) {
+        size_t need = (size_t)n * n_inc * 2 * sizeof(double);
+        if (need > ctx->xs_tmp_cap) {
+            if (ctx->d_xs_tmp) cudaFree(ctx->d_xs_tmp);
+            ctx->d_xs_tmp = nullptr; ctx->xs_tmp_cap = 0;
+            CK(cudaMalloc(&ctx->d_xs_tmp, need));
+            ctx->xs_tmp_cap = need;
+        }
+        xs_inc = ctx->d_xs_tmp;
+    }
+    hs::ScArgs a;
+    a.n = n; a.tarena = d_tarena; a.toff = d_toff; a.nmax = d_nmax; a.status = d_status; a.lam = d_lam;
+    a.n_inc = n_inc; a.inc = dblk; a.g_begin = dib; a.gsc = dblk + 128; a.g_out = dib + 65; a.n_geom = n_geom;
+    a.n_orient = n_orient; a.alpha = d_alpha; a.beta = d_beta; a.weight = d_weight; a.scale = scale;
+    a.S = d_S; a.Z = d_Z; a.xs = xs_inc;
+    int threads = std::min(128, std::max(32, (n_orient + 31) / 32 * 32));
+    size_t smem = ((size_t)threads * (SC_MAXG * 24 + 3) + SC_MAXG * 24 + 2) * sizeof(double);
+    CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hs::k_scatter<<<n, threads, smem, st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (d_xs) {
+        long tot = (long)n * n_geom * 2;
+        k_xs_expand<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, n_geom, n_inc, dib + 130, xs_inc, d_xs);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
     return 0;
 }

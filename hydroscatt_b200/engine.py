@@ -244,6 +244,29 @@ class TMatrixBatch:
             raise EngineError(f"hs_calcampl_batch rc={rc}: " + eng._err())
         return S, Z
 
+    def scatter(self, geoms, alpha=(0.0,), beta=(0.0,), weight=None, scale=1.0, want_xs=True):
+        """Fused orientation-averaged S [n,G,2,2], Z [n,G,4,4] and (sca_xsect_h, sca_xsect_v) [n,G,2] of each
+        geometry's incidence direction: one T-matrix sweep per (orientation, incidence direction)."""
+        eng = self.eng
+        dev = eng.device
+        g = np.ascontiguousarray(np.asarray(geoms, dtype=np.float64).reshape(-1, 4))
+        G = g.shape[0]
+        al = eng._dev(alpha)
+        be = eng._dev(beta)
+        O = al.numel()
+        w = eng._dev(weight if weight is not None else np.ones(O))
+        S = torch.empty((self.n, G, 2, 2), dtype=torch.complex128, device=dev)
+        Z = torch.empty((self.n, G, 4, 4), dtype=torch.float64, device=dev)
+        xs = torch.empty((self.n, G, 2), dtype=torch.float64, device=dev) if want_xs else None
+        with torch.cuda.device(dev):
+            rc = eng.lib.hs_scatter_batch(eng._h, self.n, _ptr(self.arena), _ptr(self.toff), _ptr(self.nmax),
+                                          _ptr(self.status), _ptr(self.lam), G,
+                                          g.ctypes.data_as(C.POINTER(C.c_double)), O, _ptr(al), _ptr(be), _ptr(w),
+                                          float(scale), _ptr(S), _ptr(Z), _ptr(xs), eng._stream())
+        if rc != 0:
+            raise EngineError(f"hs_scatter_batch rc={rc}: " + eng._err())
+        return S, Z, xs
+
     def xsect(self, inc, alpha=(0.0,), beta=(0.0,), weight=None, scale=1.0):
         """[n, n_inc, 2] orientation-averaged (sca_xsect_h, sca_xsect_v) for incidence directions inc [n_inc][2]."""
         eng = self.eng

@@ -24,8 +24,8 @@ def build_rows(eng, radius, wavelength, m_re, m_im, axis_ratio, geom_back, geom_
                ddelt=1e-3, ndgs=2, rescale_ddelt=True, rat=1.0):
     """T-matrices + orientation-averaged S/Z + cross sections for a flat particle list.
 
-    Returns (rows [n, 56] float64 on the device, TMatrixBatch).  Three kernel families: k_calctmat (per bucket),
-    k_ampl (orientation-reduced), k_xsect.
+    Returns (rows [n, 56] float64 on the device, TMatrixBatch).  Two kernel families: k_calctmat (one launch per size bucket, concurrent streams)
+    and the fused k_scatter (orientation-averaged S/Z of all geometries + cross sections in one T-matrix sweep).
     """
     tb = eng.calctmat(radius, wavelength, m_re, m_im, axis_ratio, rat=rat, ddelt=ddelt, ndgs=ndgs,
                       rescale_ddelt=rescale_ddelt)
@@ -33,21 +33,17 @@ def build_rows(eng, radius, wavelength, m_re, m_im, axis_ratio, geom_back, geom_
     geoms = [gb, gf]
     # forward amplitudes for the optical theorem at each geometry's incidence direction
     fw = [(g[0], g[0], g[2], g[2]) for g in geoms]
-    extra = [f for f in dict.fromkeys(fw) if f not in geoms]
-    S, Z = tb.ampl(geoms + extra, alpha, beta, weight=weight, scale=scale, reduce=True)
-    inc = [(g[0], g[2]) for g in geoms]
-    uniq_inc = list(dict.fromkeys(inc))
-    xs = tb.xsect(uniq_inc, alpha, beta, weight, scale)
+    allg = geoms + [f for f in dict.fromkeys(fw) if f not in geoms]
+    S, Z, xs = tb.scatter(allg, alpha, beta, weight=weight, scale=scale, want_xs=True)
     n = tb.n
     rows = torch.empty((n, ROW), dtype=torch.float64, device=eng.device)
-    Sr = torch.view_as_real(S).reshape(n, len(geoms) + len(extra), 8)
-    Zr = Z.reshape(n, len(geoms) + len(extra), 16)
-    allg = geoms + extra
+    Sr = torch.view_as_real(S).reshape(n, len(allg), 8)
+    Zr = Z.reshape(n, len(allg), 16)
     lam = tb.lam
     for gi in range(2):
         rows[:, 24 * gi:24 * gi + 8] = Sr[:, gi]
         rows[:, 24 * gi + 8:24 * gi + 24] = Zr[:, gi]
-        rows[:, 48 + 2 * gi:50 + 2 * gi] = xs[:, uniq_inc.index(inc[gi])]
+        rows[:, 48 + 2 * gi:50 + 2 * gi] = xs[:, gi]
         fi = allg.index(fw[gi])
         rows[:, 52 + 2 * gi] = 2.0 * lam * Sr[:, fi, 7]   # 2 lambda Im S22
         rows[:, 53 + 2 * gi] = 2.0 * lam * Sr[:, fi, 1]   # 2 lambda Im S11

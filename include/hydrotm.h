@@ -115,6 +115,19 @@ int hs_xsect_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *
                    double *d_out, void *stream);
 
 /*
+ * Fused scatter-table evaluation: orientation-averaged S and Z for n_geom geometries AND the h/v scattering cross
+ * sections of each geometry's incidence direction, from ONE sweep over the T-matrix per (orientation, incidence
+ * direction) (hs_calcampl_batch + hs_xsect_batch in a single kernel; see csrc/hs_scatter.cuh).
+ *   h_geom : HOST [n_geom][4] thet0, thet, phi0, phi (degrees); geometries sharing (thet0, phi0) share the sweep
+ *   d_S [n][n_geom][4] complex, d_Z [n][n_geom][16], d_xs [n][n_geom][2] (sca_xsect h, v; may be NULL)
+ *   results = scale * sum_o weight[o] * value(o).  Asynchronous on `stream`.
+ */
+int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff, const int *d_nmax,
+                     const int *d_status, const double *d_lam, int n_geom, const double *h_geom, int n_orient,
+                     const double *d_alpha, const double *d_beta, const double *d_weight, double scale, double *d_S,
+                     double *d_Z, double *d_xs, void *stream);
+
+/*
  * PSD weights W[d][i] = wq[i] * N_d(D[i]) for n_dsd size distributions (pytmatrix.psd classes, row P11).
  *   kind 0: GammaPSD (p0=D0, p1=Nw, p2=mu)   1: ExponentialPSD (p0=N0, p1=Lambda)
  *   kind 2: UnnormalizedGammaPSD (p0=N0, p1=Lambda, p2=mu);   d_dmax[d] = D_max cut-off

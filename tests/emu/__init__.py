@@ -71,3 +71,16 @@ def tm2l(p8, wl_cm):
     st = np.zeros(n, np.int32)
     lib().emu_tm2l(n, _dp(p8), C.c_double(wl_cm), _dp(amp), st.ctypes.data_as(C.POINTER(C.c_int)))
     return amp, st
+
+
+def scatter(t, nmax, lam, thet0, phi0, gsc, alpha=0.0, beta=0.0):
+    """fused device function: returns (S[ng,2,2], Z[ng,4,4], xs[2]) for scattered directions gsc [ng][2]."""
+    t = np.ascontiguousarray(t, dtype=np.complex128).view(np.float64)
+    gsc = np.ascontiguousarray(gsc, dtype=np.float64).reshape(-1, 2)
+    ng = gsc.shape[0]
+    out = np.zeros(ng * 24)
+    xs = np.zeros(2)
+    lib().emu_scatter(_dp(t), int(nmax), C.c_double(lam), C.c_double(thet0), C.c_double(phi0), ng, _dp(gsc),
+                      C.c_double(alpha), C.c_double(beta), _dp(out), _dp(xs))
+    o = out.reshape(ng, 24)
+    return o[:, :8].copy().view(np.complex128).reshape(ng, 2, 2), o[:, 8:].reshape(ng, 4, 4), xs

@@ -65,3 +65,12 @@ extern "C" void emu_tm2l(int n, const double *p8, double alamd, double *amp, int
     double cmx[T2_NRANKI], acc[8];
     for (int i = 0; i < n; i++) { ctl.sing = 0; hs::tm2l_particle(a, i, smem.data(), &ctl, cmx, acc, 0, 1); }
 }
+
+#include "../../hydroscatt_b200/csrc/hs_scatter.cuh"
+extern "C" void emu_scatter(const double *t, int nmax, double lam, double thet0, double phi0, int ng, const double *gsc,
+                            double alpha, double beta, double *out, double *xs2)
+{
+    std::vector<double> fn(HS_NPN1 + 1);
+    for (int k = 1; k <= HS_NPN1; k++) fn[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1)));
+    hs::scatter_one(reinterpret_cast<const double2 *>(t), nmax, lam, thet0, phi0, ng, gsc, alpha, beta, fn.data(), out, xs2);
+}

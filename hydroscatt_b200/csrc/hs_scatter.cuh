@@ -40,6 +40,7 @@ struct ScArgs {
     double scale;
     double *S, *Z;          // [n][n_geom][8], [n][n_geom][16]
     double *xs;             // [n][n_inc][2] or null
+    int nmax_bound;         // upper bound of nmax over the batch (sizes the shared-memory T stage)
 };
 
 // Wigner pi_n = d/sin, tau_n = dd/dtheta generated in lock-step with n (VIGAMPL as a recurrence)
@@ -259,56 +260,270 @@ __device__ void scatter_one(const double2 *__restrict__ t, int nmax, double lam,
 }
 
 #ifndef HS_HOST_EMU
-// grid.x = particles; threads over orientations; in-order weighted sums (same order as orient_averaged_fixed)
-__global__ void k_scatter(ScArgs a)
+// ---- production kernel: same mathematics as scatter_one (which stays as the single-lane reference used by the
+// host-emulation tests), restructured for the machine:
+//   * one CTA per particle, one thread per orientation; every thread walks the same T elements, so the T block of
+//     each azimuthal mode is staged ONCE in shared memory by the whole CTA (coalesced) and read back as broadcasts;
+//   * sqrt(n^2-m^2), its reciprocal, 1/(n+1), 1/(2n+1) and prod sqrt((2i-1)/2i) come from per-CTA tables instead of
+//     per-thread sqrt/div chains;
+//   * the phases b_n' = i^n' f_n' are folded out of the inner loop (n' runs with stride 2, so i^n' = i^(n'&1) * sign):
+//     the T . vector product is complex x real.
+#define SCK_G 2  // scattered directions handled per sweep
+
+struct WigTab {
+    double x, qs, qs1, qspow, d1, d2;
+    bool pole;
+    __device__ __forceinline__ void setup(double x_)
+    {
+        x = x_;
+        pole = fabs(1.0 - fabs(x)) <= 1e-10;
+        qs = pole ? 0.0 : sqrt(1.0 - x * x);
+        qs1 = pole ? 0.0 : 1.0 / qs;
+        qspow = 1.0;
+    }
+    __device__ __forceinline__ void start(int m, const double *cm)
+    {
+        if (m == 0) { d1 = 1.0; d2 = x; }
+        else { qspow *= qs; d1 = 0.0; d2 = cm[m] * qspow; }
+    }
+    __device__ __forceinline__ void next(int n, int m, const double *sq, const double *rsq, const double *rn1,
+                                         const double *r2n1, double &pi_n, double &tau_n)
+    {
+        if (pole) {
+            if (m != 1) { pi_n = 0.0; tau_n = 0.0; return; }
+            double dn = 0.5 * sqrt((double)(n * (n + 1)));
+            if (x < 0.0) dn = dn * (((n + 1) & 1) ? -1.0 : 1.0);
+            pi_n = dn;
+            tau_n = (x < 0.0) ? -dn : dn;
+            return;
+        }
+        const double qn = n, qn1 = n + 1, qn2 = 2 * n + 1;
+        double d3, der;
+        if (m == 0) {
+            d3 = (qn2 * x * d2 - qn * d1) * rn1[n];
+            der = qs1 * (qn1 * qn * r2n1[n]) * (-d1 + d3);
+        } else {
+            const double qnm = sq[n], qnm1 = sq[n + 1];
+            d3 = (qn2 * x * d2 - qnm * d1) * rsq[n + 1];
+            der = qs1 * (-qn1 * qnm * d1 + qn * qnm1 * d3) * r2n1[n];
+        }
+        pi_n = d2 * qs1;
+        tau_n = der;
+        d1 = d2; d2 = d3;
+    }
+};
+
+__global__ void __launch_bounds__(64) k_scatter(ScArgs a)
 {
-    extern __shared__ __align__(16) double sm[];  // [blockDim][SC_MAXG*24 + 2 + 1 pad]
-    __shared__ double s_fn[HS_NPN1 + 1];
-    for (int n = threadIdx.x; n <= HS_NPN1; n += blockDim.x)
-        s_fn[n] = (n == 0) ? 0.0 : sqrt((double)(2 * n + 1) / (double)(n * (n + 1)));
-    __syncthreads();
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_fn[HS_NPN1 + 2], s_cm[HS_NPN1 + 2], s_rn1[HS_NPN1 + 2], s_r2n1[HS_NPN1 + 2];
+    __shared__ double s_sq[HS_NPN1 + 3], s_rsq[HS_NPN1 + 3];
+    const int tid = threadIdx.x, nt = blockDim.x;
     const int p = blockIdx.x;
     const bool bad = (a.status[p] != HS_ST_OK && a.status[p] != HS_ST_NGAUSS_LIMIT && a.status[p] != HS_ST_SINGULAR) || a.toff[p] < 0;
     if (bad) {
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
-        for (int t = threadIdx.x; t < a.n_geom * 8; t += blockDim.x) a.S[(long)p * a.n_geom * 8 + t] = nan;
-        for (int t = threadIdx.x; t < a.n_geom * 16; t += blockDim.x) a.Z[(long)p * a.n_geom * 16 + t] = nan;
-        if (a.xs) for (int t = threadIdx.x; t < a.n_inc * 2; t += blockDim.x) a.xs[(long)p * a.n_inc * 2 + t] = nan;
+        for (int t = tid; t < a.n_geom * 8; t += nt) a.S[(long)p * a.n_geom * 8 + t] = nan;
+        for (int t = tid; t < a.n_geom * 16; t += nt) a.Z[(long)p * a.n_geom * 16 + t] = nan;
+        if (a.xs) for (int t = tid; t < a.n_inc * 2; t += nt) a.xs[(long)p * a.n_inc * 2 + t] = nan;
         return;
     }
-    const double2 *t = reinterpret_cast<const double2 *>(a.tarena) + a.toff[p];
+    const double2 *tg = reinterpret_cast<const double2 *>(a.tarena) + a.toff[p];
     const int nmax = a.nmax[p];
     const double lam = a.lam[p];
-    const int stride = SC_MAXG * 24 + 3;
-    double *accs = sm + (long)blockDim.x * stride;  // [SC_MAXG*24 + 2] running sums, one owner thread per component
-    double out[SC_MAXG * 24], xs2[2];
+    for (int n = tid; n <= nmax + 1; n += nt) {
+        s_fn[n] = (n == 0) ? 0.0 : sqrt((double)(2 * n + 1) / (double)(n * (n + 1)));
+        s_rn1[n] = 1.0 / (double)(n + 1);
+        s_r2n1[n] = 1.0 / (double)(2 * n + 1);
+    }
+    if (tid == 0) {
+        double c = 1.0;
+        s_cm[0] = 1.0;
+        for (int i = 1; i <= nmax; i++) { c = c * sqrt((double)(2 * i - 1) / (double)(2 * i)); s_cm[i] = c; }
+    }
+    // dynamic smem: [T stage: 2*nmax*nmax complex][reduction rows: nt * stride][accs]
+    double2 *sT = reinterpret_cast<double2 *>(sm);
+    const int stride = SCK_G * 24 + 3;
+    double *srow = sm + 4L * a.nmax_bound * a.nmax_bound;
+    double *accs = srow + (long)nt * stride;
+    const double pin = 3.14159265358979323846, pin2 = pin * 0.5, rad = pin / 180.0, eps = 1e-7;
+
     for (int d = 0; d < a.n_inc; d++) {
         const int gend = a.g_begin[d + 1];
-        for (int gb = a.g_begin[d];; gb += SC_MAXG) {
-            const int ng = max(0, min(SC_MAXG, gend - gb));
+        for (int gb = a.g_begin[d];; gb += SCK_G) {
+            const int ng = max(0, min(SCK_G, gend - gb));
             const int ncomp = ng * 24 + 2;
-            for (int c = threadIdx.x; c < ncomp; c += blockDim.x) accs[c] = 0.0;
-            for (int o0 = 0; o0 < a.n_orient; o0 += blockDim.x) {
-                int o = o0 + threadIdx.x;
-                if (o < a.n_orient) {
-                    scatter_one(t, nmax, lam, a.inc[2 * d], a.inc[2 * d + 1], ng, a.gsc + 2 * gb, a.alpha[o], a.beta[o],
-                                s_fn, out, xs2);
-                    const double w = a.weight[o];
-                    double *row = sm + (long)threadIdx.x * stride;
-                    for (int k = 0; k < ng * 24; k++) row[k] = w * out[k];
-                    row[ng * 24] = w * xs2[0];
-                    row[ng * 24 + 1] = w * xs2[1];
+            for (int c = tid; c < ncomp; c += nt) accs[c] = 0.0;
+            for (int o0 = 0; o0 < a.n_orient; o0 += nt) {
+                const int o = o0 + tid;
+                const bool active = o < a.n_orient;
+                // ---- per-thread setup ----
+                double R[2][2], R1[SCK_G][2][2], dphi[SCK_G];
+                WigTab w0, ws[SCK_G];
+                double acc[SCK_G][8];
+                double acc_t = 0.0, acc_p = 0.0;
+                if (active) {
+                    double alph = a.alpha[o] * rad, bet = a.beta[o] * rad;
+                    if (bet <= pin2 && pin2 - bet <= eps) bet -= eps;
+                    if (bet > pin2 && bet - pin2 <= eps) bet += eps;
+                    double ctp0, phip0;
+                    frame(a.inc[2 * d], a.inc[2 * d + 1], alph, bet, ctp0, phip0, R);
+                    w0.setup(ctp0);
+#pragma unroll
+                    for (int g = 0; g < SCK_G; g++) {
+                        if (g < ng) {
+                            double ph, ct, Rg[2][2];
+                            frame(a.gsc[2 * (gb + g)], a.gsc[2 * (gb + g) + 1], alph, bet, ct, ph, Rg);
+                            dphi[g] = ph - phip0;
+                            ws[g].setup(ct);
+                            double dd = 1.0 / (Rg[0][0] * Rg[1][1] - Rg[0][1] * Rg[1][0]);
+                            R1[g][0][0] = Rg[1][1] * dd; R1[g][0][1] = -Rg[0][1] * dd;
+                            R1[g][1][0] = -Rg[1][0] * dd; R1[g][1][1] = Rg[0][0] * dd;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; k++) acc[g][k] = 0.0;
+                    }
+                }
+                double Pp[HS_NPN1 + 1], Qp[HS_NPN1 + 1];  // P' = sgn f m pi0, Q' = sgn f tau0, sgn = (-1)^(n'>>1)
+                long moff = 0;
+                for (int m = 0; m <= nmax; m++) {
+                    const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
+                    __syncthreads();
+                    for (int e = tid; e < 2 * NM * NM; e += nt) sT[e] = tg[moff + e];
+                    for (int n = nmin + tid; n <= nmax + 1; n += nt) {
+                        double v = sqrt((double)n * (double)n - (double)(m * m));
+                        s_sq[n] = v;
+                        s_rsq[n] = (n > m) ? 1.0 / v : 0.0;
+                    }
+                    __syncthreads();
+                    moff += 2L * NM * NM;
+                    if (!active) continue;
+                    w0.start(m, s_cm);
+                    for (int nn = nmin; nn <= nmax; nn++) {
+                        double p0, t0;
+                        w0.next(nn, m, s_sq, s_rsq, s_rn1, s_r2n1, p0, t0);
+                        const double f = (nn & 2) ? -s_fn[nn] : s_fn[nn];
+                        Pp[nn] = m * p0 * f;
+                        Qp[nn] = t0 * f;
+                    }
+                    double fc[SCK_G], fs[SCK_G];
+#pragma unroll
+                    for (int g = 0; g < SCK_G; g++)
+                        if (g < ng) {
+                            ws[g].start(m, s_cm);
+                            if (m == 0) { fc[g] = 1.0; fs[g] = 0.0; }
+                            else { double sn, cs; sincos(m * dphi[g], &sn, &cs); fc[g] = 2.0 * cs; fs[g] = 2.0 * sn; }
+                        }
+                    const double wm = (m == 0) ? 1.0 : 2.0;
+                    for (int n = nmin; n <= nmax; n++) {
+                        const int k = n - nmin;
+                        const double2 *ta = sT + (long)(((n + 1) & 1) * NM) * NM + k;  // tau = 1 row, stride NM over n'
+                        const double2 *tb = sT + (long)((n & 1) * NM) * NM + k;        // tau = 2 row
+                        // same-parity n': T11 (ta), T22 (tb); phase i^(n&1)
+                        double e1r = 0, e1i = 0, e3r = 0, e3i = 0, e2r = 0, e2i = 0, e4r = 0, e4i = 0;
+                        for (int nn = nmin + (k & 1); nn <= nmax; nn += 2) {
+                            const long o_ = (long)(nn - nmin) * NM;
+                            const double2 a_ = ta[o_], b_ = tb[o_];
+                            const double P = Pp[nn], Q = Qp[nn];
+                            e1r += a_.x * P; e1i += a_.y * P; e3r += a_.x * Q; e3i += a_.y * Q;
+                            e2r += b_.x * Q; e2i += b_.y * Q; e4r += b_.x * P; e4i += b_.y * P;
+                        }
+                        // other-parity n': T12 (ta), T21 (tb); phase i^((n+1)&1)
+                        double o1r = 0, o1i = 0, o3r = 0, o3i = 0, o2r = 0, o2i = 0, o4r = 0, o4i = 0;
+                        for (int nn = nmin + ((k + 1) & 1); nn <= nmax; nn += 2) {
+                            const long o_ = (long)(nn - nmin) * NM;
+                            const double2 a_ = ta[o_], b_ = tb[o_];
+                            const double P = Pp[nn], Q = Qp[nn];
+                            o1r += a_.x * Q; o1i += a_.y * Q; o3r += a_.x * P; o3i += a_.y * P;
+                            o2r += b_.x * P; o2i += b_.y * P; o4r += b_.x * Q; o4i += b_.y * Q;
+                        }
+                        double g1r, g1i, g2r, g2i, g3r, g3i, g4r, g4i;
+                        if (n & 1) {  // same-parity phase = i, other-parity phase = 1
+                            g1r = -e1i + o1r; g1i = e1r + o1i; g2r = -e2i + o2r; g2i = e2r + o2i;
+                            g3r = -e3i + o3r; g3i = e3r + o3i; g4r = -e4i + o4r; g4i = e4r + o4i;
+                        } else {      // same-parity phase = 1, other-parity phase = i
+                            g1r = e1r - o1i; g1i = e1i + o1r; g2r = e2r - o2i; g2i = e2i + o2r;
+                            g3r = e3r - o3i; g3i = e3i + o3r; g4r = e4r - o4i; g4i = e4i + o4r;
+                        }
+                        acc_t += wm * (g1r * g1r + g1i * g1i + g2r * g2r + g2i * g2i);
+                        acc_p += wm * (g3r * g3r + g3i * g3i + g4r * g4r + g4i * g4i);
+                        const double f = s_fn[n];
+                        const int pw = (-(n + 1)) & 3;
+                        const double ar = (pw == 0) ? f : (pw == 2) ? -f : 0.0, ai = (pw == 1) ? f : (pw == 3) ? -f : 0.0;
+#pragma unroll
+                        for (int g = 0; g < SCK_G; g++) {
+                            if (g >= ng) continue;
+                            double p_, t_;
+                            ws[g].next(n, m, s_sq, s_rsq, s_rn1, s_r2n1, p_, t_);
+                            const double mp = m * p_;
+                            const double ur = mp * g1r + t_ * g2r, ui = mp * g1i + t_ * g2i;
+                            const double vr = mp * g3r + t_ * g4r, vi = mp * g3i + t_ * g4i;
+                            const double wr = t_ * g1r + mp * g2r, wi = t_ * g1i + mp * g2i;
+                            const double zr = t_ * g3r + mp * g4r, zi = t_ * g3i + mp * g4i;
+                            const double cr = ar * fc[g], ci = ai * fc[g], sr = ar * fs[g], si = ai * fs[g];
+                            acc[g][0] += ur * cr - ui * ci; acc[g][1] += ur * ci + ui * cr;
+                            acc[g][2] += vr * sr - vi * si; acc[g][3] += vr * si + vi * sr;
+                            acc[g][4] -= wr * sr - wi * si; acc[g][5] -= wr * si + wi * sr;
+                            acc[g][6] += zr * cr - zi * ci; acc[g][7] += zr * ci + zi * cr;
+                        }
+                    }
+                }
+                // ---- per-thread epilogue: S, Z, cross sections -> weighted row in shared memory ----
+                if (active) {
+                    const double dk = 2.0 * pin / lam, w = a.weight[o];
+                    double *row = srow + (long)tid * stride;
+                    const double c0 = 4.0 * pin / (dk * dk);
+                    row[ng * 24] = w * c0 * (R[0][1] * R[0][1] * acc_t + R[1][1] * R[1][1] * acc_p);
+                    row[ng * 24 + 1] = w * c0 * (R[0][0] * R[0][0] * acc_t + R[1][0] * R[1][0] * acc_p);
+#pragma unroll
+                    for (int g = 0; g < SCK_G; g++) {
+                        if (g >= ng) continue;
+                        double vvr = acc[g][0] / dk, vvi = acc[g][1] / dk, vhr = acc[g][2] / dk, vhi = acc[g][3] / dk;
+                        double hvr = acc[g][4] / dk, hvi = acc[g][5] / dk, hhr = acc[g][6] / dk, hhi = acc[g][7] / dk;
+                        double cvvr = vvr * R[0][0] + vhr * R[1][0], cvvi = vvi * R[0][0] + vhi * R[1][0];
+                        double cvhr = vvr * R[0][1] + vhr * R[1][1], cvhi = vvi * R[0][1] + vhi * R[1][1];
+                        double chvr = hvr * R[0][0] + hhr * R[1][0], chvi = hvi * R[0][0] + hhi * R[1][0];
+                        double chhr = hvr * R[0][1] + hhr * R[1][1], chhi = hvi * R[0][1] + hhi * R[1][1];
+                        double s11r = R1[g][0][0] * cvvr + R1[g][0][1] * chvr, s11i = R1[g][0][0] * cvvi + R1[g][0][1] * chvi;
+                        double s12r = R1[g][0][0] * cvhr + R1[g][0][1] * chhr, s12i = R1[g][0][0] * cvhi + R1[g][0][1] * chhi;
+                        double s21r = R1[g][1][0] * cvvr + R1[g][1][1] * chvr, s21i = R1[g][1][0] * cvvi + R1[g][1][1] * chvi;
+                        double s22r = R1[g][1][0] * cvhr + R1[g][1][1] * chhr, s22i = R1[g][1][0] * cvhi + R1[g][1][1] * chhi;
+                        double *o_ = row + g * 24;
+                        o_[0] = w * s11r; o_[1] = w * s11i; o_[2] = w * s12r; o_[3] = w * s12i;
+                        o_[4] = w * s21r; o_[5] = w * s21i; o_[6] = w * s22r; o_[7] = w * s22i;
+#define RE(a, b) (a##r * b##r + a##i * b##i)
+#define IM(a, b) (a##i * b##r - a##r * b##i)
+                        double *Z = o_ + 8;
+                        Z[0] = w * 0.5 * (RE(s11, s11) + RE(s12, s12) + RE(s21, s21) + RE(s22, s22));
+                        Z[1] = w * 0.5 * (RE(s11, s11) - RE(s12, s12) + RE(s21, s21) - RE(s22, s22));
+                        Z[2] = w * -(RE(s11, s12) + RE(s22, s21));
+                        Z[3] = w * -(IM(s11, s12) - IM(s22, s21));
+                        Z[4] = w * 0.5 * (RE(s11, s11) + RE(s12, s12) - RE(s21, s21) - RE(s22, s22));
+                        Z[5] = w * 0.5 * (RE(s11, s11) - RE(s12, s12) - RE(s21, s21) + RE(s22, s22));
+                        Z[6] = w * -(RE(s11, s12) - RE(s22, s21));
+                        Z[7] = w * -(IM(s11, s12) + IM(s22, s21));
+                        Z[8] = w * -(RE(s11, s21) + RE(s22, s12));
+                        Z[9] = w * -(RE(s11, s21) - RE(s22, s12));
+                        Z[10] = w * (RE(s11, s22) + RE(s12, s21));
+                        Z[11] = w * (IM(s11, s22) + IM(s21, s12));
+                        Z[12] = w * -(IM(s21, s11) + IM(s22, s12));
+                        Z[13] = w * -(IM(s21, s11) - IM(s22, s12));
+                        Z[14] = w * (IM(s22, s11) - IM(s12, s21));
+                        Z[15] = w * (RE(s22, s11) - RE(s12, s21));
+#undef RE
+#undef IM
+                    }
                 }
                 __syncthreads();
-                const int cnt = min((int)blockDim.x, a.n_orient - o0);
-                for (int c = threadIdx.x; c < ncomp; c += blockDim.x) {
-                    double acc = accs[c];
-                    for (int j = 0; j < cnt; j++) acc += sm[(long)j * stride + c];
-                    accs[c] = acc;
+                const int cnt = min(nt, a.n_orient - o0);
+                for (int c = tid; c < ncomp; c += nt) {
+                    double acc_ = accs[c];
+                    for (int j = 0; j < cnt; j++) acc_ += srow[(long)j * stride + c];
+                    accs[c] = acc_;
                 }
                 __syncthreads();
             }
-            for (int c = threadIdx.x; c < ncomp; c += blockDim.x) {
+            for (int c = tid; c < ncomp; c += nt) {
                 const double v = accs[c] * a.scale;
                 if (c < ng * 24) {
                     const int g = c / 24, k = c - g * 24, slot = a.g_out[gb + g];
@@ -319,7 +534,7 @@ __global__ void k_scatter(ScArgs a)
                 }
             }
             __syncthreads();
-            if (gb + SC_MAXG >= gend) break;
+            if (gb + SCK_G >= gend) break;
         }
     }
 }

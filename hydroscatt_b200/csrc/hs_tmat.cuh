@@ -30,6 +30,10 @@ struct TmArgs {
     int *nmax, *ngauss, *ntrials, *status;
     int ws_cap;         // doubles available per group
     double *ws_global;  // GLOBAL_WS variant: per-CTA slices of ws_cap doubles
+    double *ws_fb;      // fall-back workspace in global memory (L2-resident) for particles that outgrow the
+    long long *prof;    // optional phase-cycle counters [8] (thread 0 of each group, clock64), null in production
+    int debug;          // timing experiments only: bit0 skip solve, bit1 skip assembly, bit2 skip radial functions
+    int fb_cap;         // shared-memory slice of their bucket: per-group slices of fb_cap doubles (or null / 0)
 };
 
 __host__ __device__ inline long long ws_need(int nmax, int g)
@@ -71,9 +75,10 @@ __device__ inline void carve(Carve &c, double *ws, int nmax, int g)
 struct Ctl {
     int item, nmax, g, phase, done, status, ntr, sing;
     double qsca1, qext1;
-    int piv[2];
-    double2 pivinv[2];
     unsigned long long toff;
+    // storage for the solver's system descriptors / pivot records (SysDesc[8], SolveCtl)
+    alignas(16) unsigned char sd[8 * 32];
+    alignas(16) unsigned char sc[8 * 4 + 8 * 16 + 16];
 };
 
 template <bool WARP>
@@ -392,26 +397,44 @@ __device__ void assemble(const Grp<WARP> &grp, const Carve &c, int nmax, int g, 
     grp.sync();
 }
 
-// ---- K3: Gauss-Jordan with row pivoting on both class systems at once (P7: TT, T = -RgQ Q^-1) ----
-// Solves Q_c^T X_c = -RgQ_c^T in place; on exit columns NM..2NM-1 hold X_c = T_c^T.
-// Per elimination step: (1) pivot search (one warp per class), (2) swap + scale of the pivot row, (3) rank-1 update
-// of all other rows with every thread of the group busy (threads tile [row group] x [live column of either class]).
-template <bool WARP>
-__device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
+// ---- K3: lock-step Gauss-Jordan with row pivoting over several independent systems (P7: TT, T = -RgQ Q^-1) ----
+// Each system solves A X = B in place inside an augmented row-major block; element (r, j) of [A | B] lives at
+//   base[(off + stride*r) * ld + (j < n ? off + stride*j : rhs + off + stride*(j - n))].
+// A parity-class system of a mode is {n = NM, off = 0, stride = 1, rhs = NM}; for m = 0 each class splits further into
+// two interleaved sub-systems (stride 2), because T12 = T21 = 0.  All systems advance through the elimination steps
+// together, so the serial latency of a step (pivot search, barriers) is paid once for up to HS_MAXSYS systems.
+#define HS_MAXSYS 8
+struct SysDesc {
+    double2 *base;
+    int n, ld, off, stride, rhs;
+};
+struct SolveCtl {
+    int piv[HS_MAXSYS];
+    double2 pivinv[HS_MAXSYS];
+};
+__device__ __forceinline__ long sys_at(const SysDesc &d, int r, int j)
 {
-    const int ldc = 2 * NM;
-    double2 *sys = c.sys;
-    const int nl = grp.nt < 32 ? grp.nt : 32;  // lanes searching for the pivot (32 on the GPU)
+    return (long)(d.off + d.stride * r) * d.ld + (j < d.n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - d.n));
+}
+
+template <bool WARP>
+__device__ void solve_multi(const Grp<WARP> &grp, const SysDesc *sd, int nsys, SolveCtl *sc, int *sing)
+{
+    const int nl = grp.nt < 32 ? grp.nt : 32;
     const int lane = grp.tid & 31;
-    const int wid = grp.tid >> 5;
-    const bool two_warps = grp.nt >= 64;
-    for (int k = 0; k < NM; k++) {
-        if (grp.tid < (two_warps ? 64 : nl)) {
-            for (int cl = (two_warps ? wid : 0); cl < (two_warps ? wid + 1 : 2); cl++) {
+    const int nwarp = grp.nt >= 32 ? grp.nt >> 5 : 1, wid = grp.tid >> 5;
+    int nmaxsys = 0;
+    for (int s = 0; s < nsys; s++) nmaxsys = sd[s].n > nmaxsys ? sd[s].n : nmaxsys;
+    for (int k = 0; k < nmaxsys; k++) {
+        // (1) pivot search: one warp per system
+        if (grp.tid < nwarp * nl) {
+            for (int s = wid; s < nsys; s += nwarp) {
+                const SysDesc d = sd[s];
+                if (k >= d.n) continue;
                 double best = -1.0;
                 int bi = k;
-                for (int r = k + lane; r < NM; r += nl) {
-                    double2 v = sys[(long)(cl * NM + r) * ldc + k];
+                for (int r = k + lane; r < d.n; r += nl) {
+                    double2 v = d.base[sys_at(d, r, k)];
                     double av = fabs(v.x) + fabs(v.y);
                     if (av > best) { best = av; bi = r; }
                 }
@@ -421,47 +444,62 @@ __device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
                     if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
                 }
                 if (lane == 0) {
-                    double2 pv = sys[(long)(cl * NM + bi) * ldc + k];
+                    double2 pv = d.base[sys_at(d, bi, k)];
                     double den = pv.x * pv.x + pv.y * pv.y;
-                    if (!(best > 0.0)) ctl->sing = 1;
-                    ctl->piv[cl] = bi;
-                    ctl->pivinv[cl] = make_double2(pv.x / den, -pv.y / den);
+                    if (!(best > 0.0)) *sing = 1;
+                    sc->piv[s] = bi;
+                    sc->pivinv[s] = make_double2(pv.x / den, -pv.y / den);
                 }
             }
         }
         grp.sync();
-        const int ncol = ldc - k - 1;  // live columns k+1 .. 2NM-1 of each class
-        for (int t = grp.tid; t < 2 * ncol; t += grp.nt) {
-            const int cl = t >= ncol;
-            const int col = k + 1 + (t - cl * ncol);
-            double2 *S = sys + (long)cl * NM * ldc;
-            const int p = ctl->piv[cl];
-            const double2 inv = ctl->pivinv[cl];
-            double2 a = S[(long)k * ldc + col], b = S[(long)p * ldc + col];
-            S[(long)k * ldc + col] = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
-            if (p != k) S[(long)p * ldc + col] = a;
+        // total live columns over the active systems
+        int cstart[HS_MAXSYS + 1];
+        int tot = 0;
+#pragma unroll
+        for (int s = 0; s < HS_MAXSYS; s++) {
+            cstart[s] = tot;
+            if (s < nsys && k < sd[s].n) tot += 2 * sd[s].n - k - 1;
+        }
+        cstart[HS_MAXSYS] = tot;
+        // (2) swap + scale the pivot rows
+        for (int t = grp.tid; t < tot; t += grp.nt) {
+            int s = 0;
+#pragma unroll
+            for (int q = 1; q < HS_MAXSYS; q++) s += (t >= cstart[q]) ? 1 : 0;
+            const SysDesc d = sd[s];
+            const int j = k + 1 + (t - cstart[s]);
+            const int p = sc->piv[s];
+            const double2 inv = sc->pivinv[s];
+            const long ik = sys_at(d, k, j), ip = sys_at(d, p, j);
+            double2 a = d.base[ik], b = d.base[ip];
+            d.base[ik] = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
+            if (p != k) d.base[ip] = a;
         }
         grp.sync();
-        {
-            const int n2 = 2 * ncol;
-            const int w = n2 < grp.nt ? n2 : grp.nt;  // threads per row group
+        // (3) rank-1 update of all other rows: threads tile [row group] x [live column of any system]
+        if (tot > 0) {
+            const int w = tot < grp.nt ? tot : grp.nt;
             const int nrg = grp.nt / w, rg = grp.tid / w, c0 = grp.tid - rg * w;
             if (rg < nrg) {
-                for (int t = c0; t < n2; t += w) {
-                    const int cl = t >= ncol;
-                    const int col = k + 1 + (t - cl * ncol);
-                    double2 *S = sys + (long)cl * NM * ldc;
-                    const int p = ctl->piv[cl];
-                    const double2 nk = S[(long)k * ldc + col];
-                    const double2 fkk = S[(long)k * ldc + k];
-                    for (int r = rg; r < NM; r += nrg) {
+                for (int t = c0; t < tot; t += w) {
+                    int s = 0;
+#pragma unroll
+                    for (int q = 1; q < HS_MAXSYS; q++) s += (t >= cstart[q]) ? 1 : 0;
+                    const SysDesc d = sd[s];
+                    const int j = k + 1 + (t - cstart[s]);
+                    const int p = sc->piv[s];
+                    const double2 nk = d.base[sys_at(d, k, j)];
+                    const double2 fkk = d.base[sys_at(d, k, k)];
+                    for (int r = rg; r < d.n; r += nrg) {
                         if (r == k) continue;
-                        // after the row swap, row p holds the old row k whose column-k entry is still at S[k][k]
-                        const double2 f = (r == p) ? fkk : S[(long)r * ldc + k];
-                        double2 v = S[(long)r * ldc + col];
+                        // after the row swap, row p holds the old row k whose column-k entry is still at (k, k)
+                        const double2 f = (r == p) ? fkk : d.base[sys_at(d, r, k)];
+                        const long ir = sys_at(d, r, j);
+                        double2 v = d.base[ir];
                         v.x -= f.x * nk.x - f.y * nk.y;
                         v.y -= f.x * nk.y + f.y * nk.x;
-                        S[(long)r * ldc + col] = v;
+                        d.base[ir] = v;
                     }
                 }
             }
@@ -470,9 +508,35 @@ __device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
     }
 }
 
+// Both parity-class systems of one mode stored as [2][NM][2NM] (used by the two-layer kernel).
+template <bool WARP>
+__device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
+{
+    SysDesc *sd = reinterpret_cast<SysDesc *>(ctl->sd);
+    if (grp.tid == 0) {
+        for (int cl = 0; cl < 2; cl++) {
+            SysDesc d;
+            d.base = c.sys + (long)cl * NM * 2 * NM; d.n = NM; d.ld = 2 * NM; d.off = 0; d.stride = 1; d.rhs = NM;
+            sd[cl] = d;
+        }
+    }
+    grp.sync();
+    solve_multi(grp, sd, 2, reinterpret_cast<SolveCtl *>(ctl->sc), &ctl->sing);
+}
+
+#ifdef HS_HOST_EMU
+#define HS_PROF(slot)
+#else
+#define HS_PROF(slot)                                                         \
+    if (a.prof && grp.tid == 0) {                                             \
+        long long now_ = clock64();                                           \
+        atomicAdd((unsigned long long *)&a.prof[slot], (unsigned long long)(now_ - tprof)); \
+        tprof = now_;                                                         \
+    }
+#endif
 // ---- one particle: convergence loop (A.1) + mode sweep ----
 template <bool WARP>
-__device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, const Grp<WARP> &grp, Ctl *ctl,
+__device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, double *ws_fb, const Grp<WARP> &grp, Ctl *ctl,
                                   const double *an, const double *dd)
 {
     const double PI = 3.14159265358979323846;
@@ -507,6 +571,9 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, const G
     }
     grp.sync();
     Carve c;
+#ifndef HS_HOST_EMU
+    long long tprof = clock64();
+#endif
     while (true) {
         if (ctl->done) break;
         int nmax = ctl->nmax, g;
@@ -517,16 +584,41 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, const G
         int stop = 0;
         if (g > HS_NPNG1) stop = HS_ST_NGAUSS_LIMIT;
         else if (g > a.gmax) stop = HS_ST_INTERNAL_GAUSS;
-        else if (ws_need(nmax, g) > (long long)a.ws_cap) stop = HS_ST_INTERNAL_ESCALATE;
+        double *wsp = ws;
+        if (ws_need(nmax, g) > (long long)a.ws_cap) {
+            // outgrew the shared-memory slice: continue in the global-memory fall-back slice (slower, no re-launch)
+            if (ws_fb && ws_need(nmax, g) <= (long long)a.fb_cap) wsp = ws_fb;
+            else stop = HS_ST_INTERNAL_ESCALATE;
+        }
         if (stop) {
             if (grp.tid == 0) { ctl->status = stop; ctl->done = 2; }
             grp.sync();
             break;
         }
-        carve(c, ws, nmax, g);
-        trial_setup(grp, c, nmax, g, arev, lam, mrr, mri, eps, a.gx, a.gw);
-        assemble(grp, c, nmax, g, 0, ppi, pir, pii, an, dd);
-        solve(grp, c, nmax, ctl);
+        carve(c, wsp, nmax, g);
+        HS_PROF(0)
+        if (!(a.debug & 4) || ctl->ntr == 0) trial_setup(grp, c, nmax, g, arev, lam, mrr, mri, eps, a.gx, a.gw);
+        HS_PROF(1)
+        if (!(a.debug & 2)) assemble(grp, c, nmax, g, 0, ppi, pir, pii, an, dd);
+        HS_PROF(2)
+        if (!(a.debug & 1)) {
+            // m = 0: T12 = T21 = 0, so each parity class splits into two interleaved half-size systems
+            SysDesc *sd = reinterpret_cast<SysDesc *>(ctl->sd);
+            if (grp.tid == 0) {
+                int q = 0;
+                for (int cl = 0; cl < 2; cl++)
+                    for (int par = 0; par < 2; par++) {
+                        SysDesc d;
+                        d.base = c.sys + (long)cl * nmax * 2 * nmax; d.ld = 2 * nmax; d.off = par; d.stride = 2; d.rhs = nmax;
+                        d.n = (nmax + 1 - par) >> 1;
+                        if (d.n > 0) sd[q++] = d;
+                    }
+                ctl->item = q;
+            }
+            grp.sync();
+            solve_multi(grp, sd, ctl->item, reinterpret_cast<SolveCtl *>(ctl->sc), &ctl->sing);
+        }
+        HS_PROF(3)
         if (grp.tid == 0) {
             const int NM = nmax, ldc = 2 * NM;
             double qext = 0.0, qsca = 0.0;
@@ -566,13 +658,9 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, const G
         grp.sync();
         if (ctl->done == 1) {
             double2 *tg = reinterpret_cast<double2 *>(a.tarena) + ctl->toff;
-            for (int m = 0; m <= nmax; m++) {
-                const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1, ldc = 2 * NM;
-                if (m >= 1) {
-                    mode_setup(grp, c, nmax, g, m);
-                    assemble(grp, c, nmax, g, m, ppi, pir, pii, an, dd);
-                    solve(grp, c, NM, ctl);
-                }
+            // m = 0 block: already solved by the last trial
+            {
+                const int NM = nmax, ldc = 2 * NM;
                 for (int t = grp.tid; t < 2 * NM * NM; t += grp.nt) {
                     int row = t / NM, col = t - row * NM;  // row = c*NM + k'
                     tg[t] = c.sys[(long)row * ldc + NM + col];
@@ -580,6 +668,60 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, const G
                 tg += 2 * NM * NM;
                 grp.sync();
             }
+            // m >= 1: assemble as many modes as fit in the remaining workspace, then solve them in lock-step
+            const long base_dbl = 12L * g + 10L * g * c.ld;
+            const long cap_dbl = (c.x == ws ? (long)a.ws_cap : (long)a.fb_cap);
+            const long sys_cap = (cap_dbl - base_dbl) / 2;  // complex entries available for systems
+            double2 *sysbase = c.sys;
+            SysDesc *sd = reinterpret_cast<SysDesc *>(ctl->sd);
+            int m = 1;
+            while (m <= nmax) {
+                int M = 0;
+                long used = 0;
+                while (m + M <= nmax && M < HS_MAXSYS / 2) {
+                    long nm = nmax - (m + M) + 1;
+                    if (M > 0 && used + 4 * nm * nm > sys_cap) break;
+                    used += 4 * nm * nm;
+                    M++;
+                }
+                long off = 0;
+                for (int i = 0; i < M; i++) {
+                    const int mm = m + i, NM = nmax - mm + 1;
+                    c.sys = sysbase + off;
+                    HS_PROF(0)
+                    mode_setup(grp, c, nmax, g, mm);
+                    HS_PROF(4)
+                    if (!(a.debug & 2)) assemble(grp, c, nmax, g, mm, ppi, pir, pii, an, dd);
+                    HS_PROF(5)
+                    if (grp.tid == 0) {
+                        for (int cl = 0; cl < 2; cl++) {
+                            SysDesc d;
+                            d.base = c.sys + (long)cl * NM * 2 * NM; d.n = NM; d.ld = 2 * NM; d.off = 0; d.stride = 1; d.rhs = NM;
+                            sd[2 * i + cl] = d;
+                        }
+                    }
+                    off += 4L * NM * NM;
+                }
+                grp.sync();
+                HS_PROF(0)
+                if (!(a.debug & 1)) solve_multi(grp, sd, 2 * M, reinterpret_cast<SolveCtl *>(ctl->sc), &ctl->sing);
+                HS_PROF(6)
+                off = 0;
+                for (int i = 0; i < M; i++) {
+                    const int NM = nmax - (m + i) + 1, ldc = 2 * NM;
+                    const double2 *sy = sysbase + off;
+                    for (int t = grp.tid; t < 2 * NM * NM; t += grp.nt) {
+                        int row = t / NM, col = t - row * NM;
+                        tg[t] = sy[(long)row * ldc + NM + col];
+                    }
+                    tg += 2 * NM * NM;
+                    off += 4L * NM * NM;
+                }
+                grp.sync();
+                HS_PROF(7)
+                m += M;
+            }
+            c.sys = sysbase;
         }
     }
     if (grp.tid == 0) {
@@ -598,7 +740,7 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, const G
 #ifndef HS_HOST_EMU
 
 template <bool WARP, bool GLOBAL_WS>
-__global__ void k_calctmat(TmArgs a)
+__global__ void __launch_bounds__(256) k_calctmat(TmArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ Ctl ctls[HS_MAX_GROUPS];
@@ -617,6 +759,8 @@ __global__ void k_calctmat(TmArgs a)
     if (WARP) { grp.tid = threadIdx.x & 31; grp.nt = 32; gidx = threadIdx.x >> 5; }
     else { grp.tid = threadIdx.x; grp.nt = blockDim.x; gidx = 0; }
     double *ws = GLOBAL_WS ? (a.ws_global + (long long)blockIdx.x * a.ws_cap) : (smem + (long long)gidx * a.ws_cap);
+    const int ngrp = WARP ? (blockDim.x >> 5) : 1;
+    double *ws_fb = (GLOBAL_WS || !a.ws_fb) ? nullptr : a.ws_fb + ((long long)blockIdx.x * ngrp + gidx) * a.fb_cap;
     Ctl *ctl = &ctls[gidx];
     while (true) {
         if (grp.tid == 0) ctl->item = atomicAdd(a.queue, 1);
@@ -624,7 +768,7 @@ __global__ void k_calctmat(TmArgs a)
         int it = ctl->item;
         grp.sync();
         if (it >= a.n_items) break;
-        calctmat_particle<WARP>(a, a.items[it], ws, grp, ctl, s_an, s_dd);
+        calctmat_particle<WARP>(a, a.items[it], ws, ws_fb, grp, ctl, s_an, s_dd);
     }
 }
 

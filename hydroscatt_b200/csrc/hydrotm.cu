@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <chrono>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -23,6 +25,7 @@ struct hs_ctx {
     int smem_optin = 227 * 1024;
     std::string err;
     long long launches = 0;
+    int last_nmax_max = 0;       // largest converged NMAX seen by hs_calctmat_batch (sizes k_scatter's T stage)
     // Gauss table
     int gmax = 0;
     double *d_gx = nullptr, *d_gw = nullptr;
@@ -32,11 +35,13 @@ struct hs_ctx {
     int items_cap = 0;
     int *h_pin = nullptr;        // pinned staging
     size_t h_pin_cap = 0;
-    cudaStream_t bstream[4] = {nullptr, nullptr, nullptr, nullptr};  // one stream per size bucket
-    cudaEvent_t ev_start = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t bstream[8] = {};  // one stream per size bucket
+    cudaEvent_t ev_start = nullptr, ev_done[8] = {};
     double *d_sc = nullptr;      // scatter geometry tables (device)
     double *d_xs_tmp = nullptr;
     size_t xs_tmp_cap = 0;
+    long long *d_prof = nullptr; // phase-cycle counters (HYDROTM_PROF=1)
+    double *d_ws_fb = nullptr;   // global-memory fall-back workspace slices
     double *d_ws_global = nullptr;
     size_t ws_global_bytes = 0;
 };
@@ -94,7 +99,7 @@ extern "C" int hs_ctx_create(hs_ctx **out, int device)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaMalloc(&ctx->d_queue, 16 * sizeof(int)));
-    for (int b = 0; b < 4; b++) {
+    for (int b = 0; b < 8; b++) {
         CK(cudaStreamCreateWithFlags(&ctx->bstream[b], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming));
     }
@@ -107,9 +112,9 @@ extern "C" void hs_ctx_destroy(hs_ctx *ctx)
 {
     if (!ctx) return;
     cudaFree(ctx->d_gx); cudaFree(ctx->d_gw); cudaFree(ctx->d_queue); cudaFree(ctx->d_items);
-    cudaFree(ctx->d_ws_global); cudaFree(ctx->d_sc); cudaFree(ctx->d_xs_tmp);
+    cudaFree(ctx->d_ws_global); cudaFree(ctx->d_ws_fb); cudaFree(ctx->d_sc); cudaFree(ctx->d_xs_tmp);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    for (int b = 0; b < 4; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
+    for (int b = 0; b < 8; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     delete ctx;
 }
@@ -136,7 +141,12 @@ struct Bucket {
     int ws_cap;       // doubles per group
 };
 
-__global__ void k_nmax0(int n, const double *axi, const double *lam, const double *eps, double rat, int *out)
+// Predicted converged NMAX per particle (bucket choice only; the kernel still starts from upstream's NMAX0).
+// NMAX0 = max(4, int(x + 4.05 x^(1/3))) underestimates the converged order when |m| x is large (W band: 14 -> 25);
+// max(NMAX0 + 1, ceil(|m| k a_max + 2)) is a tight estimate on the 6-band rain sweep; particles that still outgrow
+// their shared-memory slice continue in the global-memory fall-back workspace (no re-launch).
+__global__ void k_nmax0(int n, const double *axi, const double *lam, const double *mr, const double *mi,
+                        const double *eps, double rat, int *out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -151,7 +161,12 @@ __global__ void k_nmax0(int n, const double *axi, const double *lam, const doubl
     }
     double xev = 2.0 * PI * r * axi[i] / lam[i];
     int ixxx = (xev > 0.0 && xev < 1e6) ? (int)(xev + 4.05 * pow(xev, 0.333333)) : 0;
-    out[i] = ixxx > 4 ? ixxx : 4;
+    int n0 = ixxx > 4 ? ixxx : 4;
+    double a = (e_ > 0.0) ? pow(e_, 1.0 / 3.0) : 1.0;
+    double xa = xev * fmax(a, a / e_);
+    double mx = sqrt(mr[i] * mr[i] + mi[i] * mi[i]) * xa;
+    int pred = (mx > 0.0 && mx < 1e6) ? (int)ceil(mx + 2.0) : 0;
+    out[i] = max(n0 + 1, pred);
 }
 
 template <bool WARP, bool GLOBAL_WS>
@@ -176,15 +191,58 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
     if (rescale_ddelt) ddelt = 0.1 * ddelt;
-
-    const Bucket buckets[4] = {
-        {true, false, 128, 4, 2816},
-        {false, false, 128, 1, 12000},
-        {false, false, 256, 1, (ctx->smem_optin - 4096) / 8},
-        {false, true, 256, 1, (int)hs::ws_need(HS_NPN1, HS_NPNG1)},
+    const bool trace = getenv("HYDROTM_TRACE") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[hydrotm] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count());
     };
-    const int NB = 4;
 
+    // Size buckets (launch configurations), smallest first; a particle that outgrows its bucket is re-run in the
+    // next one.  Bucket i packs k_i CTAs per SM: its per-particle workspace is the k_i-th share of the 227 KB of
+    // shared memory.  Small CTAs + many particles in flight beat big CTAs here: the per-particle critical path
+    // (recurrences, pivot searches, barriers) does not shrink with more threads.
+    // Override for experiments: HYDROTM_BUCKETS="k:threads[:w],..." (w = warp-per-particle groups).
+    Bucket buckets[8];
+    int NB = 0;
+    {
+        int ks[7] = {8, 5, 3, 2, 1, 0, 0}, th[7] = {64, 128, 128, 128, 256, 0, 0}, wg[7] = {0, 0, 0, 0, 0, 0, 0};
+        int nk = 5;
+        const char *env = getenv("HYDROTM_BUCKETS");
+        if (env && *env) {
+            nk = 0;
+            const char *q = env;
+            while (*q && nk < 7) {
+                int k = 0, t = 0, w = 0, used = 0;
+                if (sscanf(q, "%d:%d%n", &k, &t, &used) < 2) break;
+                q += used;
+                if (*q == ':') { w = 1; q += 2; }
+                ks[nk] = k; th[nk] = t; wg[nk] = w; nk++;
+                if (*q == ',') q++;
+            }
+        }
+        for (int i = 0; i < nk; i++) {
+            int k = std::max(1, ks[i]);
+            // 228 KB per SM; each resident CTA also needs ~6 KB static smem (control blocks, tables) + 1 KB reserved
+            int per_cta = std::min(ctx->smem_optin - 6144, (233472 - k * 7168) / k);  // bytes of dynamic smem per CTA
+            Bucket B;
+            B.global_ws = false;
+            B.warp = wg[i] != 0;
+            B.threads = th[i];
+            B.groups = B.warp ? std::max(1, th[i] / 32) : 1;
+            B.ws_cap = per_cta / 8 / B.groups;
+            buckets[NB++] = B;
+        }
+        Bucket G = {false, true, 256, 1, (int)hs::ws_need(HS_NPN1, HS_NPNG1)};
+        buckets[NB++] = G;
+    }
+
+    // fall-back workspace: one slice per resident group (<= 8 groups per SM), sized for NMAX 48 at NDGS 2
+    const int fb_cap = (int)hs::ws_need(48, 97);
+    if (!ctx->d_ws_fb) {
+        if (cudaMalloc(&ctx->d_ws_fb, (size_t)ctx->sm_count * 8 * fb_cap * sizeof(double)) != cudaSuccess) { ctx->d_ws_fb = nullptr; cudaGetLastError(); }
+    }
     if (ensure_pin(ctx, (size_t)n * sizeof(int) * 2)) return -1;
     if (n > ctx->items_cap) {
         if (ctx->d_items) cudaFree(ctx->d_items);
@@ -193,19 +251,22 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         ctx->items_cap = n;
     }
     // predicted starting NMAX -> initial bucket
-    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_eps, rat, d_nmax);
+    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, d_nmax);
     ctx->launches++;
     CK(cudaGetLastError());
     int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n;
     CK(cudaMemcpyAsync(h_n0, d_nmax, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
 
+    if (getenv("HYDROTM_PROF") && !ctx->d_prof) { CK(cudaMalloc(&ctx->d_prof, 8 * sizeof(long long))); }
+    if (ctx->d_prof) CK(cudaMemsetAsync(ctx->d_prof, 0, 8 * sizeof(long long), st));
+    lap("nmax0 kernel + D2H");
     std::vector<int> bucket_of(n), nm0(n);
     std::vector<std::vector<int>> lists(NB);
     for (int i = 0; i < n; i++) {
         int n0 = h_n0[i];
         nm0[i] = n0;
-        int np_ = std::min(n0 + 4, HS_NPN1);
+        int np_ = std::min(n0, HS_NPN1);
         long long need = hs::ws_need(np_, np_ * ndgs + 1);
         int b = 0;
         while (b < NB - 1 && need > buckets[b].ws_cap) b++;
@@ -227,6 +288,7 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         }
         seg_start[NB] = (int)order.size();
         if (!any) break;
+        lap("host bucketing/sort");
         CK(cudaMemcpyAsync(ctx->d_items, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(ctx->d_queue, 0, 16 * sizeof(int), st));
         CK(cudaEventRecord(ctx->ev_start, st));
@@ -242,10 +304,13 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
             a.tarena = d_tarena; a.arena_cap = arena_cap; a.arena_top = d_arena_top;
             a.toff = d_toff; a.nmax = d_nmax; a.ngauss = d_ngauss; a.ntrials = d_ntrials; a.status = d_status;
             a.ws_cap = B.ws_cap; a.ws_global = nullptr;
+            a.prof = ctx->d_prof;
+            a.debug = getenv("HYDROTM_DEBUG") ? atoi(getenv("HYDROTM_DEBUG")) : 0;
+            a.ws_fb = B.global_ws ? nullptr : ctx->d_ws_fb; a.fb_cap = B.global_ws ? 0 : fb_cap;
             size_t smem = B.global_ws ? 0 : (size_t)B.groups * B.ws_cap * sizeof(double);
             int ctas_needed = (cnt + B.groups - 1) / B.groups;
             int per_sm = B.global_ws ? 1 : std::max(1, (int)((size_t)(ctx->smem_optin + 1024) / (smem + 4096)));
-            int grid = std::min(ctas_needed, ctx->sm_count * per_sm);
+            int grid = std::min(ctas_needed, ctx->sm_count * std::min(per_sm, 8 / B.groups));
             cudaError_t e;
             cudaStream_t bs = ctx->bstream[b];
             CK(cudaStreamWaitEvent(bs, ctx->ev_start, 0));
@@ -270,8 +335,10 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
             CK(cudaEventRecord(ctx->ev_done[b], bs));
             CK(cudaStreamWaitEvent(st, ctx->ev_done[b], 0));
         }
+        lap("launches issued");
         CK(cudaMemcpyAsync(h_st, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        lap("round done (status D2H)");
         // escalations
         std::vector<std::vector<int>> next(NB);
         bool need_gauss = false;
@@ -292,6 +359,17 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         }
         lists.swap(next);
     }
+    if (ctx->d_prof) {
+        long long hp[8];
+        CK(cudaMemcpy(hp, ctx->d_prof, sizeof(hp), cudaMemcpyDeviceToHost));
+        double tot = 0; for (int i = 0; i < 8; i++) tot += (double)hp[i];
+        const char *nm[8] = {"other", "trial_setup", "assemble m=0", "solve m=0", "mode_setup", "assemble m>=1", "solve m>=1", "write T"};
+        for (int i = 0; i < 8; i++) fprintf(stderr, "[hydrotm-prof] %-14s %6.2f%%  %.3e cycles\n", nm[i], 100.0 * hp[i] / tot, (double)hp[i]);
+    }
+    // remember the largest converged NMAX (bounds the T stage of the scatter kernel)
+    CK(cudaMemcpyAsync(h_n0, d_nmax, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) if (h_n0[i] > ctx->last_nmax_max && h_n0[i] <= HS_NPN1) ctx->last_nmax_max = h_n0[i];
     return 0;
 }
 
@@ -521,8 +599,13 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
     a.n_inc = n_inc; a.inc = dblk; a.g_begin = dib; a.gsc = dblk + 128; a.g_out = dib + 65; a.n_geom = n_geom;
     a.n_orient = n_orient; a.alpha = d_alpha; a.beta = d_beta; a.weight = d_weight; a.scale = scale;
     a.S = d_S; a.Z = d_Z; a.xs = xs_inc;
-    int threads = std::min(128, std::max(32, (n_orient + 31) / 32 * 32));
-    size_t smem = ((size_t)threads * (SC_MAXG * 24 + 3) + SC_MAXG * 24 + 2) * sizeof(double);
+    // one thread per orientation (up to 64 per pass); dynamic smem = T stage sized for the largest converged NMAX the
+    // context has produced (2*nmax^2 complex) + the per-orientation reduction rows
+    int threads = std::min(64, std::max(32, (n_orient + 31) / 32 * 32));
+    int nmax_bound = ctx->last_nmax_max > 0 ? ctx->last_nmax_max : HS_NPN1;
+    a.nmax_bound = nmax_bound;
+    size_t smem = ((size_t)4 * nmax_bound * nmax_bound + (size_t)threads * (SCK_G * 24 + 3) + SCK_G * 24 + 2) * sizeof(double);
+    if (smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
     CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hs::k_scatter<<<n, threads, smem, st>>>(a);
     ctx->launches++;

@@ -26,11 +26,11 @@ extern "C" int emu_calctmat(int n, const double *axi, const double *lam, const d
     a.gx = hx.data(); a.gw = hw.data(); a.gmax = gmax;
     a.tarena = tarena; a.arena_cap = cap; a.arena_top = &top;
     a.toff = toff; a.nmax = nmax; a.ngauss = ngauss; a.ntrials = ntrials; a.status = status;
-    a.ws_cap = ws_cap; a.ws_global = nullptr;
+    a.ws_cap = ws_cap; a.ws_global = nullptr; a.ws_fb = nullptr; a.fb_cap = 0; a.debug = 0; a.prof = nullptr;
     std::vector<double> ws((size_t)ws_cap + 16);
     hs::Grp<true> grp; grp.tid = 0; grp.nt = 1;
     hs::Ctl ctl;
-    for (int i = 0; i < n; i++) hs::calctmat_particle<true>(a, i, ws.data(), grp, &ctl, an.data(), dd.data());
+    for (int i = 0; i < n; i++) hs::calctmat_particle<true>(a, i, ws.data(), nullptr, grp, &ctl, an.data(), dd.data());
     return 0;
 }
 

@@ -1,0 +1,77 @@
+"""CPU suite: the multi-GPU sharding / gather logic with world_size 2 over gloo (no GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hydroscatt_b200 import dist as hdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        cost = rng.uniform(1, 100, n) ** 2
+        idx = hdist.shard_indices(cost, world, rank)
+        local = torch.from_numpy(np.stack([idx * 1.0, idx * 2.0 + 0.5, cost[idx]], axis=1))
+        full = hdist.gather_rows(local, idx, n)
+        ok = bool(torch.equal(full[:, 0], torch.arange(n, dtype=torch.float64))) and \
+            bool(torch.allclose(full[:, 2], torch.from_numpy(cost)))
+        part = torch.full((4, 3), float(rank + 1), dtype=torch.float64)
+        hdist.allreduce_sum(part)
+        ok = ok and bool((part == 3.0).all())
+        q.put((rank, ok, float(cost[idx].sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_is_a_partition_and_balanced():
+    rng = np.random.default_rng(0)
+    cost = rng.uniform(1, 30, 1001) ** 4
+    parts = [hdist.shard_indices(cost, 4, r) for r in range(4)]
+    allidx = np.sort(np.concatenate(parts))
+    assert np.array_equal(allidx, np.arange(1001))
+    loads = np.array([cost[p].sum() for p in parts])
+    assert loads.max() / loads.min() < 1.05
+
+
+def test_predicted_cost_orders_bands():
+    c = hdist.predicted_cost([3.5, 3.5], [53.5, 3.19], [8.6, 3.1], [1.7, 1.7], [1.6, 1.6])
+    assert c[1] > 50 * c[0]
+
+
+def test_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n = 257
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    loads = [l for _, _, l in res]
+    assert max(loads) / min(loads) < 1.2
+
+
+def test_gather_single_process():
+    idx = np.array([2, 0, 1])
+    rows = torch.tensor([[20.0], [0.0], [10.0]], dtype=torch.float64)
+    full = hdist.gather_rows(rows, idx, 3)
+    assert full[:, 0].tolist() == [0.0, 10.0, 20.0]

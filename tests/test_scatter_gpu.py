@@ -133,3 +133,34 @@ def test_shim_end_to_end_on_gpu(engine):
     for k in o:
         assert abs(g[k] - o[k]) <= 1e-6 * abs(o[k]), (k, g[k], o[k])
     assert g["Ai"] > 0 and g["sca"] > 0
+
+
+def test_golden_rain_amplitudes_through_shim(engine):
+    """The amplitudes the unmodified reference script feeds to its canting formulas (fixture generated by running
+    scattering_rain.py on the oracle back-end, tools/gen_golden_rain.py) reproduced by the shim on the CUDA back-end."""
+    import json
+    import os
+    import hydroscatt_b200
+    hydroscatt_b200.install_shims()
+    from pytmatrix import orientation, tmatrix_aux, refractive
+    from pytmatrix import tmatrix as tmod
+    from pytmatrix.tmatrix import Scatterer
+    tmod.set_backend(None)
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rain_C10.json")))
+    wl = tmatrix_aux.wl_C
+    tm = Scatterer(wavelength=wl, m=refractive.m_w_10C[wl])
+    tm.orient = orientation.orient_single
+    for i in range(0, 70, 4):
+        d = fx["D"][i]
+        tm.radius = d / 2.0
+        tm.axis_ratio = 1.0 / tmatrix_aux.dsr_thurai_2007(d)
+        tm.set_geometry(tmatrix_aux.geom_horiz_back)
+        S = tm.get_S()
+        ref = fx["S_back_vv_hh"][i]
+        assert abs(S[0, 0] - complex(ref[0], ref[1])) <= 1e-6 * abs(complex(ref[0], ref[1]))
+        assert abs(S[1, 1] - complex(ref[2], ref[3])) <= 1e-6 * abs(complex(ref[2], ref[3]))
+        tm.set_geometry(tmatrix_aux.geom_horiz_forw)
+        S = tm.get_S()
+        ref = fx["S_forw_vv_hh"][i]
+        assert abs(S[0, 0] - complex(ref[0], ref[1])) <= 1e-6 * abs(complex(ref[0], ref[1]))
+        assert abs(S[1, 1] - complex(ref[2], ref[3])) <= 1e-6 * abs(complex(ref[2], ref[3]))

@@ -32,6 +32,8 @@ GEOM_BACK = (90.0, 90.0, 0.0, 180.0)
 GEOM_FORW = (90.0, 90.0, 0.0, 0.0)
 CANTING = 10.0
 DDELT, NDGS = 1e-3, 2
+W2_NAME = ("W2 rain-sweep scatter-table build: 6 bands x 0..40 degC x 70 D = 17220 spheroids per GPU, "
+           "2 geometries x 50 orientations, 9300 gamma DSDs x 246 tables")
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -209,8 +211,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "T-matrix solves/s", "value": val, "unit": "solves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "W2 rain-sweep: 6 bands x 0..40 degC x 70 D (17220 spheroids), bounded sample",
-                       "parallelism": f"multiprocessing x{cores}"},
+            "config": {"workload": W2_NAME, "sample": sample, "parallelism": f"multiprocessing x{cores}",
+                       "ddelt_rescale": True},
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -365,8 +367,7 @@ def run_gpu(args):
             "metric": "T-matrix solves/s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "W2 rain-sweep scatter-table build: 6 bands x 0..40 degC x 70 D = 17220 spheroids "
-                                   "per GPU, 2 geometries x 50 orientations, 9300 gamma DSDs x 246 tables",
+            "config": {"workload": W2_NAME,
                        "l2": "working set per step (T arena + 1 GB PSD output) exceeds the 126 MB L2",
                        "parallelism": f"particles sharded x{world}" if world > 1 else "single GPU",
                        "ddelt_rescale": True},

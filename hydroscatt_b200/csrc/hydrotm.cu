@@ -270,6 +270,9 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         long long need = hs::ws_need(np_, np_ * ndgs + 1);
         int b = 0;
         while (b < NB - 1 && need > buckets[b].ws_cap) b++;
+        // the last shared-memory bucket also takes particles predicted slightly beyond its slice: they start in smem
+        // (the trial sequence grows from NMAX0) and only move to the fall-back workspace if they really outgrow it
+        if (b == NB - 1 && NB >= 2 && ctx->d_ws_fb && need <= fb_cap) b = NB - 2;
         bucket_of[i] = b;
         lists[b].push_back(i);
     }

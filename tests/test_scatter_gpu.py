@@ -164,3 +164,35 @@ def test_golden_rain_amplitudes_through_shim(engine):
         ref = fx["S_forw_vv_hh"][i]
         assert abs(S[0, 0] - complex(ref[0], ref[1])) <= 1e-6 * abs(complex(ref[0], ref[1]))
         assert abs(S[1, 1] - complex(ref[2], ref[3])) <= 1e-6 * abs(complex(ref[2], ref[3]))
+
+
+def test_asym_product_rule_matches_brute_force(engine):
+    """scatter.asym via the exact product rule against a much finer brute-force quadrature of the oracle's Z."""
+    import hydroscatt_b200
+    hydroscatt_b200.install_shims()
+    from pytmatrix import scatter, tmatrix_aux, orientation
+    from pytmatrix import tmatrix as tmod
+    from pytmatrix.tmatrix import Scatterer
+    tmod.set_backend(None)
+    tm = Scatterer(radius=2.0, wavelength=6.5, m=complex(1.5, 0.5), axis_ratio=1.0 / 0.6)
+    tm.orient = orientation.orient_single
+    tm.set_geometry((60.0, 60.0, 10.0, 10.0, 30.0, 20.0))
+    g_h, g_v = scatter.asym(tm, True), scatter.asym(tm, False)
+    o = oracle.TMatrix(2.0, 6.5, 1.5 + 0.5j, 1 / 0.6)
+    x, w = np.polynomial.legendre.leggauss(24)
+    nph = 48
+    num = np.zeros(2)
+    den = np.zeros(2)
+    t0, p0 = np.radians(60.0), np.radians(10.0)
+    for xi, wi in zip(x, w):
+        th = np.arccos(xi)
+        for p in (np.arange(nph) + 0.5) * 2 * np.pi / nph:
+            _, Z = o.ampl(60.0, np.degrees(th), 10.0, np.degrees(p), 30.0, 20.0)
+            c = np.sin(t0) * np.sin(th) * np.cos(p - p0) + np.cos(t0) * np.cos(th)
+            for k, s in enumerate((-1.0, 1.0)):
+                I = Z[0, 0] + s * Z[0, 1]
+                num[k] += wi * I * c
+                den[k] += wi * I
+    assert abs(g_h - num[0] / den[0]) < 1e-6 and abs(g_v - num[1] / den[1]) < 1e-6
+    assert 0.0 < g_h < 1.0
+    assert abs(scatter.ssa(tm) - scatter.sca_xsect(tm) / scatter.ext_xsect(tm)) < 1e-12

@@ -66,3 +66,63 @@ def test_orientation_reduce(engine):
     Zr = (Z1.cpu().numpy() * wd[None, None, :, None, None]).sum(2) * 0.2 / wt[:10].sum()
     assert _rel(S2.cpu().numpy(), Sr) < 1e-12
     assert _rel(Z2.cpu().numpy(), Zr) < 1e-12
+
+
+def test_ice_crystal_like_ndgs15(engine):
+    """scattering_ice_crystals.py regime: ndgs=15 (NGAUSS up to ~150, exercises the Gauss-table extension), extreme
+    axis ratios, RADIUS_MAXIMUM converted to equal volume as Scatterer.equal_volume_from_maximum does."""
+    cases = [(0.5, 8.0, 33.3, 1.5 + 0.002j), (1.0, 15.0, 33.3, 1.4 + 0.001j), (1.4, 29.5, 53.5, 1.35 + 0.001j),
+             (2.5, 41.0, 33.3, 1.3 + 0.001j), (0.3, 0.5, 8.43, 1.78 + 0.002j)]
+    L = np.array([c[0] for c in cases])
+    ar = np.array([c[1] for c in cases])
+    wl = np.array([c[2] for c in cases])
+    m = np.array([c[3] for c in cases])
+    req = np.where(ar > 1, (L / 2) / ar ** (1 / 3), (L / 2) / ar ** (2 / 3))
+    tb = engine.calctmat(req, wl, m.real, m.imag, ar, ndgs=15)
+    S, Z = tb.ampl(GEOMS, alpha=[0.0, 30.0], beta=[0.0, 15.0])
+    S = S.cpu().numpy()
+    for i in range(len(cases)):
+        tm = oracle.TMatrix(req[i], wl[i], m[i], ar[i], ndgs=15)
+        assert (int(tb.nmax[i]), int(tb.ngauss[i]), int(tb.ntrials[i]), int(tb.status[i])) == \
+            (tm.nmax, tm.ngauss, tm.ntrials, tm.status), i
+        for g, geom in enumerate(GEOMS):
+            for o, (a, b) in enumerate([(0.0, 0.0), (30.0, 15.0)]):
+                So, _ = tm.ampl(*geom, a, b)
+                assert _rel(S[i, g, o], So) < 1e-6, (i, g, o)
+
+
+def test_status_codes(engine):
+    """bad input -> 5, starting NMAX beyond NPN1 -> 1 (upstream: print + STOP), others unaffected in the same batch."""
+    tb = engine.calctmat([1.0, -1.0, 900.0, 1.0], [33.3, 33.3, 33.3, 33.3], [7.9, 7.9, 1.5, 7.9], [2.3, 2.3, 0.0, 2.3],
+                         [1.2, 1.2, 1.1, 0.0])
+    st = tb.status.cpu().numpy()
+    assert st.tolist() == [0, 5, 1, 5]
+    S, Z = tb.ampl(GEOMS)
+    S = S.cpu().numpy()
+    assert np.isfinite(S[0]).all() and np.isnan(S[1]).all() and np.isnan(S[2]).all()
+    import hydroscatt_b200
+    hydroscatt_b200.install_shims()
+    from pytmatrix.tmatrix import Scatterer
+    from pytmatrix import tmatrix as tmod
+    from hydroscatt_b200.backend import ConvergenceError
+    tmod.set_backend(None)
+    with pytest.raises(ConvergenceError):
+        Scatterer(radius=900.0, wavelength=33.3, m=1.5 + 0j, axis_ratio=1.1).get_SZ()
+
+
+def test_equal_area_radius_and_large_batch_escalation(engine):
+    """radius_type = equal surface area (SAREA) and a particle that outgrows every shared-memory bucket."""
+    tb = engine.calctmat([2.0], [6.5], [1.5], [0.5], [1 / 0.6], rat=0.0)
+    tm = oracle.TMatrix(2.0, 6.5, 1.5 + 0.5j, 1 / 0.6, rat=0.0)
+    assert (int(tb.nmax[0]), int(tb.ngauss[0])) == (tm.nmax, tm.ngauss)
+    S, _ = tb.ampl([GEOMS[0]])
+    So, _ = tm.ampl(*GEOMS[0])
+    assert _rel(S.cpu().numpy()[0, 0, 0], So) < 1e-6
+    # hail-sized dry ice sphere-ish at W band: NMAX ~ 60 -> global-memory workspace bucket
+    tb = engine.calctmat([20.0], [3.19], [1.78], [0.003], [1.05])
+    tm = oracle.TMatrix(20.0, 3.19, 1.78 + 0.003j, 1.05)
+    assert (int(tb.nmax[0]), int(tb.ngauss[0]), int(tb.status[0])) == (tm.nmax, tm.ngauss, tm.status)
+    if tm.status == 0:
+        S, _ = tb.ampl([GEOMS[1]])
+        So, _ = tm.ampl(*GEOMS[1])
+        assert _rel(S.cpu().numpy()[0, 0, 0], So) < 1e-5

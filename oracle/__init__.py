@@ -30,14 +30,15 @@ def build(force=False):
                 ["gcc", "-O2", "-fPIC", "-std=c11", "-fno-fast-math", "-shared", "-o", out, src, "-lm"])
     # rounding-perturbed twin of the two-layer oracle (FMA contraction on): used only to measure how sensitive the
     # ORACLE's own answer is to last-bit rounding, i.e. to flag ill-conditioned particles (hard part 3)
-    src = os.path.join(_HERE, "tm2l_oracle.c")
-    out = os.path.join(_HERE, "libtm2l_oracle_fma.so")
-    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
-        try:
-            subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-mfma", "-ffp-contract=fast", "-shared",
-                                   "-o", out, src, "-lm"])
-        except subprocess.CalledProcessError:
-            pass
+    for name in ("tm2l_oracle", "sl_oracle"):
+        src = os.path.join(_HERE, name + ".c")
+        out = os.path.join(_HERE, "lib" + name + "_fma.so")
+        if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            try:
+                subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-mfma", "-ffp-contract=fast", "-shared",
+                                       "-o", out, src, "-lm"])
+            except subprocess.CalledProcessError:
+                pass
 
 
 _sl = None
@@ -49,6 +50,35 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _sl_proto(lib):
+    lib.hso_calctmat.restype = C.c_void_p
+    lib.hso_calctmat.argtypes = [C.c_double] * 6 + [C.c_int, C.c_double, C.c_int, C.c_int]
+    lib.hso_free.argtypes = [C.c_void_p]
+    lib.hso_calcampl.argtypes = [C.c_void_p] + [C.c_double] * 7 + [C.POINTER(C.c_double)] * 2
+    return lib
+
+
+def sl_sensitivity(radius, wavelength, m, axis_ratio, geom=(90.0, 90.0, 0.0, 180.0), ddelt=1e-3, ndgs=2,
+                   rescale_ddelt=True):
+    """Relative change of the single-layer oracle's own S under last-bit rounding perturbation (FMA-contracted twin
+    build): flags ill-conditioned particles (extreme axis ratios), cf. SURVEY.md 7 hard part 3."""
+    build()
+    path = os.path.join(_HERE, "libsl_oracle_fma.so")
+    if not os.path.exists(path):
+        return 0.0
+    m = complex(m)
+    out = []
+    for lib in (_sl_proto(C.CDLL(os.path.join(_HERE, "libsl_oracle.so"))), _sl_proto(C.CDLL(path))):
+        h = lib.hso_calctmat(float(radius), 1.0, float(wavelength), m.real, m.imag, float(axis_ratio), -1,
+                             float(ddelt), int(ndgs), 1 if rescale_ddelt else 0)
+        S = np.zeros(8)
+        Z = np.zeros(16)
+        lib.hso_calcampl(h, float(wavelength), *[float(g) for g in geom[:4]], 0.0, 0.0, _dp(S), _dp(Z))
+        lib.hso_free(h)
+        out.append(S.view(np.complex128).copy())
+    return float(np.abs(out[0] - out[1]).max() / np.abs(out[0]).max())
 
 
 def sl_lib():

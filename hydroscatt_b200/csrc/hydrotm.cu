@@ -169,12 +169,12 @@ __global__ void k_nmax0(int n, const double *axi, const double *lam, const doubl
     out[i] = max(n0 + 1, pred);
 }
 
-template <bool WARP, bool GLOBAL_WS>
+template <bool WARP, bool GLOBAL_WS, bool TILED>
 static cudaError_t launch_tm(const hs::TmArgs &a, int grid, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(hs::k_calctmat<WARP, GLOBAL_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(hs::k_calctmat<WARP, GLOBAL_WS, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hs::k_calctmat<WARP, GLOBAL_WS><<<grid, threads, smem, st>>>(a);
+    hs::k_calctmat<WARP, GLOBAL_WS, TILED><<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -224,22 +224,23 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         }
         for (int i = 0; i < nk; i++) {
             int k = std::max(1, ks[i]);
-            // 228 KB per SM; each resident CTA also needs ~6 KB static smem (control blocks, tables) + 1 KB reserved
-            int per_cta = std::min(ctx->smem_optin - 6144, (233472 - k * 7168) / k);  // bytes of dynamic smem per CTA
+            // 228 KB per SM; each resident CTA also needs ~7 KB static smem (control blocks, tables) + 1 KB reserved
+            int per_cta = std::min(ctx->smem_optin - 8192, (233472 - k * 9216) / k);  // bytes of dynamic smem per CTA
             Bucket B;
             B.global_ws = false;
             B.warp = wg[i] != 0;
             B.threads = th[i];
             B.groups = B.warp ? std::max(1, th[i] / 32) : 1;
-            B.ws_cap = per_cta / 8 / B.groups;
+            if (k == 1 && getenv("HYDROTM_HEAVY_CAP_KB")) per_cta = std::min(per_cta, atoi(getenv("HYDROTM_HEAVY_CAP_KB")) * 1024);
+            B.ws_cap = (per_cta / 8 / B.groups) & ~1;
             buckets[NB++] = B;
         }
-        Bucket G = {false, true, 256, 1, (int)hs::ws_need(HS_NPN1, HS_NPNG1)};
+        Bucket G = {false, true, 256, 1, (int)((hs::ws_need(HS_NPN1, HS_NPNG1) + 1) & ~1LL)};
         buckets[NB++] = G;
     }
 
     // fall-back workspace: one slice per resident group (<= 8 groups per SM), sized for NMAX 48 at NDGS 2
-    const int fb_cap = (int)hs::ws_need(48, 97);
+    const int fb_cap = (int)(hs::ws_need(48, 97) + 1) & ~1;
     if (!ctx->d_ws_fb) {
         if (cudaMalloc(&ctx->d_ws_fb, (size_t)ctx->sm_count * 8 * fb_cap * sizeof(double)) != cudaSuccess) { ctx->d_ws_fb = nullptr; cudaGetLastError(); }
     }
@@ -308,6 +309,7 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
             a.toff = d_toff; a.nmax = d_nmax; a.ngauss = d_ngauss; a.ntrials = d_ntrials; a.status = d_status;
             a.ws_cap = B.ws_cap; a.ws_global = nullptr;
             a.prof = ctx->d_prof;
+            a.tile_min = getenv("HYDROTM_TILE_MIN") ? atoi(getenv("HYDROTM_TILE_MIN")) : 12;
             a.debug = getenv("HYDROTM_DEBUG") ? atoi(getenv("HYDROTM_DEBUG")) : 0;
             a.ws_fb = B.global_ws ? nullptr : ctx->d_ws_fb; a.fb_cap = B.global_ws ? 0 : fb_cap;
             size_t smem = B.global_ws ? 0 : (size_t)B.groups * B.ws_cap * sizeof(double);
@@ -327,11 +329,12 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
                     ctx->ws_global_bytes = bytes;
                 }
                 a.ws_global = ctx->d_ws_global;
-                e = launch_tm<false, true>(a, grid, B.threads, 0, bs);
+                e = launch_tm<false, true, false>(a, grid, B.threads, 0, bs);
             } else if (B.warp) {
-                e = launch_tm<true, false>(a, grid, B.threads, smem, bs);
+                e = launch_tm<true, false, false>(a, grid, B.threads, smem, bs);
             } else {
-                e = launch_tm<false, false>(a, grid, B.threads, smem, bs);
+                e = (per_sm <= 2) ? launch_tm<false, false, true>(a, grid, B.threads, smem, bs)
+                                 : launch_tm<false, false, false>(a, grid, B.threads, smem, bs);
             }
             ctx->launches++;
             if (e != cudaSuccess) { ctx->err = std::string("k_calctmat launch: ") + cudaGetErrorString(e); return -1; }

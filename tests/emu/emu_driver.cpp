@@ -15,8 +15,13 @@ extern "C" int emu_calctmat(int n, const double *axi, const double *lam, const d
     size_t tot = (size_t)gmax * (gmax + 1) / 2;
     std::vector<double> hx(tot), hw(tot);
     for (int g = 1; g <= gmax; g++) hs::gauss_positive(2 * g, &hx[(size_t)g * (g - 1) / 2], &hw[(size_t)g * (g - 1) / 2]);
-    std::vector<double> an(HS_NPN1 + 1), dd(HS_NPN1 + 1);
-    for (int k = 1; k <= HS_NPN1; k++) { an[k] = (double)(k * (k + 1)); dd[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1))); }
+    const int T1 = HS_NPN1 + 1;
+    std::vector<double> an(4 * T1, 0.0);
+    double *dd_ = an.data() + T1;
+    for (int k = 1; k <= HS_NPN1; k++) { an[k] = (double)(k * (k + 1)); dd_[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1))); }
+    { double cacc = 1.0; an[2 * T1] = 1.0; for (int i = 1; i <= HS_NPN1; i++) { cacc = cacc * sqrt((double)(2 * i - 1) / (double)(2 * i)); an[2 * T1 + i] = cacc; } }
+    for (int k = 0; k <= HS_NPN1; k++) an[3 * T1 + k] = 1.0 / (double)(2 * k + 1);
+    struct { double *p; double *data() { return p; } } dd{dd_};
     unsigned long long top = 0;
     int queue = 0;
     hs::TmArgs a;
@@ -26,11 +31,12 @@ extern "C" int emu_calctmat(int n, const double *axi, const double *lam, const d
     a.gx = hx.data(); a.gw = hw.data(); a.gmax = gmax;
     a.tarena = tarena; a.arena_cap = cap; a.arena_top = &top;
     a.toff = toff; a.nmax = nmax; a.ngauss = ngauss; a.ntrials = ntrials; a.status = status;
-    a.ws_cap = ws_cap; a.ws_global = nullptr; a.ws_fb = nullptr; a.fb_cap = 0; a.debug = 0; a.prof = nullptr;
+    a.ws_cap = ws_cap; a.ws_global = nullptr; a.ws_fb = nullptr; a.fb_cap = 0; a.debug = 0; a.prof = nullptr; a.tile_min = getenv("HS_EMU_TILE_MIN") ? atoi(getenv("HS_EMU_TILE_MIN")) : 1000;
     std::vector<double> ws((size_t)ws_cap + 16);
     hs::Grp<true> grp; grp.tid = 0; grp.nt = 1;
     hs::Ctl ctl;
-    for (int i = 0; i < n; i++) hs::calctmat_particle<true>(a, i, ws.data(), nullptr, grp, &ctl, an.data(), dd.data());
+    for (int i = 0; i < n; i++) if (a.tile_min < 1000) hs::calctmat_particle<true, true>(a, i, ws.data(), nullptr, grp, &ctl, an.data(), dd.data());
+        else hs::calctmat_particle<true, false>(a, i, ws.data(), nullptr, grp, &ctl, an.data(), dd.data());
     return 0;
 }
 

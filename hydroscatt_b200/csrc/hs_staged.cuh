@@ -1,0 +1,804 @@
+// hs_staged.cuh -- single-layer EBCM T-matrix as a staged pipeline: one kernel per stage, work items =
+// (particle, trial configuration (NMAX, NGAUSS), azimuthal mode).
+//
+// Same algorithm as hs_tmat.cuh (pytmatrix `calctmat` = Mishchenko CONST/VARY/BESS/VIG/TMATR0/TMATR/TT, SURVEY.md
+// rows P2-P7), different decomposition.  The fused kernel keeps one particle on one CTA for its whole life, so a
+// W-band drop (NMAX 30: ~15 convergence trials, then 30 modes) is a 3.4 ms serial chain on one SM.  Here every trial
+// and every mode is its own work item:
+//   S  k_st_radial    thread = (item, quadrature node, function kind): j_n(kr), y_n(kr), j_n(m kr) + derivative forms
+//   W  k_st_wigner    CTA = (item, mode), thread = node: Wigner d^n_{0m}, d/dtheta
+//   A  k_st_assemble  CTA = (item, mode, 32x32 block of (n, n')): Q / RgQ integrals as FP64 DMMA (mma.sync.m8n8k4.f64)
+//                     contractions over the quadrature nodes
+//   G  k_st_solve     CTA = (item, mode): lock-step Gauss-Jordan of the parity-class systems, T block -> arena,
+//                     Qsca/Qext of the m = 0 block -> host
+// The host (hydrotm.cu: calctmat_staged) runs the NMAX / NGAUSS convergence controller between rounds and speculates
+// trials, which are independent computations: only their Qsca/Qext feed the controller.
+// Intermediates (radial tables, Wigner tables, [Q | RgQ] systems) travel through L2-resident global scratch.
+#pragma once
+#include "hs_tmat.cuh"
+
+namespace hs {
+
+struct StItem {
+    int p, nmax, g, gp;        // particle, trial order, Gauss nodes on the half range, padded node count (multiple of 4)
+    int nmodes, first_mi;      // 1 (trial: m = 0 only) or nmax + 1 (final: every mode); first mode-item index
+    long long tab_off;         // doubles: 8 node arrays [gp] then 8 radial tables [nmax][gp]
+    long long wig_off;         // doubles: per mode d1 [NM][gp], d2 [NM][gp]
+    long long sys_off;         // complex: per mode [2][NM][2 NM]
+    long long t_off;           // complex offset of the packed T in the caller's arena (set on the device), -1 = none
+};
+struct StModeItem { int item, m; };
+struct StRadTask { int item, kn; };        // kn = node0 << 2 | kind (0 = j + node arrays, 1 = y, 2 = j of the complex argument)
+struct StATask { int mi; short sr, sc; };  // mode-item, 32-wide row range, 32-wide column range of k = n - nmin
+struct StResult { double qsca, qext; long long t_off; int sing, pad; };
+
+struct StArgs {
+    const StItem *items;
+    const StModeItem *mitems;
+    const double *axi, *lam, *mr, *mi, *eps;
+    double rat;
+    const double *gx, *gw;   // Gauss table (see TmArgs)
+    const double *cm, *dd;   // cm[m] = prod_{i<=m} sqrt((2i-1)/2i); dd[n] = sqrt((2n+1)/(n(n+1)))
+    double *tab, *wig;
+    double2 *sys;
+    double *tarena;
+    long long arena_cap;
+    unsigned long long *arena_top;
+    long long *toff;
+    StResult *res;
+};
+
+enum { NA_X = 0, NA_S, NA_SS, NA_DR, NA_DDR, NA_DRR, NA_DRI, NA_RR, NA_COUNT };
+
+__host__ __device__ inline long long st_tab_size(int nmax, int gp) { return (long long)(NA_COUNT + 8 * nmax) * gp; }
+__host__ __device__ inline long long st_modes_nm_prefix(int nmax, int m)  // sum of NM over modes < m
+{
+    if (m == 0) return 0;
+    return (long long)nmax + (long long)(m - 1) * (nmax + 1) - (long long)(m - 1) * m / 2;
+}
+__host__ __device__ inline long long st_sumsq(long long n) { return n * (n + 1) * (2 * n + 1) / 6; }
+__host__ __device__ inline long long st_modes_nm2_prefix(int nmax, int m)  // sum of NM^2 over modes < m
+{
+    if (m == 0) return 0;
+    return (long long)nmax * nmax + st_sumsq(nmax) - st_sumsq(nmax - m + 1);
+}
+__host__ __device__ inline long long st_wig_mode_off(int nmax, int m, int gp) { return 2LL * gp * st_modes_nm_prefix(nmax, m); }
+__host__ __device__ inline long long st_sys_mode_off(int nmax, int m) { return 4LL * st_modes_nm2_prefix(nmax, m); }
+__host__ __device__ inline long long st_t_mode_off(int nmax, int m) { return 2LL * st_modes_nm2_prefix(nmax, m); }
+
+#ifndef HS_HOST_EMU
+
+// equal-volume radius of the particle (calctmat_particle: RAT != 1 -> SAREA)
+__device__ inline double st_arev(double axi, double rat, double eps)
+{
+    if (fabs(rat - 1.0) > 1e-8) {
+        double e, r;
+        if (eps < 1.0) {
+            e = sqrt(1.0 - eps * eps);
+            r = 0.5 * (pow(eps, 2.0 / 3.0) + pow(eps, -1.0 / 3.0) * asin(e) / e);
+        } else {
+            e = sqrt(1.0 - 1.0 / (eps * eps));
+            r = 0.25 * (2.0 * pow(eps, 2.0 / 3.0) + pow(eps, -4.0 / 3.0) * log((1.0 + e) / (1.0 - e)) / e);
+        }
+        rat = 1.0 / sqrt(r);
+    }
+    return rat * axi;
+}
+
+// ---- S: radial functions.  Same recurrences as rjb / ryb / cjb, with the ratios parked in a thread-local array and the
+// results written n-major ([n][gp], coalesced over the nodes of a warp).
+__device__ inline void st_rjb(double x, double *y, double *u, int nmax, int nnmax, int st)
+{
+    double zz[HS_NPN1];
+    const int l = nmax + nnmax;
+    const double xx = 1.0 / x;
+    double zc = 1.0 / ((double)(2 * l + 1) * xx);
+    for (int i1 = l - 1; i1 >= 1; i1--) {
+        zc = 1.0 / ((double)(2 * i1 + 1) * xx - zc);
+        if (i1 <= nmax) zz[i1 - 1] = zc;
+    }
+    const double z1 = zz[0];
+    const double z0 = 1.0 / (xx - z1);
+    const double y0 = z0 * cos(x) * xx;
+    double yp = y0 * z1;
+    u[0] = y0 - yp * xx;
+    y[0] = yp;
+    for (int i = 2; i <= nmax; i++) {
+        const double yi = yp * zz[i - 1];
+        u[(long)(i - 1) * st] = yp - (double)i * yi * xx;
+        y[(long)(i - 1) * st] = yi;
+        yp = yi;
+    }
+}
+
+__device__ inline void st_ryb(double x, double *y, double *v, int nmax, int st)
+{
+    double s, c;
+    sincos(x, &s, &c);
+    const double x1 = 1.0 / x, x2 = x1 * x1, x3 = x2 * x1;
+    const double y1 = -c * x2 - s * x1;
+    y[0] = y1;
+    v[0] = -x1 * (c + y1);
+    if (nmax < 2) return;
+    double ym2 = y1, ym1 = (-3.0 * x3 + x1) * c - 3.0 * x2 * s;  // y_1, y_2
+    y[st] = ym1;
+    v[st] = ym2 - 2.0 * x1 * ym1;
+    for (int i = 2; i <= nmax - 1; i++) {
+        const double yi = (double)(2 * i + 1) * x1 * ym1 - ym2;  // y_{i+1}
+        y[(long)i * st] = yi;
+        v[(long)i * st] = ym1 - (double)(i + 1) * x1 * yi;
+        ym2 = ym1; ym1 = yi;
+    }
+}
+
+__device__ inline void st_cjb(double xr, double xi, double *yr, double *yi, double *ur, double *ui, int nmax, int nnmax,
+                              int st)
+{
+    double zr_[HS_NPN1], zi_[HS_NPN1];
+    const int l = nmax + nnmax;
+    const double xrxi = 1.0 / (xr * xr + xi * xi);
+    const double cxxr = xr * xrxi, cxxi = -xi * xrxi;
+    double qf = 1.0 / (double)(2 * l + 1);
+    double czr = xr * qf, czi = xi * qf;
+    for (int i1 = l - 1; i1 >= 1; i1--) {
+        qf = (double)(2 * i1 + 1);
+        const double ar = qf * cxxr - czr;
+        const double ai = qf * cxxi - czi;
+        const double ari = 1.0 / (ar * ar + ai * ai);
+        czr = ar * ari;
+        czi = -ai * ari;
+        if (i1 <= nmax) { zr_[i1 - 1] = czr; zi_[i1 - 1] = czi; }
+    }
+    const double z1r = zr_[0], z1i = zi_[0];
+    double ar = cxxr - z1r, ai = cxxi - z1i;
+    const double ari = 1.0 / (ar * ar + ai * ai);
+    const double cz0r = ar * ari, cz0i = -ai * ari;
+    double sxr, cxr;
+    sincos(xr, &sxr, &cxr);
+    const double cr = cxr * cosh(xi), ci = -sxr * sinh(xi);
+    ar = cz0r * cr - cz0i * ci;
+    ai = cz0i * cr + cz0r * ci;
+    const double cy0r = ar * cxxr - ai * cxxi, cy0i = ai * cxxr + ar * cxxi;
+    double p1r = cy0r * z1r - cy0i * z1i, p1i = cy0i * z1r + cy0r * z1i;
+    ar = p1r * cxxr - p1i * cxxi;
+    ai = p1i * cxxr + p1r * cxxi;
+    yr[0] = p1r; yi[0] = p1i;
+    ur[0] = cy0r - ar; ui[0] = cy0i - ai;
+    for (int i = 2; i <= nmax; i++) {
+        const double qi = (double)i;
+        const double zr = zr_[i - 1], zi = zi_[i - 1];
+        const double cyir = p1r * zr - p1i * zi;
+        const double cyii = p1i * zr + p1r * zi;
+        ar = cyir * cxxr - cyii * cxxi;
+        ai = cyii * cxxr + cyir * cxxi;
+        const long o = (long)(i - 1) * st;
+        yr[o] = cyir; yi[o] = cyii;
+        ur[o] = p1r - qi * ar; ui[o] = p1i - qi * ai;
+        p1r = cyir; p1i = cyii;
+    }
+}
+
+__device__ __forceinline__ double st_r_of_node(double xp, double aa, double ee)
+{
+    const double x = -xp;
+    const double cc = x * x, ssq = 1.0 - cc;
+    return aa * (1.0 / (ssq + ee * cc));
+}
+
+__global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *tasks, int ntasks)
+{
+    const int wt = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (wt >= ntasks) return;
+    const StRadTask t = tasks[wt];
+    const StItem it = a.items[t.item];
+    const int kind = t.kn & 3, i = (t.kn >> 2) + (threadIdx.x & 31);
+    const int g = it.g, nmax = it.nmax, gp = it.gp;
+    if (i >= g) return;
+    const double PI = 3.14159265358979323846;
+    const int p = it.p;
+    const double lam = a.lam[p], mrr = a.mr[p], mri = a.mi[p], eps = a.eps[p];
+    const double arev = st_arev(a.axi[p], a.rat, eps);
+    const double kw = PI * 2.0 / lam;
+    const double A = arev * pow(eps, 1.0 / 3.0);
+    const double aa = A * A, ee = eps * eps, ee1 = ee - 1.0;
+    const long goff = (long)g * (g - 1) / 2;
+    const double xp = a.gx[goff + g - 1 - i], wv = a.gw[goff + g - 1 - i];
+    const double x = -xp;
+    const double cc = x * x, ssq = 1.0 - cc, sth = sqrt(ssq);
+    const double rq = 1.0 / (ssq + ee * cc);
+    const double r = aa * rq;
+    const double v = sqrt(r) * kw;
+    double *tab = a.tab + it.tab_off;
+    double *tb = tab + (long)NA_COUNT * gp;
+    const long tsz = (long)nmax * gp;
+    // extra orders of the downward recurrences (VARY): from the largest k r over the nodes
+    const double r0 = st_r_of_node(a.gx[goff + g - 1], aa, ee), r1 = st_r_of_node(a.gx[goff], aa, ee);
+    const double ta = fmax(sqrt(r0) * kw, sqrt(r1) * kw);
+    if (kind == 0) {
+        const double v0 = 1.0 / (mrr * mrr + mri * mri);
+        const double prr = mrr * v0, pri = -mri * v0;
+        const double yv = 1.0 / (1.0 - x * x);
+        const double vi = 1.0 / v;
+        tab[NA_X * gp + i] = xp;
+        tab[NA_S * gp + i] = sqrt(yv);
+        tab[NA_SS * gp + i] = yv;
+        tab[NA_DR * gp + i] = rq * x * sth * ee1;
+        tab[NA_DDR * gp + i] = vi;
+        tab[NA_DRR * gp + i] = prr * vi;
+        tab[NA_DRI * gp + i] = pri * vi;
+        tab[NA_RR * gp + i] = wv * r;
+        const double tmx = fmax(ta, (double)nmax);
+        const int nnmax1 = (int)(1.2 * sqrt(tmx) + 3.0);
+        st_rjb(v, tb + 0 * tsz + i, tb + 1 * tsz + i, nmax, nnmax1, gp);
+    } else if (kind == 1) {
+        st_ryb(v, tb + 2 * tsz + i, tb + 3 * tsz + i, nmax, gp);
+    } else {
+        double tbv = ta * sqrt(mrr * mrr + mri * mri);
+        tbv = fmax(tbv, (double)nmax);
+        int nnmax2 = (int)(tbv + 4.0 * pow(tbv, 0.33333) + 1.2 * sqrt(tbv));
+        nnmax2 = nnmax2 - nmax + 5;
+        st_cjb(v * mrr, v * mri, tb + 4 * tsz + i, tb + 5 * tsz + i, tb + 6 * tsz + i, tb + 7 * tsz + i, nmax, nnmax2, gp);
+    }
+}
+
+// ---- W: Wigner functions of one (item, mode); rows k = n - nmin, n-major ----
+__global__ void __launch_bounds__(64) k_st_wigner(StArgs a, int n_mi)
+{
+    __shared__ double sq[HS_NPN1 + 2], rsq[HS_NPN1 + 2];
+    if ((int)blockIdx.x >= n_mi) return;
+    const StModeItem mi = a.mitems[blockIdx.x];
+    const StItem it = a.items[mi.item];
+    const int m = mi.m, nmax = it.nmax, g = it.g, gp = it.gp;
+    const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
+    double *d1 = a.wig + it.wig_off + st_wig_mode_off(nmax, m, gp);
+    double *d2 = d1 + (long)NM * gp;
+    const long goff = (long)g * (g - 1) / 2;
+    if (m > 0) {
+        const double qmm = (double)m * (double)m;
+        for (int n = m + threadIdx.x; n <= nmax + 1; n += blockDim.x) {
+            const double v = sqrt((double)n * (double)n - qmm);
+            sq[n] = v;
+            rsq[n] = (n > m) ? 1.0 / v : 0.0;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < g; i += blockDim.x) {
+        const double x = a.gx[goff + g - 1 - i];
+        const double qs = sqrt(1.0 - x * x), qs1 = 1.0 / qs;
+        if (m == 0) {
+            double a1 = 1.0, a2 = x;
+            for (int n = 1; n <= nmax; n++) {
+                const double qn = n, qn1 = n + 1, qn2 = 2 * n + 1;
+                const double a3 = (qn2 * x * a2 - qn * a1) / qn1;
+                const double der = qs1 * (qn1 * qn / qn2) * (-a1 + a3);
+                const double si = (n & 1) ? -1.0 : 1.0;
+                d1[(long)(n - 1) * gp + i] = a2 * si;
+                d2[(long)(n - 1) * gp + i] = -der * si;
+                a1 = a2; a2 = a3;
+            }
+        } else {
+            double qp = qs;
+            for (int j = 2; j <= m; j++) qp = qp * qs;
+            double a1 = 0.0, a2 = a.cm[m] * qp;
+            for (int n = m; n <= nmax; n++) {
+                const double qn = n, qn1 = n + 1, qn2 = 2 * n + 1;
+                const double qnm = sq[n], qnm1 = sq[n + 1];
+                const double a3 = (qn2 * x * a2 - qnm * a1) * rsq[n + 1];
+                const double der = qs1 * (-qn1 * qnm * a1 + qn * qnm1 * a3) * (1.0 / qn2);
+                const double si = ((n + m) & 1) ? -1.0 : 1.0;
+                d1[(long)(n - nmin) * gp + i] = a2 * si;
+                d2[(long)(n - nmin) * gp + i] = -der * si;
+                a1 = a2; a2 = a3;
+            }
+        }
+    }
+}
+
+// ---- A: Q / RgQ integrals of one 32 x 32 block of (k1, k2) = (n1 - nmin, n2 - nmin) as DMMA contractions ----
+// See assemble_tiled (hs_tmat.cuh) for the factorisation: X = sum over nodes of (left factor of (n1, node)) x (right
+// factor of (n2, node)).  Left operand tables L_t[(k1, F)][node], F in {j, y}: P1 = d1 dF, P2 = d2 dF, P3 = d1 F,
+// P4 = d2 F, P3a = n1(n1+1) P3.  Right operand tables R_t[(k2, re|im)][node]: q1..q5 for same-parity pairs, r1..r5 for
+// opposite-parity pairs.  Rows are parity-sorted (even k: rows 0..31, odd k: rows 32..63) so that each parity block is
+// a dense GEMM:  X12 = P1 q1 + P2 q2 + P3a q3,  X21 = P3 q4 + P4 q5,  X11 = P3 r1 + P4 r2,  X22 = P1 r3 + P2 r4 + P3a r5.
+// A chunk of 8 nodes is staged in shared memory ([15 tables][64 rows][8 nodes], k4-group XOR-swizzled by row pair so
+// the fragment loads are conflict-free); each warp owns one parity block's tile rows for both outputs (so the
+// epilogue that combines X_A and X_B into Q and RgQ entries stays in registers).
+#define ST_OP_DOUBLES (15 * 64 * 8)
+
+__device__ __forceinline__ void st_dmma(double *c, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <bool M0>
+__global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask *tasks, int ntasks)
+{
+    extern __shared__ __align__(16) double op[];
+    if ((int)blockIdx.x >= ntasks) return;
+    const StATask tk = tasks[blockIdx.x];
+    const StModeItem mi = a.mitems[tk.mi];
+    const StItem it = a.items[mi.item];
+    const int m = M0 ? 0 : mi.m;
+    const int nmax = it.nmax, g = it.g, gp = it.gp;
+    const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
+    const int kr0 = 32 * tk.sr, kc0 = 32 * tk.sc;
+    const double *nod = a.tab + it.tab_off;
+    const double *tb = nod + (long)NA_COUNT * gp;
+    const long tsz = (long)nmax * gp;
+    const double *w1 = a.wig + it.wig_off + st_wig_mode_off(nmax, m, gp);
+    const double *w2 = w1 + (long)NM * gp;
+    const double qm = (double)m, qmm = qm * qm;
+    const int tid = threadIdx.x, kk = tid >> 3, ii = tid & 7;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    // warp -> parity block (prow, pcol) and tile rows [tr0, tr0 + NTR)
+    constexpr int NTR = M0 ? 1 : 2;
+    int prow, pcol, tr0;
+    // tile rows are dealt to a block's warps round-robin (m >= 1: rows tr0, tr0 + 2), so half-empty blocks stay balanced
+    if (M0) { prow = pcol = warp >> 2; tr0 = warp & 3; }
+    else { const int beta = warp >> 1; prow = (beta == 1 || beta == 3) ? 1 : 0; pcol = (beta == 1 || beta == 2) ? 1 : 0; tr0 = warp & 1; }
+    const bool even = prow == pcol;
+    int hrow = (NM - kr0 - prow + 1) >> 1; hrow = hrow < 0 ? 0 : (hrow > 16 ? 16 : hrow);
+    int hcol = (NM - kc0 - pcol + 1) >> 1; hcol = hcol < 0 ? 0 : (hcol > 16 ? 16 : hcol);
+    const int TMv = (2 * hrow + 7) >> 3, TNv = (2 * hcol + 7) >> 3;
+
+    double acc[NTR][4][2][2];
+#pragma unroll
+    for (int r = 0; r < NTR; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[r][c][e >> 1][e & 1] = 0.0;
+
+    // build-phase constants of this thread: rows (kk, F) / (kk, re|im) of every table, column ii (swizzled)
+    const int rho = (kk & 1) * 32 + 2 * (kk >> 1);
+    const int col = ii ^ (((rho >> 1) & 1) << 2);
+    double *o0 = op + rho * 8 + col, *o1 = o0 + 8;
+    const int k1 = kr0 + kk, k2 = kc0 + kk;
+    const int n1 = nmin + k1, n2 = nmin + k2;
+    const double an1 = (double)(n1 * (n1 + 1)), an2 = (double)(n2 * (n2 + 1));
+    const int fragrow = lane >> 2, fragk = lane & 3;
+
+    for (int i0 = 0; i0 < g; i0 += 8) {
+        {
+            const int i = i0 + ii;
+            const bool vi = i < g;
+            // left operand rows (k1, j | y)
+            {
+                double d1 = 0.0, d2 = 0.0, fj = 0.0, fdj = 0.0, fy = 0.0, fdy = 0.0;
+                if (vi && k1 < NM) {
+                    const long o = (long)(n1 - 1) * gp + i;
+                    d1 = w1[(long)k1 * gp + i]; d2 = w2[(long)k1 * gp + i];
+                    fj = tb[o]; fdj = tb[tsz + o]; fy = tb[2 * tsz + o]; fdy = tb[3 * tsz + o];
+                }
+                o0[0 * 512] = d1 * fdj; o1[0 * 512] = d1 * fdy;  // P1
+                o0[1 * 512] = d2 * fdj; o1[1 * 512] = d2 * fdy;  // P2
+                const double p3j = d1 * fj, p3y = d1 * fy;
+                o0[2 * 512] = p3j; o1[2 * 512] = p3y;            // P3
+                o0[3 * 512] = d2 * fj; o1[3 * 512] = d2 * fy;    // P4
+                o0[4 * 512] = an1 * p3j; o1[4 * 512] = an1 * p3y;  // P3a
+            }
+            // right operand rows (k2, re | im)
+            {
+                double d1 = 0.0, d2 = 0.0, jr = 0.0, ji = 0.0, djr = 0.0, dji = 0.0;
+                double rri = 0.0, uri = 0.0, ddri = 0.0, drri = 0.0, drii = 0.0, ssi = 0.0, si = 0.0;
+                if (vi && k2 < NM) {
+                    const long o = (long)(n2 - 1) * gp + i;
+                    d1 = w1[(long)k2 * gp + i]; d2 = w2[(long)k2 * gp + i];
+                    jr = tb[4 * tsz + o]; ji = tb[5 * tsz + o]; djr = tb[6 * tsz + o]; dji = tb[7 * tsz + o];
+                    rri = nod[NA_RR * gp + i]; uri = nod[NA_DR * gp + i]; ddri = nod[NA_DDR * gp + i];
+                    drri = nod[NA_DRR * gp + i]; drii = nod[NA_DRI * gp + i];
+                    if (!M0) { ssi = nod[NA_SS * gp + i]; si = nod[NA_S * gp + i]; }
+                }
+                const double jzr = jr * drri - ji * drii, jzi = ji * drri + jr * drii;
+                const double wb = rri * d2, wd = an2 * rri * uri * d1;
+                o0[6 * 512] = wb * jr; o1[6 * 512] = wb * ji;    // q2
+                const double wc = wb * uri * ddri;
+                o0[7 * 512] = wc * jr; o1[7 * 512] = wc * ji;    // q3
+                o0[9 * 512] = wb * djr + wd * jzr; o1[9 * 512] = wb * dji + wd * jzi;  // q5
+                if (!M0) {
+                    const double wa = rri * (ssi * qmm) * d1;
+                    o0[5 * 512] = wa * jr; o1[5 * 512] = wa * ji;    // q1
+                    o0[8 * 512] = wa * djr; o1[8 * 512] = wa * dji;  // q4
+                    const double dsi = si * qm * rri;
+                    const double va = dsi * d1, vb = dsi * d2;
+                    o0[10 * 512] = vb * jr; o1[10 * 512] = vb * ji;  // r1
+                    o0[11 * 512] = va * jr; o1[11 * 512] = va * ji;  // r2
+                    const double vf = an2 * va * uri;
+                    o0[12 * 512] = vb * djr + vf * jzr; o1[12 * 512] = vb * dji + vf * jzi;  // r3
+                    o0[13 * 512] = va * djr; o1[13 * 512] = va * dji;  // r4
+                    const double ve = va * uri * ddri;
+                    o0[14 * 512] = ve * djr; o1[14 * 512] = ve * dji;  // r5
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+            // fragment element of table t, rows [row0, row0 + 8): row0 + (lane >> 2), node 4 ks + (lane & 3)
+            auto frag = [&](int t, int row0) -> double {
+                const int r = row0 + fragrow;
+                return op[(t * 64 + r) * 8 + ((((ks ^ (r >> 1)) & 1) << 2) | fragk)];
+            };
+            double la[NTR][5];
+#pragma unroll
+            for (int r = 0; r < NTR; r++)
+                if (tr0 + 2 * r < TMv) {
+#pragma unroll
+                    for (int t = 0; t < 5; t++) la[r][t] = frag(t, prow * 32 + 8 * (tr0 + 2 * r));
+                }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (c >= TNv) continue;
+                double rb[5];
+                const int rbase = (M0 || even) ? 5 : 10;
+#pragma unroll
+                for (int t = 0; t < 5; t++) rb[t] = frag(rbase + t, pcol * 32 + 8 * c);
+                if (M0) {
+                    // m = 0: dss = 0, the q1 and q4 terms vanish
+#pragma unroll
+                    for (int r = 0; r < NTR; r++)
+                        if (tr0 + 2 * r < TMv) {
+                            st_dmma(acc[r][c][0], la[r][1], rb[1]);
+                            st_dmma(acc[r][c][1], la[r][3], rb[4]);
+                            st_dmma(acc[r][c][0], la[r][4], rb[2]);
+                        }
+                } else if (even) {
+#pragma unroll
+                    for (int r = 0; r < NTR; r++)
+                        if (tr0 + 2 * r < TMv) { st_dmma(acc[r][c][0], la[r][0], rb[0]); st_dmma(acc[r][c][1], la[r][2], rb[3]); }
+#pragma unroll
+                    for (int r = 0; r < NTR; r++)
+                        if (tr0 + 2 * r < TMv) { st_dmma(acc[r][c][0], la[r][1], rb[1]); st_dmma(acc[r][c][1], la[r][3], rb[4]); }
+#pragma unroll
+                    for (int r = 0; r < NTR; r++)
+                        if (tr0 + 2 * r < TMv) st_dmma(acc[r][c][0], la[r][4], rb[2]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NTR; r++)
+                        if (tr0 + 2 * r < TMv) { st_dmma(acc[r][c][0], la[r][2], rb[0]); st_dmma(acc[r][c][1], la[r][0], rb[2]); }
+#pragma unroll
+                    for (int r = 0; r < NTR; r++)
+                        if (tr0 + 2 * r < TMv) { st_dmma(acc[r][c][0], la[r][3], rb[1]); st_dmma(acc[r][c][1], la[r][1], rb[3]); }
+#pragma unroll
+                    for (int r = 0; r < NTR; r++)
+                        if (tr0 + 2 * r < TMv) st_dmma(acc[r][c][1], la[r][4], rb[4]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // epilogue: lane holds (re, im) of X_F[a][b] with a = 4 tr + (lane >> 3), F = (lane >> 2) & 1, b = 4 tc + (lane & 3);
+    // the y values come from lane ^ 4; lanes with F = 0 write the four system entries of the pair
+    const int p = it.p;
+    const double PI = 3.14159265358979323846;
+    const double kw = PI * 2.0 / a.lam[p];
+    const double ppi = kw * kw, pir = ppi * a.mr[p], pii = ppi * a.mi[p];
+    double2 *sys = a.sys + it.sys_off + st_sys_mode_off(nmax, m);
+#pragma unroll
+    for (int r = 0; r < NTR; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const bool tv = (tr0 + 2 * r < TMv) && (c < TNv);  // warp-uniform
+            if (!tv) continue;
+            double xa[4], xb[4];
+            xa[0] = acc[r][c][0][0]; xa[1] = acc[r][c][0][1];
+            xb[0] = acc[r][c][1][0]; xb[1] = acc[r][c][1][1];
+            xa[2] = __shfl_xor_sync(0xffffffffu, xa[0], 4); xa[3] = __shfl_xor_sync(0xffffffffu, xa[1], 4);
+            xb[2] = __shfl_xor_sync(0xffffffffu, xb[0], 4); xb[3] = __shfl_xor_sync(0xffffffffu, xb[1], 4);
+            const int al = 4 * (tr0 + 2 * r) + (lane >> 3), bl = 4 * c + (lane & 3);
+            if (((lane >> 2) & 1) == 0 && al < hrow && bl < hcol) {
+                const int kk1 = kr0 + 2 * al + prow, kk2 = kc0 + 2 * bl + pcol;
+                if (even) store_even(sys, NM, nmin, kk1, kk2, ppi, pir, pii, a.dd, xa, xa + 2, xb, xb + 2);
+                else store_odd(sys, NM, nmin, kk1, kk2, ppi, pir, pii, a.dd, xa, xa + 2, xb, xb + 2);
+            }
+        }
+    if (M0) {
+        // opposite-parity pairs vanish identically for m = 0
+        const int ldc = 2 * NM;
+        const double2 z = make_double2(0.0, 0.0);
+        for (int t = tid; t < 32 * 32; t += 256) {
+            const int q1 = kr0 + (t >> 5), q2 = kc0 + (t & 31);
+            if (q1 >= NM || q2 >= NM || (((q1 + q2) & 1) == 0)) continue;
+            for (int cl = 0; cl < 2; cl++) {
+                sys[(long)(cl * NM + q2) * ldc + q1] = z;
+                sys[(long)(cl * NM + q2) * ldc + NM + q1] = z;
+            }
+        }
+    }
+}
+
+// ---- G: parity-class systems of one (item, mode): T = -RgQ Q^-1 by the lock-step Gauss-Jordan of hs_tmat.cuh ----
+template <int THREADS, bool GLOBAL>
+__global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist, int n)
+{
+    extern __shared__ __align__(16) double2 ssys[];
+    __shared__ SysDesc sd[HS_MAXSYS];
+    __shared__ SolveCtl sc;
+    __shared__ int sing;
+    if ((int)blockIdx.x >= n) return;
+    const int mix = mlist[blockIdx.x];
+    const StModeItem mi = a.mitems[mix];
+    const StItem it = a.items[mi.item];
+    const int m = mi.m, nmax = it.nmax;
+    const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1, ldc = 2 * NM;
+    double2 *gsys = a.sys + it.sys_off + st_sys_mode_off(nmax, m);
+    const int tot = 4 * NM * NM;
+    double2 *wk = GLOBAL ? gsys : ssys;
+    if (!GLOBAL)
+        for (int t = threadIdx.x; t < tot; t += THREADS) wk[t] = gsys[t];
+    int nsys;
+    if (m == 0) {
+        // T12 = T21 = 0: each parity class splits into two interleaved half-size systems
+        nsys = 0;
+        for (int cl = 0; cl < 2; cl++)
+            for (int par = 0; par < 2; par++) {
+                const int nn = (NM + 1 - par) >> 1;
+                if (nn > 0) {
+                    if (threadIdx.x == 0) {
+                        SysDesc d;
+                        d.base = wk + (long)cl * NM * ldc; d.ld = ldc; d.off = par; d.stride = 2; d.rhs = NM; d.n = nn;
+                        sd[nsys] = d;
+                    }
+                    nsys++;
+                }
+            }
+    } else {
+        nsys = 2;
+        if (threadIdx.x < 2) {
+            SysDesc d;
+            d.base = wk + (long)threadIdx.x * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
+            sd[threadIdx.x] = d;
+        }
+    }
+    if (threadIdx.x == 0) sing = 0;
+    __syncthreads();
+    Grp<false> grp;
+    grp.tid = threadIdx.x; grp.nt = THREADS;
+    solve_multi(grp, sd, nsys, &sc, &sing);
+    const long long toff = it.t_off;
+    if (toff >= 0) {
+        double2 *tg = reinterpret_cast<double2 *>(a.tarena) + toff + st_t_mode_off(nmax, m);
+        for (int t = threadIdx.x; t < 2 * NM * NM; t += THREADS) {
+            const int row = t / NM, col = t - row * NM;
+            tg[t] = wk[(long)row * ldc + NM + col];
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (m == 0) {
+            double qext = 0.0, qsca = 0.0;
+            for (int n_ = 1; n_ <= nmax; n_++) {
+                const int k = n_ - 1;
+                const double2 t1 = wk[(long)(((n_ + 1) & 1) * NM + k) * ldc + NM + k];
+                const double2 t2 = wk[(long)((n_ & 1) * NM + k) * ldc + NM + k];
+                const double dn1 = (double)(2 * n_ + 1);
+                qsca += dn1 * (t1.x * t1.x + t1.y * t1.y + t2.x * t2.x + t2.y * t2.y);
+                qext += (t1.x + t2.x) * dn1;
+            }
+            a.res[mi.item].qsca = qsca;
+            a.res[mi.item].qext = qext;
+        }
+        if (sing) atomicOr(&a.res[mi.item].sing, 1);
+    }
+}
+
+
+// ---- A + G for small blocks (NM <= 8): one warp per (item, mode) ----
+// The four parity blocks are single 8 x 8 DMMA tiles, so a CTA-wide kernel would be all padding and barriers.  Here a
+// warp builds its own operand rows for 4 nodes at a time ([15 tables][16 rows][4 nodes], private shared-memory slice),
+// contracts them, combines the accumulators into the two parity-class systems in the same slice, solves them with the
+// warp-wide lock-step Gauss-Jordan and writes the T block / (Qsca, Qext): no CTA barrier, no global round trip of Q.
+#define ST_SMALL_NM 8
+#define ST_SMALL_SLICE (15 * 16 * 4)  // doubles per warp
+
+__global__ void __launch_bounds__(256) k_st_mode_small(StArgs a, const int *mlist, int n)
+{
+    extern __shared__ __align__(16) double smraw[];
+    __shared__ SysDesc sds[8][4];
+    __shared__ SolveCtl scs[8];
+    __shared__ int sings[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = blockIdx.x * 8 + warp;
+    if (wi >= n) return;
+    double *op = smraw + warp * ST_SMALL_SLICE;
+    const StModeItem mi = a.mitems[mlist[wi]];
+    const StItem it = a.items[mi.item];
+    const int m = mi.m, nmax = it.nmax, g = it.g, gp = it.gp;
+    const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
+    const int h0 = (NM + 1) >> 1, h1 = NM >> 1;
+    const double *nod = a.tab + it.tab_off;
+    const double *tb = nod + (long)NA_COUNT * gp;
+    const long tsz = (long)nmax * gp;
+    const double *w1 = a.wig + it.wig_off + st_wig_mode_off(nmax, m, gp);
+    const double *w2 = w1 + (long)NM * gp;
+    const double qm = (double)m, qmm = qm * qm;
+    const int kk = lane >> 2, ii = lane & 3;
+    const int rho = (kk & 1) * 8 + 2 * (kk >> 1);
+    double *o0 = op + rho * 4 + ii, *o1 = o0 + 4;
+    const int n1 = nmin + kk;
+    const double an1 = (double)(n1 * (n1 + 1));
+    const int fragrow = lane >> 2, fragk = lane & 3;
+    double acc[4][2][2];  // [EE, OO, EO, OE][A, B][re, im]
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc[b][e >> 1][e & 1] = 0.0;
+    for (int i0 = 0; i0 < g; i0 += 4) {
+        {
+            const int i = i0 + ii;
+            double d1 = 0.0, d2 = 0.0, fj = 0.0, fdj = 0.0, fy = 0.0, fdy = 0.0, jr = 0.0, ji = 0.0, djr = 0.0, dji = 0.0;
+            double rri = 0.0, uri = 0.0, ddri = 0.0, drri = 0.0, drii = 0.0, ssi = 0.0, si = 0.0;
+            if (i < g && kk < NM) {
+                const long o = (long)(n1 - 1) * gp + i;
+                d1 = w1[(long)kk * gp + i]; d2 = w2[(long)kk * gp + i];
+                fj = tb[o]; fdj = tb[tsz + o]; fy = tb[2 * tsz + o]; fdy = tb[3 * tsz + o];
+                jr = tb[4 * tsz + o]; ji = tb[5 * tsz + o]; djr = tb[6 * tsz + o]; dji = tb[7 * tsz + o];
+                rri = nod[NA_RR * gp + i]; uri = nod[NA_DR * gp + i]; ddri = nod[NA_DDR * gp + i];
+                drri = nod[NA_DRR * gp + i]; drii = nod[NA_DRI * gp + i];
+                if (m) { ssi = nod[NA_SS * gp + i]; si = nod[NA_S * gp + i]; }
+            }
+            __syncwarp();  // previous contraction has read the slice
+            o0[0 * 64] = d1 * fdj; o1[0 * 64] = d1 * fdy;
+            o0[1 * 64] = d2 * fdj; o1[1 * 64] = d2 * fdy;
+            const double p3j = d1 * fj, p3y = d1 * fy;
+            o0[2 * 64] = p3j; o1[2 * 64] = p3y;
+            o0[3 * 64] = d2 * fj; o1[3 * 64] = d2 * fy;
+            o0[4 * 64] = an1 * p3j; o1[4 * 64] = an1 * p3y;
+            const double jzr = jr * drri - ji * drii, jzi = ji * drri + jr * drii;
+            const double wb = rri * d2, wd = an1 * rri * uri * d1;
+            const double wa = rri * (ssi * qmm) * d1;
+            o0[5 * 64] = wa * jr; o1[5 * 64] = wa * ji;
+            o0[6 * 64] = wb * jr; o1[6 * 64] = wb * ji;
+            const double wc = wb * uri * ddri;
+            o0[7 * 64] = wc * jr; o1[7 * 64] = wc * ji;
+            o0[8 * 64] = wa * djr; o1[8 * 64] = wa * dji;
+            o0[9 * 64] = wb * djr + wd * jzr; o1[9 * 64] = wb * dji + wd * jzi;
+            if (m) {
+                const double dsi = si * qm * rri;
+                const double va = dsi * d1, vb = dsi * d2;
+                o0[10 * 64] = vb * jr; o1[10 * 64] = vb * ji;
+                o0[11 * 64] = va * jr; o1[11 * 64] = va * ji;
+                const double vf = an1 * va * uri;
+                o0[12 * 64] = vb * djr + vf * jzr; o1[12 * 64] = vb * dji + vf * jzi;
+                o0[13 * 64] = va * djr; o1[13 * 64] = va * dji;
+                const double ve = va * uri * ddri;
+                o0[14 * 64] = ve * djr; o1[14 * 64] = ve * dji;
+            }
+            __syncwarp();
+        }
+        auto frag = [&](int t, int row0) -> double { return op[(t * 16 + row0 + fragrow) * 4 + fragk]; };
+        double lE[5], lO[5];
+#pragma unroll
+        for (int t = 0; t < 5; t++) { lE[t] = frag(t, 0); lO[t] = frag(t, 8); }
+        {
+            double rE[5], rO[5];
+#pragma unroll
+            for (int t = 0; t < 5; t++) { rE[t] = frag(5 + t, 0); rO[t] = frag(5 + t, 8); }
+            if (m) {
+                st_dmma(acc[0][0], lE[0], rE[0]); st_dmma(acc[1][0], lO[0], rO[0]);
+                st_dmma(acc[0][1], lE[2], rE[3]); st_dmma(acc[1][1], lO[2], rO[3]);
+            }
+            st_dmma(acc[0][0], lE[1], rE[1]); st_dmma(acc[1][0], lO[1], rO[1]);
+            st_dmma(acc[0][1], lE[3], rE[4]); st_dmma(acc[1][1], lO[3], rO[4]);
+            st_dmma(acc[0][0], lE[4], rE[2]); st_dmma(acc[1][0], lO[4], rO[2]);
+        }
+        if (m) {
+            double rE[5], rO[5];
+#pragma unroll
+            for (int t = 0; t < 5; t++) { rE[t] = frag(10 + t, 0); rO[t] = frag(10 + t, 8); }
+            st_dmma(acc[2][0], lE[2], rO[0]); st_dmma(acc[3][0], lO[2], rE[0]);
+            st_dmma(acc[2][1], lE[0], rO[2]); st_dmma(acc[3][1], lO[0], rE[2]);
+            st_dmma(acc[2][0], lE[3], rO[1]); st_dmma(acc[3][0], lO[3], rE[1]);
+            st_dmma(acc[2][1], lE[1], rO[3]); st_dmma(acc[3][1], lO[1], rE[3]);
+            st_dmma(acc[2][1], lE[4], rO[4]); st_dmma(acc[3][1], lO[4], rE[4]);
+        }
+    }
+    __syncwarp();
+    // combine into the parity-class systems, stored in the same slice ([2][NM][2 NM] complex <= 512 doubles)
+    const int p = it.p;
+    const double PI = 3.14159265358979323846;
+    const double kw = PI * 2.0 / a.lam[p];
+    const double ppi = kw * kw, pir = ppi * a.mr[p], pii = ppi * a.mi[p];
+    double2 *sys = reinterpret_cast<double2 *>(op);
+    const int ldc = 2 * NM;
+    if (m == 0) {
+        const double2 z = make_double2(0.0, 0.0);
+        for (int t = lane; t < NM * NM; t += 32) {
+            const int q1 = t / NM, q2 = t - q1 * NM;
+            if (((q1 + q2) & 1) == 0) continue;
+            for (int cl = 0; cl < 2; cl++) { sys[(cl * NM + q2) * ldc + q1] = z; sys[(cl * NM + q2) * ldc + NM + q1] = z; }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        if (b >= 2 && m == 0) break;
+        const int prow = (b == 1 || b == 3) ? 1 : 0, pcol = (b == 1 || b == 2) ? 1 : 0;
+        const int hrow = prow ? h1 : h0, hcol = pcol ? h1 : h0;
+        double xa[4], xb[4];
+        xa[0] = acc[b][0][0]; xa[1] = acc[b][0][1]; xb[0] = acc[b][1][0]; xb[1] = acc[b][1][1];
+        xa[2] = __shfl_xor_sync(0xffffffffu, xa[0], 4); xa[3] = __shfl_xor_sync(0xffffffffu, xa[1], 4);
+        xb[2] = __shfl_xor_sync(0xffffffffu, xb[0], 4); xb[3] = __shfl_xor_sync(0xffffffffu, xb[1], 4);
+        const int al = lane >> 3, bl = lane & 3;
+        if (((lane >> 2) & 1) == 0 && al < hrow && bl < hcol) {
+            const int kk1 = 2 * al + prow, kk2 = 2 * bl + pcol;
+            if (b < 2) store_even(sys, NM, nmin, kk1, kk2, ppi, pir, pii, a.dd, xa, xa + 2, xb, xb + 2);
+            else store_odd(sys, NM, nmin, kk1, kk2, ppi, pir, pii, a.dd, xa, xa + 2, xb, xb + 2);
+        }
+    }
+    // solve
+    SysDesc *sd = sds[warp];
+    int nsys;
+    if (m == 0) {
+        nsys = 0;
+        for (int cl = 0; cl < 2; cl++)
+            for (int par = 0; par < 2; par++) {
+                const int nn = (NM + 1 - par) >> 1;
+                if (nn > 0) {
+                    if (lane == 0) {
+                        SysDesc d;
+                        d.base = sys + cl * NM * ldc; d.ld = ldc; d.off = par; d.stride = 2; d.rhs = NM; d.n = nn;
+                        sd[nsys] = d;
+                    }
+                    nsys++;
+                }
+            }
+    } else {
+        nsys = 2;
+        if (lane < 2) {
+            SysDesc d;
+            d.base = sys + lane * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
+            sd[lane] = d;
+        }
+    }
+    if (lane == 0) sings[warp] = 0;
+    __syncwarp();
+    Grp<true> grp;
+    grp.tid = lane; grp.nt = 32;
+    solve_multi(grp, sd, nsys, &scs[warp], &sings[warp]);
+    const long long toff = it.t_off;
+    if (toff >= 0) {
+        double2 *tg = reinterpret_cast<double2 *>(a.tarena) + toff + st_t_mode_off(nmax, m);
+        for (int t = lane; t < 2 * NM * NM; t += 32) {
+            const int row = t / NM, col = t - row * NM;
+            tg[t] = sys[row * ldc + NM + col];
+        }
+    }
+    if (lane == 0) {
+        if (m == 0) {
+            double qext = 0.0, qsca = 0.0;
+            for (int n_ = 1; n_ <= nmax; n_++) {
+                const int k = n_ - 1;
+                const double2 t1 = sys[(((n_ + 1) & 1) * NM + k) * ldc + NM + k];
+                const double2 t2 = sys[((n_ & 1) * NM + k) * ldc + NM + k];
+                const double dn1 = (double)(2 * n_ + 1);
+                qsca += dn1 * (t1.x * t1.x + t1.y * t1.y + t2.x * t2.x + t2.y * t2.y);
+                qext += (t1.x + t2.x) * dn1;
+            }
+            a.res[mi.item].qsca = qsca;
+            a.res[mi.item].qext = qext;
+        }
+        if (sings[warp]) atomicOr(&a.res[mi.item].sing, 1);
+    }
+}
+
+// final items: reserve the packed T in the caller's arena (same bump allocator as the fused kernel)
+__global__ void k_st_reserve(StItem *items, StResult *res, int n_items, unsigned long long *arena_top, long long arena_cap,
+                             long long *toff)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    res[i].sing = 0;
+    res[i].t_off = -1;
+    if (items[i].nmodes <= 1) { items[i].t_off = -1; return; }
+    if (items[i].t_off >= 0) { res[i].t_off = items[i].t_off; return; }  // retry of a final trial: keep the slot
+    const unsigned long long sz = (unsigned long long)tmat_size(items[i].nmax);
+    const unsigned long long off = atomicAdd(arena_top, sz);
+    long long o = (off + sz > (unsigned long long)arena_cap) ? -2 : (long long)off;
+    items[i].t_off = o;
+    res[i].t_off = o;
+}
+
+#endif  // HS_HOST_EMU
+
+}  // namespace hs

@@ -1,0 +1,420 @@
+// hs_staged_host.h -- host side of the staged T-matrix pipeline (hs_staged.cuh): the NMAX / NGAUSS convergence
+// controller of `calctmat` run between rounds of stage kernels.
+//
+// Round = { plan items -> one H2D of the lists -> reserve, S, W, A, G kernels -> one D2H of (Qsca, Qext) -> controller }.
+// Trials are independent computations, so each round runs K speculative trials per unconverged particle
+// (NMAX, NMAX+1, ...; the controller consumes them in the reference's order and discards the ones past convergence)
+// and, once NMAX has converged, the first NGAUSS trial together with every mode m >= 1 of that configuration
+// ("final" item): on the rain sweep the NGAUSS phase always converges at its first trial, so the T-matrix is
+// complete in the same round.
+// The particles are dealt into ST_GROUPS independent groups, each with its own stream, scratch and round loop; the
+// host plans / consumes one group while the others' kernels run, so neither the host work nor the tail of a stage
+// kernel leaves the GPU idle.  Included by hydrotm.cu after hs_ctx / CK are defined.
+#pragma once
+
+namespace {
+
+#define ST_GROUPS 3
+
+struct StBufs {
+    char *d_lists = nullptr; size_t lists_cap = 0;    // items | mitems | rad tasks | A tasks (m=0) | A tasks | G lists | small list
+    char *h_lists = nullptr; size_t h_lists_cap = 0;  // pinned staging of the same
+    hs::StResult *d_res = nullptr, *h_res = nullptr; size_t res_cap = 0;
+    double *d_tab = nullptr; size_t tab_cap = 0;
+    double *d_wig = nullptr; size_t wig_cap = 0;
+    double2 *d_sys = nullptr; size_t sys_cap = 0;
+    int *d_out = nullptr, *h_out = nullptr; size_t out_cap = 0;  // final per-particle records for the scatter-out kernel
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+
+struct StShared {
+    StBufs g[ST_GROUPS];
+    double *d_cm = nullptr, *d_dd = nullptr;
+    cudaEvent_t ev_in = nullptr;
+};
+
+struct StP {  // controller state of one particle (Ctl of the fused kernel)
+    int idx, phase, nmax, g, ntr, status, done, sing;
+    double q1s, q1e;
+    long long t_off;
+    int first_item, n_items;  // this round's items
+};
+
+template <class T>
+static int st_grow(hs_ctx *ctx, T **p, size_t *cap, size_t need, bool pinned = false)
+{
+    if (need <= *cap) return 0;
+    size_t ncap = std::max(need, *cap + *cap / 2);
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); }
+    *p = nullptr; *cap = 0;
+    if (pinned) CK(cudaMallocHost((void **)p, ncap * sizeof(T)));
+    else CK(cudaMalloc((void **)p, ncap * sizeof(T)));
+    *cap = ncap;
+    return 0;
+}
+
+__global__ void k_st_scatter_out(int n, const int *rec, const long long *toffs, int *nmax, int *ngauss, int *ntrials,
+                                 int *status, long long *toff)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = rec[5 * i];
+    nmax[p] = rec[5 * i + 1];
+    ngauss[p] = rec[5 * i + 2];
+    ntrials[p] = rec[5 * i + 3];
+    status[p] = rec[5 * i + 4];
+    toff[p] = toffs[i];
+}
+
+struct StCall {  // arguments of one hs_calctmat_batch call
+    const double *d_axi, *d_lam, *d_mr, *d_mi, *d_eps;
+    double rat, ddelt;
+    int ndgs;
+    double *d_tarena;
+    long long arena_cap;
+    unsigned long long *d_arena_top;
+    long long *d_toff;
+    int *d_nmax, *d_ngauss, *d_ntrials, *d_status;
+    size_t scratch_budget;
+    int spec;
+    bool trace;
+};
+
+struct StGroup {
+    hs_ctx *ctx;
+    StShared *S;
+    StBufs *B;
+    const StCall *C;
+    int id = 0;
+    std::vector<StP> P;
+    std::vector<hs::StItem> items;
+    std::vector<hs::StModeItem> mitems;
+    std::vector<hs::StRadTask> rad;
+    std::vector<hs::StATask> at0, at1;
+    std::vector<int> gl[4], sm;
+    std::vector<int> order;
+    int nround = 0, K = 2;
+    bool inflight = false;
+    double t_plan = 0, t_wait = 0, t_ctl = 0;
+
+    bool active() const
+    {
+        for (const StP &s : P) if (!s.done) return true;
+        return false;
+    }
+
+    // plan the next round and enqueue it; returns 0 (inflight may stay false if nothing was left to launch)
+    int issue()
+    {
+        using namespace hs;
+        auto T0 = std::chrono::steady_clock::now();
+        const int ndgs = C->ndgs;
+        cudaStream_t st = B->stream;
+        order.clear();
+        for (int j = 0; j < (int)P.size(); j++) if (!P[j].done) order.push_back(j);
+        if (order.empty()) return 0;
+        {   // heaviest particles first (counting sort on the current order)
+            std::vector<int> cnt(HS_NPN1 + 2, 0), tmp(order.size());
+            for (int j : order) cnt[std::min(std::max(P[j].nmax, 0), HS_NPN1)]++;
+            int acc = 0;
+            for (int v = HS_NPN1; v >= 0; v--) { int c = cnt[v]; cnt[v] = acc; acc += c; }
+            for (int j : order) tmp[cnt[std::min(std::max(P[j].nmax, 0), HS_NPN1)]++] = j;
+            order.swap(tmp);
+        }
+        const int active_n = (int)order.size();
+        K = C->spec > 0 ? C->spec : (active_n > 1000 ? 2 : (active_n > 200 ? 3 : 4));
+        items.clear(); mitems.clear(); rad.clear(); at0.clear(); at1.clear(); sm.clear();
+        for (auto &v : gl) v.clear();
+        long long tab_off = 0, wig_off = 0, sys_off = 0;
+        int gneed = 0;
+        for (int j : order) {
+            StP &s = P[j];
+            s.first_item = (int)items.size(); s.n_items = 0;
+            if (s.phase == 0 && (long long)s.nmax * ndgs > HS_NPNG1) { s.status = HS_ST_NGAUSS_LIMIT; s.done = 2; continue; }
+            if ((size_t)(tab_off + wig_off) * 8 + (size_t)sys_off * 16 > C->scratch_budget && !items.empty()) continue;  // next round
+            const int cnt = s.phase == 0 ? K : 1;
+            for (int q = 0; q < cnt; q++) {
+                StItem it;
+                it.p = s.idx;
+                it.nmax = s.phase == 0 ? s.nmax + q : s.nmax;
+                it.g = s.phase == 0 ? it.nmax * ndgs : (s.phase == 1 ? s.g + 1 : s.g);
+                if (it.nmax > HS_NPN1 || it.g > HS_NPNG1) break;  // the controller reports the limit when it gets there
+                it.gp = (it.g + 3) & ~3;
+                it.nmodes = s.phase == 0 ? 1 : it.nmax + 1;
+                it.first_mi = (int)mitems.size();
+                it.tab_off = tab_off; it.wig_off = wig_off; it.sys_off = sys_off;
+                it.t_off = s.phase == 0 ? -1 : s.t_off;
+                tab_off += st_tab_size(it.nmax, it.gp);
+                wig_off += st_wig_mode_off(it.nmax, it.nmodes, it.gp);
+                sys_off += st_sys_mode_off(it.nmax, it.nmodes);
+                gneed = std::max(gneed, it.g);
+                const int ii = (int)items.size();
+                for (int m = 0; m < it.nmodes; m++) {
+                    const int mix = (int)mitems.size();
+                    mitems.push_back({ii, m});
+                    const int NM = it.nmax - (m > 1 ? m : 1) + 1;
+                    if (NM <= ST_SMALL_NM) { sm.push_back(mix); continue; }
+                    const int nst = (NM + 31) / 32;
+                    for (int sr = 0; sr < nst; sr++)
+                        for (int sc = 0; sc < nst; sc++) (m == 0 ? at0 : at1).push_back({mix, (short)sr, (short)sc});
+                    gl[NM <= 16 ? 0 : (NM <= 32 ? 1 : (NM <= 56 ? 2 : 3))].push_back(mix);
+                }
+                for (int kind = 2; kind >= 0; kind--)
+                    for (int node0 = 0; node0 < it.g; node0 += 32) rad.push_back({ii, (node0 << 2) | kind});
+                items.push_back(it);
+                s.n_items++;
+            }
+        }
+        if (items.empty()) return 0;
+        if (ensure_gauss(ctx, std::max(gneed, 64))) return -1;
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t o_items = 0, o_mi = al(o_items + items.size() * sizeof(StItem)), o_rad = al(o_mi + mitems.size() * sizeof(StModeItem)),
+                     o_a0 = al(o_rad + rad.size() * sizeof(StRadTask)), o_a1 = al(o_a0 + at0.size() * sizeof(StATask)),
+                     o_g0 = al(o_a1 + at1.size() * sizeof(StATask)), o_g1 = al(o_g0 + gl[0].size() * 4), o_g2 = al(o_g1 + gl[1].size() * 4),
+                     o_g3 = al(o_g2 + gl[2].size() * 4), o_sm = al(o_g3 + gl[3].size() * 4), o_end = al(o_sm + sm.size() * 4);
+        if (st_grow(ctx, &B->d_lists, &B->lists_cap, o_end)) return -1;
+        if (st_grow(ctx, &B->h_lists, &B->h_lists_cap, o_end, true)) return -1;
+        if (items.size() > B->res_cap) {
+            if (B->d_res) cudaFree(B->d_res);
+            if (B->h_res) cudaFreeHost(B->h_res);
+            B->d_res = nullptr; B->h_res = nullptr; B->res_cap = 0;
+            const size_t cap2 = items.size() + items.size() / 2;
+            CK(cudaMalloc(&B->d_res, cap2 * sizeof(StResult)));
+            CK(cudaMallocHost(&B->h_res, cap2 * sizeof(StResult)));
+            B->res_cap = cap2;
+        }
+        if (st_grow(ctx, &B->d_tab, &B->tab_cap, (size_t)tab_off)) return -1;
+        if (st_grow(ctx, &B->d_wig, &B->wig_cap, (size_t)wig_off)) return -1;
+        if (st_grow(ctx, &B->d_sys, &B->sys_cap, (size_t)std::max<long long>(sys_off, 1))) return -1;
+        char *h = B->h_lists, *d = B->d_lists;
+        memcpy(h + o_items, items.data(), items.size() * sizeof(StItem));
+        memcpy(h + o_mi, mitems.data(), mitems.size() * sizeof(StModeItem));
+        memcpy(h + o_rad, rad.data(), rad.size() * sizeof(StRadTask));
+        memcpy(h + o_a0, at0.data(), at0.size() * sizeof(StATask));
+        memcpy(h + o_a1, at1.data(), at1.size() * sizeof(StATask));
+        const size_t og[5] = {o_g0, o_g1, o_g2, o_g3, o_sm};
+        for (int c = 0; c < 5; c++) {
+            // heaviest systems first (counting sort on NM), written straight into the staging buffer
+            const std::vector<int> &L = c < 4 ? gl[c] : sm;
+            int cnt[HS_NPN1 + 2] = {0};
+            for (int x : L) cnt[items[mitems[x].item].nmax - std::max(mitems[x].m, 1) + 1]++;
+            int acc = 0;
+            for (int v = HS_NPN1; v >= 0; v--) { int q = cnt[v]; cnt[v] = acc; acc += q; }
+            int *dst = (int *)(h + og[c]);
+            for (int x : L) dst[cnt[items[mitems[x].item].nmax - std::max(mitems[x].m, 1) + 1]++] = x;
+        }
+        CK(cudaMemcpyAsync(d, h, o_end, cudaMemcpyHostToDevice, st));
+        StArgs a;
+        a.items = (const StItem *)(d + o_items); a.mitems = (const StModeItem *)(d + o_mi);
+        a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
+        a.gx = ctx->d_gx; a.gw = ctx->d_gw; a.cm = S->d_cm; a.dd = S->d_dd;
+        a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
+        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->d_res;
+        const int ni = (int)items.size();
+        k_st_reserve<<<(ni + 127) / 128, 128, 0, st>>>((StItem *)(d + o_items), B->d_res, ni, C->d_arena_top, C->arena_cap, C->d_toff);
+        k_st_radial<<<((int)rad.size() + 3) / 4, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
+        k_st_wigner<<<(int)mitems.size(), 64, 0, st>>>(a, (int)mitems.size());
+        ctx->launches += 3;
+        if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_OP_DOUBLES * 8, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); ctx->launches++; }
+        if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_OP_DOUBLES * 8, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); ctx->launches++; }
+        if (!gl[3].empty()) { k_st_solve<256, true><<<(int)gl[3].size(), 256, 0, st>>>(a, (const int *)(d + o_g3), (int)gl[3].size()); ctx->launches++; }
+        if (!gl[2].empty()) { k_st_solve<256, false><<<(int)gl[2].size(), 256, 200704, st>>>(a, (const int *)(d + o_g2), (int)gl[2].size()); ctx->launches++; }
+        if (!gl[1].empty()) { k_st_solve<256, false><<<(int)gl[1].size(), 256, 65536, st>>>(a, (const int *)(d + o_g1), (int)gl[1].size()); ctx->launches++; }
+        if (!gl[0].empty()) { k_st_solve<128, false><<<(int)gl[0].size(), 128, 16384, st>>>(a, (const int *)(d + o_g0), (int)gl[0].size()); ctx->launches++; }
+        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, st>>>(a, (const int *)(d + o_sm), (int)sm.size()); ctx->launches++; }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(B->h_res, B->d_res, (size_t)ni * sizeof(StResult), cudaMemcpyDeviceToHost, st));
+        inflight = true;
+        if (C->trace)
+            fprintf(stderr, "[hydrotm-staged] group %d round %d: %d active, K=%d, %d items, %zu mode-items (%zu small), %zu+%zu A tasks, scratch %.1f MB\n",
+                    id, nround, active_n, K, ni, mitems.size(), sm.size(), at0.size(), at1.size(),
+                    ((double)(tab_off + wig_off) * 8 + (double)sys_off * 16) / 1048576.0);
+        t_plan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+        return 0;
+    }
+
+    // wait for the round in flight and run the controller (calctmat_particle: the block after HS_PROF(3))
+    int finish()
+    {
+        using namespace hs;
+        if (!inflight) return 0;
+        auto T0 = std::chrono::steady_clock::now();
+        CK(cudaStreamSynchronize(B->stream));
+        auto T1 = std::chrono::steady_clock::now();
+        inflight = false;
+        const double ddelt = C->ddelt;
+        for (int j : order) {
+            StP &s = P[j];
+            if (s.done || s.n_items == 0) continue;  // limit hit while planning, or deferred by the scratch budget
+            for (int q = 0; q < s.n_items; q++) {
+                const StItem &it = items[s.first_item + q];
+                const StResult &r = B->h_res[s.first_item + q];
+                if (s.phase == 2) {  // modes of a configuration whose convergence is already decided
+                    if (r.t_off == -2) { s.status = HS_ST_ARENA_FULL; s.done = 2; break; }
+                    s.t_off = r.t_off; s.sing |= r.sing; s.done = 1;
+                    break;
+                }
+                const double dsca = fabs((s.q1s - r.qsca) / r.qsca), dext = fabs((s.q1e - r.qext) / r.qext);
+                s.q1s = r.qsca; s.q1e = r.qext;
+                s.ntr++;
+                s.g = it.g;
+                s.sing |= r.sing;
+                const bool ok = (dsca <= ddelt && dext <= ddelt);
+                if (s.phase == 0) {
+                    if (ok) { s.phase = (it.g == HS_NPNG1) ? 2 : 1; break; }
+                    else if (s.nmax + 1 > HS_NPN1) { s.status = HS_ST_NMAX_LIMIT; s.done = 2; break; }
+                    else s.nmax = s.nmax + 1;
+                } else {
+                    if (r.t_off == -2) { s.status = HS_ST_ARENA_FULL; s.done = 2; break; }
+                    s.t_off = r.t_off;
+                    if (ok) s.done = 1;
+                    else if (it.g == HS_NPNG1) { s.status = HS_ST_NGAUSS_LIMIT; s.done = 1; }
+                    break;
+                }
+            }
+        }
+        nround++;
+        if (nround > 4 * HS_NPN1 + HS_NPNG1) { ctx->err = "staged controller did not terminate"; return -4; }
+        auto T2 = std::chrono::steady_clock::now();
+        t_wait += std::chrono::duration<double, std::milli>(T1 - T0).count();
+        t_ctl += std::chrono::duration<double, std::milli>(T2 - T1).count();
+        return 0;
+    }
+
+    // per-particle records -> device arrays
+    int write_out()
+    {
+        const int ns = (int)P.size();
+        if (!ns) return 0;
+        cudaStream_t st = B->stream;
+        if ((size_t)ns > B->out_cap) {
+            if (B->d_out) cudaFree(B->d_out);
+            if (B->h_out) cudaFreeHost(B->h_out);
+            B->d_out = nullptr; B->h_out = nullptr; B->out_cap = 0;
+            CK(cudaMalloc(&B->d_out, ((size_t)ns * 7 + 2) * sizeof(int)));
+            CK(cudaMallocHost(&B->h_out, ((size_t)ns * 7 + 2) * sizeof(int)));
+            B->out_cap = ns;
+        }
+        const size_t toffs_off = ((size_t)5 * ns + ((5 * ns) & 1));
+        long long *h_toffs = reinterpret_cast<long long *>(B->h_out + toffs_off);
+        for (int j = 0; j < ns; j++) {
+            const StP &s = P[j];
+            int stt = s.status;
+            if (stt == HS_ST_OK && s.sing) stt = HS_ST_SINGULAR;
+            B->h_out[5 * j] = s.idx; B->h_out[5 * j + 1] = s.nmax; B->h_out[5 * j + 2] = s.g; B->h_out[5 * j + 3] = s.ntr; B->h_out[5 * j + 4] = stt;
+            h_toffs[j] = (s.done == 1) ? s.t_off : -1;
+        }
+        CK(cudaMemcpyAsync(B->d_out, B->h_out, ((size_t)ns * 7 + 2) * sizeof(int), cudaMemcpyHostToDevice, st));
+        k_st_scatter_out<<<(ns + 255) / 256, 256, 0, st>>>(ns, B->d_out, reinterpret_cast<const long long *>(B->d_out + toffs_off), C->d_nmax,
+                                                           C->d_ngauss, C->d_ntrials, C->d_status, C->d_toff);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
+};
+
+}  // namespace
+
+static int st_init(hs_ctx *ctx, StShared &S)
+{
+    using namespace hs;
+    if (S.d_cm) return 0;
+    std::vector<double> cm(HS_NPN1 + 1), dd(HS_NPN1 + 1);
+    double cacc = 1.0;
+    cm[0] = 1.0; dd[0] = 0.0;
+    for (int i = 1; i <= HS_NPN1; i++) {
+        cacc = cacc * sqrt((double)(2 * i - 1) / (double)(2 * i));
+        cm[i] = cacc;
+        dd[i] = sqrt((double)(2 * i + 1) / (double)(i * (i + 1)));
+    }
+    CK(cudaMalloc(&S.d_cm, cm.size() * sizeof(double)));
+    CK(cudaMalloc(&S.d_dd, dd.size() * sizeof(double)));
+    CK(cudaMemcpy(S.d_cm, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S.d_dd, dd.data(), dd.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(k_st_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_OP_DOUBLES * 8));
+    CK(cudaFuncSetAttribute(k_st_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_OP_DOUBLES * 8));
+    CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
+    CK(cudaFuncSetAttribute(k_st_solve<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
+    CK(cudaFuncSetAttribute(k_st_mode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ST_SMALL_SLICE * 8));
+    CK(cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming));
+    for (int g = 0; g < ST_GROUPS; g++) {
+        CK(cudaStreamCreateWithFlags(&S.g[g].stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&S.g[g].ev, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+static void st_destroy(StShared &S)
+{
+    for (int g = 0; g < ST_GROUPS; g++) {
+        StBufs &b = S.g[g];
+        cudaFree(b.d_lists); cudaFree(b.d_res); cudaFree(b.d_tab); cudaFree(b.d_wig); cudaFree(b.d_sys); cudaFree(b.d_out);
+        if (b.h_lists) cudaFreeHost(b.h_lists);
+        if (b.h_res) cudaFreeHost(b.h_res);
+        if (b.h_out) cudaFreeHost(b.h_out);
+        if (b.stream) cudaStreamDestroy(b.stream);
+        if (b.ev) cudaEventDestroy(b.ev);
+    }
+    cudaFree(S.d_cm); cudaFree(S.d_dd);
+    if (S.ev_in) cudaEventDestroy(S.ev_in);
+}
+
+// Converged T-matrices of the particles `sel` (indices into the batch; n0_of = their starting NMAX, -1 = invalid input)
+// through the staged pipeline.  `st` is the caller's stream: the groups' streams wait for it (inputs) and it waits for
+// them (outputs) before this returns.
+static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std::vector<int> &sel, const std::vector<int> &n0_of,
+                           const StCall &C)
+{
+    const int ns = (int)sel.size();
+    if (!ns) return 0;
+    if (st_init(ctx, S)) return -1;
+    CK(cudaEventRecord(S.ev_in, st));
+    const int ng = std::max(1, std::min(ST_GROUPS, getenv("HYDROTM_GROUPS") ? atoi(getenv("HYDROTM_GROUPS")) : (ns >= 256 ? ST_GROUPS : 1)));
+    // deal the particles, heaviest first, round-robin: every group gets the same size mix
+    std::vector<int> ord(ns);
+    for (int j = 0; j < ns; j++) ord[j] = j;
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return n0_of[x] > n0_of[y]; });
+    StGroup G[ST_GROUPS];
+    for (int g = 0; g < ng; g++) {
+        G[g].ctx = ctx; G[g].S = &S; G[g].B = &S.g[g]; G[g].C = &C; G[g].id = g;
+        CK(cudaStreamWaitEvent(S.g[g].stream, S.ev_in, 0));
+    }
+    for (int r = 0; r < ns; r++) {
+        const int j = ord[r];
+        StP s;
+        s.idx = sel[j]; s.phase = 0; s.nmax = n0_of[j]; s.g = 0; s.ntr = 0; s.status = HS_ST_OK; s.done = 0; s.sing = 0;
+        s.q1s = 0.0; s.q1e = 0.0; s.t_off = -1; s.first_item = 0; s.n_items = 0;
+        if (s.nmax < 0) { s.done = 2; s.status = HS_ST_BAD_INPUT; s.nmax = 0; }
+        else if (s.nmax >= HS_NPN1) { s.done = 2; s.status = HS_ST_NMAX_LIMIT; }
+        G[r % ng].P.push_back(s);
+    }
+    auto T0 = std::chrono::steady_clock::now();
+    for (int g = 0; g < ng; g++) { int rc = G[g].issue(); if (rc) return rc; }
+    while (true) {
+        bool any = false;
+        for (int g = 0; g < ng; g++) {
+            if (!G[g].inflight && !G[g].active()) continue;
+            any = true;
+            int rc = G[g].finish();
+            if (rc) return rc;
+            rc = G[g].issue();
+            if (rc) return rc;
+        }
+        if (!any) break;
+    }
+    for (int g = 0; g < ng; g++) {
+        int rc = G[g].write_out();
+        if (rc) return rc;
+        CK(cudaEventRecord(S.g[g].ev, S.g[g].stream));
+        CK(cudaStreamWaitEvent(st, S.g[g].ev, 0));
+    }
+    if (C.trace) {
+        double tot = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+        for (int g = 0; g < ng; g++)
+            fprintf(stderr, "[hydrotm-staged] group %d: %zu particles, %d rounds: plan+issue %.2f ms, wait %.2f ms, controller %.2f ms\n", g,
+                    G[g].P.size(), G[g].nround, G[g].t_plan, G[g].t_wait, G[g].t_ctl);
+        fprintf(stderr, "[hydrotm-staged] %d particles, %d groups, %.2f ms\n", ns, ng, tot);
+    }
+    return 0;
+}

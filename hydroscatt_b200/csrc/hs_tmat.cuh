@@ -436,7 +436,7 @@ __device__ void assemble(const Grp<WARP> &grp, const Carve &c, int nmax, int g, 
 // X_j and X_y.  That is 20 real FMAs per (pair, node) instead of ~60, and a TM x TN tile of same-parity pairs per
 // thread re-uses each loaded row TN (TM) times: the per-pair loop above is shared-memory-bandwidth bound
 // (18 LDS per pair-node), the tiled one is not.
-__device__ __forceinline__ void store_even(const Carve &c, int NM, int nmin, int k1, int k2, double ppi, double pir,
+__device__ __forceinline__ void store_even(double2 *sys, int NM, int nmin, int k1, int k2, double ppi, double pir,
                                            double pii, const double *dd, const double *x12j, const double *x12y,
                                            const double *x21j, const double *x21y)
 {
@@ -452,14 +452,13 @@ __device__ __forceinline__ void store_even(const Carve &c, int NM, int nmin, int
     double2 ga = combine(pir, pii, ppi, -ig21, rg21, ig12, -rg12);
     double2 gb = combine(pir, pii, ppi, ig12, -rg12, -ig21, rg21);
     const int ca = (n1 + 1) & 1, cb = ca ^ 1;
-    double2 *sys = c.sys;
     sys[(long)(ca * NM + k2) * ldc + k1] = qa;
     sys[(long)(ca * NM + k2) * ldc + NM + k1] = make_double2(-ga.x, -ga.y);
     sys[(long)(cb * NM + k2) * ldc + k1] = qb;
     sys[(long)(cb * NM + k2) * ldc + NM + k1] = make_double2(-gb.x, -gb.y);
 }
 
-__device__ __forceinline__ void store_odd(const Carve &c, int NM, int nmin, int k1, int k2, double ppi, double pir,
+__device__ __forceinline__ void store_odd(double2 *sys, int NM, int nmin, int k1, int k2, double ppi, double pir,
                                           double pii, const double *dd, const double *x11j, const double *x11y,
                                           const double *x22j, const double *x22y)
 {
@@ -474,7 +473,6 @@ __device__ __forceinline__ void store_odd(const Carve &c, int NM, int nmin, int 
     double2 ga = combine(pir, pii, ppi, -rg11, -ig11, -rg22, -ig22);
     double2 gb = combine(pir, pii, ppi, -rg22, -ig22, -rg11, -ig11);
     const int ca = (n1 + 1) & 1, cb = ca ^ 1;
-    double2 *sys = c.sys;
     sys[(long)(ca * NM + k2) * ldc + k1] = qa;
     sys[(long)(ca * NM + k2) * ldc + NM + k1] = make_double2(-ga.x, -ga.y);
     sys[(long)(cb * NM + k2) * ldc + k1] = qb;
@@ -602,8 +600,8 @@ __device__ void assemble_tiled(const Grp<WARP> &grp, const Carve &c, int nmax, i
 #pragma unroll
             for (int q = 0; q < TN; q++) {
                 if (!(v1[r] && v2[q])) continue;
-                if (even) store_even(c, NM, nmin, k1[r], k2[q], ppi, pir, pii, dd, xa[r][q], xa[r][q] + 2, xb[r][q], xb[r][q] + 2);
-                else store_odd(c, NM, nmin, k1[r], k2[q], ppi, pir, pii, dd, xa[r][q], xa[r][q] + 2, xb[r][q], xb[r][q] + 2);
+                if (even) store_even(c.sys, NM, nmin, k1[r], k2[q], ppi, pir, pii, dd, xa[r][q], xa[r][q] + 2, xb[r][q], xb[r][q] + 2);
+                else store_odd(c.sys, NM, nmin, k1[r], k2[q], ppi, pir, pii, dd, xa[r][q], xa[r][q] + 2, xb[r][q], xb[r][q] + 2);
             }
     }
     if (m == 0) {

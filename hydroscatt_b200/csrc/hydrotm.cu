@@ -18,6 +18,7 @@
 #include "hs_scatter.cuh"
 #include "hs_psd.cuh"
 #include "hs_tm2l.cuh"
+#include "hs_staged.cuh"
 
 struct hs_ctx {
     int device = 0;
@@ -44,6 +45,7 @@ struct hs_ctx {
     double *d_ws_fb = nullptr;   // global-memory fall-back workspace slices
     double *d_ws_global = nullptr;
     size_t ws_global_bytes = 0;
+    struct StBufsHolder *st = nullptr;  // staged pipeline buffers (hs_staged_host.h)
 };
 
 #define CK(call)                                                                                   \
@@ -54,6 +56,10 @@ struct hs_ctx {
             return -1;                                                                             \
         }                                                                                          \
     } while (0)
+
+static int ensure_gauss(hs_ctx *ctx, int gmax);
+#include "hs_staged_host.h"
+struct StBufsHolder { StShared s; };
 
 static int ensure_gauss(hs_ctx *ctx, int gmax)
 {
@@ -116,6 +122,7 @@ extern "C" void hs_ctx_destroy(hs_ctx *ctx)
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int b = 0; b < 8; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->st) { st_destroy(ctx->st->s); delete ctx->st; }
     delete ctx;
 }
 
@@ -146,7 +153,7 @@ struct Bucket {
 // max(NMAX0 + 1, ceil(|m| k a_max + 2)) is a tight estimate on the 6-band rain sweep; particles that still outgrow
 // their shared-memory slice continue in the global-memory fall-back workspace (no re-launch).
 __global__ void k_nmax0(int n, const double *axi, const double *lam, const double *mr, const double *mi,
-                        const double *eps, double rat, int *out)
+                        const double *eps, double rat, int *out, int *out_n0)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -167,6 +174,8 @@ __global__ void k_nmax0(int n, const double *axi, const double *lam, const doubl
     double mx = sqrt(mr[i] * mr[i] + mi[i] * mi[i]) * xa;
     int pred = (mx > 0.0 && mx < 1e6) ? (int)ceil(mx + 2.0) : 0;
     out[i] = max(n0 + 1, pred);
+    const bool bad = !(axi[i] > 0.0) || !(lam[i] > 0.0) || !(e_ > 0.0) || !isfinite(mr[i]) || !isfinite(mi[i]) || !(mr[i] * mr[i] + mi[i] * mi[i] > 0.0);
+    out_n0[i] = bad ? -1 : n0;
 }
 
 template <bool WARP, bool GLOBAL_WS, bool TILED>
@@ -244,7 +253,7 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
     if (!ctx->d_ws_fb) {
         if (cudaMalloc(&ctx->d_ws_fb, (size_t)ctx->sm_count * 8 * fb_cap * sizeof(double)) != cudaSuccess) { ctx->d_ws_fb = nullptr; cudaGetLastError(); }
     }
-    if (ensure_pin(ctx, (size_t)n * sizeof(int) * 2)) return -1;
+    if (ensure_pin(ctx, (size_t)n * sizeof(int) * 3)) return -1;
     if (n > ctx->items_cap) {
         if (ctx->d_items) cudaFree(ctx->d_items);
         ctx->d_items = nullptr; ctx->items_cap = 0;
@@ -252,12 +261,30 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         ctx->items_cap = n;
     }
     // predicted starting NMAX -> initial bucket
-    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, d_nmax);
+    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, d_nmax, d_ngauss);
     ctx->launches++;
     CK(cudaGetLastError());
-    int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n;
+    int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n, *h_start = ctx->h_pin + 2 * (size_t)n;
     CK(cudaMemcpyAsync(h_n0, d_nmax, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_start, d_ngauss, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    // Particles whose predicted order reaches HYDROTM_STAGED_MIN go through the staged pipeline (one kernel per stage,
+    // trials and modes as independent work items); the small ones stay on the fused one-particle-per-group kernel.
+    const int staged_min = getenv("HYDROTM_STAGED_MIN") ? atoi(getenv("HYDROTM_STAGED_MIN")) : 9;
+    std::vector<int> st_sel, st_n0;
+    if (!ctx->st) ctx->st = new StBufsHolder();
+    bool staged_done = false;
+    StCall SC;
+    SC.d_axi = d_axi; SC.d_lam = d_lam; SC.d_mr = d_mr; SC.d_mi = d_mi; SC.d_eps = d_eps; SC.rat = rat; SC.ddelt = ddelt; SC.ndgs = ndgs;
+    SC.d_tarena = d_tarena; SC.arena_cap = arena_cap; SC.d_arena_top = d_arena_top; SC.d_toff = d_toff;
+    SC.d_nmax = d_nmax; SC.d_ngauss = d_ngauss; SC.d_ntrials = d_ntrials; SC.d_status = d_status;
+    SC.scratch_budget = (size_t)((getenv("HYDROTM_SCRATCH_GB") ? atof(getenv("HYDROTM_SCRATCH_GB")) : 4.0) * (double)(1ull << 30));
+    SC.spec = getenv("HYDROTM_SPEC") ? atoi(getenv("HYDROTM_SPEC")) : 0;
+    SC.trace = trace;
+    auto run_staged = [&]() -> int {
+        staged_done = true;
+        return calctmat_staged(ctx, ctx->st->s, st, st_sel, st_n0, SC);
+    };
 
     if (getenv("HYDROTM_PROF") && !ctx->d_prof) { CK(cudaMalloc(&ctx->d_prof, 8 * sizeof(long long))); }
     if (ctx->d_prof) CK(cudaMemsetAsync(ctx->d_prof, 0, 8 * sizeof(long long), st));
@@ -267,6 +294,7 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
     for (int i = 0; i < n; i++) {
         int n0 = h_n0[i];
         nm0[i] = n0;
+        if (n0 >= staged_min && h_start[i] >= 0) { st_sel.push_back(i); st_n0.push_back(h_start[i]); bucket_of[i] = -1; continue; }
         int np_ = std::min(n0, HS_NPN1);
         long long need = hs::ws_need(np_, np_ * ndgs + 1);
         int b = 0;
@@ -342,6 +370,7 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
             CK(cudaStreamWaitEvent(st, ctx->ev_done[b], 0));
         }
         lap("launches issued");
+        if (!staged_done) { int rc = run_staged(); if (rc) return rc; lap("staged pipeline"); }
         CK(cudaMemcpyAsync(h_st, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         lap("round done (status D2H)");
@@ -365,6 +394,7 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         }
         lists.swap(next);
     }
+    if (!staged_done) { int rc = run_staged(); if (rc) return rc; lap("staged pipeline (alone)"); }
     if (ctx->d_prof) {
         long long hp[8];
         CK(cudaMemcpy(hp, ctx->d_prof, sizeof(hp), cudaMemcpyDeviceToHost));

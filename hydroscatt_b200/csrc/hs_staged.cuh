@@ -509,6 +509,58 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     }
 }
 
+// ---- Gauss-Jordan with row pivoting of one system by a (sub-)warp: lane = column of the augmented block ----
+// Same pivot rule and arithmetic as solve_multi (hs_tmat.cuh); no CTA barrier: a lane only ever touches its own
+// columns plus the (read-only during the step) pivot column, so one __syncwarp per elimination step is enough, and
+// the pivot of the next step is found by the lane that has just updated that column.  `gw` lanes (8, 16 or 32) work
+// on one system, so a warp solves 32 / gw small systems side by side; kmax = largest order among them.
+__device__ __forceinline__ void solve_sub(const SysDesc d, int gl, int gw, int kmax, int *sing)
+{
+    const int n = d.n, nc = 2 * n;
+    const long rstep = (long)d.stride * d.ld, row0 = (long)d.off * d.ld;
+    auto colof = [&](int j) -> long { return (j < n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - n)); };
+    double2 *b0 = d.base + row0;
+    unsigned long long key = 0ull;
+    {
+        const double2 *c0 = b0 + colof(0);
+        for (int r = gl; r < n; r += gw) { const unsigned long long ky = pivot_key(c0[r * rstep], r); key = ky > key ? ky : key; }
+        for (int o = gw >> 1; o; o >>= 1) { const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o, gw); key = ok > key ? ok : key; }
+    }
+    for (int k = 0; k < kmax; k++) {
+        unsigned long long nkey = 0ull;
+        if (k < n) {
+            const int p = 255 - (int)(key & 0xFFull);
+            if ((key >> 8) == 0ull && gl == 0) *sing = 1;
+            const double2 *ck = b0 + colof(k);
+            const double2 pv = ck[p * rstep];
+            const double den = pv.x * pv.x + pv.y * pv.y;
+            const double2 inv = make_double2(pv.x / den, -pv.y / den);
+            const double2 fkk = ck[k * rstep];
+            for (int j = k + 1 + gl; j < nc; j += gw) {
+                double2 *cj = b0 + colof(j);
+                const double2 a = cj[k * rstep], b = cj[p * rstep];
+                const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
+                cj[k * rstep] = nk;
+                if (p != k) cj[p * rstep] = a;
+                const bool next_col = (j == k + 1) && (k + 1 < n);
+#pragma unroll 4
+                for (int r = 0; r < n; r++) {
+                    if (r == k) continue;
+                    // after the row swap, row p holds the old row k whose column-k entry is still at (k, k)
+                    const double2 f = (r == p) ? fkk : ck[r * rstep];
+                    double2 v = cj[r * rstep];
+                    v.x -= f.x * nk.x - f.y * nk.y;
+                    v.y -= f.x * nk.y + f.y * nk.x;
+                    cj[r * rstep] = v;
+                    if (next_col && r > k) { const unsigned long long ky = pivot_key(v, r); nkey = ky > nkey ? ky : nkey; }
+                }
+            }
+        }
+        key = __shfl_sync(0xffffffffu, nkey, 0, gw);  // column k + 1 belongs to lane 0 of the group
+        __syncwarp();
+    }
+}
+
 // ---- G: parity-class systems of one (item, mode): T = -RgQ Q^-1 by the lock-step Gauss-Jordan of hs_tmat.cuh ----
 template <int THREADS, bool GLOBAL>
 __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist, int n)
@@ -554,9 +606,16 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
     }
     if (threadIdx.x == 0) sing = 0;
     __syncthreads();
-    Grp<false> grp;
-    grp.tid = threadIdx.x; grp.nt = THREADS;
-    solve_multi(grp, sd, nsys, &sc, &sing);
+    if (GLOBAL) {
+        Grp<false> grp;
+        grp.tid = threadIdx.x; grp.nt = THREADS;
+        solve_multi(grp, sd, nsys, &sc, &sing);
+    } else {
+        // one warp per system (m = 0: four half-size systems, m >= 1: the two parity classes)
+        const int w = threadIdx.x >> 5;
+        if (w < nsys) solve_sub(sd[w], threadIdx.x & 31, 32, sd[w].n, &sing);
+        __syncthreads();
+    }
     const long long toff = it.t_off;
     if (toff >= 0) {
         double2 *tg = reinterpret_cast<double2 *>(a.tarena) + toff + st_t_mode_off(nmax, m);
@@ -582,6 +641,7 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
         if (sing) atomicOr(&a.res[mi.item].sing, 1);
     }
 }
+
 
 
 // ---- A + G for small blocks (NM <= 8): one warp per (item, mode) ----
@@ -753,9 +813,14 @@ __global__ void __launch_bounds__(256) k_st_mode_small(StArgs a, const int *mlis
     }
     if (lane == 0) sings[warp] = 0;
     __syncwarp();
-    Grp<true> grp;
-    grp.tid = lane; grp.nt = 32;
-    solve_multi(grp, sd, nsys, &scs[warp], &sings[warp]);
+    {
+        // m = 0: four half-size systems on 8 lanes each; m >= 1: the two parity classes on 16 lanes each
+        const int gw = m == 0 ? 8 : 16, grp_ = lane / gw, gl = lane - grp_ * gw;
+        SysDesc d;
+        if (grp_ < nsys) d = sd[grp_];
+        else { d = sd[0]; d.n = 0; }
+        solve_sub(d, gl, gw, m == 0 ? ((NM + 1) >> 1) : NM, &sings[warp]);
+    }
     const long long toff = it.t_off;
     if (toff >= 0) {
         double2 *tg = reinterpret_cast<double2 *>(a.tarena) + toff + st_t_mode_off(nmax, m);

@@ -14,7 +14,7 @@
 
 namespace {
 
-#define ST_GROUPS 3
+#define ST_GROUPS 4
 
 struct StBufs {
     char *d_lists = nullptr; size_t lists_cap = 0;    // items | mitems | rad tasks | A tasks (m=0) | A tasks | G lists | small list
@@ -92,11 +92,13 @@ struct StGroup {
     std::vector<hs::StModeItem> mitems;
     std::vector<hs::StRadTask> rad;
     std::vector<hs::StATask> at0, at1;
-    std::vector<int> gl[4], sm;
+    std::vector<int> gl[5], sm;
     std::vector<int> order;
     int nround = 0, K = 2;
     bool inflight = false;
     double t_plan = 0, t_wait = 0, t_ctl = 0;
+    long long launches = 0;
+    int rc = 0;
 
     bool active() const
     {
@@ -158,7 +160,7 @@ struct StGroup {
                     const int nst = (NM + 31) / 32;
                     for (int sr = 0; sr < nst; sr++)
                         for (int sc = 0; sc < nst; sc++) (m == 0 ? at0 : at1).push_back({mix, (short)sr, (short)sc});
-                    gl[NM <= 16 ? 0 : (NM <= 32 ? 1 : (NM <= 56 ? 2 : 3))].push_back(mix);
+                    gl[NM <= 16 ? 0 : (NM <= 24 ? 1 : (NM <= 32 ? 2 : (NM <= 56 ? 3 : 4)))].push_back(mix);
                 }
                 for (int kind = 2; kind >= 0; kind--)
                     for (int node0 = 0; node0 < it.g; node0 += 32) rad.push_back({ii, (node0 << 2) | kind});
@@ -167,12 +169,17 @@ struct StGroup {
             }
         }
         if (items.empty()) return 0;
-        if (ensure_gauss(ctx, std::max(gneed, 64))) return -1;
+        if (gneed > ctx->gmax) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            if (ensure_gauss(ctx, std::max(gneed, 64))) return -1;
+        }
+        const double *gx, *gw;
+        { std::lock_guard<std::mutex> lk(ctx->mu); gx = ctx->d_gx; gw = ctx->d_gw; }
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
         const size_t o_items = 0, o_mi = al(o_items + items.size() * sizeof(StItem)), o_rad = al(o_mi + mitems.size() * sizeof(StModeItem)),
                      o_a0 = al(o_rad + rad.size() * sizeof(StRadTask)), o_a1 = al(o_a0 + at0.size() * sizeof(StATask)),
                      o_g0 = al(o_a1 + at1.size() * sizeof(StATask)), o_g1 = al(o_g0 + gl[0].size() * 4), o_g2 = al(o_g1 + gl[1].size() * 4),
-                     o_g3 = al(o_g2 + gl[2].size() * 4), o_sm = al(o_g3 + gl[3].size() * 4), o_end = al(o_sm + sm.size() * 4);
+                     o_g3 = al(o_g2 + gl[2].size() * 4), o_g4 = al(o_g3 + gl[3].size() * 4), o_sm = al(o_g4 + gl[4].size() * 4), o_end = al(o_sm + sm.size() * 4);
         if (st_grow(ctx, &B->d_lists, &B->lists_cap, o_end)) return -1;
         if (st_grow(ctx, &B->h_lists, &B->h_lists_cap, o_end, true)) return -1;
         if (items.size() > B->res_cap) {
@@ -193,10 +200,10 @@ struct StGroup {
         memcpy(h + o_rad, rad.data(), rad.size() * sizeof(StRadTask));
         memcpy(h + o_a0, at0.data(), at0.size() * sizeof(StATask));
         memcpy(h + o_a1, at1.data(), at1.size() * sizeof(StATask));
-        const size_t og[5] = {o_g0, o_g1, o_g2, o_g3, o_sm};
-        for (int c = 0; c < 5; c++) {
+        const size_t og[6] = {o_g0, o_g1, o_g2, o_g3, o_g4, o_sm};
+        for (int c = 0; c < 6; c++) {
             // heaviest systems first (counting sort on NM), written straight into the staging buffer
-            const std::vector<int> &L = c < 4 ? gl[c] : sm;
+            const std::vector<int> &L = c < 5 ? gl[c] : sm;
             int cnt[HS_NPN1 + 2] = {0};
             for (int x : L) cnt[items[mitems[x].item].nmax - std::max(mitems[x].m, 1) + 1]++;
             int acc = 0;
@@ -208,21 +215,21 @@ struct StGroup {
         StArgs a;
         a.items = (const StItem *)(d + o_items); a.mitems = (const StModeItem *)(d + o_mi);
         a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
-        a.gx = ctx->d_gx; a.gw = ctx->d_gw; a.cm = S->d_cm; a.dd = S->d_dd;
+        a.gx = gx; a.gw = gw; a.cm = S->d_cm; a.dd = S->d_dd;
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
         a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->d_res;
         const int ni = (int)items.size();
         k_st_reserve<<<(ni + 127) / 128, 128, 0, st>>>((StItem *)(d + o_items), B->d_res, ni, C->d_arena_top, C->arena_cap, C->d_toff);
         k_st_radial<<<((int)rad.size() + 3) / 4, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
         k_st_wigner<<<(int)mitems.size(), 64, 0, st>>>(a, (int)mitems.size());
-        ctx->launches += 3;
-        if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_OP_DOUBLES * 8, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); ctx->launches++; }
-        if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_OP_DOUBLES * 8, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); ctx->launches++; }
-        if (!gl[3].empty()) { k_st_solve<256, true><<<(int)gl[3].size(), 256, 0, st>>>(a, (const int *)(d + o_g3), (int)gl[3].size()); ctx->launches++; }
-        if (!gl[2].empty()) { k_st_solve<256, false><<<(int)gl[2].size(), 256, 200704, st>>>(a, (const int *)(d + o_g2), (int)gl[2].size()); ctx->launches++; }
-        if (!gl[1].empty()) { k_st_solve<256, false><<<(int)gl[1].size(), 256, 65536, st>>>(a, (const int *)(d + o_g1), (int)gl[1].size()); ctx->launches++; }
-        if (!gl[0].empty()) { k_st_solve<128, false><<<(int)gl[0].size(), 128, 16384, st>>>(a, (const int *)(d + o_g0), (int)gl[0].size()); ctx->launches++; }
-        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, st>>>(a, (const int *)(d + o_sm), (int)sm.size()); ctx->launches++; }
+        launches += 3;
+        if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_OP_DOUBLES * 8, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; }
+        if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_OP_DOUBLES * 8, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; }
+        if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
+        const int gsm[4] = {16384, 36864, 65536, 200704};
+        for (int c = 3; c >= 0; c--)
+            if (!gl[c].empty()) { k_st_solve<128, false><<<(int)gl[c].size(), 128, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; }
+        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, st>>>(a, (const int *)(d + o_sm), (int)sm.size()); launches++; }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(B->h_res, B->d_res, (size_t)ni * sizeof(StResult), cudaMemcpyDeviceToHost, st));
         inflight = true;
@@ -282,6 +289,18 @@ struct StGroup {
         return 0;
     }
 
+    // the group's whole life on its own host thread
+    void run()
+    {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { rc = -1; return; }
+        rc = issue();
+        while (!rc && inflight) {
+            rc = finish();
+            if (!rc) rc = issue();
+        }
+        if (!rc) rc = write_out();
+    }
+
     // per-particle records -> device arrays
     int write_out()
     {
@@ -308,7 +327,7 @@ struct StGroup {
         CK(cudaMemcpyAsync(B->d_out, B->h_out, ((size_t)ns * 7 + 2) * sizeof(int), cudaMemcpyHostToDevice, st));
         k_st_scatter_out<<<(ns + 255) / 256, 256, 0, st>>>(ns, B->d_out, reinterpret_cast<const long long *>(B->d_out + toffs_off), C->d_nmax,
                                                            C->d_ngauss, C->d_ntrials, C->d_status, C->d_toff);
-        ctx->launches++;
+        launches++;
         CK(cudaGetLastError());
         return 0;
     }
@@ -334,8 +353,7 @@ static int st_init(hs_ctx *ctx, StShared &S)
     CK(cudaMemcpy(S.d_dd, dd.data(), dd.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaFuncSetAttribute(k_st_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_OP_DOUBLES * 8));
     CK(cudaFuncSetAttribute(k_st_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_OP_DOUBLES * 8));
-    CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
-    CK(cudaFuncSetAttribute(k_st_solve<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
+    CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
     CK(cudaFuncSetAttribute(k_st_mode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ST_SMALL_SLICE * 8));
     CK(cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming));
     for (int g = 0; g < ST_GROUPS; g++) {
@@ -390,22 +408,15 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         G[r % ng].P.push_back(s);
     }
     auto T0 = std::chrono::steady_clock::now();
-    for (int g = 0; g < ng; g++) { int rc = G[g].issue(); if (rc) return rc; }
-    while (true) {
-        bool any = false;
-        for (int g = 0; g < ng; g++) {
-            if (!G[g].inflight && !G[g].active()) continue;
-            any = true;
-            int rc = G[g].finish();
-            if (rc) return rc;
-            rc = G[g].issue();
-            if (rc) return rc;
-        }
-        if (!any) break;
+    if (ng == 1) G[0].run();
+    else {
+        std::thread th[ST_GROUPS];
+        for (int g = 0; g < ng; g++) th[g] = std::thread([&G, g]() { G[g].run(); });
+        for (int g = 0; g < ng; g++) th[g].join();
     }
     for (int g = 0; g < ng; g++) {
-        int rc = G[g].write_out();
-        if (rc) return rc;
+        ctx->launches += G[g].launches;
+        if (G[g].rc) return G[g].rc;
         CK(cudaEventRecord(S.g[g].ev, S.g[g].stream));
         CK(cudaStreamWaitEvent(st, S.g[g].ev, 0));
     }

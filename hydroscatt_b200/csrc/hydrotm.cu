@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
+#include <thread>
 
 #include "../../include/hydrotm.h"
 #include "hs_gauss.h"
@@ -45,6 +47,8 @@ struct hs_ctx {
     double *d_ws_fb = nullptr;   // global-memory fall-back workspace slices
     double *d_ws_global = nullptr;
     size_t ws_global_bytes = 0;
+    std::mutex mu;               // guards err / the Gauss table when the staged groups run on their own host threads
+    std::vector<double *> gauss_old;  // superseded Gauss tables (kernels in flight may still read them; freed with the context)
     struct StBufsHolder *st = nullptr;  // staged pipeline buffers (hs_staged_host.h)
 };
 
@@ -73,8 +77,8 @@ static int ensure_gauss(hs_ctx *ctx, int gmax)
     CK(cudaMalloc(&nw, tot * sizeof(double)));
     CK(cudaMemcpy(nx, hx.data(), tot * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(nw, hw.data(), tot * sizeof(double), cudaMemcpyHostToDevice));
-    if (ctx->d_gx) cudaFree(ctx->d_gx);
-    if (ctx->d_gw) cudaFree(ctx->d_gw);
+    if (ctx->d_gx) ctx->gauss_old.push_back(ctx->d_gx);
+    if (ctx->d_gw) ctx->gauss_old.push_back(ctx->d_gw);
     ctx->d_gx = nx; ctx->d_gw = nw; ctx->gmax = gmax;
     return 0;
 }
@@ -123,6 +127,7 @@ extern "C" void hs_ctx_destroy(hs_ctx *ctx)
     for (int b = 0; b < 8; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->st) { st_destroy(ctx->st->s); delete ctx->st; }
+    for (double *q : ctx->gauss_old) cudaFree(q);
     delete ctx;
 }
 

@@ -294,6 +294,121 @@ __global__ void __launch_bounds__(64) k_st_wigner(StArgs a, int n_mi)
     }
 }
 
+// ---- Gauss-Jordan with row pivoting of one system by a (sub-)warp: lane = column of the augmented block ----
+// Same pivot rule and arithmetic as solve_multi (hs_tmat.cuh); no CTA barrier: a lane only ever touches its own
+// columns plus the (read-only during the step) pivot column, so one __syncwarp per elimination step is enough, and
+// the pivot of the next step is found by the lane that has just updated that column.  `gw` lanes (8, 16 or 32) work
+// on one system, so a warp solves 32 / gw small systems side by side; kmax = largest order among them.
+__device__ __forceinline__ void solve_sub(const SysDesc d, int gl, int gw, int kmax, int *sing)
+{
+    const int n = d.n, nc = 2 * n;
+    const long rstep = (long)d.stride * d.ld, row0 = (long)d.off * d.ld;
+    auto colof = [&](int j) -> long { return (j < n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - n)); };
+    double2 *b0 = d.base + row0;
+    unsigned long long key = 0ull;
+    {
+        const double2 *c0 = b0 + colof(0);
+        for (int r = gl; r < n; r += gw) { const unsigned long long ky = pivot_key(c0[r * rstep], r); key = ky > key ? ky : key; }
+        for (int o = gw >> 1; o; o >>= 1) { const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o, gw); key = ok > key ? ok : key; }
+    }
+    for (int k = 0; k < kmax; k++) {
+        unsigned long long nkey = 0ull;
+        if (k < n) {
+            const int p = 255 - (int)(key & 0xFFull);
+            if ((key >> 8) == 0ull && gl == 0) *sing = 1;
+            const double2 *ck = b0 + colof(k);
+            const double2 pv = ck[p * rstep];
+            const double den = pv.x * pv.x + pv.y * pv.y;
+            const double2 inv = make_double2(pv.x / den, -pv.y / den);
+            const double2 fkk = ck[k * rstep];
+            for (int j = k + 1 + gl; j < nc; j += gw) {
+                double2 *cj = b0 + colof(j);
+                const double2 a = cj[k * rstep], b = cj[p * rstep];
+                const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
+                cj[k * rstep] = nk;
+                if (p != k) cj[p * rstep] = a;
+                const bool next_col = (j == k + 1) && (k + 1 < n);
+#pragma unroll 4
+                for (int r = 0; r < n; r++) {
+                    if (r == k) continue;
+                    // after the row swap, row p holds the old row k whose column-k entry is still at (k, k)
+                    const double2 f = (r == p) ? fkk : ck[r * rstep];
+                    double2 v = cj[r * rstep];
+                    v.x -= f.x * nk.x - f.y * nk.y;
+                    v.y -= f.x * nk.y + f.y * nk.x;
+                    cj[r * rstep] = v;
+                    if (next_col && r > k) { const unsigned long long ky = pivot_key(v, r); nkey = ky > nkey ? ky : nkey; }
+                }
+            }
+        }
+        key = __shfl_sync(0xffffffffu, nkey, 0, gw);  // column k + 1 belongs to lane 0 of the group
+        __syncwarp();
+    }
+}
+
+
+// The same elimination by a group of `nl` lanes (64 or 128 = 2 or 4 whole warps): two adjacent lanes share a column
+// (even / odd rows), so a step is n / 2 row updates per lane; one named barrier per step; the two lanes that own
+// column k + 1 publish the next pivot through shared memory.
+__device__ __forceinline__ void solve_grp(const SysDesc d, int t, int nl, int barid, unsigned long long *keyslot, int *sing)
+{
+    const int n = d.n, nc = 2 * n;
+    const long rstep = (long)d.stride * d.ld, row0 = (long)d.off * d.ld;
+    auto colof = [&](int j) -> long { return (j < n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - n)); };
+    double2 *b0 = d.base + row0;
+    const int ct = t >> 1, rs = t & 1, ncl = nl >> 1;
+    if (t < 32) {
+        unsigned long long key = 0ull;
+        const double2 *c0 = b0 + colof(0);
+        for (int r = t; r < n; r += 32) { const unsigned long long ky = pivot_key(c0[r * rstep], r); key = ky > key ? ky : key; }
+        for (int o = 16; o; o >>= 1) { const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o); key = ok > key ? ok : key; }
+        if (t == 0) keyslot[0] = key;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nl) : "memory");
+    for (int k = 0; k < n; k++) {
+        const unsigned long long key = keyslot[k & 1];
+        unsigned long long nkey = 0ull;
+        const int p = 255 - (int)(key & 0xFFull);
+        if ((key >> 8) == 0ull && t == 0) *sing = 1;
+        const double2 *ck = b0 + colof(k);
+        const double2 pv = ck[p * rstep];
+        const double den = pv.x * pv.x + pv.y * pv.y;
+        const double2 inv = make_double2(pv.x / den, -pv.y / den);
+        const double2 fkk = ck[k * rstep];
+        // all lanes of a warp run the same number of passes (the __syncwarp below is warp-wide)
+        const int npass = (nc - k - 1 + ncl - 1) / ncl;
+        for (int ps = 0; ps < npass; ps++) {
+            const int j = k + 1 + ps * ncl + ct;
+            const bool live = j < nc;
+            double2 *cj = b0 + colof(live ? j : k);
+            double2 a = make_double2(0.0, 0.0), b = a;
+            if (live) { a = cj[k * rstep]; b = cj[p * rstep]; }
+            __syncwarp();  // both lanes of the column have read rows k and p before one of them rewrites them
+            if (!live) continue;
+            const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
+            if (rs == 0) { cj[k * rstep] = nk; if (p != k) cj[p * rstep] = a; }
+            const bool next_col = (j == k + 1) && (k + 1 < n);
+#pragma unroll 4
+            for (int r = rs; r < n; r += 2) {
+                if (r == k) continue;
+                // after the row swap, row p holds the old row k (value a; its column-k entry is still at (k, k))
+                const double2 f = (r == p) ? fkk : ck[r * rstep];
+                double2 v = (r == p) ? a : cj[r * rstep];
+                v.x -= f.x * nk.x - f.y * nk.y;
+                v.y -= f.x * nk.y + f.y * nk.x;
+                cj[r * rstep] = v;
+                if (next_col && r > k) { const unsigned long long ky = pivot_key(v, r); nkey = ky > nkey ? ky : nkey; }
+            }
+        }
+        if (t < 32) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, nkey, 1);
+            nkey = ok > nkey ? ok : nkey;
+            if (t == 0) keyslot[(k + 1) & 1] = nkey;
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nl) : "memory");
+    }
+}
+
 // ---- A: Q / RgQ integrals of one 32 x 32 block of (k1, k2) = (n1 - nmin, n2 - nmin) as DMMA contractions ----
 // See assemble_tiled (hs_tmat.cuh) for the factorisation: X = sum over nodes of (left factor of (n1, node)) x (right
 // factor of (n2, node)).  Left operand tables L_t[(k1, F)][node], F in {j, y}: P1 = d1 dF, P2 = d2 dF, P3 = d1 F,
@@ -304,6 +419,7 @@ __global__ void __launch_bounds__(64) k_st_wigner(StArgs a, int n_mi)
 // the fragment loads are conflict-free); each warp owns one parity block's tile rows for both outputs (so the
 // epilogue that combines X_A and X_B into Q and RgQ entries stays in registers).
 #define ST_OP_DOUBLES (15 * 64 * 8)
+#define ST_ASM_SMEM 65536  // operand area (61 440 B), re-used for the [2][32][64] complex systems of a fused solve
 
 __device__ __forceinline__ void st_dmma(double *c, double a, double b)
 {
@@ -475,7 +591,10 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     const double PI = 3.14159265358979323846;
     const double kw = PI * 2.0 / a.lam[p];
     const double ppi = kw * kw, pir = ppi * a.mr[p], pii = ppi * a.mi[p];
-    double2 *sys = a.sys + it.sys_off + st_sys_mode_off(nmax, m);
+    // NM <= 32: the block is the whole mode; the systems are combined in the (now free) operand area, solved here and only
+    // the T block leaves the SM.  Larger modes write their part of [Q | RgQ] to global memory for k_st_solve.
+    const bool fused = NM <= 32;
+    double2 *sys = fused ? reinterpret_cast<double2 *>(op) : a.sys + it.sys_off + st_sys_mode_off(nmax, m);
 #pragma unroll
     for (int r = 0; r < NTR; r++)
 #pragma unroll
@@ -507,57 +626,49 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
             }
         }
     }
-}
-
-// ---- Gauss-Jordan with row pivoting of one system by a (sub-)warp: lane = column of the augmented block ----
-// Same pivot rule and arithmetic as solve_multi (hs_tmat.cuh); no CTA barrier: a lane only ever touches its own
-// columns plus the (read-only during the step) pivot column, so one __syncwarp per elimination step is enough, and
-// the pivot of the next step is found by the lane that has just updated that column.  `gw` lanes (8, 16 or 32) work
-// on one system, so a warp solves 32 / gw small systems side by side; kmax = largest order among them.
-__device__ __forceinline__ void solve_sub(const SysDesc d, int gl, int gw, int kmax, int *sing)
-{
-    const int n = d.n, nc = 2 * n;
-    const long rstep = (long)d.stride * d.ld, row0 = (long)d.off * d.ld;
-    auto colof = [&](int j) -> long { return (j < n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - n)); };
-    double2 *b0 = d.base + row0;
-    unsigned long long key = 0ull;
-    {
-        const double2 *c0 = b0 + colof(0);
-        for (int r = gl; r < n; r += gw) { const unsigned long long ky = pivot_key(c0[r * rstep], r); key = ky > key ? ky : key; }
-        for (int o = gw >> 1; o; o >>= 1) { const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o, gw); key = ok > key ? ok : key; }
+    if (!fused) return;
+    __shared__ unsigned long long keyslot[4][2];
+    __shared__ int sing;
+    if (tid == 0) sing = 0;
+    __syncthreads();
+    const int ldc = 2 * NM;
+    if (M0) {
+        // four half-size systems (T12 = T21 = 0), a pair of warps each
+        const int q = warp >> 1;
+        SysDesc d;
+        d.base = sys + (long)(q >> 1) * NM * ldc; d.ld = ldc; d.off = q & 1; d.stride = 2; d.rhs = NM; d.n = (NM + 1 - (q & 1)) >> 1;
+        if (d.n > 0) solve_grp(d, tid & 63, 64, 1 + q, keyslot[q], &sing);
+    } else {
+        // the two parity classes, four warps each
+        const int q = warp >> 2;
+        SysDesc d;
+        d.base = sys + (long)q * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
+        solve_grp(d, tid & 127, 128, 1 + q, keyslot[q], &sing);
     }
-    for (int k = 0; k < kmax; k++) {
-        unsigned long long nkey = 0ull;
-        if (k < n) {
-            const int p = 255 - (int)(key & 0xFFull);
-            if ((key >> 8) == 0ull && gl == 0) *sing = 1;
-            const double2 *ck = b0 + colof(k);
-            const double2 pv = ck[p * rstep];
-            const double den = pv.x * pv.x + pv.y * pv.y;
-            const double2 inv = make_double2(pv.x / den, -pv.y / den);
-            const double2 fkk = ck[k * rstep];
-            for (int j = k + 1 + gl; j < nc; j += gw) {
-                double2 *cj = b0 + colof(j);
-                const double2 a = cj[k * rstep], b = cj[p * rstep];
-                const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
-                cj[k * rstep] = nk;
-                if (p != k) cj[p * rstep] = a;
-                const bool next_col = (j == k + 1) && (k + 1 < n);
-#pragma unroll 4
-                for (int r = 0; r < n; r++) {
-                    if (r == k) continue;
-                    // after the row swap, row p holds the old row k whose column-k entry is still at (k, k)
-                    const double2 f = (r == p) ? fkk : ck[r * rstep];
-                    double2 v = cj[r * rstep];
-                    v.x -= f.x * nk.x - f.y * nk.y;
-                    v.y -= f.x * nk.y + f.y * nk.x;
-                    cj[r * rstep] = v;
-                    if (next_col && r > k) { const unsigned long long ky = pivot_key(v, r); nkey = ky > nkey ? ky : nkey; }
-                }
-            }
+    __syncthreads();
+    const long long toff = it.t_off;
+    if (toff >= 0) {
+        double2 *tg = reinterpret_cast<double2 *>(a.tarena) + toff + st_t_mode_off(nmax, m);
+        for (int t = tid; t < 2 * NM * NM; t += 256) {
+            const int row = t / NM, col = t - row * NM;
+            tg[t] = sys[(long)row * ldc + NM + col];
         }
-        key = __shfl_sync(0xffffffffu, nkey, 0, gw);  // column k + 1 belongs to lane 0 of the group
-        __syncwarp();
+    }
+    if (tid == 0) {
+        if (M0) {
+            double qext = 0.0, qsca = 0.0;
+            for (int n_ = 1; n_ <= nmax; n_++) {
+                const int k = n_ - 1;
+                const double2 t1 = sys[(long)(((n_ + 1) & 1) * NM + k) * ldc + NM + k];
+                const double2 t2 = sys[(long)((n_ & 1) * NM + k) * ldc + NM + k];
+                const double dn1 = (double)(2 * n_ + 1);
+                qsca += dn1 * (t1.x * t1.x + t1.y * t1.y + t2.x * t2.x + t2.y * t2.y);
+                qext += (t1.x + t2.x) * dn1;
+            }
+            a.res[mi.item].qsca = qsca;
+            a.res[mi.item].qext = qext;
+        }
+        if (sing) atomicOr(&a.res[mi.item].sing, 1);
     }
 }
 
@@ -652,7 +763,7 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
 #define ST_SMALL_NM 8
 #define ST_SMALL_SLICE (15 * 16 * 4)  // doubles per warp
 
-__global__ void __launch_bounds__(256) k_st_mode_small(StArgs a, const int *mlist, int n)
+__global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *mlist, int n)
 {
     extern __shared__ __align__(16) double smraw[];
     __shared__ SysDesc sds[8][4];

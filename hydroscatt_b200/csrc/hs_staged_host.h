@@ -14,7 +14,7 @@
 
 namespace {
 
-#define ST_GROUPS 4
+#define ST_GROUPS 8
 
 struct StBufs {
     char *d_lists = nullptr; size_t lists_cap = 0;    // items | mitems | rad tasks | A tasks (m=0) | A tasks | G lists | small list
@@ -149,7 +149,7 @@ struct StGroup {
                 it.t_off = s.phase == 0 ? -1 : s.t_off;
                 tab_off += st_tab_size(it.nmax, it.gp);
                 wig_off += st_wig_mode_off(it.nmax, it.nmodes, it.gp);
-                sys_off += st_sys_mode_off(it.nmax, it.nmodes);
+                sys_off += st_sys_mode_off(it.nmax, std::min(it.nmodes, std::max(0, it.nmax - 31)));  // only modes with NM > 32 leave the SM
                 gneed = std::max(gneed, it.g);
                 const int ii = (int)items.size();
                 for (int m = 0; m < it.nmodes; m++) {
@@ -160,7 +160,7 @@ struct StGroup {
                     const int nst = (NM + 31) / 32;
                     for (int sr = 0; sr < nst; sr++)
                         for (int sc = 0; sc < nst; sc++) (m == 0 ? at0 : at1).push_back({mix, (short)sr, (short)sc});
-                    gl[NM <= 16 ? 0 : (NM <= 24 ? 1 : (NM <= 32 ? 2 : (NM <= 56 ? 3 : 4)))].push_back(mix);
+                    if (NM > 32) gl[NM <= 56 ? 3 : 4].push_back(mix);  // smaller modes are solved inside k_st_assemble
                 }
                 for (int kind = 2; kind >= 0; kind--)
                     for (int node0 = 0; node0 < it.g; node0 += 32) rad.push_back({ii, (node0 << 2) | kind});
@@ -223,8 +223,8 @@ struct StGroup {
         k_st_radial<<<((int)rad.size() + 3) / 4, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
         k_st_wigner<<<(int)mitems.size(), 64, 0, st>>>(a, (int)mitems.size());
         launches += 3;
-        if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_OP_DOUBLES * 8, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; }
-        if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_OP_DOUBLES * 8, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; }
+        if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; }
+        if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; }
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
         const int gsm[4] = {16384, 36864, 65536, 200704};
         for (int c = 3; c >= 0; c--)
@@ -351,8 +351,8 @@ static int st_init(hs_ctx *ctx, StShared &S)
     CK(cudaMalloc(&S.d_dd, dd.size() * sizeof(double)));
     CK(cudaMemcpy(S.d_cm, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(S.d_dd, dd.data(), dd.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaFuncSetAttribute(k_st_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_OP_DOUBLES * 8));
-    CK(cudaFuncSetAttribute(k_st_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_OP_DOUBLES * 8));
+    CK(cudaFuncSetAttribute(k_st_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
+    CK(cudaFuncSetAttribute(k_st_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
     CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
     CK(cudaFuncSetAttribute(k_st_mode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ST_SMALL_SLICE * 8));
     CK(cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming));
@@ -388,7 +388,7 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
     if (!ns) return 0;
     if (st_init(ctx, S)) return -1;
     CK(cudaEventRecord(S.ev_in, st));
-    const int ng = std::max(1, std::min(ST_GROUPS, getenv("HYDROTM_GROUPS") ? atoi(getenv("HYDROTM_GROUPS")) : (ns >= 256 ? ST_GROUPS : 1)));
+    const int ng = std::max(1, std::min(ST_GROUPS, getenv("HYDROTM_GROUPS") ? atoi(getenv("HYDROTM_GROUPS")) : (ns >= 2048 ? 4 : (ns >= 256 ? 2 : 1))));
     // deal the particles, heaviest first, round-robin: every group gets the same size mix
     std::vector<int> ord(ns);
     for (int j = 0; j < ns; j++) ord[j] = j;

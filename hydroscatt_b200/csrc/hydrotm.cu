@@ -275,7 +275,7 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
     CK(cudaStreamSynchronize(st));
     // Particles whose predicted order reaches HYDROTM_STAGED_MIN go through the staged pipeline (one kernel per stage,
     // trials and modes as independent work items); the small ones stay on the fused one-particle-per-group kernel.
-    const int staged_min = getenv("HYDROTM_STAGED_MIN") ? atoi(getenv("HYDROTM_STAGED_MIN")) : 9;
+    const int staged_min = getenv("HYDROTM_STAGED_MIN") ? atoi(getenv("HYDROTM_STAGED_MIN")) : 0;
     std::vector<int> st_sel, st_n0;
     if (!ctx->st) ctx->st = new StBufsHolder();
     bool staged_done = false;

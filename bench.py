@@ -279,7 +279,7 @@ def run_gpu(args):
         if world > 1:
             dist.all_gather(gathered, rows)  # every rank ends up with every replica's scatter tables
         obs, _ = tables.integrate_psd(eng, rows, w["n_tab"], w["D"], "gamma", dsd["d0"], dsd["nw"], dsd["mu"], dmax,
-                                      w["lam_tab"], rule="trapz")
+                                      w["lam_tab"], rule="trapz", want_integ=False)
         e[4].record()
         if timed:
             last["e"] = e

@@ -125,6 +125,98 @@ __global__ void k_observables(int n, int stride, const double *in, int ob, int o
     o[14] = Ah - Av;
 }
 
+
+// ---- fused PSD integration + observables ----
+// The observables of compute_scattering_psd_tm (scattering.py:530-587) read 14 of the 56 integrated columns of a table
+// record (8 phase-matrix elements of the back geometry, 4 amplitude components of the forward geometry, the two
+// extinction cross sections; + the 2 scattering cross sections when asked for).  This kernel integrates exactly those
+// over the diameters (same i-ascending sum as k_psd_gemm) for a tile of 64 DSDs x 4 tables at a time and turns them
+// into the 15 observables on the spot, so the [n_dsd][n_tab][56] array (1 GB for the rain sweep) is never written:
+// HBM sees the table records (L2-resident), the weights and the observables.
+// rows: [n_tab][n_D][56] table records (tables.py layout); W: [n_dsd][n_D]; obs: [n_dsd][n_tab][15].
+#define PSDF_RB 64
+#define PSDF_TB 4
+#define PSDF_NC 16
+__constant__ int c_psdf_col[PSDF_NC] = {8, 9, 12, 13, 18, 19, 22, 23, 24, 25, 30, 31, 54, 55, 48, 49};
+
+__global__ void __launch_bounds__(256) k_psd_obs_fused(int n_dsd, int n_D, int n_tab, int tabs_per_cta, const double *__restrict__ W,
+                                                        const double *__restrict__ rows, const double *__restrict__ lam_tab,
+                                                        double kw_sqr, int hpol_quirk, int want_sca, double *__restrict__ obs)
+{
+    extern __shared__ double psm[];
+    const int ldw = n_D | 1;
+    double *sW = psm;                                  // [64][ldw]
+    double *sT = sW + PSDF_RB * ldw;                   // [n_D][64] (4 tables x 16 columns)
+    double *sO = sT + (size_t)n_D * (PSDF_TB * PSDF_NC);  // [64][65] integrated values
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * PSDF_RB;
+    const int t_begin = blockIdx.y * tabs_per_cta, t_end = min(n_tab, t_begin + tabs_per_cta);
+    for (int e = tid; e < PSDF_RB * n_D; e += 256) {
+        const int r = e / n_D, i = e - r * n_D;
+        sW[r * ldw + i] = (r0 + r < n_dsd) ? W[(long)(r0 + r) * n_D + i] : 0.0;
+    }
+    // thread tile: rows {rr, rr + 32}, 8 of the 64 (table, column) slots
+    const int rr = tid & 31, cg = tid >> 5;
+    const double PI = 3.14159265358979323846;
+    for (int t0 = t_begin; t0 < t_end; t0 += PSDF_TB) {
+        __syncthreads();  // previous observables phase has read sO; first pass: sW complete
+        for (int e = tid; e < n_D * (PSDF_TB * PSDF_NC); e += 256) {
+            const int i = e >> 6, sc = e & 63, tt = sc >> 4, c = sc & 15;
+            const int t = t0 + tt;
+            sT[e] = (t < t_end) ? rows[((long)t * n_D + i) * 56 + c_psdf_col[c]] : 0.0;
+        }
+        __syncthreads();
+        double acc[2][8];
+#pragma unroll
+        for (int q = 0; q < 16; q++) acc[q >> 3][q & 7] = 0.0;
+        for (int i = 0; i < n_D; i++) {
+            const double w0 = sW[rr * ldw + i], w1 = sW[(rr + 32) * ldw + i];
+            const double2 *tp = reinterpret_cast<const double2 *>(sT + i * 64 + cg * 8);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double2 tv = tp[q];
+                acc[0][2 * q] += w0 * tv.x; acc[0][2 * q + 1] += w0 * tv.y;
+                acc[1][2 * q] += w1 * tv.x; acc[1][2 * q + 1] += w1 * tv.y;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) { sO[rr * 65 + cg * 8 + q] = acc[0][q]; sO[(rr + 32) * 65 + cg * 8 + q] = acc[1][q]; }
+        __syncthreads();
+        // observables: thread = (row, table)
+        {
+            const int r = tid & 63, tt = tid >> 6, t = t0 + tt;
+            if (r0 + r < n_dsd && t < t_end) {
+                const double *v = sO + r * 65 + tt * 16;
+                const double z0 = v[0], z1 = v[1], z4 = v[2], z5 = v[3], z10 = v[4], z11 = v[5], z14 = v[6], z15 = v[7];
+                const double wl = lam_tab[t];
+                const double xs_h = 2.0 * PI * (z0 - z1 - z4 + z5), xs_v = 2.0 * PI * (z0 + z1 + z4 + z5);
+                const double pref = wl * wl * wl * wl / (PI * PI * PI * PI * PI * kw_sqr);
+                double *o = obs + ((long)(r0 + r) * n_tab + t) * 15;
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                o[0] = want_sca ? 10.0 * log10(v[14] / 1e6) : nan;
+                o[1] = want_sca ? 10.0 * log10(v[15] / 1e6) : nan;
+                o[2] = 10.0 * log10(pref * xs_h);
+                o[3] = 10.0 * log10(pref * xs_v);
+                o[4] = 10.0 * log10(xs_h / xs_v);
+                o[5] = 10.0 * log10((z0 - z1 + z4 - z5) / (z0 - z1 - z4 + z5));
+                o[6] = 10.0 * log10((z0 + z1 - z4 - z5) / (z0 + z1 + z4 + z5));
+                const double a = (z10 + z15) * (z10 + z15) + (z14 - z11) * (z14 - z11);
+                const double b = (z0 - z1 - z4 + z5), c = (z0 + z1 + z4 + z5);
+                o[7] = sqrt(a / (b * c));
+                o[8] = 180.0 / PI * atan2(z11 - z14, -z10 - z15);
+                const double ext_h = v[12], ext_v = hpol_quirk ? v[12] : v[13];
+                o[9] = 10.0 * log10(ext_h / 1e6);
+                o[10] = 10.0 * log10(ext_v / 1e6);
+                o[11] = 1e-3 * (180.0 / PI) * wl * (v[10] - v[8]);
+                const double Ah = 2.0 * 4.343e-3 * ext_h, Av = 2.0 * 4.343e-3 * ext_v;
+                o[12] = Ah;
+                o[13] = Av;
+                o[14] = Ah - Av;
+            }
+        }
+    }
+}
+
 #endif  // HS_HOST_EMU
 
 }  // namespace hs

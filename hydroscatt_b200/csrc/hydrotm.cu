@@ -502,6 +502,29 @@ extern "C" int hs_observables(hs_ctx *ctx, int n, int stride, const double *d_in
     return 0;
 }
 
+
+extern "C" int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double *d_W, const double *d_rows,
+                                  const double *d_lam_tab, double kw_sqr, int hpol_quirk, int want_sca, double *d_obs, void *stream)
+{
+    if (!ctx) return -2;
+    if (n_dsd <= 0 || n_D <= 0 || n_tab <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    const size_t smem = ((size_t)PSDF_RB * (n_D | 1) + (size_t)n_D * PSDF_TB * PSDF_NC + PSDF_RB * 65) * sizeof(double);
+    if (smem > (size_t)ctx->smem_optin) { ctx->err = "hs_psd_observables: too many diameters for one shared-memory tile"; return -3; }
+    CK(cudaFuncSetAttribute(hs::k_psd_obs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int rb = (n_dsd + PSDF_RB - 1) / PSDF_RB;
+    // enough CTAs for two waves of the SMs: split the tables when there are few DSD tiles
+    int splits = std::max(1, std::min((n_tab + PSDF_TB - 1) / PSDF_TB, (2 * ctx->sm_count + rb - 1) / rb));
+    int per = ((n_tab + splits - 1) / splits + PSDF_TB - 1) / PSDF_TB * PSDF_TB;
+    splits = (n_tab + per - 1) / per;
+    dim3 grid(rb, splits);
+    hs::k_psd_obs_fused<<<grid, 256, smem, st>>>(n_dsd, n_D, n_tab, per, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, want_sca, d_obs);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // FP64 FMA peak: 8 independent DFMA chains per thread, enough CTAs to fill every SM.
 __global__ void k_dfma_peak(double *out, int iters)
 {

@@ -154,6 +154,22 @@ class Engine:
             raise EngineError(f"hs_psd_integrate rc={rc}: " + self._err())
         return out
 
+    def psd_observables(self, W, rows, n_tab, lam_tab, kw_sqr=0.93, hpol_quirk=True, want_sca=False):
+        """obs[n_dsd, n_tab, 15] straight from the weights W[n_dsd, n_D] and the table records rows[n_tab*n_D, 56]
+        (fused PSD integration + radar observables; the integrated S/Z array is never written)."""
+        W = W.contiguous()
+        rows = rows.contiguous()
+        nd, nD = W.shape
+        assert rows.shape[0] == n_tab * nD and rows.shape[1] == 56
+        lam_tab = self._dev(lam_tab, n_tab)
+        obs = torch.empty((nd, n_tab, 15), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_psd_observables(self._h, nd, nD, n_tab, _ptr(W), _ptr(rows), _ptr(lam_tab), float(kw_sqr),
+                                             1 if hpol_quirk else 0, 1 if want_sca else 0, _ptr(obs), self._stream())
+        if rc != 0:
+            raise EngineError(f"hs_psd_observables rc={rc}: " + self._err())
+        return obs
+
     def observables(self, rows, off_back, off_forw, off_ext, off_sca, lam, kw_sqr=0.93):
         """[n,15] radar observables from rows [n, stride] (layout: include/hydrotm.h hs_observables)."""
         rows = rows.contiguous()

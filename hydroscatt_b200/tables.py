@@ -56,16 +56,19 @@ def sp_observables(eng, rows, lam, kw_sqr=0.93):
 
 
 def integrate_psd(eng, rows, n_tab, D, kind, p0, p1, p2, dmax, lam_tab, rule="trapz", kw_sqr=0.93,
-                  hpol_quirk=True):
+                  hpol_quirk=True, want_integ=True):
     """PSD-integrate n_tab tables (rows [n_tab*n_D, 56], table-major) over n_dsd size distributions and derive the
     observables of compute_scattering_psd_tm (scattering.py:530-587).
 
-    Returns (obs [n_dsd, n_tab, 15], integ [n_dsd, n_tab, 56]) on the device.
+    Returns (obs [n_dsd, n_tab, 15], integ [n_dsd, n_tab, 56]) on the device.  want_integ=False runs the fused kernel
+    (hs_psd_observables): only the integrals the observables read are formed, on chip, and integ is None.
     """
     D = np.asarray(D, dtype=np.float64)
     n_D = D.size
     wq = trapz_weights(D) if rule == "trapz" else rect_weights(D)
     W = eng.psd_weights(kind, p0, p1, p2, dmax, D, wq)                       # [n_dsd, n_D]
+    if not want_integ:
+        return eng.psd_observables(W, rows, n_tab, lam_tab, kw_sqr, hpol_quirk, want_sca=False), None
     Tt = rows.reshape(n_tab, n_D, ROW).permute(1, 0, 2).reshape(n_D, n_tab * ROW).contiguous()
     integ = eng.psd_integrate(W, Tt)                                          # [n_dsd, n_tab*56]
     n_dsd = integ.shape[0]

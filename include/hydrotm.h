@@ -20,6 +20,7 @@
  *   hs_psd_integrate    PSDIntegrator.get_SZ / get_angular_integrated (trapz over D, row P10) and the
  *                       rectangle-rule sums of scattering.py:312-448 (row S5).
  *   hs_observables      radar.refl/Zdr/ldr/rho_hv/delta_hv/Kdp/Ai (row P12; scattering.py:530-587).
+ *   hs_psd_observables  the two above fused: compute_scattering_psd_tm for every (DSD, table) in one kernel.
  *   hs_tm2l_batch       f_2l_tmatrix.tm2l.tmatrix(2) = hydroscatt/f_2l_tmatrix/tmatrix_py.f:1-473
  *                       (two-layer EBCM, rows F1-F11), called from scattering.py:32-67.
  *
@@ -140,6 +141,16 @@ int hs_psd_weights(hs_ctx *ctx, int kind, int n_dsd, const double *d_p0, const d
 /* PSD integration as an FP64 GEMM: out[n_dsd][ncol] = W[n_dsd][n_D] * Tt[n_D][ncol]. */
 int hs_psd_integrate(hs_ctx *ctx, int n_dsd, int n_D, int ncol, const double *d_W, const double *d_Tt,
                      double *d_out, void *stream);
+
+/*
+ * Fused PSD integration + observables (what compute_scattering_psd_tm, scattering.py:530-587, does one DSD at a time
+ * through PSDIntegrator.get_SZ + radar.*): obs[d][t][15] (columns as hs_observables) for n_dsd weight rows
+ * d_W [n_dsd][n_D] and n_tab tables of records d_rows [n_tab][n_D][56] (layout: hydroscatt_b200/tables.py), without
+ * materialising the integrated [n_dsd][n_tab][56] array.  hpol_quirk != 0: ext_xsect_v := ext_xsect_h (upstream
+ * scatter.ext_xsect ignores h_pol once an angular table exists).  want_sca == 0: sca_xsect columns are NaN.
+ */
+int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double *d_W, const double *d_rows,
+                       const double *d_lam_tab, double kw_sqr, int hpol_quirk, int want_sca, double *d_obs, void *stream);
 
 /*
  * Radar observables per row (radar.refl/Zdr/ldr/rho_hv/delta_hv/Kdp/Ai, scatter.sca_xsect/ext_xsect as combined

@@ -86,6 +86,30 @@ def test_psd_integration_and_observables(engine):
     assert abs(obs[1 - 1 + 1, 2] - obs[1, 2]) == 0.0
 
 
+def test_fused_psd_observables_equal_unfused(engine):
+    """hs_psd_observables (integration + observables in one kernel, nothing but the observables written) against the
+    two-kernel path, several tables, ragged DSD / table counts, both settings of the h_pol quirk."""
+    from hydroscatt_b200 import tables
+    al, be, wt, scale = tables.fixed_orientation_nodes(10.0)
+    ws = [rain_grid(b) for b in ("S", "C", "X", "Ku", "W")]
+    cat = lambda k: np.concatenate([w[k] for w in ws])
+    rows, tb = tables.build_rows(engine, cat("radius"), cat("wavelength"), cat("mr"), cat("mi"), cat("axis_ratio"), GB, GF,
+                                 al, be, wt, scale)
+    D = ws[0]["D"]
+    rng = np.random.default_rng(5)
+    nd = 131
+    d0, nw, mu = rng.uniform(0.3, 3.0, nd), 10 ** rng.uniform(1, 4, nd), rng.integers(-1, 8, nd).astype(float)
+    lam = [w["wavelength"][0] for w in ws]
+    for quirk in (True, False):
+        o1, _ = tables.integrate_psd(engine, rows, len(ws), D, "gamma", d0, nw, mu, np.full(nd, 7.0), lam, hpol_quirk=quirk)
+        o2, none = tables.integrate_psd(engine, rows, len(ws), D, "gamma", d0, nw, mu, np.full(nd, 7.0), lam, hpol_quirk=quirk,
+                                        want_integ=False)
+        assert none is None
+        o1, o2 = o1.cpu().numpy(), o2.cpu().numpy()
+        assert np.isnan(o1[..., :2]).all() and np.isnan(o2[..., :2]).all()
+        assert np.abs(o1[..., 2:] - o2[..., 2:]).max() < 1e-10  # dB / deg / deg km-1
+
+
 def test_shim_end_to_end_on_gpu(engine):
     """pytmatrix shim on the CUDA back-end: the scattering_rain.py PSD flow for a few DSDs vs the oracle back-end."""
     import hydroscatt_b200

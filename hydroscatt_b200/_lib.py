@@ -43,6 +43,7 @@ SIGNATURES = {
     "hs_tm2l_batch": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp,
                                 C.c_void_p]),
     "hs_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "hs_fp64_tensor_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
 }
 
 

@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
             a.res[mi.item].qsca = qsca;
             a.res[mi.item].qext = qext;
         }
-        if (sing) atomicOr(&a.res[mi.item].sing, 1);
+        if (sing) a.res[mi.item].sing = 1;
     }
 }
 
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
             a.res[mi.item].qsca = qsca;
             a.res[mi.item].qext = qext;
         }
-        if (sing) atomicOr(&a.res[mi.item].sing, 1);
+        if (sing) a.res[mi.item].sing = 1;
     }
 }
 
@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
             a.res[mi.item].qsca = qsca;
             a.res[mi.item].qext = qext;
         }
-        if (sings[warp]) atomicOr(&a.res[mi.item].sing, 1);
+        if (sings[warp]) a.res[mi.item].sing = 1;
     }
 }
 

@@ -19,7 +19,7 @@ namespace {
 struct StBufs {
     char *d_lists = nullptr; size_t lists_cap = 0;    // items | mitems | rad tasks | A tasks (m=0) | A tasks | G lists | small list
     char *h_lists = nullptr; size_t h_lists_cap = 0;  // pinned staging of the same
-    hs::StResult *d_res = nullptr, *h_res = nullptr; size_t res_cap = 0;
+    hs::StResult *h_res = nullptr; size_t res_cap = 0;  // pinned + mapped: the stage kernels write their results straight into it
     double *d_tab = nullptr; size_t tab_cap = 0;
     double *d_wig = nullptr; size_t wig_cap = 0;
     double2 *d_sys = nullptr; size_t sys_cap = 0;
@@ -79,6 +79,8 @@ struct StCall {  // arguments of one hs_calctmat_batch call
     size_t scratch_budget;
     int spec;
     bool trace;
+    mutable int nmax_max = 0;        // out: largest converged NMAX among the staged particles
+    mutable bool arena_full = false;  // out: some particle did not fit the caller's arena
 };
 
 struct StGroup {
@@ -182,15 +184,7 @@ struct StGroup {
                      o_g3 = al(o_g2 + gl[2].size() * 4), o_g4 = al(o_g3 + gl[3].size() * 4), o_sm = al(o_g4 + gl[4].size() * 4), o_end = al(o_sm + sm.size() * 4);
         if (st_grow(ctx, &B->d_lists, &B->lists_cap, o_end)) return -1;
         if (st_grow(ctx, &B->h_lists, &B->h_lists_cap, o_end, true)) return -1;
-        if (items.size() > B->res_cap) {
-            if (B->d_res) cudaFree(B->d_res);
-            if (B->h_res) cudaFreeHost(B->h_res);
-            B->d_res = nullptr; B->h_res = nullptr; B->res_cap = 0;
-            const size_t cap2 = items.size() + items.size() / 2;
-            CK(cudaMalloc(&B->d_res, cap2 * sizeof(StResult)));
-            CK(cudaMallocHost(&B->h_res, cap2 * sizeof(StResult)));
-            B->res_cap = cap2;
-        }
+        if (st_grow(ctx, &B->h_res, &B->res_cap, items.size(), true)) return -1;
         if (st_grow(ctx, &B->d_tab, &B->tab_cap, (size_t)tab_off)) return -1;
         if (st_grow(ctx, &B->d_wig, &B->wig_cap, (size_t)wig_off)) return -1;
         if (st_grow(ctx, &B->d_sys, &B->sys_cap, (size_t)std::max<long long>(sys_off, 1))) return -1;
@@ -217,9 +211,9 @@ struct StGroup {
         a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
         a.gx = gx; a.gw = gw; a.cm = S->d_cm; a.dd = S->d_dd;
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
-        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->d_res;
+        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res;
         const int ni = (int)items.size();
-        k_st_reserve<<<(ni + 127) / 128, 128, 0, st>>>((StItem *)(d + o_items), B->d_res, ni, C->d_arena_top, C->arena_cap, C->d_toff);
+        k_st_reserve<<<(ni + 127) / 128, 128, 0, st>>>((StItem *)(d + o_items), B->h_res, ni, C->d_arena_top, C->arena_cap, C->d_toff);
         k_st_radial<<<((int)rad.size() + 3) / 4, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
         k_st_wigner<<<(int)mitems.size(), 64, 0, st>>>(a, (int)mitems.size());
         launches += 3;
@@ -231,7 +225,6 @@ struct StGroup {
             if (!gl[c].empty()) { k_st_solve<128, false><<<(int)gl[c].size(), 128, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; }
         if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, st>>>(a, (const int *)(d + o_sm), (int)sm.size()); launches++; }
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(B->h_res, B->d_res, (size_t)ni * sizeof(StResult), cudaMemcpyDeviceToHost, st));
         inflight = true;
         if (C->trace)
             fprintf(stderr, "[hydrotm-staged] group %d round %d: %d active, K=%d, %d items, %zu mode-items (%zu small), %zu+%zu A tasks, scratch %.1f MB\n",
@@ -367,7 +360,7 @@ static void st_destroy(StShared &S)
 {
     for (int g = 0; g < ST_GROUPS; g++) {
         StBufs &b = S.g[g];
-        cudaFree(b.d_lists); cudaFree(b.d_res); cudaFree(b.d_tab); cudaFree(b.d_wig); cudaFree(b.d_sys); cudaFree(b.d_out);
+        cudaFree(b.d_lists); cudaFree(b.d_tab); cudaFree(b.d_wig); cudaFree(b.d_sys); cudaFree(b.d_out);
         if (b.h_lists) cudaFreeHost(b.h_lists);
         if (b.h_res) cudaFreeHost(b.h_res);
         if (b.h_out) cudaFreeHost(b.h_out);
@@ -414,6 +407,11 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         for (int g = 0; g < ng; g++) th[g] = std::thread([&G, g]() { G[g].run(); });
         for (int g = 0; g < ng; g++) th[g].join();
     }
+    for (int g = 0; g < ng; g++)
+        for (const StP &s : G[g].P) {
+            if (s.done == 1 && s.nmax > C.nmax_max) C.nmax_max = s.nmax;
+            if (s.status == HS_ST_ARENA_FULL) C.arena_full = true;
+        }
     for (int g = 0; g < ng; g++) {
         ctx->launches += G[g].launches;
         if (G[g].rc) return G[g].rc;

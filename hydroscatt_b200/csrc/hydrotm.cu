@@ -266,12 +266,11 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         ctx->items_cap = n;
     }
     // predicted starting NMAX -> initial bucket
-    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, d_nmax, d_ngauss);
+    // (the kernel writes straight into the pinned host block: no D2H copy that could queue behind a caller's bulk transfer)
+    int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n, *h_start = ctx->h_pin + 2 * (size_t)n;
+    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, h_n0, h_start);
     ctx->launches++;
     CK(cudaGetLastError());
-    int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n, *h_start = ctx->h_pin + 2 * (size_t)n;
-    CK(cudaMemcpyAsync(h_n0, d_nmax, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_start, d_ngauss, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     // Particles whose predicted order reaches HYDROTM_STAGED_MIN go through the staged pipeline (one kernel per stage,
     // trials and modes as independent work items); the small ones stay on the fused one-particle-per-group kernel.
@@ -407,11 +406,19 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         const char *nm[8] = {"other", "trial_setup", "assemble m=0", "solve m=0", "mode_setup", "assemble m>=1", "solve m>=1", "write T"};
         for (int i = 0; i < 8; i++) fprintf(stderr, "[hydrotm-prof] %-14s %6.2f%%  %.3e cycles\n", nm[i], 100.0 * hp[i] / tot, (double)hp[i]);
     }
-    // remember the largest converged NMAX (bounds the T stage of the scatter kernel)
-    CK(cudaMemcpyAsync(h_n0, d_nmax, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < n; i++) if (h_n0[i] > ctx->last_nmax_max && h_n0[i] <= HS_NPN1) ctx->last_nmax_max = h_n0[i];
-    return 0;
+    // remember the largest converged NMAX (bounds the T stage of the scatter kernel); the staged pipeline reports its own
+    if (SC.nmax_max > ctx->last_nmax_max) ctx->last_nmax_max = SC.nmax_max;
+    bool arena_full = SC.arena_full;
+    if ((int)st_sel.size() < n) {
+        CK(cudaMemcpyAsync(h_n0, d_nmax, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_st, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < n; i++) {
+            if (h_n0[i] > ctx->last_nmax_max && h_n0[i] <= HS_NPN1) ctx->last_nmax_max = h_n0[i];
+            if (h_st[i] == HS_ST_ARENA_FULL) arena_full = true;
+        }
+    }
+    return arena_full ? HS_RC_ARENA_FULL : 0;
 }
 
 extern "C" int hs_calcampl_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff,
@@ -558,6 +565,54 @@ extern "C" int hs_fp64_peak(hs_ctx *ctx, double *tflops, void *stream)
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    ctx->launches += 5;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *tflops = best;
+    return 0;
+}
+
+
+// FP64 tensor-core (DMMA m8n8k4) peak: 8 independent accumulator pairs per warp.
+__global__ void __launch_bounds__(256) k_dmma_peak(double *out, int iters)
+{
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) hs::st_dmma(c + 2 * i, a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int hs_fp64_tensor_peak(hs_ctx *ctx, double *tflops, void *stream)
+{
+    if (!ctx) return -2;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->sm_count * 4, iters = 20000;
+    double *d_out = nullptr;
+    CK(cudaMalloc(&d_out, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0, st));
+        k_dmma_peak<<<blocks, threads, 0, st>>>(d_out, iters);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        // per warp and iteration: 8 DMMA x (8 x 8 x 4) FMA
+        double fl = 2.0 * 8.0 * 256.0 * (double)iters * (threads / 32) * blocks;
         double tf = fl / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }

@@ -91,11 +91,16 @@ class Engine:
         mi = self._dev(m_im, n)
         eps = self._dev(axis_ratio, n)
         dev = self.device
-        # arena estimate from the starting truncation (converged NMAX is typically NMAX0+1..+4)
-        xev = 2.0 * np.pi * axi / lam
-        n0 = torch.clamp((xev + 4.05 * xev.clamp_min(0) ** 0.333333).nan_to_num(0.0).floor().to(torch.int64), 4, 100)
-        est = tmat_size(torch.clamp(n0 + 5, max=100))
-        cap = int(est.sum().item() * arena_margin) + 1024
+        # Arena estimate from the starting truncation and the |m| x predictor of the converged order; the size found for
+        # a batch of n particles is remembered, so that steady-state calls need no device->host read at all.
+        cap = getattr(self, "_arena_hint", {}).get(n)
+        if cap is None:
+            xev = 2.0 * np.pi * axi / lam
+            n0 = torch.clamp((xev + 4.05 * xev.clamp_min(0) ** 0.333333).nan_to_num(0.0).floor().to(torch.int64), 4, 100)
+            a3 = eps.clamp_min(1e-30) ** (1.0 / 3.0)
+            pred = (torch.sqrt(mr * mr + mi * mi) * xev * torch.maximum(a3, a3 / eps) + 2.0).nan_to_num(0.0).ceil().to(torch.int64)
+            est = tmat_size(torch.clamp(torch.maximum(n0 + 3, torch.minimum(pred, n0 + 12)), max=100))
+            cap = int(est.sum().item() * arena_margin) + 1024
         stream = torch.cuda.current_stream(dev)
         while True:
             arena = torch.empty(2 * cap, dtype=torch.float64, device=dev)
@@ -110,12 +115,15 @@ class Engine:
                     self._h, n, _ptr(axi), _ptr(lam), _ptr(mr), _ptr(mi), _ptr(eps), float(rat), int(shape),
                     float(ddelt), int(ndgs), 1 if rescale_ddelt else 0, _ptr(arena), cap, _ptr(top), _ptr(toff),
                     _ptr(nmax), _ptr(ngauss), _ptr(ntr), _ptr(status), C.c_void_p(stream.cuda_stream))
-            if rc != 0:
-                raise EngineError(f"hs_calctmat_batch rc={rc}: " + self._err())
-            if bool((status == ST_ARENA_FULL).any().item()):
+            if rc == 1:  # HS_RC_ARENA_FULL: the arena counter holds what the batch needs
                 cap = max(2 * cap, int(top.item()) + 1024)
                 continue
+            if rc != 0:
+                raise EngineError(f"hs_calctmat_batch rc={rc}: " + self._err())
             break
+        if not hasattr(self, "_arena_hint"):
+            self._arena_hint = {}
+        self._arena_hint[n] = cap
         return TMatrixBatch(self, n, arena, top, toff, nmax, ngauss, ntr, status, lam)
 
     # ---- PSD integration / observables ---------------------------------------------------------------------
@@ -204,11 +212,11 @@ class Engine:
             raise EngineError(f"hs_tm2l_batch rc={rc}: " + self._err())
         return amp, status
 
-    def fp64_peak(self):
-        """Measured DFMA peak of this device, TFLOP/s."""
+    def fp64_peak(self, tensor=False):
+        """Measured FP64 peak of this device, TFLOP/s: DFMA loop, or (tensor=True) DMMA m8n8k4 loop."""
         v = C.c_double(0.0)
         with torch.cuda.device(self.device):
-            rc = self.lib.hs_fp64_peak(self._h, C.byref(v), self._stream())
+            rc = (self.lib.hs_fp64_tensor_peak if tensor else self.lib.hs_fp64_peak)(self._h, C.byref(v), self._stream())
         if rc != 0:
             raise EngineError(f"hs_fp64_peak rc={rc}: " + self._err())
         return v.value

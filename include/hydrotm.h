@@ -42,6 +42,7 @@ extern "C" {
 #define HS_NPNG1 500  /* NGAUSS limit (upstream NPNG1) */
 
 /* per-particle status codes */
+#define HS_RC_ARENA_FULL 1  /* return value of hs_calctmat_batch: some particles have HS_ST_ARENA_FULL; *d_arena_top = entries needed */
 #define HS_ST_OK 0
 #define HS_ST_NMAX_LIMIT 1    /* NMAX reached HS_NPN1 without convergence (upstream: print + STOP) */
 #define HS_ST_NGAUSS_LIMIT 2  /* NGAUSS reached HS_NPNG1 (upstream: warning, continues) */
@@ -180,6 +181,8 @@ int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const double *d_dco
 
 /* Measured FP64 FMA peak of the device (dependent-chain-free DFMA loop), TFLOP/s; used as roofline denominator. */
 int hs_fp64_peak(hs_ctx *ctx, double *tflops, void *stream);
+/* Measured FP64 tensor-core peak (DMMA m8n8k4, the instruction the Q / RgQ assembly runs on), TFLOP/s. */
+int hs_fp64_tensor_peak(hs_ctx *ctx, double *tflops, void *stream);
 
 #ifdef __cplusplus
 }

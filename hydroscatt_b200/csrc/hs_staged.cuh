@@ -27,14 +27,16 @@ struct StItem {
     long long sys_off;         // complex: per mode [2][NM][2 NM]
     long long t_off;           // complex offset of the packed T in the caller's arena (set on the device), -1 = none
 };
-struct StModeItem { int item, m; };
+struct StModeItem { int item, m; };          // travels packed in one int: (m << 24) | item
+__host__ __device__ inline int st_pack_mode(int item, int m) { return (m << 24) | item; }
+__host__ __device__ inline StModeItem st_unpack_mode(int pm) { StModeItem r; r.item = pm & 0xFFFFFF; r.m = pm >> 24; return r; }
 struct StRadTask { int item, kn; };        // kn = node0 << 2 | kind (0 = j + node arrays, 1 = y, 2 = j of the complex argument)
-struct StATask { int mi; short sr, sc; };  // mode-item, 32-wide row range, 32-wide column range of k = n - nmin
+struct StATask { int mi; short sr, sc; };  // packed (item, mode), 32-wide row range, 32-wide column range of k = n - nmin
 struct StResult { double qsca, qext; long long t_off; int sing, pad; };
 
 struct StArgs {
     const StItem *items;
-    const StModeItem *mitems;
+    const int *modes;        // every (item, mode) of the round, packed (k_st_wigner's work list)
     const double *axi, *lam, *mr, *mi, *eps;
     double rat;
     const double *gx, *gw;   // Gauss table (see TmArgs)
@@ -193,6 +195,22 @@ __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *ta
     const StItem it = a.items[t.item];
     const int kind = t.kn & 3, i = (t.kn >> 2) + (threadIdx.x & 31);
     const int g = it.g, nmax = it.nmax, gp = it.gp;
+    if (t.kn == 2 && (threadIdx.x & 31) == 0) {
+        // first task of the item: clear its result record and, for a final item, reserve the packed T in the caller's arena
+        // (same bump allocator as the fused kernel; a retried final trial keeps its slot)
+        long long o = -1;
+        if (it.nmodes > 1) {
+            o = it.t_off;
+            if (o < 0) {
+                const unsigned long long sz = (unsigned long long)tmat_size(nmax);
+                const unsigned long long off = atomicAdd(a.arena_top, sz);
+                o = (off + sz > (unsigned long long)a.arena_cap) ? -2 : (long long)off;
+            }
+        }
+        const_cast<StItem *>(a.items)[t.item].t_off = o;
+        a.res[t.item].t_off = o;
+        a.res[t.item].sing = 0;
+    }
     if (i >= g) return;
     const double PI = 3.14159265358979323846;
     const int p = it.p;
@@ -246,7 +264,7 @@ __global__ void __launch_bounds__(64) k_st_wigner(StArgs a, int n_mi)
 {
     __shared__ double sq[HS_NPN1 + 2], rsq[HS_NPN1 + 2];
     if ((int)blockIdx.x >= n_mi) return;
-    const StModeItem mi = a.mitems[blockIdx.x];
+    const StModeItem mi = st_unpack_mode(a.modes[blockIdx.x]);
     const StItem it = a.items[mi.item];
     const int m = mi.m, nmax = it.nmax, g = it.g, gp = it.gp;
     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
@@ -432,7 +450,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     extern __shared__ __align__(16) double op[];
     if ((int)blockIdx.x >= ntasks) return;
     const StATask tk = tasks[blockIdx.x];
-    const StModeItem mi = a.mitems[tk.mi];
+    const StModeItem mi = st_unpack_mode(tk.mi);
     const StItem it = a.items[mi.item];
     const int m = M0 ? 0 : mi.m;
     const int nmax = it.nmax, g = it.g, gp = it.gp;
@@ -682,7 +700,7 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
     __shared__ int sing;
     if ((int)blockIdx.x >= n) return;
     const int mix = mlist[blockIdx.x];
-    const StModeItem mi = a.mitems[mix];
+    const StModeItem mi = st_unpack_mode(mix);
     const StItem it = a.items[mi.item];
     const int m = mi.m, nmax = it.nmax;
     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1, ldc = 2 * NM;
@@ -767,13 +785,12 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
 {
     extern __shared__ __align__(16) double smraw[];
     __shared__ SysDesc sds[8][4];
-    __shared__ SolveCtl scs[8];
     __shared__ int sings[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wi = blockIdx.x * 8 + warp;
     if (wi >= n) return;
     double *op = smraw + warp * ST_SMALL_SLICE;
-    const StModeItem mi = a.mitems[mlist[wi]];
+    const StModeItem mi = st_unpack_mode(mlist[wi]);
     const StItem it = a.items[mi.item];
     const int m = mi.m, nmax = it.nmax, g = it.g, gp = it.gp;
     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
@@ -956,23 +973,6 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
         }
         if (sings[warp]) a.res[mi.item].sing = 1;
     }
-}
-
-// final items: reserve the packed T in the caller's arena (same bump allocator as the fused kernel)
-__global__ void k_st_reserve(StItem *items, StResult *res, int n_items, unsigned long long *arena_top, long long arena_cap,
-                             long long *toff)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_items) return;
-    res[i].sing = 0;
-    res[i].t_off = -1;
-    if (items[i].nmodes <= 1) { items[i].t_off = -1; return; }
-    if (items[i].t_off >= 0) { res[i].t_off = items[i].t_off; return; }  // retry of a final trial: keep the slot
-    const unsigned long long sz = (unsigned long long)tmat_size(items[i].nmax);
-    const unsigned long long off = atomicAdd(arena_top, sz);
-    long long o = (off + sz > (unsigned long long)arena_cap) ? -2 : (long long)off;
-    items[i].t_off = o;
-    res[i].t_off = o;
 }
 
 #endif  // HS_HOST_EMU

@@ -91,7 +91,7 @@ struct StGroup {
     int id = 0;
     std::vector<StP> P;
     std::vector<hs::StItem> items;
-    std::vector<hs::StModeItem> mitems;
+    std::vector<int> mitems;  // packed (item, mode)
     std::vector<hs::StRadTask> rad;
     std::vector<hs::StATask> at0, at1;
     std::vector<int> gl[5], sm;
@@ -155,8 +155,8 @@ struct StGroup {
                 gneed = std::max(gneed, it.g);
                 const int ii = (int)items.size();
                 for (int m = 0; m < it.nmodes; m++) {
-                    const int mix = (int)mitems.size();
-                    mitems.push_back({ii, m});
+                    const int mix = st_pack_mode(ii, m);
+                    mitems.push_back(mix);
                     const int NM = it.nmax - (m > 1 ? m : 1) + 1;
                     if (NM <= ST_SMALL_NM) { sm.push_back(mix); continue; }
                     const int nst = (NM + 31) / 32;
@@ -178,7 +178,7 @@ struct StGroup {
         const double *gx, *gw;
         { std::lock_guard<std::mutex> lk(ctx->mu); gx = ctx->d_gx; gw = ctx->d_gw; }
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-        const size_t o_items = 0, o_mi = al(o_items + items.size() * sizeof(StItem)), o_rad = al(o_mi + mitems.size() * sizeof(StModeItem)),
+        const size_t o_items = 0, o_mi = al(o_items + items.size() * sizeof(StItem)), o_rad = al(o_mi + mitems.size() * sizeof(int)),
                      o_a0 = al(o_rad + rad.size() * sizeof(StRadTask)), o_a1 = al(o_a0 + at0.size() * sizeof(StATask)),
                      o_g0 = al(o_a1 + at1.size() * sizeof(StATask)), o_g1 = al(o_g0 + gl[0].size() * 4), o_g2 = al(o_g1 + gl[1].size() * 4),
                      o_g3 = al(o_g2 + gl[2].size() * 4), o_g4 = al(o_g3 + gl[3].size() * 4), o_sm = al(o_g4 + gl[4].size() * 4), o_end = al(o_sm + sm.size() * 4);
@@ -190,7 +190,7 @@ struct StGroup {
         if (st_grow(ctx, &B->d_sys, &B->sys_cap, (size_t)std::max<long long>(sys_off, 1))) return -1;
         char *h = B->h_lists, *d = B->d_lists;
         memcpy(h + o_items, items.data(), items.size() * sizeof(StItem));
-        memcpy(h + o_mi, mitems.data(), mitems.size() * sizeof(StModeItem));
+        memcpy(h + o_mi, mitems.data(), mitems.size() * sizeof(int));
         memcpy(h + o_rad, rad.data(), rad.size() * sizeof(StRadTask));
         memcpy(h + o_a0, at0.data(), at0.size() * sizeof(StATask));
         memcpy(h + o_a1, at1.data(), at1.size() * sizeof(StATask));
@@ -199,24 +199,23 @@ struct StGroup {
             // heaviest systems first (counting sort on NM), written straight into the staging buffer
             const std::vector<int> &L = c < 5 ? gl[c] : sm;
             int cnt[HS_NPN1 + 2] = {0};
-            for (int x : L) cnt[items[mitems[x].item].nmax - std::max(mitems[x].m, 1) + 1]++;
+            for (int x : L) cnt[items[x & 0xFFFFFF].nmax - std::max(x >> 24, 1) + 1]++;
             int acc = 0;
             for (int v = HS_NPN1; v >= 0; v--) { int q = cnt[v]; cnt[v] = acc; acc += q; }
             int *dst = (int *)(h + og[c]);
-            for (int x : L) dst[cnt[items[mitems[x].item].nmax - std::max(mitems[x].m, 1) + 1]++] = x;
+            for (int x : L) dst[cnt[items[x & 0xFFFFFF].nmax - std::max(x >> 24, 1) + 1]++] = x;
         }
         CK(cudaMemcpyAsync(d, h, o_end, cudaMemcpyHostToDevice, st));
         StArgs a;
-        a.items = (const StItem *)(d + o_items); a.mitems = (const StModeItem *)(d + o_mi);
+        a.items = (const StItem *)(d + o_items); a.modes = (const int *)(d + o_mi);
         a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
         a.gx = gx; a.gw = gw; a.cm = S->d_cm; a.dd = S->d_dd;
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
         a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res;
         const int ni = (int)items.size();
-        k_st_reserve<<<(ni + 127) / 128, 128, 0, st>>>((StItem *)(d + o_items), B->h_res, ni, C->d_arena_top, C->arena_cap, C->d_toff);
         k_st_radial<<<((int)rad.size() + 3) / 4, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
         k_st_wigner<<<(int)mitems.size(), 64, 0, st>>>(a, (int)mitems.size());
-        launches += 3;
+        launches += 2;
         if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; }
         if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; }
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }

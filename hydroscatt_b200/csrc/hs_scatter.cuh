@@ -41,6 +41,9 @@ struct ScArgs {
     double *S, *Z;          // [n][n_geom][8], [n][n_geom][16]
     double *xs;             // [n][n_inc][2] or null
     int nmax_bound;         // upper bound of nmax over the batch (sizes the shared-memory T stage)
+    const int *order;       // CTA -> particle, heaviest (largest NMAX) first, or null
+    const double *frames;   // [n_inc][max blocks][n_orient][SC_FR]: particle-frame directions + polarisation rotations (k_scatter_frames)
+    int frame_blocks;       // geometry blocks per incident direction in `frames`
 };
 
 // Wigner pi_n = d/sin, tau_n = dd/dtheta generated in lock-step with n (VIGAMPL as a recurrence)
@@ -313,13 +316,46 @@ struct WigTab {
     }
 };
 
+#define SC_FR (6 + 6 * SCK_G)
+// frames[(d, block, o)]: ctp0, phip0, R (2x2) of the incident direction, then per scattered direction of the block
+// cos(theta'), phi' - phi0', R1 = inverse polarisation rotation (what the orientation threads of k_scatter used to set up
+// for every particle although it only depends on (orientation, geometry))
+__global__ void k_scatter_frames(ScArgs a, double *frames)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = blockIdx.y, b = blockIdx.z;
+    if (o >= a.n_orient) return;
+    const int gb = a.g_begin[d] + b * SCK_G, gend = a.g_begin[d + 1];
+    const int ng = max(0, min(SCK_G, gend - gb));
+    const double pin = 3.14159265358979323846, pin2 = pin * 0.5, rad = pin / 180.0, eps = 1e-7;
+    double alph = a.alpha[o] * rad, bet = a.beta[o] * rad;
+    if (bet <= pin2 && pin2 - bet <= eps) bet -= eps;
+    if (bet > pin2 && bet - pin2 <= eps) bet += eps;
+    double ctp0, phip0, R[2][2];
+    frame(a.inc[2 * d], a.inc[2 * d + 1], alph, bet, ctp0, phip0, R);
+    double *fr = frames + (((long)d * a.frame_blocks + b) * a.n_orient + o) * SC_FR;
+    fr[0] = ctp0; fr[1] = phip0; fr[2] = R[0][0]; fr[3] = R[0][1]; fr[4] = R[1][0]; fr[5] = R[1][1];
+    for (int g = 0; g < SCK_G; g++) {
+        double *fg = fr + 6 + 6 * g;
+        if (g < ng) {
+            double ph, ct, Rg[2][2];
+            frame(a.gsc[2 * (gb + g)], a.gsc[2 * (gb + g) + 1], alph, bet, ct, ph, Rg);
+            const double dd = 1.0 / (Rg[0][0] * Rg[1][1] - Rg[0][1] * Rg[1][0]);
+            fg[0] = ct; fg[1] = ph - phip0;
+            fg[2] = Rg[1][1] * dd; fg[3] = -Rg[0][1] * dd; fg[4] = -Rg[1][0] * dd; fg[5] = Rg[0][0] * dd;
+        } else {
+            for (int k = 0; k < 6; k++) fg[k] = 0.0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     __shared__ double s_fn[HS_NPN1 + 2], s_cm[HS_NPN1 + 2], s_rn1[HS_NPN1 + 2], s_r2n1[HS_NPN1 + 2];
     __shared__ double s_sq[HS_NPN1 + 3], s_rsq[HS_NPN1 + 3];
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int p = blockIdx.x;
+    const int p = a.order ? a.order[blockIdx.x] : blockIdx.x;
     const bool bad = (a.status[p] != HS_ST_OK && a.status[p] != HS_ST_NGAUSS_LIMIT && a.status[p] != HS_ST_SINGULAR) || a.toff[p] < 0;
     if (bad) {
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -346,7 +382,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
     const int stride = SCK_G * 24 + 3;
     double *srow = sm + 4L * a.nmax_bound * a.nmax_bound;
     double *accs = srow + (long)nt * stride;
-    const double pin = 3.14159265358979323846, pin2 = pin * 0.5, rad = pin / 180.0, eps = 1e-7;
+    const double pin = 3.14159265358979323846;
 
     for (int d = 0; d < a.n_inc; d++) {
         const int gend = a.g_begin[d + 1];
@@ -363,22 +399,18 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                 double acc[SCK_G][8];
                 double acc_t = 0.0, acc_p = 0.0;
                 if (active) {
-                    double alph = a.alpha[o] * rad, bet = a.beta[o] * rad;
-                    if (bet <= pin2 && pin2 - bet <= eps) bet -= eps;
-                    if (bet > pin2 && bet - pin2 <= eps) bet += eps;
-                    double ctp0, phip0;
-                    frame(a.inc[2 * d], a.inc[2 * d + 1], alph, bet, ctp0, phip0, R);
-                    w0.setup(ctp0);
+                    // orientation / geometry quantities do not depend on the particle: read them from the table built
+                    // once per call by k_scatter_frames (AMPL's angle nudges and Euler rotations)
+                    const double *fr = a.frames + (((long)d * a.frame_blocks + (gb - a.g_begin[d]) / SCK_G) * a.n_orient + o) * SC_FR;
+                    R[0][0] = fr[2]; R[0][1] = fr[3]; R[1][0] = fr[4]; R[1][1] = fr[5];
+                    w0.setup(fr[0]);
 #pragma unroll
                     for (int g = 0; g < SCK_G; g++) {
                         if (g < ng) {
-                            double ph, ct, Rg[2][2];
-                            frame(a.gsc[2 * (gb + g)], a.gsc[2 * (gb + g) + 1], alph, bet, ct, ph, Rg);
-                            dphi[g] = ph - phip0;
-                            ws[g].setup(ct);
-                            double dd = 1.0 / (Rg[0][0] * Rg[1][1] - Rg[0][1] * Rg[1][0]);
-                            R1[g][0][0] = Rg[1][1] * dd; R1[g][0][1] = -Rg[0][1] * dd;
-                            R1[g][1][0] = -Rg[1][0] * dd; R1[g][1][1] = Rg[0][0] * dd;
+                            const double *fg = fr + 6 + 6 * g;
+                            dphi[g] = fg[1];
+                            ws[g].setup(fg[0]);
+                            R1[g][0][0] = fg[2]; R1[g][0][1] = fg[3]; R1[g][1][0] = fg[4]; R1[g][1][1] = fg[5];
                         }
 #pragma unroll
                         for (int k = 0; k < 8; k++) acc[g][k] = 0.0;
@@ -536,6 +568,30 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
             __syncthreads();
             if (gb + SCK_G >= gend) break;
         }
+    }
+}
+// CTA -> particle map with the largest NMAX first (one block; counting sort on NMAX): the heavy particles start first
+// instead of forming the tail of the launch.
+__global__ void __launch_bounds__(1024) k_order_by_nmax(int n, const int *nmax, const int *status, int *order)
+{
+    __shared__ int cnt[HS_NPN1 + 2];
+    for (int t = threadIdx.x; t < HS_NPN1 + 2; t += blockDim.x) cnt[t] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int v = nmax[i];
+        v = (status[i] == HS_ST_OK && v > 0 && v <= HS_NPN1) ? v : 0;
+        atomicAdd(&cnt[v], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int v = HS_NPN1; v >= 0; v--) { int c = cnt[v]; cnt[v] = acc; acc += c; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int v = nmax[i];
+        v = (status[i] == HS_ST_OK && v > 0 && v <= HS_NPN1) ? v : 0;
+        order[atomicAdd(&cnt[v], 1)] = i;
     }
 }
 #endif

@@ -189,13 +189,15 @@ __device__ __forceinline__ double st_r_of_node(double xp, double aa, double ee)
 
 __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *tasks, int ntasks)
 {
-    const int wt = blockIdx.x * 4 + (threadIdx.x >> 5);
+    // one half-warp per task of 16 nodes (most trial items have 10..16 nodes); the host orders the tasks kind-major, so
+    // the two halves of a warp run the same recurrence on items of similar size
+    const int wt = blockIdx.x * 8 + (threadIdx.x >> 4);
     if (wt >= ntasks) return;
     const StRadTask t = tasks[wt];
     const StItem it = a.items[t.item];
-    const int kind = t.kn & 3, i = (t.kn >> 2) + (threadIdx.x & 31);
+    const int kind = t.kn & 3, i = (t.kn >> 2) + (threadIdx.x & 15);
     const int g = it.g, nmax = it.nmax, gp = it.gp;
-    if (t.kn == 2 && (threadIdx.x & 31) == 0) {
+    if (t.kn == 2 && (threadIdx.x & 15) == 0) {
         // first task of the item: clear its result record and, for a final item, reserve the packed T in the caller's arena
         // (same bump allocator as the fused kernel; a retried final trial keeps its slot)
         long long o = -1;
@@ -260,27 +262,31 @@ __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *ta
 }
 
 // ---- W: Wigner functions of one (item, mode); rows k = n - nmin, n-major ----
-__global__ void __launch_bounds__(64) k_st_wigner(StArgs a, int n_mi)
+__global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
 {
-    __shared__ double sq[HS_NPN1 + 2], rsq[HS_NPN1 + 2];
-    if ((int)blockIdx.x >= n_mi) return;
-    const StModeItem mi = st_unpack_mode(a.modes[blockIdx.x]);
+    // one half-warp per (item, mode): most modes have 10..16 nodes; larger ones loop over node chunks
+    __shared__ double sq_[8][HS_NPN1 + 2], rsq_[8][HS_NPN1 + 2];
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    const int idx = blockIdx.x * 8 + hw;
+    const bool live = idx < n_mi;
+    const StModeItem mi = st_unpack_mode(live ? a.modes[idx] : 0);
     const StItem it = a.items[mi.item];
-    const int m = mi.m, nmax = it.nmax, g = it.g, gp = it.gp;
+    const int m = live ? mi.m : 0, nmax = it.nmax, g = live ? it.g : 0, gp = it.gp;
     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
     double *d1 = a.wig + it.wig_off + st_wig_mode_off(nmax, m, gp);
     double *d2 = d1 + (long)NM * gp;
     const long goff = (long)g * (g - 1) / 2;
-    if (m > 0) {
+    double *sq = sq_[hw], *rsq = rsq_[hw];
+    if (live && m > 0) {
         const double qmm = (double)m * (double)m;
-        for (int n = m + threadIdx.x; n <= nmax + 1; n += blockDim.x) {
+        for (int n = m + l16; n <= nmax + 1; n += 16) {
             const double v = sqrt((double)n * (double)n - qmm);
             sq[n] = v;
             rsq[n] = (n > m) ? 1.0 / v : 0.0;
         }
-        __syncthreads();
     }
-    for (int i = threadIdx.x; i < g; i += blockDim.x) {
+    __syncwarp();
+    for (int i = l16; i < g; i += 16) {
         const double x = a.gx[goff + g - 1 - i];
         const double qs = sqrt(1.0 - x * x), qs1 = 1.0 / qs;
         if (m == 0) {
@@ -365,7 +371,7 @@ __device__ __forceinline__ void solve_sub(const SysDesc d, int gl, int gw, int k
 }
 
 
-// The same elimination by a group of `nl` lanes (64 or 128 = 2 or 4 whole warps): two adjacent lanes share a column
+// The same elimination by a group of `nl` lanes (64 or 128 = 2 or 4 whole warps): two lanes of a warp share a column
 // (even / odd rows), so a step is n / 2 row updates per lane; one named barrier per step; the two lanes that own
 // column k + 1 publish the next pivot through shared memory.
 __device__ __forceinline__ void solve_grp(const SysDesc d, int t, int nl, int barid, unsigned long long *keyslot, int *sing)
@@ -374,7 +380,9 @@ __device__ __forceinline__ void solve_grp(const SysDesc d, int t, int nl, int ba
     const long rstep = (long)d.stride * d.ld, row0 = (long)d.off * d.ld;
     auto colof = [&](int j) -> long { return (j < n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - n)); };
     double2 *b0 = d.base + row0;
-    const int ct = t >> 1, rs = t & 1, ncl = nl >> 1;
+    // within a warp: lanes 0-15 take the even rows of 16 consecutive columns, lanes 16-31 the odd rows of the same columns
+    // (each half-warp access is one contiguous 256-byte run: no bank conflicts whatever the row stride)
+    const int ct = (t & 15) | ((t >> 5) << 4), rs = (t >> 4) & 1, ncl = nl >> 1;
     if (t < 32) {
         unsigned long long key = 0ull;
         const double2 *c0 = b0 + colof(0);
@@ -419,7 +427,7 @@ __device__ __forceinline__ void solve_grp(const SysDesc d, int t, int nl, int ba
             }
         }
         if (t < 32) {
-            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, nkey, 1);
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, nkey, 16);
             nkey = ok > nkey ? ok : nkey;
             if (t == 0) keyslot[(k + 1) & 1] = nkey;
         }

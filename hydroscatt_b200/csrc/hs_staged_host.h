@@ -101,6 +101,17 @@ struct StGroup {
     double t_plan = 0, t_wait = 0, t_ctl = 0;
     long long launches = 0;
     int rc = 0;
+    struct TL { cudaEvent_t ev; const char *what; int round; double host_ms; };
+    std::vector<TL> tl;  // HYDROTM_TIMELINE=1: an event after every launch
+    bool timeline = false;
+    std::chrono::steady_clock::time_point t_base;
+    void mark(const char *what)
+    {
+        if (!timeline) return;
+        TL e; e.what = what; e.round = nround;
+        e.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_base).count();
+        cudaEventCreate(&e.ev); cudaEventRecord(e.ev, B->stream); tl.push_back(e);
+    }
 
     bool active() const
     {
@@ -164,13 +175,15 @@ struct StGroup {
                         for (int sc = 0; sc < nst; sc++) (m == 0 ? at0 : at1).push_back({mix, (short)sr, (short)sc});
                     if (NM > 32) gl[NM <= 56 ? 3 : 4].push_back(mix);  // smaller modes are solved inside k_st_assemble
                 }
-                for (int kind = 2; kind >= 0; kind--)
-                    for (int node0 = 0; node0 < it.g; node0 += 32) rad.push_back({ii, (node0 << 2) | kind});
                 items.push_back(it);
                 s.n_items++;
             }
         }
         if (items.empty()) return 0;
+        // radial tasks of 16 nodes, kind-major (the complex-argument recurrence, the longest, first)
+        for (int kind = 2; kind >= 0; kind--)
+            for (int ii = 0; ii < (int)items.size(); ii++)
+                for (int node0 = 0; node0 < items[ii].g; node0 += 16) rad.push_back({ii, (node0 << 2) | kind});
         if (gneed > ctx->gmax) {
             std::lock_guard<std::mutex> lk(ctx->mu);
             if (ensure_gauss(ctx, std::max(gneed, 64))) return -1;
@@ -205,7 +218,9 @@ struct StGroup {
             int *dst = (int *)(h + og[c]);
             for (int x : L) dst[cnt[items[x & 0xFFFFFF].nmax - std::max(x >> 24, 1) + 1]++] = x;
         }
+        mark("begin");
         CK(cudaMemcpyAsync(d, h, o_end, cudaMemcpyHostToDevice, st));
+        mark("h2d");
         StArgs a;
         a.items = (const StItem *)(d + o_items); a.modes = (const int *)(d + o_mi);
         a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
@@ -213,16 +228,18 @@ struct StGroup {
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
         a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res;
         const int ni = (int)items.size();
-        k_st_radial<<<((int)rad.size() + 3) / 4, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
-        k_st_wigner<<<(int)mitems.size(), 64, 0, st>>>(a, (int)mitems.size());
+        k_st_radial<<<((int)rad.size() + 7) / 8, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
+        mark("radial");
+        k_st_wigner<<<((int)mitems.size() + 7) / 8, 128, 0, st>>>(a, (int)mitems.size());
+        mark("wigner");
         launches += 2;
-        if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; }
-        if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; }
+        if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; mark("asm m>=1"); }
+        if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; mark("asm m=0"); }
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
         const int gsm[4] = {16384, 36864, 65536, 200704};
         for (int c = 3; c >= 0; c--)
             if (!gl[c].empty()) { k_st_solve<128, false><<<(int)gl[c].size(), 128, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; }
-        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, st>>>(a, (const int *)(d + o_sm), (int)sm.size()); launches++; }
+        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, st>>>(a, (const int *)(d + o_sm), (int)sm.size()); launches++; mark("small"); }
         CK(cudaGetLastError());
         inflight = true;
         if (C->trace)
@@ -241,6 +258,7 @@ struct StGroup {
         auto T0 = std::chrono::steady_clock::now();
         CK(cudaStreamSynchronize(B->stream));
         auto T1 = std::chrono::steady_clock::now();
+        if (timeline) { TL e; e.ev = nullptr; e.what = "host: synced"; e.round = nround; e.host_ms = std::chrono::duration<double, std::milli>(T1 - t_base).count(); tl.push_back(e); }
         inflight = false;
         const double ddelt = C->ddelt;
         for (int j : order) {
@@ -347,7 +365,7 @@ static int st_init(hs_ctx *ctx, StShared &S)
     CK(cudaFuncSetAttribute(k_st_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
     CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
     CK(cudaFuncSetAttribute(k_st_mode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ST_SMALL_SLICE * 8));
-    CK(cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming));
+    CK(cudaEventCreate(&S.ev_in));
     for (int g = 0; g < ST_GROUPS; g++) {
         CK(cudaStreamCreateWithFlags(&S.g[g].stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&S.g[g].ev, cudaEventDisableTiming));
@@ -400,6 +418,8 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         G[r % ng].P.push_back(s);
     }
     auto T0 = std::chrono::steady_clock::now();
+    const bool timeline = getenv("HYDROTM_TIMELINE") != nullptr;
+    for (int g = 0; g < ng; g++) { G[g].timeline = timeline; G[g].t_base = T0; }
     if (ng == 1) G[0].run();
     else {
         std::thread th[ST_GROUPS];
@@ -416,6 +436,15 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         if (G[g].rc) return G[g].rc;
         CK(cudaEventRecord(S.g[g].ev, S.g[g].stream));
         CK(cudaStreamWaitEvent(st, S.g[g].ev, 0));
+    }
+    if (timeline) {
+        cudaDeviceSynchronize();
+        for (int g = 0; g < ng; g++)
+            for (auto &e : G[g].tl) {
+                float ms = -1.f;
+                if (e.ev) { cudaEventElapsedTime(&ms, S.ev_in, e.ev); cudaEventDestroy(e.ev); }
+                fprintf(stderr, "[timeline] g%d r%d %-12s host %7.3f ms  gpu-done %7.3f ms\n", g, e.round, e.what, e.host_ms, ms);
+            }
     }
     if (C.trace) {
         double tot = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();

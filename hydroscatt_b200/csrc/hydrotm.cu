@@ -41,6 +41,10 @@ struct hs_ctx {
     cudaStream_t bstream[8] = {};  // one stream per size bucket
     cudaEvent_t ev_start = nullptr, ev_done[8] = {};
     double *d_sc = nullptr;      // scatter geometry tables (device)
+    double *d_frames = nullptr;  // scatter kernel: per (orientation, geometry) frames
+    size_t frames_cap = 0;
+    int *d_order = nullptr;      // scatter kernel: CTA -> particle map, heaviest first
+    int order_cap = 0;
     double *d_xs_tmp = nullptr;
     size_t xs_tmp_cap = 0;
     long long *d_prof = nullptr; // phase-cycle counters (HYDROTM_PROF=1)
@@ -122,7 +126,7 @@ extern "C" void hs_ctx_destroy(hs_ctx *ctx)
 {
     if (!ctx) return;
     cudaFree(ctx->d_gx); cudaFree(ctx->d_gw); cudaFree(ctx->d_queue); cudaFree(ctx->d_items);
-    cudaFree(ctx->d_ws_global); cudaFree(ctx->d_ws_fb); cudaFree(ctx->d_sc); cudaFree(ctx->d_xs_tmp);
+    cudaFree(ctx->d_ws_global); cudaFree(ctx->d_ws_fb); cudaFree(ctx->d_sc); cudaFree(ctx->d_xs_tmp); cudaFree(ctx->d_order); cudaFree(ctx->d_frames);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int b = 0; b < 8; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -718,6 +722,33 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
     a.n_inc = n_inc; a.inc = dblk; a.g_begin = dib; a.gsc = dblk + 128; a.g_out = dib + 65; a.n_geom = n_geom;
     a.n_orient = n_orient; a.alpha = d_alpha; a.beta = d_beta; a.weight = d_weight; a.scale = scale;
     a.S = d_S; a.Z = d_Z; a.xs = xs_inc;
+    {   // orientation / geometry frames: once per call instead of once per particle
+        int maxblk = 1;
+        for (int d = 0; d < n_inc; d++) maxblk = std::max(maxblk, (g_begin[d + 1] - g_begin[d] + SCK_G - 1) / SCK_G);
+        size_t need = (size_t)n_inc * maxblk * n_orient * SC_FR;
+        if (need > ctx->frames_cap) {
+            if (ctx->d_frames) cudaFree(ctx->d_frames);
+            ctx->d_frames = nullptr; ctx->frames_cap = 0;
+            CK(cudaMalloc(&ctx->d_frames, need * sizeof(double)));
+            ctx->frames_cap = need;
+        }
+        a.frames = ctx->d_frames; a.frame_blocks = maxblk;
+        dim3 fg((n_orient + 63) / 64, n_inc, maxblk);
+        hs::k_scatter_frames<<<fg, 64, 0, st>>>(a, ctx->d_frames);
+        ctx->launches++;
+    }
+    a.order = nullptr;
+    if (n >= 1024) {
+        if (n > ctx->order_cap) {
+            if (ctx->d_order) cudaFree(ctx->d_order);
+            ctx->d_order = nullptr; ctx->order_cap = 0;
+            CK(cudaMalloc(&ctx->d_order, (size_t)n * sizeof(int)));
+            ctx->order_cap = n;
+        }
+        hs::k_order_by_nmax<<<1, 1024, 0, st>>>(n, d_nmax, d_status, ctx->d_order);
+        ctx->launches++;
+        a.order = ctx->d_order;
+    }
     // one thread per orientation (up to 64 per pass); dynamic smem = T stage sized for the largest converged NMAX the
     // context has produced (2*nmax^2 complex) + the per-orientation reduction rows
     int threads = std::min(64, std::max(32, (n_orient + 31) / 32 * 32));

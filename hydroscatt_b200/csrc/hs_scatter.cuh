@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
 }
 // CTA -> particle map with the largest NMAX first (one block; counting sort on NMAX): the heavy particles start first
 // instead of forming the tail of the launch.
-__global__ void __launch_bounds__(1024) k_order_by_nmax(int n, const int *nmax, const int *status, int *order)
+__global__ void __launch_bounds__(1024) k_order_by_nmax(int n, const int *nmax, const int *status, int *order, int *hist_out)
 {
     __shared__ int cnt[HS_NPN1 + 2];
     for (int t = threadIdx.x; t < HS_NPN1 + 2; t += blockDim.x) cnt[t] = 0;
@@ -582,6 +582,9 @@ __global__ void __launch_bounds__(1024) k_order_by_nmax(int n, const int *nmax, 
         v = (status[i] == HS_ST_OK && v > 0 && v <= HS_NPN1) ? v : 0;
         atomicAdd(&cnt[v], 1);
     }
+    __syncthreads();
+    if (hist_out)
+        for (int t = threadIdx.x; t < HS_NPN1 + 1; t += blockDim.x) hist_out[t] = cnt[t];  // pinned host memory: class sizes for the launcher
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;

@@ -737,6 +737,11 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
         hs::k_scatter_frames<<<fg, 64, 0, st>>>(a, ctx->d_frames);
         ctx->launches++;
     }
+    // one thread per orientation (up to 64 per pass); dynamic smem = T stage (2*nmax^2 complex) + the per-orientation
+    // reduction rows.  Large batches are ordered heaviest-first on the device and launched as three NMAX classes on
+    // concurrent streams, each with a T stage sized for its own largest NMAX (more CTAs per SM for the small particles).
+    int threads = std::min(64, std::max(32, (n_orient + 31) / 32 * 32));
+    auto smem_for = [&](int nb) { return ((size_t)4 * nb * nb + (size_t)threads * (SCK_G * 24 + 3) + SCK_G * 24 + 2) * sizeof(double); };
     a.order = nullptr;
     if (n >= 1024) {
         if (n > ctx->order_cap) {
@@ -745,21 +750,49 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
             CK(cudaMalloc(&ctx->d_order, (size_t)n * sizeof(int)));
             ctx->order_cap = n;
         }
-        hs::k_order_by_nmax<<<1, 1024, 0, st>>>(n, d_nmax, d_status, ctx->d_order);
+        if (ensure_pin(ctx, (HS_NPN1 + 2) * sizeof(int))) return -1;
+        int *hist = ctx->h_pin;
+        hs::k_order_by_nmax<<<1, 1024, 0, st>>>(n, d_nmax, d_status, ctx->d_order, hist);
         ctx->launches++;
-        a.order = ctx->d_order;
+        CK(cudaStreamSynchronize(st));
+        const int bounds[3] = {HS_NPN1, 20, 10};  // classes (20, NPN1], (10, 20], [0, 10] in the sorted (descending) order
+        int start = 0;
+        size_t max_smem = 0;
+        int cls_start[3], cls_cnt[3], cls_bound[3];
+        for (int c = 0; c < 3; c++) {
+            const int lo = c < 2 ? bounds[c + 1] + 1 : 0, hi = bounds[c];
+            int cnt = 0, top = 0;
+            for (int v = hi; v >= lo; v--) { cnt += hist[v]; if (hist[v] && !top) top = v; }
+            cls_start[c] = start; cls_cnt[c] = cnt; cls_bound[c] = std::max(top, 1);
+            start += cnt;
+            if (cnt) max_smem = std::max(max_smem, smem_for(cls_bound[c]));
+        }
+        if (max_smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
+        CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        CK(cudaEventRecord(ctx->ev_start, st));
+        for (int c = 0; c < 3; c++) {
+            if (!cls_cnt[c]) continue;
+            cudaStream_t bs = ctx->bstream[c];
+            CK(cudaStreamWaitEvent(bs, ctx->ev_start, 0));
+            hs::ScArgs ac = a;
+            ac.order = ctx->d_order + cls_start[c];
+            ac.nmax_bound = cls_bound[c];
+            hs::k_scatter<<<cls_cnt[c], threads, smem_for(cls_bound[c]), bs>>>(ac);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev_done[c], bs));
+            CK(cudaStreamWaitEvent(st, ctx->ev_done[c], 0));
+        }
+    } else {
+        int nmax_bound = ctx->last_nmax_max > 0 ? ctx->last_nmax_max : HS_NPN1;
+        a.nmax_bound = nmax_bound;
+        size_t smem = smem_for(nmax_bound);
+        if (smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
+        CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hs::k_scatter<<<n, threads, smem, st>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
     }
-    // one thread per orientation (up to 64 per pass); dynamic smem = T stage sized for the largest converged NMAX the
-    // context has produced (2*nmax^2 complex) + the per-orientation reduction rows
-    int threads = std::min(64, std::max(32, (n_orient + 31) / 32 * 32));
-    int nmax_bound = ctx->last_nmax_max > 0 ? ctx->last_nmax_max : HS_NPN1;
-    a.nmax_bound = nmax_bound;
-    size_t smem = ((size_t)4 * nmax_bound * nmax_bound + (size_t)threads * (SCK_G * 24 + 3) + SCK_G * 24 + 2) * sizeof(double);
-    if (smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
-    CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hs::k_scatter<<<n, threads, smem, st>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
     if (d_xs) {
         long tot = (long)n * n_geom * 2;
         k_xs_expand<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, n_geom, n_inc, dib + 130, xs_inc, d_xs);

@@ -261,12 +261,22 @@ def run_gpu(args):
     stage_ms = {"calctmat": 0.0, "scatter": 0.0, "psd": 0.0}
     last = {}
 
+    split = {"on": False}
+
     def step(inp, dsd, timed):
         e = [ev() for _ in range(5)]
         e[0].record()
-        tb = eng.calctmat(inp["radius"], inp["wavelength"], inp["mr"], inp["mi"], inp["eps"], ddelt=DDELT, ndgs=NDGS)
-        e[1].record()
-        S, Z, xs = tb.scatter([GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, want_xs=True)
+        if args.unfused_scatter or split["on"]:
+            tb = eng.calctmat(inp["radius"], inp["wavelength"], inp["mr"], inp["mi"], inp["eps"], ddelt=DDELT, ndgs=NDGS)
+            e[1].record()
+            S, Z, xs = tb.scatter([GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, want_xs=True)
+        else:
+            # one library call: T-matrices + orientation-averaged S/Z + cross sections, the scatter kernels of finished
+            # particles overlapping the convergence rounds of the others
+            tb, S, Z, xs = eng.calctmat_scatter(inp["radius"], inp["wavelength"], inp["mr"], inp["mi"], inp["eps"],
+                                                [GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, want_xs=True,
+                                                ddelt=DDELT, ndgs=NDGS)
+            e[1].record()
         e[2].record()
         e[3].record()
         rows = torch.empty((n, tables.ROW), dtype=torch.float64, device=dev)
@@ -338,10 +348,21 @@ def run_gpu(args):
         sync_all()
         ms_total = t0.elapsed_time(t1)
     launches = eng.launch_count - l0
-    # stage split of the last timed step
-    e = last["e"]
-    for k, (a, b) in zip(("calctmat", "scatter", "psd"), ((0, 1), (1, 2), (3, 4))):
-        stage_ms[k] = e[a].elapsed_time(e[b])
+    # stage split (and the roofline of the dominant stage): a short pass with the T-matrix and scatter calls issued
+    # separately, so that CUDA events on the launching stream bracket each stage
+    split["on"] = True
+    nsplit = max(3, min(args.steps, 10))
+    step(dev_in, dev_dsd, True)
+    sync_all()
+    acc = {"calctmat": 0.0, "scatter": 0.0, "psd": 0.0}
+    for _ in range(nsplit):
+        step(dev_in, dev_dsd, True)
+        sync_all()
+        e = last["e"]
+        for k, (a, b) in zip(("calctmat", "scatter", "psd"), ((0, 1), (1, 2), (3, 4))):
+            acc[k] += e[a].elapsed_time(e[b]) / nsplit
+    stage_ms.update(acc)
+    split["on"] = False
     # e2e: host buffers in, host results out, same K
     for k in range(2):
         step_e2e(k)
@@ -418,6 +439,8 @@ def run_gpu(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
+            "stage_ms_note": "stages timed in a separate pass with hs_calctmat_batch and hs_scatter_batch issued one after the other; "
+                             "the headline step issues them as one hs_calctmat_scatter_batch call (scatter overlaps the convergence rounds)",
             # dominant stage of the step: the staged T-matrix pipeline (k_st_radial, k_st_wigner, k_st_assemble with the
             # DMMA contraction + fused solve, k_st_mode_small), timed live with CUDA events on the launching stream; its
             # kernels overlap on several streams, so the stage (not one launch) is the unit
@@ -451,6 +474,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-stride", type=int, default=1, dest="cpu_stride")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused-scatter", action="store_true", dest="unfused_scatter",
+                    help="separate hs_calctmat_batch / hs_scatter_batch calls (per-stage timing) instead of hs_calctmat_scatter_batch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -33,6 +33,9 @@ SIGNATURES = {
     "hs_scatter_batch": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                                    C.POINTER(C.c_double), C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp,
                                    C.c_void_p]),
+    "hs_calctmat_scatter_batch": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int, C.c_double, C.c_int,
+                                            C.c_int, _dp, C.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int,
+                                            C.POINTER(C.c_double), C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, C.c_void_p]),
     "hs_psd_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp,
                                  C.c_void_p]),
     "hs_psd_integrate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_void_p]),

@@ -26,6 +26,11 @@ struct StBufs {
     int *d_out = nullptr, *h_out = nullptr; size_t out_cap = 0;  // final per-particle records for the scatter-out kernel
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
+    // fused scatter: records / order list of finished particles, filled round by round
+    cudaStream_t sc_stream = nullptr;
+    cudaEvent_t sc_ev = nullptr;
+    int *d_screc = nullptr, *h_screc = nullptr; size_t d_screc_cap = 0, h_screc_cap = 0;  // 8 ints per particle: idx nmax g ntr status - toff(lo,hi)
+    int *d_scord = nullptr, *h_scord = nullptr; size_t d_scord_cap = 0, h_scord_cap = 0;
 };
 
 struct StShared {
@@ -39,6 +44,7 @@ struct StP {  // controller state of one particle (Ctl of the fused kernel)
     double q1s, q1e;
     long long t_off;
     int first_item, n_items;  // this round's items
+    int scattered;            // fused scatter: record written / scatter kernel launched
 };
 
 template <class T>
@@ -67,6 +73,19 @@ __global__ void k_st_scatter_out(int n, const int *rec, const long long *toffs, 
     toff[p] = toffs[i];
 }
 
+__global__ void k_st_scatter_out8(int n, const int *rec, int *nmax, int *ngauss, int *ntrials, int *status, long long *toff)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int *r = rec + 8 * (long)i;
+    const int p = r[0];
+    nmax[p] = r[1];
+    ngauss[p] = r[2];
+    ntrials[p] = r[3];
+    status[p] = r[4];
+    toff[p] = (long long)(((unsigned long long)(unsigned)r[7] << 32) | (unsigned)r[6]);
+}
+
 struct StCall {  // arguments of one hs_calctmat_batch call
     const double *d_axi, *d_lam, *d_mr, *d_mi, *d_eps;
     double rat, ddelt;
@@ -79,6 +98,7 @@ struct StCall {  // arguments of one hs_calctmat_batch call
     size_t scratch_budget;
     int spec;
     bool trace;
+    const ScPrep *sp = nullptr;      // fused scatter plan (hs_calctmat_scatter_batch) or null
     mutable int nmax_max = 0;        // out: largest converged NMAX among the staged particles
     mutable bool arena_full = false;  // out: some particle did not fit the caller's arena
 };
@@ -299,6 +319,57 @@ struct StGroup {
         return 0;
     }
 
+    // Fused scatter (hs_calctmat_scatter_batch): particles that reached a terminal state since the last call get their
+    // per-particle record written and their orientation-averaged S / Z / cross sections computed right away on the
+    // group's scatter stream, while the remaining particles go through further convergence rounds.
+    int sc_filled = 0;
+    int flush_scatter()
+    {
+        using namespace hs;
+        const ScPrep *sp = C->sp;
+        if (!sp) return 0;
+        const int ns = (int)P.size();
+        if (st_grow(ctx, &B->h_screc, &B->h_screc_cap, (size_t)ns * 8, true)) return -1;
+        if (st_grow(ctx, &B->d_screc, &B->d_screc_cap, (size_t)ns * 8)) return -1;
+        if (st_grow(ctx, &B->h_scord, &B->h_scord_cap, (size_t)ns, true)) return -1;
+        if (st_grow(ctx, &B->d_scord, &B->d_scord_cap, (size_t)ns)) return -1;
+        // newly finished particles, heaviest first
+        int cnt[HS_NPN1 + 2] = {0};
+        int nnew = 0, bound = 1;
+        for (const StP &s : P)
+            if (s.done && !s.scattered) { cnt[s.done == 1 ? std::min(std::max(s.nmax, 0), HS_NPN1) : 0]++; nnew++; }
+        if (!nnew) return 0;
+        int acc = 0;
+        for (int v = HS_NPN1; v >= 0; v--) { int c = cnt[v]; if (c && v > bound) bound = v; cnt[v] = acc; acc += c; }
+        const int off = sc_filled;
+        for (StP &s : P) {
+            if (!s.done || s.scattered) continue;
+            s.scattered = 1;
+            const int q = off + cnt[s.done == 1 ? std::min(std::max(s.nmax, 0), HS_NPN1) : 0]++;
+            int *r = B->h_screc + 8 * (size_t)q;
+            int stt = s.status;
+            if (stt == HS_ST_OK && s.sing) stt = HS_ST_SINGULAR;
+            const long long to = (s.done == 1) ? s.t_off : -1;
+            r[0] = s.idx; r[1] = s.nmax; r[2] = s.g; r[3] = s.ntr; r[4] = stt; r[5] = 0;
+            r[6] = (int)(unsigned)((unsigned long long)to & 0xFFFFFFFFull); r[7] = (int)(unsigned)((unsigned long long)to >> 32);
+            B->h_scord[q] = s.idx;
+        }
+        sc_filled += nnew;
+        cudaStream_t ss = B->sc_stream;
+        CK(cudaMemcpyAsync(B->d_screc + 8 * (size_t)off, B->h_screc + 8 * (size_t)off, (size_t)nnew * 8 * sizeof(int), cudaMemcpyHostToDevice, ss));
+        CK(cudaMemcpyAsync(B->d_scord + off, B->h_scord + off, (size_t)nnew * sizeof(int), cudaMemcpyHostToDevice, ss));
+        k_st_scatter_out8<<<(nnew + 255) / 256, 256, 0, ss>>>(nnew, B->d_screc + 8 * (size_t)off, C->d_nmax, C->d_ngauss, C->d_ntrials, C->d_status, C->d_toff);
+        const size_t smem = sc_smem(sp->threads, bound);
+        if (smem > (size_t)ctx->smem_optin - 8192) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
+        ScArgs sa = sp->a;
+        sa.order = B->d_scord + off;
+        sa.nmax_bound = bound;
+        k_scatter<<<nnew, sp->threads, smem, ss>>>(sa);
+        launches += 2;
+        CK(cudaGetLastError());
+        return 0;
+    }
+
     // the group's whole life on its own host thread
     void run()
     {
@@ -306,9 +377,10 @@ struct StGroup {
         rc = issue();
         while (!rc && inflight) {
             rc = finish();
-            if (!rc) rc = issue();
+            if (!rc) rc = issue();       // keep this group's next round ahead of its scatter work in the launch queue
+            if (!rc) rc = flush_scatter();
         }
-        if (!rc) rc = write_out();
+        if (!rc) rc = C->sp ? flush_scatter() : write_out();
     }
 
     // per-particle records -> device arrays
@@ -366,9 +438,13 @@ static int st_init(hs_ctx *ctx, StShared &S)
     CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
     CK(cudaFuncSetAttribute(k_st_mode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ST_SMALL_SLICE * 8));
     CK(cudaEventCreate(&S.ev_in));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // the convergence rounds are the critical path: scatter fills in behind them
     for (int g = 0; g < ST_GROUPS; g++) {
-        CK(cudaStreamCreateWithFlags(&S.g[g].stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&S.g[g].stream, cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&S.g[g].ev, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithPriority(&S.g[g].sc_stream, cudaStreamNonBlocking, prio_lo));
+        CK(cudaEventCreateWithFlags(&S.g[g].sc_ev, cudaEventDisableTiming));
     }
     return 0;
 }
@@ -383,6 +459,11 @@ static void st_destroy(StShared &S)
         if (b.h_out) cudaFreeHost(b.h_out);
         if (b.stream) cudaStreamDestroy(b.stream);
         if (b.ev) cudaEventDestroy(b.ev);
+        cudaFree(b.d_screc); cudaFree(b.d_scord);
+        if (b.h_screc) cudaFreeHost(b.h_screc);
+        if (b.h_scord) cudaFreeHost(b.h_scord);
+        if (b.sc_stream) cudaStreamDestroy(b.sc_stream);
+        if (b.sc_ev) cudaEventDestroy(b.sc_ev);
     }
     cudaFree(S.d_cm); cudaFree(S.d_dd);
     if (S.ev_in) cudaEventDestroy(S.ev_in);
@@ -407,12 +488,13 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
     for (int g = 0; g < ng; g++) {
         G[g].ctx = ctx; G[g].S = &S; G[g].B = &S.g[g]; G[g].C = &C; G[g].id = g;
         CK(cudaStreamWaitEvent(S.g[g].stream, S.ev_in, 0));
+        CK(cudaStreamWaitEvent(S.g[g].sc_stream, S.ev_in, 0));
     }
     for (int r = 0; r < ns; r++) {
         const int j = ord[r];
         StP s;
         s.idx = sel[j]; s.phase = 0; s.nmax = n0_of[j]; s.g = 0; s.ntr = 0; s.status = HS_ST_OK; s.done = 0; s.sing = 0;
-        s.q1s = 0.0; s.q1e = 0.0; s.t_off = -1; s.first_item = 0; s.n_items = 0;
+        s.q1s = 0.0; s.q1e = 0.0; s.t_off = -1; s.first_item = 0; s.n_items = 0; s.scattered = 0;
         if (s.nmax < 0) { s.done = 2; s.status = HS_ST_BAD_INPUT; s.nmax = 0; }
         else if (s.nmax >= HS_NPN1) { s.done = 2; s.status = HS_ST_NMAX_LIMIT; }
         G[r % ng].P.push_back(s);
@@ -436,6 +518,8 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         if (G[g].rc) return G[g].rc;
         CK(cudaEventRecord(S.g[g].ev, S.g[g].stream));
         CK(cudaStreamWaitEvent(st, S.g[g].ev, 0));
+        CK(cudaEventRecord(S.g[g].sc_ev, S.g[g].sc_stream));
+        CK(cudaStreamWaitEvent(st, S.g[g].sc_ev, 0));
     }
     if (timeline) {
         cudaDeviceSynchronize();

@@ -65,6 +65,16 @@ struct hs_ctx {
         }                                                                                          \
     } while (0)
 
+struct ScPrep {  // particle-independent part of a scatter call (scatter_prepare)
+    hs::ScArgs a;
+    int n_inc = 0, n_geom = 0, threads = 64;
+    const int *inc_of_geom = nullptr;
+    double *xs_inc = nullptr, *d_xs = nullptr;
+};
+static inline size_t sc_smem(int threads, int nmax_bound)
+{
+    return ((size_t)4 * nmax_bound * nmax_bound + (size_t)threads * (SCK_G * 24 + 3) + SCK_G * 24 + 2) * sizeof(double);
+}
 static int ensure_gauss(hs_ctx *ctx, int gmax);
 #include "hs_staged_host.h"
 struct StBufsHolder { StShared s; };
@@ -148,6 +158,97 @@ static int ensure_pin(hs_ctx *ctx, size_t bytes)
     return 0;
 }
 
+__global__ void k_xs_expand(int n, int n_geom, int n_inc, const int *inc_of_geom, const double *xs_inc, double *xs)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n * n_geom * 2) return;
+    int c = (int)(i & 1);
+    long pg = i >> 1;
+    int g = (int)(pg % n_geom);
+    long p = pg / n_geom;
+    xs[i] = xs_inc[(p * n_inc + inc_of_geom[g]) * 2 + c];
+}
+
+// Everything of a scatter call that does not depend on the particles: geometry grouping, parameter block, the
+// orientation / geometry frames.  Shared by hs_scatter_batch and the fused hs_calctmat_scatter_batch.
+static int scatter_prepare(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff, const int *d_nmax,
+                           const int *d_status, const double *d_lam, int n_geom, const double *h_geom, int n_orient,
+                           const double *d_alpha, const double *d_beta, const double *d_weight, double scale,
+                           double *d_S, double *d_Z, double *d_xs, cudaStream_t st, ScPrep &P)
+{
+    if (n_geom > 64) { ctx->err = "at most 64 geometries per call"; return -3; }
+    // group geometries by incidence direction
+    std::vector<double> inc;           // unique (thet0, phi0)
+    std::vector<int> inc_of(n_geom);
+    for (int g = 0; g < n_geom; g++) {
+        int f = -1;
+        for (size_t d = 0; d < inc.size() / 2; d++)
+            if (inc[2 * d] == h_geom[4 * g] && inc[2 * d + 1] == h_geom[4 * g + 2]) { f = (int)d; break; }
+        if (f < 0) { f = (int)(inc.size() / 2); inc.push_back(h_geom[4 * g]); inc.push_back(h_geom[4 * g + 2]); }
+        inc_of[g] = f;
+    }
+    const int n_inc = (int)(inc.size() / 2);
+    std::vector<int> g_begin(n_inc + 1, 0), g_out(n_geom);
+    std::vector<double> gsc(2 * n_geom);
+    int pos = 0;
+    for (int d = 0; d < n_inc; d++) {
+        g_begin[d] = pos;
+        for (int g = 0; g < n_geom; g++)
+            if (inc_of[g] == d) { gsc[2 * pos] = h_geom[4 * g + 1]; gsc[2 * pos + 1] = h_geom[4 * g + 3]; g_out[pos] = g; pos++; }
+    }
+    g_begin[n_inc] = pos;
+    // pack: [inc 2*64][gsc 2*64][g_begin 65 ints][g_out 64 ints][inc_of 64 ints] in one small device block
+    const size_t blk_doubles = 128 + 128 + 128;
+    if (!ctx->d_sc) CK(cudaMalloc(&ctx->d_sc, blk_doubles * sizeof(double) * 4));
+    static thread_local int slot = 0;
+    slot = (slot + 1) & 3;  // 4 rotating parameter blocks so that back-to-back async calls do not overwrite each other
+    std::vector<double> hostblk(blk_doubles, 0.0);
+    memcpy(hostblk.data(), inc.data(), inc.size() * sizeof(double));
+    memcpy(hostblk.data() + 128, gsc.data(), gsc.size() * sizeof(double));
+    int *ib = reinterpret_cast<int *>(hostblk.data() + 256);
+    memcpy(ib, g_begin.data(), g_begin.size() * sizeof(int));
+    memcpy(ib + 65, g_out.data(), g_out.size() * sizeof(int));
+    memcpy(ib + 130, inc_of.data(), inc_of.size() * sizeof(int));
+    double *dblk = ctx->d_sc + (size_t)slot * blk_doubles;
+    CK(cudaMemcpyAsync(dblk, hostblk.data(), blk_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // hostblk is pageable stack/heap memory: make the copy complete before it dies
+    const int *dib = reinterpret_cast<const int *>(dblk + 256);
+    double *xs_inc = nullptr;
+    if (d_xs) {
+        size_t need = (size_t)n * n_inc * 2 * sizeof(double);
+        if (need > ctx->xs_tmp_cap) {
+            if (ctx->d_xs_tmp) cudaFree(ctx->d_xs_tmp);
+            ctx->d_xs_tmp = nullptr; ctx->xs_tmp_cap = 0;
+            CK(cudaMalloc(&ctx->d_xs_tmp, need));
+            ctx->xs_tmp_cap = need;
+        }
+        xs_inc = ctx->d_xs_tmp;
+    }
+    hs::ScArgs a;
+    a.n = n; a.tarena = d_tarena; a.toff = d_toff; a.nmax = d_nmax; a.status = d_status; a.lam = d_lam;
+    a.n_inc = n_inc; a.inc = dblk; a.g_begin = dib; a.gsc = dblk + 128; a.g_out = dib + 65; a.n_geom = n_geom;
+    a.n_orient = n_orient; a.alpha = d_alpha; a.beta = d_beta; a.weight = d_weight; a.scale = scale;
+    a.S = d_S; a.Z = d_Z; a.xs = xs_inc;
+    {   // orientation / geometry frames: once per call instead of once per particle
+        int maxblk = 1;
+        for (int d = 0; d < n_inc; d++) maxblk = std::max(maxblk, (g_begin[d + 1] - g_begin[d] + SCK_G - 1) / SCK_G);
+        size_t need = (size_t)n_inc * maxblk * n_orient * SC_FR;
+        if (need > ctx->frames_cap) {
+            if (ctx->d_frames) cudaFree(ctx->d_frames);
+            ctx->d_frames = nullptr; ctx->frames_cap = 0;
+            CK(cudaMalloc(&ctx->d_frames, need * sizeof(double)));
+            ctx->frames_cap = need;
+        }
+        a.frames = ctx->d_frames; a.frame_blocks = maxblk;
+        dim3 fg((n_orient + 63) / 64, n_inc, maxblk);
+        hs::k_scatter_frames<<<fg, 64, 0, st>>>(a, ctx->d_frames);
+        ctx->launches++;
+    }
+    P.a = a; P.n_inc = n_inc; P.inc_of_geom = dib + 130; P.xs_inc = xs_inc; P.d_xs = d_xs; P.n_geom = n_geom;
+    P.threads = std::min(64, std::max(32, (n_orient + 31) / 32 * 32));
+    return 0;
+}
+
 // bucket = launch configuration
 struct Bucket {
     bool warp;        // group = warp (several particles per CTA) or whole CTA
@@ -196,11 +297,12 @@ static cudaError_t launch_tm(const hs::TmArgs &a, int grid, int threads, size_t 
     return cudaGetLastError();
 }
 
-extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const double *d_lam, const double *d_mr,
-                                 const double *d_mi, const double *d_eps, double rat, int np, double ddelt,
-                                 int ndgs, int rescale_ddelt, double *d_tarena, long long arena_cap,
-                                 unsigned long long *d_arena_top, long long *d_toff, int *d_nmax, int *d_ngauss,
-                                 int *d_ntrials, int *d_status, void *stream)
+// sp != null: fused scatter plan; *sp_used tells the caller whether the staged pipeline consumed it (every particle staged)
+static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *d_lam, const double *d_mr,
+                         const double *d_mi, const double *d_eps, double rat, int np, double ddelt,
+                         int ndgs, int rescale_ddelt, double *d_tarena, long long arena_cap,
+                         unsigned long long *d_arena_top, long long *d_toff, int *d_nmax, int *d_ngauss,
+                         int *d_ntrials, int *d_status, void *stream, const ScPrep *sp, bool *sp_used)
 {
     if (!ctx) return -2;
     if (n <= 0) return 0;
@@ -289,6 +391,7 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
     SC.scratch_budget = (size_t)((getenv("HYDROTM_SCRATCH_GB") ? atof(getenv("HYDROTM_SCRATCH_GB")) : 4.0) * (double)(1ull << 30));
     SC.spec = getenv("HYDROTM_SPEC") ? atoi(getenv("HYDROTM_SPEC")) : 0;
     SC.trace = trace;
+    SC.sp = nullptr;
     auto run_staged = [&]() -> int {
         staged_done = true;
         return calctmat_staged(ctx, ctx->st->s, st, st_sel, st_n0, SC);
@@ -313,6 +416,10 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         bucket_of[i] = b;
         lists[b].push_back(i);
     }
+    // Overlapping the scatter kernels of finished particles with the convergence rounds of the others measured SLOWER on
+    // B200 (12.3 vs 11.6 ms per W2 step: both sides are limited by resident-CTA resources, not by idle SMs), so the
+    // overlap is opt-in (HYDROTM_OVERLAP_SCATTER=1) and the default runs the two stages back to back.
+    if (sp && (int)st_sel.size() == n && getenv("HYDROTM_OVERLAP_SCATTER")) { SC.sp = sp; if (sp_used) *sp_used = true; }
     int gauss_needed = ctx->gmax;
     for (int round = 0; round < 16; round++) {
         bool any = false;
@@ -423,6 +530,53 @@ extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const 
         }
     }
     return arena_full ? HS_RC_ARENA_FULL : 0;
+}
+
+extern "C" int hs_calctmat_batch(hs_ctx *ctx, int n, const double *d_axi, const double *d_lam, const double *d_mr,
+                                 const double *d_mi, const double *d_eps, double rat, int np, double ddelt,
+                                 int ndgs, int rescale_ddelt, double *d_tarena, long long arena_cap,
+                                 unsigned long long *d_arena_top, long long *d_toff, int *d_nmax, int *d_ngauss,
+                                 int *d_ntrials, int *d_status, void *stream)
+{
+    return calctmat_impl(ctx, n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, np, ddelt, ndgs, rescale_ddelt, d_tarena, arena_cap, d_arena_top,
+                         d_toff, d_nmax, d_ngauss, d_ntrials, d_status, stream, nullptr, nullptr);
+}
+
+extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff, const int *d_nmax,
+                                const int *d_status, const double *d_lam, int n_geom, const double *h_geom, int n_orient,
+                                const double *d_alpha, const double *d_beta, const double *d_weight, double scale,
+                                double *d_S, double *d_Z, double *d_xs, void *stream);
+
+extern "C" int hs_calctmat_scatter_batch(hs_ctx *ctx, int n, const double *d_axi, const double *d_lam, const double *d_mr,
+                                         const double *d_mi, const double *d_eps, double rat, int np, double ddelt, int ndgs,
+                                         int rescale_ddelt, double *d_tarena, long long arena_cap, unsigned long long *d_arena_top,
+                                         long long *d_toff, int *d_nmax, int *d_ngauss, int *d_ntrials, int *d_status, int n_geom,
+                                         const double *h_geom, int n_orient, const double *d_alpha, const double *d_beta,
+                                         const double *d_weight, double scale, double *d_S, double *d_Z, double *d_xs, void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0) return 0;
+    if (n_geom <= 0 || n_orient <= 0) { ctx->err = "hs_calctmat_scatter_batch: no geometries / orientations"; return -3; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    ScPrep SP;
+    { int rc = scatter_prepare(ctx, n, d_tarena, d_toff, d_nmax, d_status, d_lam, n_geom, h_geom, n_orient, d_alpha, d_beta,
+                               d_weight, scale, d_S, d_Z, d_xs, st, SP); if (rc) return rc; }
+    CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - 8192));
+    bool used = false;
+    int rc = calctmat_impl(ctx, n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, np, ddelt, ndgs, rescale_ddelt, d_tarena, arena_cap, d_arena_top,
+                           d_toff, d_nmax, d_ngauss, d_ntrials, d_status, stream, &SP, &used);
+    if (rc != 0) return rc;  // incl. HS_RC_ARENA_FULL: the caller retries with a larger arena
+    if (!used)  // some particles went through the fused calctmat kernel: scatter afterwards
+        return hs_scatter_batch(ctx, n, d_tarena, d_toff, d_nmax, d_status, d_lam, n_geom, h_geom, n_orient, d_alpha, d_beta, d_weight, scale,
+                                d_S, d_Z, d_xs, stream);
+    if (d_xs) {
+        long tot = (long)n * n_geom * 2;
+        k_xs_expand<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, n_geom, SP.n_inc, SP.inc_of_geom, SP.xs_inc, d_xs);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return 0;
 }
 
 extern "C" int hs_calcampl_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff,
@@ -649,17 +803,6 @@ extern "C" int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const do
     return 0;
 }
 
-__global__ void k_xs_expand(int n, int n_geom, int n_inc, const int *inc_of_geom, const double *xs_inc, double *xs)
-{
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long)n * n_geom * 2) return;
-    int c = (int)(i & 1);
-    long pg = i >> 1;
-    int g = (int)(pg % n_geom);
-    long p = pg / n_geom;
-    xs[i] = xs_inc[(p * n_inc + inc_of_geom[g]) * 2 + c];
-}
-
 extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, const long long *d_toff, const int *d_nmax,
                                 const int *d_status, const double *d_lam, int n_geom, const double *h_geom, int n_orient,
                                 const double *d_alpha, const double *d_beta, const double *d_weight, double scale,
@@ -667,81 +810,20 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
 {
     if (!ctx) return -2;
     if (n <= 0 || n_geom <= 0 || n_orient <= 0) return 0;
-    if (n_geom > 64) { ctx->err = "at most 64 geometries per call"; return -3; }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
-    // group geometries by incidence direction
-    std::vector<double> inc;           // unique (thet0, phi0)
-    std::vector<int> inc_of(n_geom);
-    for (int g = 0; g < n_geom; g++) {
-        int f = -1;
-        for (size_t d = 0; d < inc.size() / 2; d++)
-            if (inc[2 * d] == h_geom[4 * g] && inc[2 * d + 1] == h_geom[4 * g + 2]) { f = (int)d; break; }
-        if (f < 0) { f = (int)(inc.size() / 2); inc.push_back(h_geom[4 * g]); inc.push_back(h_geom[4 * g + 2]); }
-        inc_of[g] = f;
-    }
-    const int n_inc = (int)(inc.size() / 2);
-    std::vector<int> g_begin(n_inc + 1, 0), g_out(n_geom);
-    std::vector<double> gsc(2 * n_geom);
-    int pos = 0;
-    for (int d = 0; d < n_inc; d++) {
-        g_begin[d] = pos;
-        for (int g = 0; g < n_geom; g++)
-            if (inc_of[g] == d) { gsc[2 * pos] = h_geom[4 * g + 1]; gsc[2 * pos + 1] = h_geom[4 * g + 3]; g_out[pos] = g; pos++; }
-    }
-    g_begin[n_inc] = pos;
-    // pack: [inc 2*64][gsc 2*64][g_begin 65 ints][g_out 64 ints][inc_of 64 ints] in one small device block
-    const size_t blk_doubles = 128 + 128 + 128;
-    if (!ctx->d_sc) CK(cudaMalloc(&ctx->d_sc, blk_doubles * sizeof(double) * 4));
-    static thread_local int slot = 0;
-    slot = (slot + 1) & 3;  // 4 rotating parameter blocks so that back-to-back async calls do not overwrite each other
-    std::vector<double> hostblk(blk_doubles, 0.0);
-    memcpy(hostblk.data(), inc.data(), inc.size() * sizeof(double));
-    memcpy(hostblk.data() + 128, gsc.data(), gsc.size() * sizeof(double));
-    int *ib = reinterpret_cast<int *>(hostblk.data() + 256);
-    memcpy(ib, g_begin.data(), g_begin.size() * sizeof(int));
-    memcpy(ib + 65, g_out.data(), g_out.size() * sizeof(int));
-    memcpy(ib + 130, inc_of.data(), inc_of.size() * sizeof(int));
-    double *dblk = ctx->d_sc + (size_t)slot * blk_doubles;
-    CK(cudaMemcpyAsync(dblk, hostblk.data(), blk_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // hostblk is pageable stack/heap memory: make the copy complete before it dies
-    const int *dib = reinterpret_cast<const int *>(dblk + 256);
-    double *xs_inc = nullptr;
-    if (d_xs) {
-        size_t need = (size_t)n * n_inc * 2 * sizeof(double);
-        if (need > ctx->xs_tmp_cap) {
-            if (ctx->d_xs_tmp) cudaFree(ctx->d_xs_tmp);
-            ctx->d_xs_tmp = nullptr; ctx->xs_tmp_cap = 0;
-            CK(cudaMalloc(&ctx->d_xs_tmp, need));
-            ctx->xs_tmp_cap = need;
-        }
-        xs_inc = ctx->d_xs_tmp;
-    }
-    hs::ScArgs a;
-    a.n = n; a.tarena = d_tarena; a.toff = d_toff; a.nmax = d_nmax; a.status = d_status; a.lam = d_lam;
-    a.n_inc = n_inc; a.inc = dblk; a.g_begin = dib; a.gsc = dblk + 128; a.g_out = dib + 65; a.n_geom = n_geom;
-    a.n_orient = n_orient; a.alpha = d_alpha; a.beta = d_beta; a.weight = d_weight; a.scale = scale;
-    a.S = d_S; a.Z = d_Z; a.xs = xs_inc;
-    {   // orientation / geometry frames: once per call instead of once per particle
-        int maxblk = 1;
-        for (int d = 0; d < n_inc; d++) maxblk = std::max(maxblk, (g_begin[d + 1] - g_begin[d] + SCK_G - 1) / SCK_G);
-        size_t need = (size_t)n_inc * maxblk * n_orient * SC_FR;
-        if (need > ctx->frames_cap) {
-            if (ctx->d_frames) cudaFree(ctx->d_frames);
-            ctx->d_frames = nullptr; ctx->frames_cap = 0;
-            CK(cudaMalloc(&ctx->d_frames, need * sizeof(double)));
-            ctx->frames_cap = need;
-        }
-        a.frames = ctx->d_frames; a.frame_blocks = maxblk;
-        dim3 fg((n_orient + 63) / 64, n_inc, maxblk);
-        hs::k_scatter_frames<<<fg, 64, 0, st>>>(a, ctx->d_frames);
-        ctx->launches++;
-    }
+    ScPrep SP;
+    { int rc = scatter_prepare(ctx, n, d_tarena, d_toff, d_nmax, d_status, d_lam, n_geom, h_geom, n_orient, d_alpha, d_beta, d_weight,
+                               scale, d_S, d_Z, d_xs, st, SP); if (rc) return rc; }
+    hs::ScArgs a = SP.a;
+    const int n_inc = SP.n_inc;
+    const int *dib = SP.inc_of_geom - 130;
+    double *xs_inc = SP.xs_inc;
     // one thread per orientation (up to 64 per pass); dynamic smem = T stage (2*nmax^2 complex) + the per-orientation
     // reduction rows.  Large batches are ordered heaviest-first on the device and launched as three NMAX classes on
     // concurrent streams, each with a T stage sized for its own largest NMAX (more CTAs per SM for the small particles).
-    int threads = std::min(64, std::max(32, (n_orient + 31) / 32 * 32));
-    auto smem_for = [&](int nb) { return ((size_t)4 * nb * nb + (size_t)threads * (SCK_G * 24 + 3) + SCK_G * 24 + 2) * sizeof(double); };
+    const int threads = SP.threads;
+    auto smem_for = [&](int nb) { return sc_smem(threads, nb); };
     a.order = nullptr;
     if (n >= 1024) {
         if (n > ctx->order_cap) {

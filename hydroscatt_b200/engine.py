@@ -79,8 +79,18 @@ class Engine:
             t = t.expand(n)
         return t.contiguous()
 
+    def calctmat_scatter(self, radius, wavelength, m_re, m_im, axis_ratio, geoms, alpha=(0.0,), beta=(0.0,), weight=None,
+                         scale=1.0, want_xs=True, **kw):
+        """calctmat + TMatrixBatch.scatter in one library call (hs_calctmat_scatter_batch): particles whose T-matrix is
+        complete are scattered while the others are still converging.  Returns (TMatrixBatch, S, Z, xs)."""
+        g = np.ascontiguousarray(np.asarray(geoms, dtype=np.float64).reshape(-1, 4))
+        al = self._dev(alpha)
+        be = self._dev(beta)
+        w = self._dev(weight if weight is not None else np.ones(al.numel()))
+        return self.calctmat(radius, wavelength, m_re, m_im, axis_ratio, _scatter=(g, al, be, w, float(scale), want_xs), **kw)
+
     def calctmat(self, radius, wavelength, m_re, m_im, axis_ratio, rat=1.0, shape=-1, ddelt=1e-3, ndgs=2,
-                 rescale_ddelt=True, arena_margin=1.0):
+                 rescale_ddelt=True, arena_margin=1.0, _scatter=None):
         """Converged T-matrices of a batch of spheroids.  All array arguments broadcast to [n]."""
         sizes = [np.size(a) if not torch.is_tensor(a) else a.numel()
                  for a in (radius, wavelength, m_re, m_im, axis_ratio)]
@@ -111,10 +121,23 @@ class Engine:
             ntr = torch.empty(n, dtype=torch.int32, device=dev)
             status = torch.empty(n, dtype=torch.int32, device=dev)
             with torch.cuda.device(dev):
-                rc = self.lib.hs_calctmat_batch(
-                    self._h, n, _ptr(axi), _ptr(lam), _ptr(mr), _ptr(mi), _ptr(eps), float(rat), int(shape),
-                    float(ddelt), int(ndgs), 1 if rescale_ddelt else 0, _ptr(arena), cap, _ptr(top), _ptr(toff),
-                    _ptr(nmax), _ptr(ngauss), _ptr(ntr), _ptr(status), C.c_void_p(stream.cuda_stream))
+                if _scatter is None:
+                    rc = self.lib.hs_calctmat_batch(
+                        self._h, n, _ptr(axi), _ptr(lam), _ptr(mr), _ptr(mi), _ptr(eps), float(rat), int(shape),
+                        float(ddelt), int(ndgs), 1 if rescale_ddelt else 0, _ptr(arena), cap, _ptr(top), _ptr(toff),
+                        _ptr(nmax), _ptr(ngauss), _ptr(ntr), _ptr(status), C.c_void_p(stream.cuda_stream))
+                else:
+                    g, al, be, w, scale, want_xs = _scatter
+                    G = g.shape[0]
+                    S = torch.empty((n, G, 2, 2), dtype=torch.complex128, device=dev)
+                    Z = torch.empty((n, G, 4, 4), dtype=torch.float64, device=dev)
+                    xs = torch.empty((n, G, 2), dtype=torch.float64, device=dev) if want_xs else None
+                    rc = self.lib.hs_calctmat_scatter_batch(
+                        self._h, n, _ptr(axi), _ptr(lam), _ptr(mr), _ptr(mi), _ptr(eps), float(rat), int(shape),
+                        float(ddelt), int(ndgs), 1 if rescale_ddelt else 0, _ptr(arena), cap, _ptr(top), _ptr(toff),
+                        _ptr(nmax), _ptr(ngauss), _ptr(ntr), _ptr(status), G, g.ctypes.data_as(C.POINTER(C.c_double)),
+                        al.numel(), _ptr(al), _ptr(be), _ptr(w), scale, _ptr(S), _ptr(Z), _ptr(xs),
+                        C.c_void_p(stream.cuda_stream))
             if rc == 1:  # HS_RC_ARENA_FULL: the arena counter holds what the batch needs
                 cap = max(2 * cap, int(top.item()) + 1024)
                 continue
@@ -124,6 +147,8 @@ class Engine:
         if not hasattr(self, "_arena_hint"):
             self._arena_hint = {}
         self._arena_hint[n] = cap
+        if _scatter is not None:
+            return TMatrixBatch(self, n, arena, top, toff, nmax, ngauss, ntr, status, lam), S, Z, xs
         return TMatrixBatch(self, n, arena, top, toff, nmax, ngauss, ntr, status, lam)
 
     # ---- PSD integration / observables ---------------------------------------------------------------------

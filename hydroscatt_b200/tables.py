@@ -27,14 +27,13 @@ def build_rows(eng, radius, wavelength, m_re, m_im, axis_ratio, geom_back, geom_
     Returns (rows [n, 56] float64 on the device, TMatrixBatch).  Two kernel families: k_calctmat (one launch per size bucket, concurrent streams)
     and the fused k_scatter (orientation-averaged S/Z of all geometries + cross sections in one T-matrix sweep).
     """
-    tb = eng.calctmat(radius, wavelength, m_re, m_im, axis_ratio, rat=rat, ddelt=ddelt, ndgs=ndgs,
-                      rescale_ddelt=rescale_ddelt)
     gb, gf = tuple(geom_back[:4]), tuple(geom_forw[:4])
     geoms = [gb, gf]
     # forward amplitudes for the optical theorem at each geometry's incidence direction
     fw = [(g[0], g[0], g[2], g[2]) for g in geoms]
     allg = geoms + [f for f in dict.fromkeys(fw) if f not in geoms]
-    S, Z, xs = tb.scatter(allg, alpha, beta, weight=weight, scale=scale, want_xs=True)
+    tb, S, Z, xs = eng.calctmat_scatter(radius, wavelength, m_re, m_im, axis_ratio, allg, alpha, beta, weight=weight,
+                                        scale=scale, want_xs=True, rat=rat, ddelt=ddelt, ndgs=ndgs, rescale_ddelt=rescale_ddelt)
     n = tb.n
     rows = torch.empty((n, ROW), dtype=torch.float64, device=eng.device)
     Sr = torch.view_as_real(S).reshape(n, len(allg), 8)

@@ -144,6 +144,20 @@ int hs_psd_integrate(hs_ctx *ctx, int n_dsd, int n_D, int ncol, const double *d_
                      double *d_out, void *stream);
 
 /*
+ * hs_calctmat_batch + hs_scatter_batch in one call (what scattering_rain.py:183-191 + PSDIntegrator.init_scatter_table do per
+ * diameter: calctmat, then 2 x 50 calcampl and the cross sections).  With HYDROTM_OVERLAP_SCATTER=1 particles whose T-matrix
+ * is complete are scattered right away on a side stream while the others are still in their convergence rounds (measured
+ * slower than back to back on B200, hence opt-in).  Arguments = those of the two calls;
+ * returns like hs_calctmat_batch (HS_RC_ARENA_FULL: retry with a larger arena, outputs undefined).
+ */
+int hs_calctmat_scatter_batch(hs_ctx *ctx, int n, const double *d_axi, const double *d_lam, const double *d_mr, const double *d_mi,
+                              const double *d_eps, double rat, int np, double ddelt, int ndgs, int rescale_ddelt, double *d_tarena,
+                              long long arena_cap, unsigned long long *d_arena_top, long long *d_toff, int *d_nmax, int *d_ngauss,
+                              int *d_ntrials, int *d_status, int n_geom, const double *h_geom, int n_orient, const double *d_alpha,
+                              const double *d_beta, const double *d_weight, double scale, double *d_S, double *d_Z, double *d_xs,
+                              void *stream);
+
+/*
  * Fused PSD integration + observables (what compute_scattering_psd_tm, scattering.py:530-587, does one DSD at a time
  * through PSDIntegrator.get_SZ + radar.*): obs[d][t][15] (columns as hs_observables) for n_dsd weight rows
  * d_W [n_dsd][n_D] and n_tab tables of records d_rows [n_tab][n_D][56] (layout: hydroscatt_b200/tables.py), without

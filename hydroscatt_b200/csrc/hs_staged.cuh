@@ -48,6 +48,7 @@ struct StArgs {
     unsigned long long *arena_top;
     long long *toff;
     StResult *res;
+    int fuse;                // solve modes with NM <= 32 inside k_st_assemble (default) or in k_st_solve
 };
 
 enum { NA_X = 0, NA_S, NA_SS, NA_DR, NA_DDR, NA_DRR, NA_DRI, NA_RR, NA_COUNT };
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     const double ppi = kw * kw, pir = ppi * a.mr[p], pii = ppi * a.mi[p];
     // NM <= 32: the block is the whole mode; the systems are combined in the (now free) operand area, solved here and only
     // the T block leaves the SM.  Larger modes write their part of [Q | RgQ] to global memory for k_st_solve.
-    const bool fused = NM <= 32;
+    const bool fused = NM <= 32 && a.fuse;
     double2 *sys = fused ? reinterpret_cast<double2 *>(op) : a.sys + it.sys_off + st_sys_mode_off(nmax, m);
 #pragma unroll
     for (int r = 0; r < NTR; r++)
@@ -748,9 +749,17 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
         grp.tid = threadIdx.x; grp.nt = THREADS;
         solve_multi(grp, sd, nsys, &sc, &sing);
     } else {
-        // one warp per system (m = 0: four half-size systems, m >= 1: the two parity classes)
-        const int w = threadIdx.x >> 5;
-        if (w < nsys) solve_sub(sd[w], threadIdx.x & 31, 32, sd[w].n, &sing);
+        if (THREADS == 256 && NM <= 32) {
+            // as in the fused path: m = 0: four half-size systems on 64 lanes each, m >= 1: two systems on 128 lanes each
+            __shared__ unsigned long long keyslot[4][2];
+            const int warp = threadIdx.x >> 5;
+            const int q = (m == 0) ? (warp >> 1) : (warp >> 2);
+            if (q < nsys && sd[q].n > 0) solve_grp(sd[q], threadIdx.x & (m == 0 ? 63 : 127), m == 0 ? 64 : 128, 1 + q, keyslot[q], &sing);
+        } else {
+            // one warp per system (m = 0: four half-size systems, m >= 1: the two parity classes)
+            const int w = threadIdx.x >> 5;
+            if (w < nsys) solve_sub(sd[w], threadIdx.x & 31, 32, sd[w].n, &sing);
+        }
         __syncthreads();
     }
     const long long toff = it.t_off;

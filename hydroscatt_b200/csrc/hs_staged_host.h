@@ -45,6 +45,8 @@ struct StP {  // controller state of one particle (Ctl of the fused kernel)
     long long t_off;
     int first_item, n_items;  // this round's items
     int scattered;            // fused scatter: record written / scatter kernel launched
+    int kspec;                // speculative trials to run next round
+    double dprev, dlast;      // max(dsca, dext) / ddelt of the last two consumed trials (convergence trend)
 };
 
 template <class T>
@@ -98,6 +100,7 @@ struct StCall {  // arguments of one hs_calctmat_batch call
     size_t scratch_budget;
     int spec;
     bool trace;
+    bool fuse_solve = true;
     const ScPrep *sp = nullptr;      // fused scatter plan (hs_calctmat_scatter_batch) or null
     mutable int nmax_max = 0;        // out: largest converged NMAX among the staged particles
     mutable bool arena_full = false;  // out: some particle did not fit the caller's arena
@@ -168,7 +171,7 @@ struct StGroup {
             s.first_item = (int)items.size(); s.n_items = 0;
             if (s.phase == 0 && (long long)s.nmax * ndgs > HS_NPNG1) { s.status = HS_ST_NGAUSS_LIMIT; s.done = 2; continue; }
             if ((size_t)(tab_off + wig_off) * 8 + (size_t)sys_off * 16 > C->scratch_budget && !items.empty()) continue;  // next round
-            const int cnt = s.phase == 0 ? K : 1;
+            const int cnt = s.phase == 0 ? (C->spec > 0 ? K : std::max(s.kspec, K)) : 1;
             for (int q = 0; q < cnt; q++) {
                 StItem it;
                 it.p = s.idx;
@@ -182,7 +185,8 @@ struct StGroup {
                 it.t_off = s.phase == 0 ? -1 : s.t_off;
                 tab_off += st_tab_size(it.nmax, it.gp);
                 wig_off += st_wig_mode_off(it.nmax, it.nmodes, it.gp);
-                sys_off += st_sys_mode_off(it.nmax, std::min(it.nmodes, std::max(0, it.nmax - 31)));  // only modes with NM > 32 leave the SM
+                sys_off += C->fuse_solve ? st_sys_mode_off(it.nmax, std::min(it.nmodes, std::max(0, it.nmax - 31)))  // only modes with NM > 32 leave the SM
+                                         : st_sys_mode_off(it.nmax, it.nmodes);
                 gneed = std::max(gneed, it.g);
                 const int ii = (int)items.size();
                 for (int m = 0; m < it.nmodes; m++) {
@@ -194,6 +198,7 @@ struct StGroup {
                     for (int sr = 0; sr < nst; sr++)
                         for (int sc = 0; sc < nst; sc++) (m == 0 ? at0 : at1).push_back({mix, (short)sr, (short)sc});
                     if (NM > 32) gl[NM <= 56 ? 3 : 4].push_back(mix);  // smaller modes are solved inside k_st_assemble
+                    else if (!C->fuse_solve) gl[NM <= 16 ? 0 : (NM <= 24 ? 1 : 2)].push_back(mix);
                 }
                 items.push_back(it);
                 s.n_items++;
@@ -246,7 +251,7 @@ struct StGroup {
         a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
         a.gx = gx; a.gw = gw; a.cm = S->d_cm; a.dd = S->d_dd;
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
-        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res;
+        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res; a.fuse = C->fuse_solve ? 1 : 0;
         const int ni = (int)items.size();
         k_st_radial<<<((int)rad.size() + 7) / 8, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
         mark("radial");
@@ -257,8 +262,9 @@ struct StGroup {
         if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; mark("asm m=0"); }
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
         const int gsm[4] = {16384, 36864, 65536, 200704};
-        for (int c = 3; c >= 0; c--)
-            if (!gl[c].empty()) { k_st_solve<128, false><<<(int)gl[c].size(), 128, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; }
+        if (!gl[3].empty()) { k_st_solve<128, false><<<(int)gl[3].size(), 128, gsm[3], st>>>(a, (const int *)(d + og[3]), (int)gl[3].size()); launches++; }
+        for (int c = 2; c >= 0; c--)
+            if (!gl[c].empty()) { k_st_solve<256, false><<<(int)gl[c].size(), 256, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; mark("solve"); }
         if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, st>>>(a, (const int *)(d + o_sm), (int)sm.size()); launches++; mark("small"); }
         CK(cudaGetLastError());
         inflight = true;
@@ -298,6 +304,7 @@ struct StGroup {
                 s.g = it.g;
                 s.sing |= r.sing;
                 const bool ok = (dsca <= ddelt && dext <= ddelt);
+                if (s.phase == 0) { s.dprev = s.dlast; s.dlast = std::max(dsca, dext) / ddelt; }
                 if (s.phase == 0) {
                     if (ok) { s.phase = (it.g == HS_NPNG1) ? 2 : 1; break; }
                     else if (s.nmax + 1 > HS_NPN1) { s.status = HS_ST_NMAX_LIMIT; s.done = 2; break; }
@@ -310,6 +317,18 @@ struct StGroup {
                     break;
                 }
             }
+        }
+        // speculation depth of the next round from the convergence trend: the relative change of Qsca / Qext shrinks roughly
+        // geometrically with NMAX, so log(d_last) / log(d_prev / d_last) more trials bring it under DDELT
+        for (int j : order) {
+            StP &s = P[j];
+            if (s.done || s.phase != 0) continue;
+            int k = 2;
+            if (s.dprev > s.dlast && s.dlast > 1.0 && std::isfinite(s.dprev)) {
+                const double r = log(s.dlast) / log(s.dprev / s.dlast);
+                k = (int)std::min(8.0, std::max(2.0, ceil(r) + 1.0));
+            }
+            s.kspec = k;
         }
         nround++;
         if (nround > 4 * HS_NPN1 + HS_NPNG1) { ctx->err = "staged controller did not terminate"; return -4; }
@@ -436,12 +455,13 @@ static int st_init(hs_ctx *ctx, StShared &S)
     CK(cudaFuncSetAttribute(k_st_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
     CK(cudaFuncSetAttribute(k_st_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
     CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
+    CK(cudaFuncSetAttribute(k_st_solve<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CK(cudaFuncSetAttribute(k_st_mode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ST_SMALL_SLICE * 8));
     CK(cudaEventCreate(&S.ev_in));
     int prio_lo = 0, prio_hi = 0;
-    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // the convergence rounds are the critical path: scatter fills in behind them
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // opt-in scatter overlap: the scatter streams run at low priority
     for (int g = 0; g < ST_GROUPS; g++) {
-        CK(cudaStreamCreateWithPriority(&S.g[g].stream, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithFlags(&S.g[g].stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&S.g[g].ev, cudaEventDisableTiming));
         CK(cudaStreamCreateWithPriority(&S.g[g].sc_stream, cudaStreamNonBlocking, prio_lo));
         CK(cudaEventCreateWithFlags(&S.g[g].sc_ev, cudaEventDisableTiming));
@@ -473,7 +493,7 @@ static void st_destroy(StShared &S)
 // through the staged pipeline.  `st` is the caller's stream: the groups' streams wait for it (inputs) and it waits for
 // them (outputs) before this returns.
 static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std::vector<int> &sel, const std::vector<int> &n0_of,
-                           const StCall &C)
+                           const std::vector<int> &lb_of, const StCall &C)
 {
     const int ns = (int)sel.size();
     if (!ns) return 0;
@@ -495,6 +515,9 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         StP s;
         s.idx = sel[j]; s.phase = 0; s.nmax = n0_of[j]; s.g = 0; s.ntr = 0; s.status = HS_ST_OK; s.done = 0; s.sing = 0;
         s.q1s = 0.0; s.q1e = 0.0; s.t_off = -1; s.first_item = 0; s.n_items = 0; s.scattered = 0;
+        // every trial from the starting order to the converged one is needed, so a lower bound of the converged order is free
+        // parallelism: the first round runs them all at once
+        s.kspec = std::max(2, std::min(12, lb_of[j] - n0_of[j] + 1)); s.dprev = 0.0; s.dlast = 0.0;
         if (s.nmax < 0) { s.done = 2; s.status = HS_ST_BAD_INPUT; s.nmax = 0; }
         else if (s.nmax >= HS_NPN1) { s.done = 2; s.status = HS_ST_NMAX_LIMIT; }
         G[r % ng].P.push_back(s);

@@ -263,7 +263,7 @@ struct Bucket {
 // max(NMAX0 + 1, ceil(|m| k a_max + 2)) is a tight estimate on the 6-band rain sweep; particles that still outgrow
 // their shared-memory slice continue in the global-memory fall-back workspace (no re-launch).
 __global__ void k_nmax0(int n, const double *axi, const double *lam, const double *mr, const double *mi,
-                        const double *eps, double rat, int *out, int *out_n0)
+                        const double *eps, double rat, int *out, int *out_n0, int *out_lb)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -286,6 +286,9 @@ __global__ void k_nmax0(int n, const double *axi, const double *lam, const doubl
     out[i] = max(n0 + 1, pred);
     const bool bad = !(axi[i] > 0.0) || !(lam[i] > 0.0) || !(e_ > 0.0) || !isfinite(mr[i]) || !isfinite(mi[i]) || !(mr[i] * mr[i] + mi[i] * mi[i] > 0.0);
     out_n0[i] = bad ? -1 : n0;
+    // lower-bound guess of the converged NMAX (speculation depth of the first round; only costs work if wrong):
+    // NMAX ~ 0.60 |m| k a_max + 4.5 on the rain sweep (r = 0.98), minus a margin of 2
+    out_lb[i] = (mx > 0.0 && mx < 1e6) ? max(n0 + 1, (int)floor(0.6035 * mx + 4.49) - 2) : n0 + 1;
 }
 
 template <bool WARP, bool GLOBAL_WS, bool TILED>
@@ -364,7 +367,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     if (!ctx->d_ws_fb) {
         if (cudaMalloc(&ctx->d_ws_fb, (size_t)ctx->sm_count * 8 * fb_cap * sizeof(double)) != cudaSuccess) { ctx->d_ws_fb = nullptr; cudaGetLastError(); }
     }
-    if (ensure_pin(ctx, (size_t)n * sizeof(int) * 3)) return -1;
+    if (ensure_pin(ctx, (size_t)n * sizeof(int) * 4)) return -1;
     if (n > ctx->items_cap) {
         if (ctx->d_items) cudaFree(ctx->d_items);
         ctx->d_items = nullptr; ctx->items_cap = 0;
@@ -373,15 +376,15 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     }
     // predicted starting NMAX -> initial bucket
     // (the kernel writes straight into the pinned host block: no D2H copy that could queue behind a caller's bulk transfer)
-    int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n, *h_start = ctx->h_pin + 2 * (size_t)n;
-    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, h_n0, h_start);
+    int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n, *h_start = ctx->h_pin + 2 * (size_t)n, *h_lb = ctx->h_pin + 3 * (size_t)n;
+    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, h_n0, h_start, h_lb);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     // Particles whose predicted order reaches HYDROTM_STAGED_MIN go through the staged pipeline (one kernel per stage,
     // trials and modes as independent work items); the small ones stay on the fused one-particle-per-group kernel.
     const int staged_min = getenv("HYDROTM_STAGED_MIN") ? atoi(getenv("HYDROTM_STAGED_MIN")) : 0;
-    std::vector<int> st_sel, st_n0;
+    std::vector<int> st_sel, st_n0, st_lb;
     if (!ctx->st) ctx->st = new StBufsHolder();
     bool staged_done = false;
     StCall SC;
@@ -392,9 +395,10 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     SC.spec = getenv("HYDROTM_SPEC") ? atoi(getenv("HYDROTM_SPEC")) : 0;
     SC.trace = trace;
     SC.sp = nullptr;
+    SC.fuse_solve = !(getenv("HYDROTM_FUSE_SOLVE") && atoi(getenv("HYDROTM_FUSE_SOLVE")) == 0);
     auto run_staged = [&]() -> int {
         staged_done = true;
-        return calctmat_staged(ctx, ctx->st->s, st, st_sel, st_n0, SC);
+        return calctmat_staged(ctx, ctx->st->s, st, st_sel, st_n0, st_lb, SC);
     };
 
     if (getenv("HYDROTM_PROF") && !ctx->d_prof) { CK(cudaMalloc(&ctx->d_prof, 8 * sizeof(long long))); }
@@ -405,7 +409,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     for (int i = 0; i < n; i++) {
         int n0 = h_n0[i];
         nm0[i] = n0;
-        if (n0 >= staged_min && h_start[i] >= 0) { st_sel.push_back(i); st_n0.push_back(h_start[i]); bucket_of[i] = -1; continue; }
+        if (n0 >= staged_min && h_start[i] >= 0) { st_sel.push_back(i); st_n0.push_back(h_start[i]); st_lb.push_back(h_lb[i]); bucket_of[i] = -1; continue; }
         int np_ = std::min(n0, HS_NPN1);
         long long need = hs::ws_need(np_, np_ * ndgs + 1);
         int b = 0;

@@ -49,6 +49,7 @@ struct StArgs {
     long long *toff;
     StResult *res;
     int fuse;                // solve modes with NM <= 32 inside k_st_assemble (default) or in k_st_solve
+    unsigned long long *prof;  // HYDROTM_PROF=1: phase cycle counters of k_st_assemble [prologue, chunks, epilogue, solve, T write, #CTAs, sum NM, sum g]
 };
 
 enum { NA_X = 0, NA_S, NA_SS, NA_DR, NA_DDR, NA_DRR, NA_DRI, NA_RR, NA_COUNT };
@@ -458,6 +459,8 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
 {
     extern __shared__ __align__(16) double op[];
     if ((int)blockIdx.x >= ntasks) return;
+    long long tprof = a.prof ? clock64() : 0;
+#define ST_PROF(slot) if (a.prof && threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&a.prof[slot], (unsigned long long)(now_ - tprof)); tprof = now_; }
     const StATask tk = tasks[blockIdx.x];
     const StModeItem mi = st_unpack_mode(tk.mi);
     const StItem it = a.items[mi.item];
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     const double an1 = (double)(n1 * (n1 + 1)), an2 = (double)(n2 * (n2 + 1));
     const int fragrow = lane >> 2, fragk = lane & 3;
 
+    ST_PROF(0)
     for (int i0 = 0; i0 < g; i0 += 8) {
         {
             const int i = i0 + ii;
@@ -612,6 +616,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
         __syncthreads();
     }
 
+    ST_PROF(1)
     // epilogue: lane holds (re, im) of X_F[a][b] with a = 4 tr + (lane >> 3), F = (lane >> 2) & 1, b = 4 tc + (lane & 3);
     // the y values come from lane ^ 4; lanes with F = 0 write the four system entries of the pair
     const int p = it.p;
@@ -658,6 +663,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     __shared__ int sing;
     if (tid == 0) sing = 0;
     __syncthreads();
+    ST_PROF(2)
     const int ldc = 2 * NM;
     if (M0) {
         // four half-size systems (T12 = T21 = 0), a pair of warps each
@@ -673,6 +679,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
         solve_grp(d, tid & 127, 128, 1 + q, keyslot[q], &sing);
     }
     __syncthreads();
+    ST_PROF(3)
     const long long toff = it.t_off;
     if (toff >= 0) {
         double2 *tg = reinterpret_cast<double2 *>(a.tarena) + toff + st_t_mode_off(nmax, m);
@@ -697,6 +704,9 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
         }
         if (sing) a.res[mi.item].sing = 1;
     }
+    ST_PROF(4)
+    if (a.prof && threadIdx.x == 0) { atomicAdd(&a.prof[5], 1ull); atomicAdd(&a.prof[6], (unsigned long long)NM); atomicAdd(&a.prof[7], (unsigned long long)g); }
+#undef ST_PROF
 }
 
 // ---- G: parity-class systems of one (item, mode): T = -RgQ Q^-1 by the lock-step Gauss-Jordan of hs_tmat.cuh ----

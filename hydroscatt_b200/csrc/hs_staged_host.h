@@ -101,6 +101,7 @@ struct StCall {  // arguments of one hs_calctmat_batch call
     int spec;
     bool trace;
     bool fuse_solve = true;
+    unsigned long long *prof = nullptr;
     const ScPrep *sp = nullptr;      // fused scatter plan (hs_calctmat_scatter_batch) or null
     mutable int nmax_max = 0;        // out: largest converged NMAX among the staged particles
     mutable bool arena_full = false;  // out: some particle did not fit the caller's arena
@@ -251,7 +252,7 @@ struct StGroup {
         a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
         a.gx = gx; a.gw = gw; a.cm = S->d_cm; a.dd = S->d_dd;
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
-        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res; a.fuse = C->fuse_solve ? 1 : 0;
+        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res; a.fuse = C->fuse_solve ? 1 : 0; a.prof = C->prof;
         const int ni = (int)items.size();
         k_st_radial<<<((int)rad.size() + 7) / 8, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
         mark("radial");

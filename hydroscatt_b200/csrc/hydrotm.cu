@@ -396,6 +396,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     SC.trace = trace;
     SC.sp = nullptr;
     SC.fuse_solve = !(getenv("HYDROTM_FUSE_SOLVE") && atoi(getenv("HYDROTM_FUSE_SOLVE")) == 0);
+    SC.prof = (unsigned long long *)ctx->d_prof;
     auto run_staged = [&]() -> int {
         staged_done = true;
         return calctmat_staged(ctx, ctx->st->s, st, st_sel, st_n0, st_lb, SC);
@@ -518,8 +519,18 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
         long long hp[8];
         CK(cudaMemcpy(hp, ctx->d_prof, sizeof(hp), cudaMemcpyDeviceToHost));
         double tot = 0; for (int i = 0; i < 8; i++) tot += (double)hp[i];
-        const char *nm[8] = {"other", "trial_setup", "assemble m=0", "solve m=0", "mode_setup", "assemble m>=1", "solve m>=1", "write T"};
-        for (int i = 0; i < 8; i++) fprintf(stderr, "[hydrotm-prof] %-14s %6.2f%%  %.3e cycles\n", nm[i], 100.0 * hp[i] / tot, (double)hp[i]);
+        if (st_sel.empty()) {
+            const char *nm[8] = {"other", "trial_setup", "assemble m=0", "solve m=0", "mode_setup", "assemble m>=1", "solve m>=1", "write T"};
+            for (int i = 0; i < 8; i++) fprintf(stderr, "[hydrotm-prof] %-14s %6.2f%%  %.3e cycles\n", nm[i], 100.0 * hp[i] / tot, (double)hp[i]);
+        } else {
+            // staged pipeline: phases of k_st_assemble (thread 0 of every CTA)
+            const char *nm[5] = {"prologue", "chunk loop", "epilogue", "solve", "T write"};
+            double t5 = 0; for (int i = 0; i < 5; i++) t5 += (double)hp[i];
+            const double ncta = (double)hp[5] > 0 ? (double)hp[5] : 1.0;
+            for (int i = 0; i < 5; i++)
+                fprintf(stderr, "[hydrotm-prof] k_st_assemble %-10s %6.2f%%  %8.0f cycles / CTA\n", nm[i], 100.0 * hp[i] / t5, (double)hp[i] / ncta);
+            fprintf(stderr, "[hydrotm-prof] k_st_assemble %.0f CTAs, mean NM %.1f, mean g %.1f, %.0f cycles / CTA\n", ncta, (double)hp[6] / ncta, (double)hp[7] / ncta, t5 / ncta);
+        }
     }
     // remember the largest converged NMAX (bounds the T stage of the scatter kernel); the staged pipeline reports its own
     if (SC.nmax_max > ctx->last_nmax_max) ctx->last_nmax_max = SC.nmax_max;

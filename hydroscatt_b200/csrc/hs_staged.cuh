@@ -510,10 +510,11 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
         {
             const int i = i0 + ii;
             const bool vi = i < g;
-            // left operand rows (k1, j | y)
-            {
+            // left operand rows (k1, j | y).  Rows of k >= NM are never stored: they only feed accumulator rows / columns
+            // that the epilogue discards (the kernel is shared-memory-bandwidth bound: mean NM is 14 of the 32 rows)
+            if (k1 < NM) {
                 double d1 = 0.0, d2 = 0.0, fj = 0.0, fdj = 0.0, fy = 0.0, fdy = 0.0;
-                if (vi && k1 < NM) {
+                if (vi) {
                     const long o = (long)(n1 - 1) * gp + i;
                     d1 = w1[(long)k1 * gp + i]; d2 = w2[(long)k1 * gp + i];
                     fj = tb[o]; fdj = tb[tsz + o]; fy = tb[2 * tsz + o]; fdy = tb[3 * tsz + o];
@@ -526,10 +527,10 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
                 o0[4 * 512] = an1 * p3j; o1[4 * 512] = an1 * p3y;  // P3a
             }
             // right operand rows (k2, re | im)
-            {
+            if (k2 < NM) {
                 double d1 = 0.0, d2 = 0.0, jr = 0.0, ji = 0.0, djr = 0.0, dji = 0.0;
                 double rri = 0.0, uri = 0.0, ddri = 0.0, drri = 0.0, drii = 0.0, ssi = 0.0, si = 0.0;
-                if (vi && k2 < NM) {
+                if (vi) {
                     const long o = (long)(n2 - 1) * gp + i;
                     d1 = w1[(long)k2 * gp + i]; d2 = w2[(long)k2 * gp + i];
                     jr = tb[4 * tsz + o]; ji = tb[5 * tsz + o]; djr = tb[6 * tsz + o]; dji = tb[7 * tsz + o];
@@ -559,7 +560,9 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
                 }
             }
         }
+        ST_PROF(8)
         __syncthreads();
+        ST_PROF(9)
 #pragma unroll
         for (int ks = 0; ks < 2; ks++) {
             // fragment element of table t, rows [row0, row0 + 8): row0 + (lane >> 2), node 4 ks + (lane & 3)
@@ -613,7 +616,9 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
                 }
             }
         }
+        ST_PROF(10)
         __syncthreads();
+        ST_PROF(11)
     }
 
     ST_PROF(1)

@@ -402,8 +402,8 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
         return calctmat_staged(ctx, ctx->st->s, st, st_sel, st_n0, st_lb, SC);
     };
 
-    if (getenv("HYDROTM_PROF") && !ctx->d_prof) { CK(cudaMalloc(&ctx->d_prof, 8 * sizeof(long long))); }
-    if (ctx->d_prof) CK(cudaMemsetAsync(ctx->d_prof, 0, 8 * sizeof(long long), st));
+    if (getenv("HYDROTM_PROF") && !ctx->d_prof) { CK(cudaMalloc(&ctx->d_prof, 16 * sizeof(long long))); }
+    if (ctx->d_prof) CK(cudaMemsetAsync(ctx->d_prof, 0, 16 * sizeof(long long), st));
     lap("nmax0 kernel + D2H");
     std::vector<int> bucket_of(n), nm0(n);
     std::vector<std::vector<int>> lists(NB);
@@ -516,7 +516,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     }
     if (!staged_done) { int rc = run_staged(); if (rc) return rc; lap("staged pipeline (alone)"); }
     if (ctx->d_prof) {
-        long long hp[8];
+        long long hp[16];
         CK(cudaMemcpy(hp, ctx->d_prof, sizeof(hp), cudaMemcpyDeviceToHost));
         double tot = 0; for (int i = 0; i < 8; i++) tot += (double)hp[i];
         if (st_sel.empty()) {
@@ -529,6 +529,8 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
             const double ncta = (double)hp[5] > 0 ? (double)hp[5] : 1.0;
             for (int i = 0; i < 5; i++)
                 fprintf(stderr, "[hydrotm-prof] k_st_assemble %-10s %6.2f%%  %8.0f cycles / CTA\n", nm[i], 100.0 * hp[i] / t5, (double)hp[i] / ncta);
+            fprintf(stderr, "[hydrotm-prof] k_st_assemble chunk loop split: build %.0f, barrier %.0f, contraction %.0f, barrier %.0f cycles / CTA\n",
+                    (double)hp[8] / ncta, (double)hp[9] / ncta, (double)hp[10] / ncta, (double)hp[11] / ncta);
             fprintf(stderr, "[hydrotm-prof] k_st_assemble %.0f CTAs, mean NM %.1f, mean g %.1f, %.0f cycles / CTA\n", ncta, (double)hp[6] / ncta, (double)hp[7] / ncta, t5 / ncta);
         }
     }

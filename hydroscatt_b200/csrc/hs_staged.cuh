@@ -437,6 +437,76 @@ __device__ __forceinline__ void solve_grp(const SysDesc d, int t, int nl, int ba
     }
 }
 
+
+// Leaner variant of solve_grp (the elimination is instruction-bound, not latency-bound: ~1 900 cycles per step were
+// measured for a step whose dependent latencies add up to ~450): fixed column ownership (lane pair ct owns columns ct,
+// ct + nl/2: no per-step pointer arithmetic), 32-bit offsets, the pivot key is formed only by the pair that owns
+// column k + 1.  Same pivot rule, same arithmetic, same results as solve_grp.
+__device__ __forceinline__ void solve_grp2(const SysDesc d, int t, int nl, int barid, unsigned long long *keyslot, int *sing)
+{
+    const int n = d.n, nc = 2 * n;
+    const int rstep = d.stride * d.ld;
+    double2 *b0 = d.base + d.off * d.ld;
+    const int ct = (t & 15) | ((t >> 5) << 4), rs = (t >> 4) & 1, ncl = nl >> 1;
+    // this lane pair's columns (at most two: nc <= 2 * ncl)
+    const int j0 = ct, j1 = ct + ncl;
+    const int c0 = j0 < n ? d.off + d.stride * j0 : d.rhs + d.off + d.stride * (j0 - n);
+    const int c1 = j1 < n ? d.off + d.stride * j1 : d.rhs + d.off + d.stride * (j1 - n);
+    if (t < 32) {
+        unsigned long long key = 0ull;
+        const double2 *cc = b0 + d.off;
+        for (int r = t; r < n; r += 32) { const unsigned long long ky = pivot_key(cc[r * rstep], r); key = ky > key ? ky : key; }
+        for (int o = 16; o; o >>= 1) { const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o); key = ok > key ? ok : key; }
+        if (t == 0) keyslot[0] = key;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nl) : "memory");
+    for (int k = 0; k < n; k++) {
+        const unsigned long long key = keyslot[k & 1];
+        const int p = 255 - (int)(key & 0xFFull);
+        if ((key >> 8) == 0ull && t == 0) *sing = 1;
+        const double2 *ck = b0 + (d.off + d.stride * k);
+        const double2 pv = ck[p * rstep];
+        const double den = pv.x * pv.x + pv.y * pv.y;
+        const double2 inv = make_double2(pv.x / den, -pv.y / den);
+        const double2 fkk = ck[k * rstep];
+        unsigned long long nkey = 0ull;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int j = h ? j1 : j0;
+            const bool live = j > k && j < nc;
+            double2 *cj = b0 + (h ? c1 : c0);
+            double2 a = make_double2(0.0, 0.0), b = a;
+            if (live) { a = cj[k * rstep]; b = cj[p * rstep]; }
+            __syncwarp();  // both lanes of the column have read rows k and p before one of them rewrites them
+            if (live) {
+                const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
+                if (rs == 0) { cj[k * rstep] = nk; if (p != k) cj[p * rstep] = a; }
+                const bool next_col = (j == k + 1) && (k + 1 < n);
+                const double2 *fr = ck + rs * rstep;
+                double2 *vr = cj + rs * rstep;
+                const int rstep2 = 2 * rstep;
+#pragma unroll 4
+                for (int r = rs; r < n; r += 2, fr += rstep2, vr += rstep2) {
+                    if (r == k) continue;
+                    // after the row swap, row p holds the old row k (value a; its column-k entry is still at (k, k))
+                    const double2 f = (r == p) ? fkk : *fr;
+                    double2 v = (r == p) ? a : *vr;
+                    v.x -= f.x * nk.x - f.y * nk.y;
+                    v.y -= f.x * nk.y + f.y * nk.x;
+                    *vr = v;
+                    if (next_col && r > k) { const unsigned long long ky = pivot_key(v, r); nkey = ky > nkey ? ky : nkey; }
+                }
+            }
+            if (ncl >= nc) break;  // group-uniform: no lane has a second column
+        }
+        // the pair that owns column k + 1 publishes the next pivot
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, nkey, 16);
+        nkey = ok > nkey ? ok : nkey;
+        if (rs == 0 && (j0 == k + 1 || j1 == k + 1)) keyslot[(k + 1) & 1] = nkey;
+        asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nl) : "memory");
+    }
+}
+
 // ---- A: Q / RgQ integrals of one 32 x 32 block of (k1, k2) = (n1 - nmin, n2 - nmin) as DMMA contractions ----
 // See assemble_tiled (hs_tmat.cuh) for the factorisation: X = sum over nodes of (left factor of (n1, node)) x (right
 // factor of (n2, node)).  Left operand tables L_t[(k1, F)][node], F in {j, y}: P1 = d1 dF, P2 = d2 dF, P3 = d1 F,
@@ -630,7 +700,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     const double ppi = kw * kw, pir = ppi * a.mr[p], pii = ppi * a.mi[p];
     // NM <= 32: the block is the whole mode; the systems are combined in the (now free) operand area, solved here and only
     // the T block leaves the SM.  Larger modes write their part of [Q | RgQ] to global memory for k_st_solve.
-    const bool fused = NM <= 32 && a.fuse;
+    const bool fused = NM <= 32 && (a.fuse & 1);
     double2 *sys = fused ? reinterpret_cast<double2 *>(op) : a.sys + it.sys_off + st_sys_mode_off(nmax, m);
 #pragma unroll
     for (int r = 0; r < NTR; r++)
@@ -675,13 +745,13 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
         const int q = warp >> 1;
         SysDesc d;
         d.base = sys + (long)(q >> 1) * NM * ldc; d.ld = ldc; d.off = q & 1; d.stride = 2; d.rhs = NM; d.n = (NM + 1 - (q & 1)) >> 1;
-        if (d.n > 0) solve_grp(d, tid & 63, 64, 1 + q, keyslot[q], &sing);
+        if (d.n > 0) { if (a.fuse & 2) solve_grp2(d, tid & 63, 64, 1 + q, keyslot[q], &sing); else solve_grp(d, tid & 63, 64, 1 + q, keyslot[q], &sing); }
     } else {
         // the two parity classes, four warps each
         const int q = warp >> 2;
         SysDesc d;
         d.base = sys + (long)q * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
-        solve_grp(d, tid & 127, 128, 1 + q, keyslot[q], &sing);
+        if (a.fuse & 2) solve_grp2(d, tid & 127, 128, 1 + q, keyslot[q], &sing); else solve_grp(d, tid & 127, 128, 1 + q, keyslot[q], &sing);
     }
     __syncthreads();
     ST_PROF(3)
@@ -710,7 +780,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
         if (sing) a.res[mi.item].sing = 1;
     }
     ST_PROF(4)
-    if (a.prof && threadIdx.x == 0) { atomicAdd(&a.prof[5], 1ull); atomicAdd(&a.prof[6], (unsigned long long)NM); atomicAdd(&a.prof[7], (unsigned long long)g); }
+    if (a.prof && threadIdx.x == 0) { atomicAdd(&a.prof[5], 1ull); atomicAdd(&a.prof[6], (unsigned long long)NM); atomicAdd(&a.prof[7], (unsigned long long)g); atomicAdd(&a.prof[12], (unsigned long long)(M0 ? (NM + 1) / 2 : NM)); }
 #undef ST_PROF
 }
 
@@ -769,7 +839,7 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
             __shared__ unsigned long long keyslot[4][2];
             const int warp = threadIdx.x >> 5;
             const int q = (m == 0) ? (warp >> 1) : (warp >> 2);
-            if (q < nsys && sd[q].n > 0) solve_grp(sd[q], threadIdx.x & (m == 0 ? 63 : 127), m == 0 ? 64 : 128, 1 + q, keyslot[q], &sing);
+            if (q < nsys && sd[q].n > 0) solve_grp2(sd[q], threadIdx.x & (m == 0 ? 63 : 127), m == 0 ? 64 : 128, 1 + q, keyslot[q], &sing);
         } else {
             // one warp per system (m = 0: four half-size systems, m >= 1: the two parity classes)
             const int w = threadIdx.x >> 5;

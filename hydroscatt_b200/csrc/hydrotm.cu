@@ -531,6 +531,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
                 fprintf(stderr, "[hydrotm-prof] k_st_assemble %-10s %6.2f%%  %8.0f cycles / CTA\n", nm[i], 100.0 * hp[i] / t5, (double)hp[i] / ncta);
             fprintf(stderr, "[hydrotm-prof] k_st_assemble chunk loop split: build %.0f, barrier %.0f, contraction %.0f, barrier %.0f cycles / CTA\n",
                     (double)hp[8] / ncta, (double)hp[9] / ncta, (double)hp[10] / ncta, (double)hp[11] / ncta);
+            fprintf(stderr, "[hydrotm-prof] k_st_assemble solve: %.1f elimination steps / CTA -> %.0f cycles / step\n", (double)hp[12] / ncta, (double)hp[3] / std::max(1.0, (double)hp[12]));
             fprintf(stderr, "[hydrotm-prof] k_st_assemble %.0f CTAs, mean NM %.1f, mean g %.1f, %.0f cycles / CTA\n", ncta, (double)hp[6] / ncta, (double)hp[7] / ncta, t5 / ncta);
         }
     }

@@ -1,0 +1,55 @@
+"""GPU parity on the other BASELINE workloads (SURVEY.md 8(d) W3 ice crystals, W4 hail): converged (NMAX, NGAUSS, trials,
+status) identical to the oracle, amplitudes within 1e-6 (ill-conditioned particles: 10x the oracle's own sensitivity)."""
+import numpy as np
+import pytest
+
+import oracle
+from tests.workloads import ice_grid, hail_grid
+
+pytestmark = pytest.mark.gpu
+GEOMS = [(90.0, 90.0, 0.0, 180.0), (90.0, 90.0, 0.0, 0.0)]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from hydroscatt_b200.engine import Engine
+    return Engine(0)
+
+
+def _check(engine, w, ndgs, max_oracle_nmax=48):
+    tb = engine.calctmat(w["radius"], w["wavelength"], w["mr"], w["mi"], w["axis_ratio"], ndgs=ndgs)
+    ref = oracle.sl_batch(w["radius"], w["wavelength"], w["mr"], w["mi"], w["axis_ratio"], geoms=GEOMS, alpha=[20.0], beta=[35.0],
+                          wgt=[1.0], ndgs=ndgs)
+    S, _ = tb.ampl(GEOMS, alpha=[20.0], beta=[35.0])
+    S = S.cpu().numpy()[:, :, 0]
+    meta = [t.cpu().numpy() for t in (tb.nmax, tb.ngauss, tb.ntrials, tb.status)]
+    n = w["radius"].size
+    checked = skipped = 0
+    for i in range(n):
+        sens = oracle.sl_sensitivity(w["radius"][i], w["wavelength"][i], complex(w["mr"][i], w["mi"][i]), w["axis_ratio"][i], ndgs=ndgs)
+        if not np.isfinite(sens) or sens > 1e-2:
+            skipped += 1  # the oracle itself is rounding noise here (hard part 3)
+            continue
+        assert (meta[0][i], meta[1][i], meta[2][i], meta[3][i]) == (ref["nmax"][i], ref["ngauss"][i], ref["ntrials"][i], ref["status"][i]), i
+        if ref["status"][i] != 0:
+            continue
+        tol = max(1e-6, 10 * sens)
+        err = np.abs(S[i] - ref["S"][i]).max() / np.abs(ref["S"][i]).max()
+        assert err < tol, (i, err, sens)
+        checked += 1
+    assert checked >= n // 2, (checked, skipped)
+    return meta
+
+
+def test_w3_ice_crystals(engine):
+    meta = _check(engine, ice_grid(), ndgs=2)
+    assert meta[0].max() >= 10
+
+
+def test_w3_ice_crystals_ndgs15(engine):
+    _check(engine, ice_grid(seed=5, n=24), ndgs=15)
+
+
+def test_w4_hail(engine):
+    meta = _check(engine, hail_grid(), ndgs=2)
+    assert meta[0].max() > 32  # multi-block assembly + separate solve path exercised

@@ -20,3 +20,30 @@ def rain_grid(band="C", m=None):
     m = M_W_10C[band] if m is None else m
     return dict(D=D, radius=D / 2.0, wavelength=lam, mr=np.full_like(D, m.real), mi=np.full_like(D, m.imag),
                 axis_ratio=1.0 / dsr_thurai_2007(D))
+
+
+def ice_grid(seed=3, n=64):
+    """W3-like (scattering_ice_crystals.py regimes): plates / columns, maximum dimension 0.05..2 mm, axis ratios 1.5..6
+    (oblate) and 1/4..1/1.5 (prolate; more extreme shapes do not converge in FP64 in either implementation), solid ice at X / Ka / W band.  Equal-volume radius from the maximum dimension as
+    Scatterer.equal_volume_from_maximum does."""
+    rng = np.random.default_rng(seed)
+    L = rng.uniform(0.05, 2.0, n)
+    ar = np.where(rng.uniform(size=n) < 0.7, rng.uniform(1.5, 6.0, n), 1.0 / rng.uniform(1.5, 4.0, n))
+    band = rng.choice(["X", "Ka", "W"], n)
+    lam = np.array([WL[b] for b in band])
+    req = np.where(ar > 1, (L / 2) / ar ** (1 / 3), (L / 2) / ar ** (2 / 3))
+    return dict(radius=req, wavelength=lam, mr=np.full(n, 1.78), mi=np.full(n, 0.0024), axis_ratio=ar)
+
+
+def hail_grid(seed=4, n=48):
+    """W4-like single-layer hail: D 2..50 mm at C / X / Ka band, dry (ice) to wet (high |m|) refractive indices, mild
+    oblateness: NMAX up to ~40, exercises the multi-block assembly and the separate solve kernel."""
+    rng = np.random.default_rng(seed)
+    D = rng.uniform(2.0, 50.0, n)
+    band = rng.choice(["C", "X", "Ka"], n)
+    lam = np.array([WL[b] for b in band])
+    wet = rng.uniform(size=n)
+    mr = 1.78 + wet * 4.0
+    mi = 0.003 + wet * 1.5
+    ar = 1.0 / rng.uniform(0.7, 1.0, n)
+    return dict(radius=D / 2.0, wavelength=lam, mr=mr, mi=mi, axis_ratio=ar)

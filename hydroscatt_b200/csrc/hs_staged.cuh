@@ -517,6 +517,7 @@ __device__ __forceinline__ void solve_grp2(const SysDesc d, int t, int nl, int b
 // the fragment loads are conflict-free); each warp owns one parity block's tile rows for both outputs (so the
 // epilogue that combines X_A and X_B into Q and RgQ entries stays in registers).
 #define ST_OP_DOUBLES (15 * 64 * 8)
+#define ST_ASM_SMEM16 (15 * 32 * 8 * 8)  // KR = 16 variant: operand area 30 720 B (>= the 16 KB of its fused systems)
 #define ST_ASM_SMEM 65536  // operand area (61 440 B), re-used for the [2][32][64] complex systems of a fused solve
 
 __device__ __forceinline__ void st_dmma(double *c, double a, double b)
@@ -524,9 +525,13 @@ __device__ __forceinline__ void st_dmma(double *c, double a, double b)
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <bool M0>
-__global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask *tasks, int ntasks)
+// KR = width of the (n, n') block handled by one CTA: 32 (256 threads, any NM, multi-block above 32) or 16 (128 threads,
+// NM <= 16 only: half the registers and a quarter of the shared memory per CTA, so twice as many CTAs per SM for the
+// majority of the modes).
+template <bool M0, int KR>
+__global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs a, const StATask *tasks, int ntasks)
 {
+    constexpr int THREADS = 8 * KR, TSTR = 16 * KR, TC = KR / 8, HMAX = KR / 2;  // table stride (doubles), tile columns, rows per parity
     extern __shared__ __align__(16) double op[];
     if ((int)blockIdx.x >= ntasks) return;
     long long tprof = a.prof ? clock64() : 0;
@@ -537,7 +542,7 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     const int m = M0 ? 0 : mi.m;
     const int nmax = it.nmax, g = it.g, gp = it.gp;
     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
-    const int kr0 = 32 * tk.sr, kc0 = 32 * tk.sc;
+    const int kr0 = KR * tk.sr, kc0 = KR * tk.sc;
     const double *nod = a.tab + it.tab_off;
     const double *tb = nod + (long)NA_COUNT * gp;
     const long tsz = (long)nmax * gp;
@@ -549,25 +554,32 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
 
     // warp -> parity block (prow, pcol) and tile rows [tr0, tr0 + NTR)
     constexpr int NTR = M0 ? 1 : 2;
+    constexpr int TRS = (KR == 32 && !M0) ? 2 : 1;  // tile-row stride between a warp's accumulator slots
     int prow, pcol, tr0;
-    // tile rows are dealt to a block's warps round-robin (m >= 1: rows tr0, tr0 + 2), so half-empty blocks stay balanced
-    if (M0) { prow = pcol = warp >> 2; tr0 = warp & 3; }
-    else { const int beta = warp >> 1; prow = (beta == 1 || beta == 3) ? 1 : 0; pcol = (beta == 1 || beta == 2) ? 1 : 0; tr0 = warp & 1; }
+    // KR = 32: tile rows are dealt to a block's two warps round-robin (m >= 1: rows tr0, tr0 + 2), so half-empty blocks
+    // stay balanced; KR = 16: one warp per block (m >= 1: both tile rows) or per (block, tile row) (m = 0)
+    if (KR == 32) {
+        if (M0) { prow = pcol = warp >> 2; tr0 = warp & 3; }
+        else { const int beta = warp >> 1; prow = (beta == 1 || beta == 3) ? 1 : 0; pcol = (beta == 1 || beta == 2) ? 1 : 0; tr0 = warp & 1; }
+    } else {
+        if (M0) { prow = pcol = warp >> 1; tr0 = warp & 1; }
+        else { prow = (warp == 1 || warp == 3) ? 1 : 0; pcol = (warp == 1 || warp == 2) ? 1 : 0; tr0 = 0; }
+    }
     const bool even = prow == pcol;
-    int hrow = (NM - kr0 - prow + 1) >> 1; hrow = hrow < 0 ? 0 : (hrow > 16 ? 16 : hrow);
-    int hcol = (NM - kc0 - pcol + 1) >> 1; hcol = hcol < 0 ? 0 : (hcol > 16 ? 16 : hcol);
+    int hrow = (NM - kr0 - prow + 1) >> 1; hrow = hrow < 0 ? 0 : (hrow > HMAX ? HMAX : hrow);
+    int hcol = (NM - kc0 - pcol + 1) >> 1; hcol = hcol < 0 ? 0 : (hcol > HMAX ? HMAX : hcol);
     const int TMv = (2 * hrow + 7) >> 3, TNv = (2 * hcol + 7) >> 3;
 
-    double acc[NTR][4][2][2];
+    double acc[NTR][TC][2][2];
 #pragma unroll
     for (int r = 0; r < NTR; r++)
 #pragma unroll
-        for (int c = 0; c < 4; c++)
+        for (int c = 0; c < TC; c++)
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[r][c][e >> 1][e & 1] = 0.0;
 
     // build-phase constants of this thread: rows (kk, F) / (kk, re|im) of every table, column ii (swizzled)
-    const int rho = (kk & 1) * 32 + 2 * (kk >> 1);
+    const int rho = (kk & 1) * KR + 2 * (kk >> 1);
     const int col = ii ^ (((rho >> 1) & 1) << 2);
     double *o0 = op + rho * 8 + col, *o1 = o0 + 8;
     const int k1 = kr0 + kk, k2 = kc0 + kk;
@@ -589,12 +601,12 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
                     d1 = w1[(long)k1 * gp + i]; d2 = w2[(long)k1 * gp + i];
                     fj = tb[o]; fdj = tb[tsz + o]; fy = tb[2 * tsz + o]; fdy = tb[3 * tsz + o];
                 }
-                o0[0 * 512] = d1 * fdj; o1[0 * 512] = d1 * fdy;  // P1
-                o0[1 * 512] = d2 * fdj; o1[1 * 512] = d2 * fdy;  // P2
+                o0[0 * TSTR] = d1 * fdj; o1[0 * TSTR] = d1 * fdy;  // P1
+                o0[1 * TSTR] = d2 * fdj; o1[1 * TSTR] = d2 * fdy;  // P2
                 const double p3j = d1 * fj, p3y = d1 * fy;
-                o0[2 * 512] = p3j; o1[2 * 512] = p3y;            // P3
-                o0[3 * 512] = d2 * fj; o1[3 * 512] = d2 * fy;    // P4
-                o0[4 * 512] = an1 * p3j; o1[4 * 512] = an1 * p3y;  // P3a
+                o0[2 * TSTR] = p3j; o1[2 * TSTR] = p3y;            // P3
+                o0[3 * TSTR] = d2 * fj; o1[3 * TSTR] = d2 * fy;    // P4
+                o0[4 * TSTR] = an1 * p3j; o1[4 * TSTR] = an1 * p3y;  // P3a
             }
             // right operand rows (k2, re | im)
             if (k2 < NM) {
@@ -610,23 +622,23 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
                 }
                 const double jzr = jr * drri - ji * drii, jzi = ji * drri + jr * drii;
                 const double wb = rri * d2, wd = an2 * rri * uri * d1;
-                o0[6 * 512] = wb * jr; o1[6 * 512] = wb * ji;    // q2
+                o0[6 * TSTR] = wb * jr; o1[6 * TSTR] = wb * ji;    // q2
                 const double wc = wb * uri * ddri;
-                o0[7 * 512] = wc * jr; o1[7 * 512] = wc * ji;    // q3
-                o0[9 * 512] = wb * djr + wd * jzr; o1[9 * 512] = wb * dji + wd * jzi;  // q5
+                o0[7 * TSTR] = wc * jr; o1[7 * TSTR] = wc * ji;    // q3
+                o0[9 * TSTR] = wb * djr + wd * jzr; o1[9 * TSTR] = wb * dji + wd * jzi;  // q5
                 if (!M0) {
                     const double wa = rri * (ssi * qmm) * d1;
-                    o0[5 * 512] = wa * jr; o1[5 * 512] = wa * ji;    // q1
-                    o0[8 * 512] = wa * djr; o1[8 * 512] = wa * dji;  // q4
+                    o0[5 * TSTR] = wa * jr; o1[5 * TSTR] = wa * ji;    // q1
+                    o0[8 * TSTR] = wa * djr; o1[8 * TSTR] = wa * dji;  // q4
                     const double dsi = si * qm * rri;
                     const double va = dsi * d1, vb = dsi * d2;
-                    o0[10 * 512] = vb * jr; o1[10 * 512] = vb * ji;  // r1
-                    o0[11 * 512] = va * jr; o1[11 * 512] = va * ji;  // r2
+                    o0[10 * TSTR] = vb * jr; o1[10 * TSTR] = vb * ji;  // r1
+                    o0[11 * TSTR] = va * jr; o1[11 * TSTR] = va * ji;  // r2
                     const double vf = an2 * va * uri;
-                    o0[12 * 512] = vb * djr + vf * jzr; o1[12 * 512] = vb * dji + vf * jzi;  // r3
-                    o0[13 * 512] = va * djr; o1[13 * 512] = va * dji;  // r4
+                    o0[12 * TSTR] = vb * djr + vf * jzr; o1[12 * TSTR] = vb * dji + vf * jzi;  // r3
+                    o0[13 * TSTR] = va * djr; o1[13 * TSTR] = va * dji;  // r4
                     const double ve = va * uri * ddri;
-                    o0[14 * 512] = ve * djr; o1[14 * 512] = ve * dji;  // r5
+                    o0[14 * TSTR] = ve * djr; o1[14 * TSTR] = ve * dji;  // r5
                 }
             }
         }
@@ -638,27 +650,27 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
             // fragment element of table t, rows [row0, row0 + 8): row0 + (lane >> 2), node 4 ks + (lane & 3)
             auto frag = [&](int t, int row0) -> double {
                 const int r = row0 + fragrow;
-                return op[(t * 64 + r) * 8 + ((((ks ^ (r >> 1)) & 1) << 2) | fragk)];
+                return op[(t * (2 * KR) + r) * 8 + ((((ks ^ (r >> 1)) & 1) << 2) | fragk)];
             };
             double la[NTR][5];
 #pragma unroll
             for (int r = 0; r < NTR; r++)
-                if (tr0 + 2 * r < TMv) {
+                if (tr0 + TRS * r < TMv) {
 #pragma unroll
-                    for (int t = 0; t < 5; t++) la[r][t] = frag(t, prow * 32 + 8 * (tr0 + 2 * r));
+                    for (int t = 0; t < 5; t++) la[r][t] = frag(t, prow * KR + 8 * (tr0 + TRS * r));
                 }
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < TC; c++) {
                 if (c >= TNv) continue;
                 double rb[5];
                 const int rbase = (M0 || even) ? 5 : 10;
 #pragma unroll
-                for (int t = 0; t < 5; t++) rb[t] = frag(rbase + t, pcol * 32 + 8 * c);
+                for (int t = 0; t < 5; t++) rb[t] = frag(rbase + t, pcol * KR + 8 * c);
                 if (M0) {
                     // m = 0: dss = 0, the q1 and q4 terms vanish
 #pragma unroll
                     for (int r = 0; r < NTR; r++)
-                        if (tr0 + 2 * r < TMv) {
+                        if (tr0 + TRS * r < TMv) {
                             st_dmma(acc[r][c][0], la[r][1], rb[1]);
                             st_dmma(acc[r][c][1], la[r][3], rb[4]);
                             st_dmma(acc[r][c][0], la[r][4], rb[2]);
@@ -666,23 +678,23 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
                 } else if (even) {
 #pragma unroll
                     for (int r = 0; r < NTR; r++)
-                        if (tr0 + 2 * r < TMv) { st_dmma(acc[r][c][0], la[r][0], rb[0]); st_dmma(acc[r][c][1], la[r][2], rb[3]); }
+                        if (tr0 + TRS * r < TMv) { st_dmma(acc[r][c][0], la[r][0], rb[0]); st_dmma(acc[r][c][1], la[r][2], rb[3]); }
 #pragma unroll
                     for (int r = 0; r < NTR; r++)
-                        if (tr0 + 2 * r < TMv) { st_dmma(acc[r][c][0], la[r][1], rb[1]); st_dmma(acc[r][c][1], la[r][3], rb[4]); }
+                        if (tr0 + TRS * r < TMv) { st_dmma(acc[r][c][0], la[r][1], rb[1]); st_dmma(acc[r][c][1], la[r][3], rb[4]); }
 #pragma unroll
                     for (int r = 0; r < NTR; r++)
-                        if (tr0 + 2 * r < TMv) st_dmma(acc[r][c][0], la[r][4], rb[2]);
+                        if (tr0 + TRS * r < TMv) st_dmma(acc[r][c][0], la[r][4], rb[2]);
                 } else {
 #pragma unroll
                     for (int r = 0; r < NTR; r++)
-                        if (tr0 + 2 * r < TMv) { st_dmma(acc[r][c][0], la[r][2], rb[0]); st_dmma(acc[r][c][1], la[r][0], rb[2]); }
+                        if (tr0 + TRS * r < TMv) { st_dmma(acc[r][c][0], la[r][2], rb[0]); st_dmma(acc[r][c][1], la[r][0], rb[2]); }
 #pragma unroll
                     for (int r = 0; r < NTR; r++)
-                        if (tr0 + 2 * r < TMv) { st_dmma(acc[r][c][0], la[r][3], rb[1]); st_dmma(acc[r][c][1], la[r][1], rb[3]); }
+                        if (tr0 + TRS * r < TMv) { st_dmma(acc[r][c][0], la[r][3], rb[1]); st_dmma(acc[r][c][1], la[r][1], rb[3]); }
 #pragma unroll
                     for (int r = 0; r < NTR; r++)
-                        if (tr0 + 2 * r < TMv) st_dmma(acc[r][c][1], la[r][4], rb[4]);
+                        if (tr0 + TRS * r < TMv) st_dmma(acc[r][c][1], la[r][4], rb[4]);
                 }
             }
         }
@@ -700,20 +712,20 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     const double ppi = kw * kw, pir = ppi * a.mr[p], pii = ppi * a.mi[p];
     // NM <= 32: the block is the whole mode; the systems are combined in the (now free) operand area, solved here and only
     // the T block leaves the SM.  Larger modes write their part of [Q | RgQ] to global memory for k_st_solve.
-    const bool fused = NM <= 32 && (a.fuse & 1);
+    const bool fused = NM <= KR && ((a.fuse & 1) || KR == 16);
     double2 *sys = fused ? reinterpret_cast<double2 *>(op) : a.sys + it.sys_off + st_sys_mode_off(nmax, m);
 #pragma unroll
     for (int r = 0; r < NTR; r++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const bool tv = (tr0 + 2 * r < TMv) && (c < TNv);  // warp-uniform
+        for (int c = 0; c < TC; c++) {
+            const bool tv = (tr0 + TRS * r < TMv) && (c < TNv);  // warp-uniform
             if (!tv) continue;
             double xa[4], xb[4];
             xa[0] = acc[r][c][0][0]; xa[1] = acc[r][c][0][1];
             xb[0] = acc[r][c][1][0]; xb[1] = acc[r][c][1][1];
             xa[2] = __shfl_xor_sync(0xffffffffu, xa[0], 4); xa[3] = __shfl_xor_sync(0xffffffffu, xa[1], 4);
             xb[2] = __shfl_xor_sync(0xffffffffu, xb[0], 4); xb[3] = __shfl_xor_sync(0xffffffffu, xb[1], 4);
-            const int al = 4 * (tr0 + 2 * r) + (lane >> 3), bl = 4 * c + (lane & 3);
+            const int al = 4 * (tr0 + TRS * r) + (lane >> 3), bl = 4 * c + (lane & 3);
             if (((lane >> 2) & 1) == 0 && al < hrow && bl < hcol) {
                 const int kk1 = kr0 + 2 * al + prow, kk2 = kc0 + 2 * bl + pcol;
                 if (even) store_even(sys, NM, nmin, kk1, kk2, ppi, pir, pii, a.dd, xa, xa + 2, xb, xb + 2);
@@ -724,8 +736,8 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
         // opposite-parity pairs vanish identically for m = 0
         const int ldc = 2 * NM;
         const double2 z = make_double2(0.0, 0.0);
-        for (int t = tid; t < 32 * 32; t += 256) {
-            const int q1 = kr0 + (t >> 5), q2 = kc0 + (t & 31);
+        for (int t = tid; t < KR * KR; t += THREADS) {
+            const int q1 = kr0 + t / KR, q2 = kc0 + t % KR;
             if (q1 >= NM || q2 >= NM || (((q1 + q2) & 1) == 0)) continue;
             for (int cl = 0; cl < 2; cl++) {
                 sys[(long)(cl * NM + q2) * ldc + q1] = z;
@@ -740,25 +752,26 @@ __global__ void __launch_bounds__(256, 2) k_st_assemble(StArgs a, const StATask 
     __syncthreads();
     ST_PROF(2)
     const int ldc = 2 * NM;
+    constexpr int LM0 = THREADS / 4, LM1 = THREADS / 2;  // lanes per system: m = 0 four half-size systems, m >= 1 two systems
     if (M0) {
-        // four half-size systems (T12 = T21 = 0), a pair of warps each
-        const int q = warp >> 1;
+        // four half-size systems (T12 = T21 = 0)
+        const int q = tid / LM0;
         SysDesc d;
         d.base = sys + (long)(q >> 1) * NM * ldc; d.ld = ldc; d.off = q & 1; d.stride = 2; d.rhs = NM; d.n = (NM + 1 - (q & 1)) >> 1;
-        if (d.n > 0) { if (a.fuse & 2) solve_grp2(d, tid & 63, 64, 1 + q, keyslot[q], &sing); else solve_grp(d, tid & 63, 64, 1 + q, keyslot[q], &sing); }
+        if (d.n > 0) { if (a.fuse & 2) solve_grp2(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing); else solve_grp(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing); }
     } else {
-        // the two parity classes, four warps each
-        const int q = warp >> 2;
+        // the two parity classes
+        const int q = tid / LM1;
         SysDesc d;
         d.base = sys + (long)q * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
-        if (a.fuse & 2) solve_grp2(d, tid & 127, 128, 1 + q, keyslot[q], &sing); else solve_grp(d, tid & 127, 128, 1 + q, keyslot[q], &sing);
+        if (a.fuse & 2) solve_grp2(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing); else solve_grp(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
     }
     __syncthreads();
     ST_PROF(3)
     const long long toff = it.t_off;
     if (toff >= 0) {
         double2 *tg = reinterpret_cast<double2 *>(a.tarena) + toff + st_t_mode_off(nmax, m);
-        for (int t = tid; t < 2 * NM * NM; t += 256) {
+        for (int t = tid; t < 2 * NM * NM; t += THREADS) {
             const int row = t / NM, col = t - row * NM;
             tg[t] = sys[(long)row * ldc + NM + col];
         }

@@ -101,6 +101,7 @@ struct StCall {  // arguments of one hs_calctmat_batch call
     int spec;
     bool trace;
     bool fuse_solve = true;
+    bool kr16 = true;                // modes with NM <= 16 through the 128-thread variant of k_st_assemble
     unsigned long long *prof = nullptr;
     const ScPrep *sp = nullptr;      // fused scatter plan (hs_calctmat_scatter_batch) or null
     mutable int nmax_max = 0;        // out: largest converged NMAX among the staged particles
@@ -117,7 +118,7 @@ struct StGroup {
     std::vector<hs::StItem> items;
     std::vector<int> mitems;  // packed (item, mode)
     std::vector<hs::StRadTask> rad;
-    std::vector<hs::StATask> at0, at1;
+    std::vector<hs::StATask> at0, at1, as0, as1;  // A tasks: KR = 32 kernel (m = 0, m >= 1), KR = 16 kernel (NM <= 16)
     std::vector<int> gl[5], sm;
     std::vector<int> order;
     int nround = 0, K = 2;
@@ -163,7 +164,7 @@ struct StGroup {
         }
         const int active_n = (int)order.size();
         K = C->spec > 0 ? C->spec : (active_n > 1000 ? 2 : (active_n > 200 ? 3 : 4));
-        items.clear(); mitems.clear(); rad.clear(); at0.clear(); at1.clear(); sm.clear();
+        items.clear(); mitems.clear(); rad.clear(); at0.clear(); at1.clear(); as0.clear(); as1.clear(); sm.clear();
         for (auto &v : gl) v.clear();
         long long tab_off = 0, wig_off = 0, sys_off = 0;
         int gneed = 0;
@@ -195,6 +196,7 @@ struct StGroup {
                     mitems.push_back(mix);
                     const int NM = it.nmax - (m > 1 ? m : 1) + 1;
                     if (NM <= ST_SMALL_NM) { sm.push_back(mix); continue; }
+                    if (NM <= 16 && C->fuse_solve && C->kr16) { (m == 0 ? as0 : as1).push_back({mix, 0, 0}); continue; }
                     const int nst = (NM + 31) / 32;
                     for (int sr = 0; sr < nst; sr++)
                         for (int sc = 0; sc < nst; sc++) (m == 0 ? at0 : at1).push_back({mix, (short)sr, (short)sc});
@@ -219,7 +221,8 @@ struct StGroup {
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
         const size_t o_items = 0, o_mi = al(o_items + items.size() * sizeof(StItem)), o_rad = al(o_mi + mitems.size() * sizeof(int)),
                      o_a0 = al(o_rad + rad.size() * sizeof(StRadTask)), o_a1 = al(o_a0 + at0.size() * sizeof(StATask)),
-                     o_g0 = al(o_a1 + at1.size() * sizeof(StATask)), o_g1 = al(o_g0 + gl[0].size() * 4), o_g2 = al(o_g1 + gl[1].size() * 4),
+                     o_s0 = al(o_a1 + at1.size() * sizeof(StATask)), o_s1 = al(o_s0 + as0.size() * sizeof(StATask)),
+                     o_g0 = al(o_s1 + as1.size() * sizeof(StATask)), o_g1 = al(o_g0 + gl[0].size() * 4), o_g2 = al(o_g1 + gl[1].size() * 4),
                      o_g3 = al(o_g2 + gl[2].size() * 4), o_g4 = al(o_g3 + gl[3].size() * 4), o_sm = al(o_g4 + gl[4].size() * 4), o_end = al(o_sm + sm.size() * 4);
         if (st_grow(ctx, &B->d_lists, &B->lists_cap, o_end)) return -1;
         if (st_grow(ctx, &B->h_lists, &B->h_lists_cap, o_end, true)) return -1;
@@ -233,6 +236,8 @@ struct StGroup {
         memcpy(h + o_rad, rad.data(), rad.size() * sizeof(StRadTask));
         memcpy(h + o_a0, at0.data(), at0.size() * sizeof(StATask));
         memcpy(h + o_a1, at1.data(), at1.size() * sizeof(StATask));
+        memcpy(h + o_s0, as0.data(), as0.size() * sizeof(StATask));
+        memcpy(h + o_s1, as1.data(), as1.size() * sizeof(StATask));
         const size_t og[6] = {o_g0, o_g1, o_g2, o_g3, o_g4, o_sm};
         for (int c = 0; c < 6; c++) {
             // heaviest systems first (counting sort on NM), written straight into the staging buffer
@@ -259,8 +264,10 @@ struct StGroup {
         k_st_wigner<<<((int)mitems.size() + 7) / 8, 128, 0, st>>>(a, (int)mitems.size());
         mark("wigner");
         launches += 2;
-        if (!at1.empty()) { k_st_assemble<false><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; mark("asm m>=1"); }
-        if (!at0.empty()) { k_st_assemble<true><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; mark("asm m=0"); }
+        if (!at1.empty()) { k_st_assemble<false, 32><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; mark("asm m>=1"); }
+        if (!as1.empty()) { k_st_assemble<false, 16><<<(int)as1.size(), 128, ST_ASM_SMEM16, st>>>(a, (const StATask *)(d + o_s1), (int)as1.size()); launches++; mark("asm16 m>=1"); }
+        if (!as0.empty()) { k_st_assemble<true, 16><<<(int)as0.size(), 128, ST_ASM_SMEM16, st>>>(a, (const StATask *)(d + o_s0), (int)as0.size()); launches++; mark("asm16 m=0"); }
+        if (!at0.empty()) { k_st_assemble<true, 32><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; mark("asm m=0"); }
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
         const int gsm[4] = {16384, 36864, 65536, 200704};
         if (!gl[3].empty()) { k_st_solve<128, false><<<(int)gl[3].size(), 128, gsm[3], st>>>(a, (const int *)(d + og[3]), (int)gl[3].size()); launches++; }
@@ -270,8 +277,8 @@ struct StGroup {
         CK(cudaGetLastError());
         inflight = true;
         if (C->trace)
-            fprintf(stderr, "[hydrotm-staged] group %d round %d: %d active, K=%d, %d items, %zu mode-items (%zu small), %zu+%zu A tasks, scratch %.1f MB\n",
-                    id, nround, active_n, K, ni, mitems.size(), sm.size(), at0.size(), at1.size(),
+            fprintf(stderr, "[hydrotm-staged] group %d round %d: %d active, K=%d, %d items, %zu mode-items (%zu small), %zu+%zu (+%zu+%zu narrow) A tasks, scratch %.1f MB\n",
+                    id, nround, active_n, K, ni, mitems.size(), sm.size(), at0.size(), at1.size(), as0.size(), as1.size(),
                     ((double)(tab_off + wig_off) * 8 + (double)sys_off * 16) / 1048576.0);
         t_plan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
         return 0;
@@ -453,8 +460,8 @@ static int st_init(hs_ctx *ctx, StShared &S)
     CK(cudaMalloc(&S.d_dd, dd.size() * sizeof(double)));
     CK(cudaMemcpy(S.d_cm, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(S.d_dd, dd.data(), dd.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaFuncSetAttribute(k_st_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
-    CK(cudaFuncSetAttribute(k_st_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
+    CK(cudaFuncSetAttribute(k_st_assemble<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
+    CK(cudaFuncSetAttribute(k_st_assemble<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
     CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
     CK(cudaFuncSetAttribute(k_st_solve<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CK(cudaFuncSetAttribute(k_st_mode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ST_SMALL_SLICE * 8));

@@ -414,7 +414,7 @@ __device__ __forceinline__ void solve_grp(const SysDesc d, int t, int nl, int ba
             __syncwarp();  // both lanes of the column have read rows k and p before one of them rewrites them
             if (!live) continue;
             const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
-            if (rs == 0) { cj[k * rstep] = nk; if (p != k) cj[p * rstep] = a; }
+            if (rs == 0) cj[k * rstep] = nk;  // (row p is rewritten below by the lane that owns its parity: no second writer)
             const bool next_col = (j == k + 1) && (k + 1 < n);
 #pragma unroll 4
             for (int r = rs; r < n; r += 2) {
@@ -480,7 +480,7 @@ __device__ __forceinline__ void solve_grp2(const SysDesc d, int t, int nl, int b
             __syncwarp();  // both lanes of the column have read rows k and p before one of them rewrites them
             if (live) {
                 const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
-                if (rs == 0) { cj[k * rstep] = nk; if (p != k) cj[p * rstep] = a; }
+                if (rs == 0) cj[k * rstep] = nk;  // (row p is rewritten below by the lane that owns its parity: no second writer)
                 const bool next_col = (j == k + 1) && (k + 1 < n);
                 const double2 *fr = ck + rs * rstep;
                 double2 *vr = cj + rs * rstep;

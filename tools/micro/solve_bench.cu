@@ -64,14 +64,14 @@ int main()
             double2 *dmp[2]; cudaMalloc(&dmp[0], h.size() * 16); cudaMalloc(&dmp[1], h.size() * 16);
             cudaFuncSetAttribute(k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             long long h3 = 0;
-            k<0><<<148 * per, 256, smem>>>(d, NM, reps, cyc, dmp[0]); cudaMemcpy(&hc[0], cyc, 8, cudaMemcpyDeviceToHost);
+            k<0><<<148 * per, 256, smem>>>(d, NM, reps, cyc, nullptr); cudaMemcpy(&hc[0], cyc, 8, cudaMemcpyDeviceToHost);
             k<1><<<148 * per, 256, smem>>>(d, NM, reps, cyc, nullptr); cudaMemcpy(&hc[1], cyc, 8, cudaMemcpyDeviceToHost);
-            k<2><<<148 * per, 256, smem>>>(d, NM, reps, cyc, nullptr); cudaMemcpy(&hc[2], cyc, 8, cudaMemcpyDeviceToHost);
+            k<2><<<148 * per, 256, smem>>>(d, NM, reps, cyc, dmp[0]); cudaMemcpy(&hc[2], cyc, 8, cudaMemcpyDeviceToHost);
             k<3><<<148 * per, 256, smem>>>(d, NM, reps, cyc, dmp[1]); cudaMemcpy(&h3, cyc, 8, cudaMemcpyDeviceToHost);
             std::vector<double2> r0(h.size()), r1(h.size());
             cudaMemcpy(r0.data(), dmp[0], h.size() * 16, cudaMemcpyDeviceToHost); cudaMemcpy(r1.data(), dmp[1], h.size() * 16, cudaMemcpyDeviceToHost);
             double md = 0; for (size_t i = 0; i < h.size(); i++) { int col = i % (2 * NM); if (col < NM) continue; md = fmax(md, fmax(fabs(r0[i].x - r1[i].x), fabs(r0[i].y - r1[i].y))); }
-            printf("NM %2d, %d CTA/SM: cycles/step  solve_grp %6.0f  solve_grp2 %6.0f (max diff %.1e)  solve_sub %6.0f  solve_multi %6.0f   (%s)\n", NM, per,
+            printf("NM %2d, %d CTA/SM: cycles/step  solve_grp %6.0f  solve_grp2 %6.0f (max diff vs solve_multi %.1e)  solve_sub %6.0f  solve_multi %6.0f   (%s)\n", NM, per,
                    (double)hc[0] / reps / NM, (double)h3 / reps / NM, md, (double)hc[1] / reps / NM, (double)hc[2] / reps / NM, cudaGetErrorString(cudaGetLastError()));
             cudaFree(dmp[0]); cudaFree(dmp[1]);
         }

@@ -173,7 +173,7 @@ struct StGroup {
             s.first_item = (int)items.size(); s.n_items = 0;
             if (s.phase == 0 && (long long)s.nmax * ndgs > HS_NPNG1) { s.status = HS_ST_NGAUSS_LIMIT; s.done = 2; continue; }
             if ((size_t)(tab_off + wig_off) * 8 + (size_t)sys_off * 16 > C->scratch_budget && !items.empty()) continue;  // next round
-            const int cnt = s.phase == 0 ? (C->spec > 0 ? K : std::max(s.kspec, K)) : 1;
+            const int cnt = s.phase == 0 ? (C->spec > 0 ? K : s.kspec) : 1;
             for (int q = 0; q < cnt; q++) {
                 StItem it;
                 it.p = s.idx;
@@ -331,10 +331,14 @@ struct StGroup {
         for (int j : order) {
             StP &s = P[j];
             if (s.done || s.phase != 0) continue;
-            int k = 2;
+            // HYDROTM_SPEC_MARGIN (default 1) trials beyond the predicted one; without a trend (a single relative change so
+            // far) one trial if the change is already within 100 x DDELT, else two.  Under-speculation costs a round for that
+            // particle, over-speculation costs discarded work: the pipeline is throughput-bound, but a shorter chain of rounds measured slightly faster than the leanest speculation (margin 0: 6 rounds, 7.6 ms; 1: 5 rounds, 7.4 ms).
+            static const int margin = getenv("HYDROTM_SPEC_MARGIN") ? atoi(getenv("HYDROTM_SPEC_MARGIN")) : 1;
+            int k = (s.dlast > 0.0 && s.dlast < 100.0) ? 1 : 2;
             if (s.dprev > s.dlast && s.dlast > 1.0 && std::isfinite(s.dprev)) {
                 const double r = log(s.dlast) / log(s.dprev / s.dlast);
-                k = (int)std::min(8.0, std::max(2.0, ceil(r) + 1.0));
+                k = (int)std::min(8.0, std::max(1.0, ceil(r) + (double)margin));
             }
             s.kspec = k;
         }

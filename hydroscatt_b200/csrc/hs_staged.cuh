@@ -894,9 +894,12 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
 // contracts them, combines the accumulators into the two parity-class systems in the same slice, solves them with the
 // warp-wide lock-step Gauss-Jordan and writes the T block / (Qsca, Qext): no CTA barrier, no global round trip of Q.
 #define ST_SMALL_NM 8
+#ifndef ST_SMALL_CTAS
+#define ST_SMALL_CTAS 2
+#endif
 #define ST_SMALL_SLICE (15 * 16 * 4)  // doubles per warp
 
-__global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *mlist, int n)
+__global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small(StArgs a, const int *mlist, int n)
 {
     extern __shared__ __align__(16) double smraw[];
     __shared__ SysDesc sds[8][4];
@@ -904,6 +907,8 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wi = blockIdx.x * 8 + warp;
     if (wi >= n) return;
+    long long tprof = a.prof ? clock64() : 0;
+#define SM_PROF(slot) if (a.prof && lane == 0) { const long long now_ = clock64(); atomicAdd(&a.prof[slot], (unsigned long long)(now_ - tprof)); tprof = now_; }
     double *op = smraw + warp * ST_SMALL_SLICE;
     const StModeItem mi = st_unpack_mode(mlist[wi]);
     const StItem it = a.items[mi.item];
@@ -927,20 +932,31 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
     for (int b = 0; b < 4; b++)
 #pragma unroll
         for (int e = 0; e < 4; e++) acc[b][e >> 1][e & 1] = 0.0;
+    // the table values of the next 4 nodes are loaded (into registers) before the current 4 are processed: the L2 latency
+    // of a chunk is covered by the build + contraction of the previous one
+    struct Vals { double d1, d2, fj, fdj, fy, fdy, jr, ji, djr, dji, rri, uri, ddri, drri, drii, ssi, si; };
+    auto load_vals = [&](int i0) -> Vals {
+        Vals v = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const int i = i0 + ii;
+        if (i < g && kk < NM) {
+            const long o = (long)(n1 - 1) * gp + i;
+            v.d1 = w1[(long)kk * gp + i]; v.d2 = w2[(long)kk * gp + i];
+            v.fj = tb[o]; v.fdj = tb[tsz + o]; v.fy = tb[2 * tsz + o]; v.fdy = tb[3 * tsz + o];
+            v.jr = tb[4 * tsz + o]; v.ji = tb[5 * tsz + o]; v.djr = tb[6 * tsz + o]; v.dji = tb[7 * tsz + o];
+            v.rri = nod[NA_RR * gp + i]; v.uri = nod[NA_DR * gp + i]; v.ddri = nod[NA_DDR * gp + i];
+            v.drri = nod[NA_DRR * gp + i]; v.drii = nod[NA_DRI * gp + i];
+            if (m) { v.ssi = nod[NA_SS * gp + i]; v.si = nod[NA_S * gp + i]; }
+        }
+        return v;
+    };
+    Vals nx = load_vals(0);
+    SM_PROF(16)
     for (int i0 = 0; i0 < g; i0 += 4) {
         {
-            const int i = i0 + ii;
-            double d1 = 0.0, d2 = 0.0, fj = 0.0, fdj = 0.0, fy = 0.0, fdy = 0.0, jr = 0.0, ji = 0.0, djr = 0.0, dji = 0.0;
-            double rri = 0.0, uri = 0.0, ddri = 0.0, drri = 0.0, drii = 0.0, ssi = 0.0, si = 0.0;
-            if (i < g && kk < NM) {
-                const long o = (long)(n1 - 1) * gp + i;
-                d1 = w1[(long)kk * gp + i]; d2 = w2[(long)kk * gp + i];
-                fj = tb[o]; fdj = tb[tsz + o]; fy = tb[2 * tsz + o]; fdy = tb[3 * tsz + o];
-                jr = tb[4 * tsz + o]; ji = tb[5 * tsz + o]; djr = tb[6 * tsz + o]; dji = tb[7 * tsz + o];
-                rri = nod[NA_RR * gp + i]; uri = nod[NA_DR * gp + i]; ddri = nod[NA_DDR * gp + i];
-                drri = nod[NA_DRR * gp + i]; drii = nod[NA_DRI * gp + i];
-                if (m) { ssi = nod[NA_SS * gp + i]; si = nod[NA_S * gp + i]; }
-            }
+            const Vals cv = nx;
+            if (i0 + 4 < g) nx = load_vals(i0 + 4);
+            const double d1 = cv.d1, d2 = cv.d2, fj = cv.fj, fdj = cv.fdj, fy = cv.fy, fdy = cv.fdy, jr = cv.jr, ji = cv.ji, djr = cv.djr, dji = cv.dji;
+            const double rri = cv.rri, uri = cv.uri, ddri = cv.ddri, drri = cv.drri, drii = cv.drii, ssi = cv.ssi, si = cv.si;
             __syncwarp();  // previous contraction has read the slice
             o0[0 * 64] = d1 * fdj; o1[0 * 64] = d1 * fdy;
             o0[1 * 64] = d2 * fdj; o1[1 * 64] = d2 * fdy;
@@ -998,6 +1014,7 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
         }
     }
     __syncwarp();
+    SM_PROF(17)
     // combine into the parity-class systems, stored in the same slice ([2][NM][2 NM] complex <= 512 doubles)
     const int p = it.p;
     const double PI = 3.14159265358979323846;
@@ -1030,6 +1047,7 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
         }
     }
     // solve
+    SM_PROF(18)
     SysDesc *sd = sds[warp];
     int nsys;
     if (m == 0) {
@@ -1064,6 +1082,7 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
         else { d = sd[0]; d.n = 0; }
         solve_sub(d, gl, gw, m == 0 ? ((NM + 1) >> 1) : NM, &sings[warp]);
     }
+    SM_PROF(19)
     const long long toff = it.t_off;
     if (toff >= 0) {
         double2 *tg = reinterpret_cast<double2 *>(a.tarena) + toff + st_t_mode_off(nmax, m);
@@ -1088,6 +1107,9 @@ __global__ void __launch_bounds__(256, 3) k_st_mode_small(StArgs a, const int *m
         }
         if (sings[warp]) a.res[mi.item].sing = 1;
     }
+    SM_PROF(20)
+    if (a.prof && lane == 0) { atomicAdd(&a.prof[21], 1ull); atomicAdd(&a.prof[22], (unsigned long long)NM); atomicAdd(&a.prof[23], (unsigned long long)g); }
+#undef SM_PROF
 }
 
 #endif  // HS_HOST_EMU

@@ -403,8 +403,8 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
         return calctmat_staged(ctx, ctx->st->s, st, st_sel, st_n0, st_lb, SC);
     };
 
-    if (getenv("HYDROTM_PROF") && !ctx->d_prof) { CK(cudaMalloc(&ctx->d_prof, 16 * sizeof(long long))); }
-    if (ctx->d_prof) CK(cudaMemsetAsync(ctx->d_prof, 0, 16 * sizeof(long long), st));
+    if (getenv("HYDROTM_PROF") && !ctx->d_prof) { CK(cudaMalloc(&ctx->d_prof, 24 * sizeof(long long))); }
+    if (ctx->d_prof) CK(cudaMemsetAsync(ctx->d_prof, 0, 24 * sizeof(long long), st));
     lap("nmax0 kernel + D2H");
     std::vector<int> bucket_of(n), nm0(n);
     std::vector<std::vector<int>> lists(NB);
@@ -517,7 +517,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     }
     if (!staged_done) { int rc = run_staged(); if (rc) return rc; lap("staged pipeline (alone)"); }
     if (ctx->d_prof) {
-        long long hp[16];
+        long long hp[24];
         CK(cudaMemcpy(hp, ctx->d_prof, sizeof(hp), cudaMemcpyDeviceToHost));
         double tot = 0; for (int i = 0; i < 8; i++) tot += (double)hp[i];
         if (st_sel.empty()) {
@@ -533,6 +533,11 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
             fprintf(stderr, "[hydrotm-prof] k_st_assemble chunk loop split: build %.0f, barrier %.0f, contraction %.0f, barrier %.0f cycles / CTA\n",
                     (double)hp[8] / ncta, (double)hp[9] / ncta, (double)hp[10] / ncta, (double)hp[11] / ncta);
             fprintf(stderr, "[hydrotm-prof] k_st_assemble solve: %.1f elimination steps / CTA -> %.0f cycles / step\n", (double)hp[12] / ncta, (double)hp[3] / std::max(1.0, (double)hp[12]));
+            {
+                const double nw = (double)hp[21] > 0 ? (double)hp[21] : 1.0;
+                fprintf(stderr, "[hydrotm-prof] k_st_mode_small %.0f warps (mean NM %.1f, g %.1f): prologue %.0f, node loop %.0f, combine %.0f, solve %.0f, T write %.0f cycles / warp\n",
+                        nw, (double)hp[22] / nw, (double)hp[23] / nw, (double)hp[16] / nw, (double)hp[17] / nw, (double)hp[18] / nw, (double)hp[19] / nw, (double)hp[20] / nw);
+            }
             fprintf(stderr, "[hydrotm-prof] k_st_assemble %.0f CTAs, mean NM %.1f, mean g %.1f, %.0f cycles / CTA\n", ncta, (double)hp[6] / ncta, (double)hp[7] / ncta, t5 / ncta);
         }
     }

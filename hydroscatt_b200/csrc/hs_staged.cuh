@@ -320,6 +320,17 @@ __global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
     }
 }
 
+__device__ __forceinline__ double2 st_lds128(unsigned addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void st_sts128(unsigned addr, double2 v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+
 // ---- Gauss-Jordan with row pivoting of one system by a (sub-)warp: lane = column of the augmented block ----
 // Same pivot rule and arithmetic as solve_multi (hs_tmat.cuh); no CTA barrier: a lane only ever touches its own
 // columns plus the (read-only during the step) pivot column, so one __syncwarp per elimination step is enough, and
@@ -371,6 +382,56 @@ __device__ __forceinline__ void solve_sub(const SysDesc d, int gl, int gw, int k
         __syncwarp();
     }
 }
+
+
+// solve_sub for systems that live in shared memory
+__device__ __forceinline__ void solve_subs(const SysDesc d, int gl, int gw, int kmax, int *sing)
+{
+    const int n = d.n, nc = 2 * n;
+    const long rstep = (long)d.stride * d.ld, row0 = (long)d.off * d.ld;
+    auto colof = [&](int j) -> long { return (j < n ? d.off + d.stride * j : d.rhs + d.off + d.stride * (j - n)); };
+    const unsigned b0 = (unsigned)__cvta_generic_to_shared(d.base + row0);  // explicit LDS / STS (see solve_grp2s)
+    unsigned long long key = 0ull;
+    {
+        const unsigned c0 = b0 + 16u * (unsigned)colof(0);
+        for (int r = gl; r < n; r += gw) { const unsigned long long ky = pivot_key(st_lds128(c0 + 16u * (unsigned)(r * rstep)), r); key = ky > key ? ky : key; }
+        for (int o = gw >> 1; o; o >>= 1) { const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o, gw); key = ok > key ? ok : key; }
+    }
+    for (int k = 0; k < kmax; k++) {
+        unsigned long long nkey = 0ull;
+        if (k < n) {
+            const int p = 255 - (int)(key & 0xFFull);
+            if ((key >> 8) == 0ull && gl == 0) *sing = 1;
+            const unsigned ck = b0 + 16u * (unsigned)colof(k);
+            const double2 pv = st_lds128(ck + 16u * (unsigned)(p * rstep));
+            const double den = pv.x * pv.x + pv.y * pv.y;
+            const double2 inv = make_double2(pv.x / den, -pv.y / den);
+            const double2 fkk = st_lds128(ck + 16u * (unsigned)(k * rstep));
+            for (int j = k + 1 + gl; j < nc; j += gw) {
+                const unsigned cj = b0 + 16u * (unsigned)colof(j);
+                const double2 a = st_lds128(cj + 16u * (unsigned)(k * rstep)), b = st_lds128(cj + 16u * (unsigned)(p * rstep));
+                const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
+                st_sts128(cj + 16u * (unsigned)(k * rstep), nk);
+                if (p != k) st_sts128(cj + 16u * (unsigned)(p * rstep), a);
+                const bool next_col = (j == k + 1) && (k + 1 < n);
+#pragma unroll 4
+                for (int r = 0; r < n; r++) {
+                    if (r == k) continue;
+                    // after the row swap, row p holds the old row k whose column-k entry is still at (k, k)
+                    const double2 f = (r == p) ? fkk : st_lds128(ck + 16u * (unsigned)(r * rstep));
+                    double2 v = st_lds128(cj + 16u * (unsigned)(r * rstep));
+                    v.x -= f.x * nk.x - f.y * nk.y;
+                    v.y -= f.x * nk.y + f.y * nk.x;
+                    st_sts128(cj + 16u * (unsigned)(r * rstep), v);
+                    if (next_col && r > k) { const unsigned long long ky = pivot_key(v, r); nkey = ky > nkey ? ky : nkey; }
+                }
+            }
+        }
+        key = __shfl_sync(0xffffffffu, nkey, 0, gw);  // column k + 1 belongs to lane 0 of the group
+        __syncwarp();
+    }
+}
+
 
 
 // The same elimination by a group of `nl` lanes (64 or 128 = 2 or 4 whole warps): two lanes of a warp share a column
@@ -506,6 +567,74 @@ __device__ __forceinline__ void solve_grp2(const SysDesc d, int t, int nl, int b
         asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nl) : "memory");
     }
 }
+
+// solve_grp2 for systems that live in shared memory
+__device__ __forceinline__ void solve_grp2s(const SysDesc d, int t, int nl, int barid, unsigned long long *keyslot, int *sing)
+{
+    const int n = d.n, nc = 2 * n;
+    const int rstep = d.stride * d.ld;
+    // explicit shared-space accesses (32-bit addresses, LDS / STS): through the generic pointer of SysDesc the compiler emits
+    // LD.E / ST.E, which resolve the address space at run time and cost ~3x the latency per row update
+    const unsigned b0 = (unsigned)__cvta_generic_to_shared(d.base + d.off * d.ld);
+    const int ct = (t & 15) | ((t >> 5) << 4), rs = (t >> 4) & 1, ncl = nl >> 1;
+    // this lane pair's columns (at most two: nc <= 2 * ncl)
+    const int j0 = ct, j1 = ct + ncl;
+    const int c0 = j0 < n ? d.off + d.stride * j0 : d.rhs + d.off + d.stride * (j0 - n);
+    const int c1 = j1 < n ? d.off + d.stride * j1 : d.rhs + d.off + d.stride * (j1 - n);
+    if (t < 32) {
+        unsigned long long key = 0ull;
+        const unsigned cc = b0 + 16u * d.off;
+        for (int r = t; r < n; r += 32) { const unsigned long long ky = pivot_key(st_lds128(cc + 16u * (r * rstep)), r); key = ky > key ? ky : key; }
+        for (int o = 16; o; o >>= 1) { const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o); key = ok > key ? ok : key; }
+        if (t == 0) keyslot[0] = key;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nl) : "memory");
+    for (int k = 0; k < n; k++) {
+        const unsigned long long key = keyslot[k & 1];
+        const int p = 255 - (int)(key & 0xFFull);
+        if ((key >> 8) == 0ull && t == 0) *sing = 1;
+        const unsigned ck = b0 + 16u * (d.off + d.stride * k);
+        const double2 pv = st_lds128(ck + 16u * (p * rstep));
+        const double den = pv.x * pv.x + pv.y * pv.y;
+        const double2 inv = make_double2(pv.x / den, -pv.y / den);
+        const double2 fkk = st_lds128(ck + 16u * (k * rstep));
+        unsigned long long nkey = 0ull;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int j = h ? j1 : j0;
+            const bool live = j > k && j < nc;
+            const unsigned cj = b0 + 16u * (h ? c1 : c0);
+            double2 a = make_double2(0.0, 0.0), b = a;
+            if (live) { a = st_lds128(cj + 16u * (k * rstep)); b = st_lds128(cj + 16u * (p * rstep)); }
+            __syncwarp();  // both lanes of the column have read rows k and p before one of them rewrites them
+            if (live) {
+                const double2 nk = make_double2(b.x * inv.x - b.y * inv.y, b.x * inv.y + b.y * inv.x);
+                if (rs == 0) st_sts128(cj + 16u * (k * rstep), nk);  // (row p is rewritten below by the lane that owns its parity: no second writer)
+                const bool next_col = (j == k + 1) && (k + 1 < n);
+                unsigned fr = ck + 16u * (rs * rstep), vr = cj + 16u * (rs * rstep);
+                const unsigned rstep2 = 32u * rstep;
+#pragma unroll 4
+                for (int r = rs; r < n; r += 2, fr += rstep2, vr += rstep2) {
+                    if (r == k) continue;
+                    // after the row swap, row p holds the old row k (value a; its column-k entry is still at (k, k))
+                    const double2 f = (r == p) ? fkk : st_lds128(fr);
+                    double2 v = (r == p) ? a : st_lds128(vr);
+                    v.x -= f.x * nk.x - f.y * nk.y;
+                    v.y -= f.x * nk.y + f.y * nk.x;
+                    st_sts128(vr, v);
+                    if (next_col && r > k) { const unsigned long long ky = pivot_key(v, r); nkey = ky > nkey ? ky : nkey; }
+                }
+            }
+            if (ncl >= nc) break;  // group-uniform: no lane has a second column
+        }
+        // the pair that owns column k + 1 publishes the next pivot
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, nkey, 16);
+        nkey = ok > nkey ? ok : nkey;
+        if (rs == 0 && (j0 == k + 1 || j1 == k + 1)) keyslot[(k + 1) & 1] = nkey;
+        asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nl) : "memory");
+    }
+}
+
 
 // ---- A: Q / RgQ integrals of one 32 x 32 block of (k1, k2) = (n1 - nmin, n2 - nmin) as DMMA contractions ----
 // See assemble_tiled (hs_tmat.cuh) for the factorisation: X = sum over nodes of (left factor of (n1, node)) x (right
@@ -758,13 +887,13 @@ __global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs
         const int q = tid / LM0;
         SysDesc d;
         d.base = sys + (long)(q >> 1) * NM * ldc; d.ld = ldc; d.off = q & 1; d.stride = 2; d.rhs = NM; d.n = (NM + 1 - (q & 1)) >> 1;
-        if (d.n > 0) { if (a.fuse & 2) solve_grp2(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing); else solve_grp(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing); }
+        if (d.n > 0) { if (a.fuse & 2) solve_grp2s(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing); else solve_grp(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing); }
     } else {
         // the two parity classes
         const int q = tid / LM1;
         SysDesc d;
         d.base = sys + (long)q * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
-        if (a.fuse & 2) solve_grp2(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing); else solve_grp(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
+        if (a.fuse & 2) solve_grp2s(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing); else solve_grp(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
     }
     __syncthreads();
     ST_PROF(3)
@@ -852,7 +981,7 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
             __shared__ unsigned long long keyslot[4][2];
             const int warp = threadIdx.x >> 5;
             const int q = (m == 0) ? (warp >> 1) : (warp >> 2);
-            if (q < nsys && sd[q].n > 0) solve_grp2(sd[q], threadIdx.x & (m == 0 ? 63 : 127), m == 0 ? 64 : 128, 1 + q, keyslot[q], &sing);
+            if (q < nsys && sd[q].n > 0) solve_grp2s(sd[q], threadIdx.x & (m == 0 ? 63 : 127), m == 0 ? 64 : 128, 1 + q, keyslot[q], &sing);
         } else {
             // one warp per system (m = 0: four half-size systems, m >= 1: the two parity classes)
             const int w = threadIdx.x >> 5;
@@ -1080,7 +1209,7 @@ __global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small(StArgs a, 
         SysDesc d;
         if (grp_ < nsys) d = sd[grp_];
         else { d = sd[0]; d.n = 0; }
-        solve_sub(d, gl, gw, m == 0 ? ((NM + 1) >> 1) : NM, &sings[warp]);
+        solve_subs(d, gl, gw, m == 0 ? ((NM + 1) >> 1) : NM, &sings[warp]);
     }
     SM_PROF(19)
     const long long toff = it.t_off;

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256, 2) k(const double2 *src, int NM, int reps
             solve_grp(sd[q], tid & 127, 128, 1 + q, keyslot[q], &sing);
         } else if (MODE == 3) {
             const int q = warp >> 2;
-            solve_grp2(sd[q], tid & 127, 128, 1 + q, keyslot[q], &sing);
+            solve_grp2s(sd[q], tid & 127, 128, 1 + q, keyslot[q], &sing);
         } else if (MODE == 1) {
             if (warp < 2) solve_sub(sd[warp], lane, 32, NM, &sing);
         } else {
@@ -71,7 +71,7 @@ int main()
             std::vector<double2> r0(h.size()), r1(h.size());
             cudaMemcpy(r0.data(), dmp[0], h.size() * 16, cudaMemcpyDeviceToHost); cudaMemcpy(r1.data(), dmp[1], h.size() * 16, cudaMemcpyDeviceToHost);
             double md = 0; for (size_t i = 0; i < h.size(); i++) { int col = i % (2 * NM); if (col < NM) continue; md = fmax(md, fmax(fabs(r0[i].x - r1[i].x), fabs(r0[i].y - r1[i].y))); }
-            printf("NM %2d, %d CTA/SM: cycles/step  solve_grp %6.0f  solve_grp2 %6.0f (max diff vs solve_multi %.1e)  solve_sub %6.0f  solve_multi %6.0f   (%s)\n", NM, per,
+            printf("NM %2d, %d CTA/SM: cycles/step  solve_grp %6.0f  solve_grp2s %6.0f (max diff vs solve_multi %.1e)  solve_sub %6.0f  solve_multi %6.0f   (%s)\n", NM, per,
                    (double)hc[0] / reps / NM, (double)h3 / reps / NM, md, (double)hc[1] / reps / NM, (double)hc[2] / reps / NM, cudaGetErrorString(cudaGetLastError()));
             cudaFree(dmp[0]); cudaFree(dmp[1]);
         }

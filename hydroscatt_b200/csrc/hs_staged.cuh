@@ -404,8 +404,8 @@ __device__ __forceinline__ void solve_subs(const SysDesc d, int gl, int gw, int 
             if ((key >> 8) == 0ull && gl == 0) *sing = 1;
             const unsigned ck = b0 + 16u * (unsigned)colof(k);
             const double2 pv = st_lds128(ck + 16u * (unsigned)(p * rstep));
-            const double den = pv.x * pv.x + pv.y * pv.y;
-            const double2 inv = make_double2(pv.x / den, -pv.y / den);
+            const double rden = 1.0 / (pv.x * pv.x + pv.y * pv.y);
+            const double2 inv = make_double2(pv.x * rden, -pv.y * rden);
             const double2 fkk = st_lds128(ck + 16u * (unsigned)(k * rstep));
             for (int j = k + 1 + gl; j < nc; j += gw) {
                 const unsigned cj = b0 + 16u * (unsigned)colof(j);
@@ -595,8 +595,8 @@ __device__ __forceinline__ void solve_grp2s(const SysDesc d, int t, int nl, int 
         if ((key >> 8) == 0ull && t == 0) *sing = 1;
         const unsigned ck = b0 + 16u * (d.off + d.stride * k);
         const double2 pv = st_lds128(ck + 16u * (p * rstep));
-        const double den = pv.x * pv.x + pv.y * pv.y;
-        const double2 inv = make_double2(pv.x / den, -pv.y / den);
+        const double rden = 1.0 / (pv.x * pv.x + pv.y * pv.y);  // one division per step (the other variants divide twice: last-ulp differences)
+        const double2 inv = make_double2(pv.x * rden, -pv.y * rden);
         const double2 fkk = st_lds128(ck + 16u * (k * rstep));
         unsigned long long nkey = 0ull;
 #pragma unroll

@@ -255,7 +255,7 @@ def run_gpu(args):
     host_obs = torch.empty((n_dsd, w["n_tab"], 15), dtype=torch.float64).pin_memory()
     host_meta = torch.empty((4, n), dtype=torch.int32).pin_memory()
     d2h = host_rows.numel() * 8 + host_obs.numel() * 8 + host_meta.numel() * 4
-    gathered = [torch.empty((n, tables.ROW), dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    gathered = torch.empty((world * n, tables.ROW), dtype=torch.float64, device=dev) if world > 1 else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     stage_ms = {"calctmat": 0.0, "scatter": 0.0, "psd": 0.0}
@@ -287,7 +287,7 @@ def run_gpu(args):
         ext_h, ext_v = 2.0 * tb.lam * Sr[:, 1, 7], 2.0 * tb.lam * Sr[:, 1, 1]
         rows[:, 52], rows[:, 53], rows[:, 54], rows[:, 55] = ext_h, ext_v, ext_h, ext_v
         if world > 1:
-            dist.all_gather(gathered, rows)  # every rank ends up with every replica's scatter tables
+            dist.all_gather_into_tensor(gathered, rows)  # every rank ends up with every replica's scatter tables
         obs, _ = tables.integrate_psd(eng, rows, w["n_tab"], w["D"], "gamma", dsd["d0"], dsd["nw"], dsd["mu"], dmax,
                                       w["lam_tab"], rule="trapz", want_integ=False)
         e[4].record()

@@ -220,3 +220,24 @@ def test_asym_product_rule_matches_brute_force(engine):
     assert abs(g_h - num[0] / den[0]) < 1e-6 and abs(g_v - num[1] / den[1]) < 1e-6
     assert 0.0 < g_h < 1.0
     assert abs(scatter.ssa(tm) - scatter.sca_xsect(tm) / scatter.ext_xsect(tm)) < 1e-12
+
+
+def test_calctmat_scatter_one_call_equals_two_calls(engine, monkeypatch):
+    """hs_calctmat_scatter_batch (also with the scatter kernels overlapping the convergence rounds) gives the same
+    tables as hs_calctmat_batch followed by hs_scatter_batch."""
+    from hydroscatt_b200 import tables
+    al, be, wt, scale = tables.fixed_orientation_nodes(10.0)
+    ws = [rain_grid(b) for b in ("C", "Ka", "W")]
+    cat = lambda k: np.concatenate([np.tile(w[k], 6) for w in ws])  # 1260 particles: the ordered / class-split scatter path
+    args = [cat(k) for k in ("radius", "wavelength", "mr", "mi", "axis_ratio")]
+    tb = engine.calctmat(*args)
+    S0, Z0, x0 = tb.scatter([GB[:4], GF[:4]], al, be, weight=wt, scale=scale, want_xs=True)
+    for overlap in (False, True):
+        if overlap:
+            monkeypatch.setenv("HYDROTM_OVERLAP_SCATTER", "1")
+        tb1, S1, Z1, x1 = engine.calctmat_scatter(*args, [GB[:4], GF[:4]], al, be, weight=wt, scale=scale, want_xs=True)
+        monkeypatch.delenv("HYDROTM_OVERLAP_SCATTER", raising=False)
+        assert (tb1.nmax == tb.nmax).all() and (tb1.ngauss == tb.ngauss).all() and (tb1.status == tb.status).all()
+        for a, b in ((S0, S1), (Z0, Z1), (x0, x1)):
+            a, b = a.cpu().numpy(), b.cpu().numpy()
+            assert np.abs(a - b).max() <= 1e-12 * np.abs(a).max(), overlap

@@ -319,7 +319,12 @@ def run_gpu(args):
             for t in (rows, obs, tb.nmax, tb.ngauss, tb.ntrials, tb.status):
                 t.record_stream(copy_stream)
             hb["rows"].copy_(rows, non_blocking=True)
-            hb["obs"].copy_(obs, non_blocking=True)
+            # 274 MB of observables: in 32 pieces, so that the pipeline's small host<->device transfers of the next step are
+            # not queued behind one 5 ms DMA (measured: 11.7 -> 11.3 ms per end-to-end step)
+            nch = 32
+            for c in range(nch):
+                a_, b_ = c * n_dsd // nch, (c + 1) * n_dsd // nch
+                hb["obs"][a_:b_].copy_(obs[a_:b_], non_blocking=True)
             hb["meta"][0].copy_(tb.nmax, non_blocking=True)
             hb["meta"][1].copy_(tb.ngauss, non_blocking=True)
             hb["meta"][2].copy_(tb.ntrials, non_blocking=True)

@@ -126,7 +126,8 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
+        self.enabled = enabled  # only rank 0 polls nvidia-smi: eight pollers on one host take cores away from the pipeline's host threads
         self.index, self.samples, self.reasons, self.stop = index, [], set(), False
         self.smax = None
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -148,12 +149,14 @@ class ClockSampler:
             time.sleep(0.05)
 
     def __enter__(self):
-        self.th.start()
+        if self.enabled:
+            self.th.start()
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.th.join(timeout=6)
+        if self.enabled:
+            self.th.join(timeout=6)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.smax,
@@ -344,7 +347,7 @@ def run_gpu(args):
         step(dev_in, dev_dsd, False)
     l0 = eng.launch_count
     sync_all()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
         t0, t1 = ev(), ev()
         t0.record()
         for _ in range(args.steps):

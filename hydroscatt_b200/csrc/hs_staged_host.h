@@ -511,7 +511,15 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
     if (!ns) return 0;
     if (st_init(ctx, S)) return -1;
     CK(cudaEventRecord(S.ev_in, st));
-    const int ng = std::max(1, std::min(ST_GROUPS, getenv("HYDROTM_GROUPS") ? atoi(getenv("HYDROTM_GROUPS")) : (ns >= 2048 ? 4 : (ns >= 256 ? 2 : 1))));
+    // one host thread per group: leave a core for the caller's thread, and share the host between the ranks of a
+    // one-process-per-GPU job (torchrun exports LOCAL_WORLD_SIZE)
+    int ng_auto = ns >= 2048 ? 4 : (ns >= 256 ? 2 : 1);
+    {
+        const int cores = (int)std::thread::hardware_concurrency();
+        const int ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+        if (cores > 0) ng_auto = std::max(1, std::min(ng_auto, cores / ranks - 1));
+    }
+    const int ng = std::max(1, std::min(ST_GROUPS, getenv("HYDROTM_GROUPS") ? atoi(getenv("HYDROTM_GROUPS")) : ng_auto));
     // deal the particles, heaviest first, round-robin: every group gets the same size mix
     std::vector<int> ord(ns);
     for (int j = 0; j < ns; j++) ord[j] = j;

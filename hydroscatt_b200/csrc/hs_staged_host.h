@@ -513,7 +513,7 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
     CK(cudaEventRecord(S.ev_in, st));
     // one host thread per group: leave a core for the caller's thread, and share the host between the ranks of a
     // one-process-per-GPU job (torchrun exports LOCAL_WORLD_SIZE)
-    int ng_auto = ns >= 2048 ? 4 : (ns >= 256 ? 2 : 1);
+    int ng_auto = ns >= 8192 ? 6 : (ns >= 2048 ? 4 : (ns >= 256 ? 2 : 1));
     {
         const int cores = (int)std::thread::hardware_concurrency();
         const int ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;

@@ -26,6 +26,8 @@ struct StBufs {
     int *d_out = nullptr, *h_out = nullptr; size_t out_cap = 0;  // final per-particle records for the scatter-out kernel
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
+    cudaStream_t stream2 = nullptr;   // second lane of a round: the narrow / small-mode kernels run beside the wide ones
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // fused scatter: records / order list of finished particles, filled round by round
     cudaStream_t sc_stream = nullptr;
     cudaEvent_t sc_ev = nullptr;
@@ -101,6 +103,7 @@ struct StCall {  // arguments of one hs_calctmat_batch call
     int spec;
     bool trace;
     bool fuse_solve = true;
+    bool one_lane = false;           // HYDROTM_ONE_LANE=1: every kernel of a round on one stream
     bool kr16 = true;                // modes with NM <= 16 through the 128-thread variant of k_st_assemble
     unsigned long long *prof = nullptr;
     const ScPrep *sp = nullptr;      // fused scatter plan (hs_calctmat_scatter_batch) or null
@@ -264,16 +267,30 @@ struct StGroup {
         k_st_wigner<<<((int)mitems.size() + 7) / 8, 128, 0, st>>>(a, (int)mitems.size());
         mark("wigner");
         launches += 2;
+        // two lanes after the tables are ready: the wide kernels (NM > 16, multi-block, separate solves) on the group's
+        // stream, the narrow (NM <= 16) and small-mode (NM <= 8) kernels on its second stream
+        cudaStream_t s2 = st;
+        const bool two = !C->one_lane && (!at1.empty() || !at0.empty()) && (!as1.empty() || !as0.empty() || !sm.empty());
+        if (two) {
+            s2 = B->stream2;
+            CK(cudaEventRecord(B->ev_fork, st));
+            CK(cudaStreamWaitEvent(s2, B->ev_fork, 0));
+        }
         if (!at1.empty()) { k_st_assemble<false, 32><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; mark("asm m>=1"); }
-        if (!as1.empty()) { k_st_assemble<false, 16><<<(int)as1.size(), 128, ST_ASM_SMEM16, st>>>(a, (const StATask *)(d + o_s1), (int)as1.size()); launches++; mark("asm16 m>=1"); }
-        if (!as0.empty()) { k_st_assemble<true, 16><<<(int)as0.size(), 128, ST_ASM_SMEM16, st>>>(a, (const StATask *)(d + o_s0), (int)as0.size()); launches++; mark("asm16 m=0"); }
         if (!at0.empty()) { k_st_assemble<true, 32><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; mark("asm m=0"); }
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
         const int gsm[4] = {16384, 36864, 65536, 200704};
         if (!gl[3].empty()) { k_st_solve<128, false><<<(int)gl[3].size(), 128, gsm[3], st>>>(a, (const int *)(d + og[3]), (int)gl[3].size()); launches++; }
         for (int c = 2; c >= 0; c--)
             if (!gl[c].empty()) { k_st_solve<256, false><<<(int)gl[c].size(), 256, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; mark("solve"); }
-        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, st>>>(a, (const int *)(d + o_sm), (int)sm.size()); launches++; mark("small"); }
+        if (!as1.empty()) { k_st_assemble<false, 16><<<(int)as1.size(), 128, ST_ASM_SMEM16, s2>>>(a, (const StATask *)(d + o_s1), (int)as1.size()); launches++; }
+        if (!as0.empty()) { k_st_assemble<true, 16><<<(int)as0.size(), 128, ST_ASM_SMEM16, s2>>>(a, (const StATask *)(d + o_s0), (int)as0.size()); launches++; }
+        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, s2>>>(a, (const int *)(d + o_sm), (int)sm.size()); launches++; }
+        if (two) {
+            CK(cudaEventRecord(B->ev_join, s2));
+            CK(cudaStreamWaitEvent(st, B->ev_join, 0));
+        }
+        mark("round end");
         CK(cudaGetLastError());
         inflight = true;
         if (C->trace)
@@ -476,6 +493,9 @@ static int st_init(hs_ctx *ctx, StShared &S)
         CK(cudaStreamCreateWithFlags(&S.g[g].stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&S.g[g].ev, cudaEventDisableTiming));
         CK(cudaStreamCreateWithPriority(&S.g[g].sc_stream, cudaStreamNonBlocking, prio_lo));
+        CK(cudaStreamCreateWithFlags(&S.g[g].stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&S.g[g].ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&S.g[g].ev_join, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&S.g[g].sc_ev, cudaEventDisableTiming));
     }
     return 0;
@@ -495,6 +515,9 @@ static void st_destroy(StShared &S)
         if (b.h_screc) cudaFreeHost(b.h_screc);
         if (b.h_scord) cudaFreeHost(b.h_scord);
         if (b.sc_stream) cudaStreamDestroy(b.sc_stream);
+        if (b.stream2) cudaStreamDestroy(b.stream2);
+        if (b.ev_fork) cudaEventDestroy(b.ev_fork);
+        if (b.ev_join) cudaEventDestroy(b.ev_join);
         if (b.sc_ev) cudaEventDestroy(b.sc_ev);
     }
     cudaFree(S.d_cm); cudaFree(S.d_dd);

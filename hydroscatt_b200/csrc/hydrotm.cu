@@ -398,6 +398,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     SC.fuse_solve = !(getenv("HYDROTM_FUSE_SOLVE") && atoi(getenv("HYDROTM_FUSE_SOLVE")) == 0);
     SC.prof = (unsigned long long *)ctx->d_prof;
     SC.kr16 = !(getenv("HYDROTM_KR16") && atoi(getenv("HYDROTM_KR16")) == 0);
+    SC.one_lane = getenv("HYDROTM_ONE_LANE") && atoi(getenv("HYDROTM_ONE_LANE")) != 0;
     auto run_staged = [&]() -> int {
         staged_done = true;
         return calctmat_staged(ctx, ctx->st->s, st, st_sel, st_n0, st_lb, SC);

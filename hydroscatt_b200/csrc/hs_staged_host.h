@@ -175,7 +175,8 @@ struct StGroup {
             StP &s = P[j];
             s.first_item = (int)items.size(); s.n_items = 0;
             if (s.phase == 0 && (long long)s.nmax * ndgs > HS_NPNG1) { s.status = HS_ST_NGAUSS_LIMIT; s.done = 2; continue; }
-            if ((size_t)(tab_off + wig_off) * 8 + (size_t)sys_off * 16 > C->scratch_budget && !items.empty()) continue;  // next round
+            // next round: scratch budget spent, or the packed (item, mode) ids (24-bit item index) would overflow
+            if (((size_t)(tab_off + wig_off) * 8 + (size_t)sys_off * 16 > C->scratch_budget || items.size() > (1u << 23)) && !items.empty()) continue;
             const int cnt = s.phase == 0 ? (C->spec > 0 ? K : s.kspec) : 1;
             for (int q = 0; q < cnt; q++) {
                 StItem it;

@@ -993,8 +993,9 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
         grp.tid = threadIdx.x; grp.nt = THREADS;
         solve_multi(grp, sd, nsys, &sc, &sing);
     } else {
-        if (THREADS == 256 && NM <= 32) {
+        if (THREADS == 256 && NM <= 64) {
             // as in the fused path: m = 0: four half-size systems on 64 lanes each, m >= 1: two systems on 128 lanes each
+            // (a lane pair owns up to two columns: 2 NM <= 128 resp. NM + 1 <= 64)
             __shared__ unsigned long long keyslot[4][2];
             const int warp = threadIdx.x >> 5;
             const int q = (m == 0) ? (warp >> 1) : (warp >> 2);

@@ -281,7 +281,7 @@ struct StGroup {
         if (!at0.empty()) { k_st_assemble<true, 32><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; mark("asm m=0"); }
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
         const int gsm[4] = {16384, 36864, 65536, 200704};
-        if (!gl[3].empty()) { k_st_solve<128, false><<<(int)gl[3].size(), 128, gsm[3], st>>>(a, (const int *)(d + og[3]), (int)gl[3].size()); launches++; }
+        if (!gl[3].empty()) { k_st_solve<256, false><<<(int)gl[3].size(), 256, gsm[3], st>>>(a, (const int *)(d + og[3]), (int)gl[3].size()); launches++; }
         for (int c = 2; c >= 0; c--)
             if (!gl[c].empty()) { k_st_solve<256, false><<<(int)gl[c].size(), 256, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; mark("solve"); }
         if (!as1.empty()) { k_st_assemble<false, 16><<<(int)as1.size(), 128, ST_ASM_SMEM16, s2>>>(a, (const StATask *)(d + o_s1), (int)as1.size()); launches++; }
@@ -485,7 +485,7 @@ static int st_init(hs_ctx *ctx, StShared &S)
     CK(cudaFuncSetAttribute(k_st_assemble<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
     CK(cudaFuncSetAttribute(k_st_assemble<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_ASM_SMEM));
     CK(cudaFuncSetAttribute(k_st_solve<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
-    CK(cudaFuncSetAttribute(k_st_solve<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    CK(cudaFuncSetAttribute(k_st_solve<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200704));
     CK(cudaFuncSetAttribute(k_st_mode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ST_SMALL_SLICE * 8));
     CK(cudaEventCreate(&S.ev_in));
     int prio_lo = 0, prio_hi = 0;

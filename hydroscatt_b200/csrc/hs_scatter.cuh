@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
     double2 *sT = reinterpret_cast<double2 *>(sm);
     const int stride = SCK_G * 24 + 3;
     double *srow = sm + 4L * a.nmax_bound * a.nmax_bound;
-    double *accs = srow + (long)nt * stride;
+    const long vec_doubles = 2L * (a.nmax_bound + 2) * nt, row_doubles = (long)nt * stride;
+    double *accs = srow + (vec_doubles > row_doubles ? vec_doubles : row_doubles);
     const double pin = 3.14159265358979323846;
 
     for (int d = 0; d < a.n_inc; d++) {
@@ -416,7 +417,10 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         for (int k = 0; k < 8; k++) acc[g][k] = 0.0;
                     }
                 }
-                double Pp[HS_NPN1 + 1], Qp[HS_NPN1 + 1];  // P' = sgn f m pi0, Q' = sgn f tau0, sgn = (-1)^(n'>>1)
+                // P' = sgn f m pi0, Q' = sgn f tau0, sgn = (-1)^(n'>>1): per-thread vectors in shared memory ([n'][thread], aliased
+                // with the reduction rows, which are only written after the mode sweep).  As thread-local arrays they lived in
+                // L1-cached local memory, which the heavy class (3 CTAs x 55 KB of shared memory per SM) leaves too small.
+                double *Pp = srow + tid, *Qp = srow + (long)(a.nmax_bound + 2) * nt + tid;
                 long moff = 0;
                 for (int m = 0; m <= nmax; m++) {
                     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
@@ -435,8 +439,8 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         double p0, t0;
                         w0.next(nn, m, s_sq, s_rsq, s_rn1, s_r2n1, p0, t0);
                         const double f = (nn & 2) ? -s_fn[nn] : s_fn[nn];
-                        Pp[nn] = m * p0 * f;
-                        Qp[nn] = t0 * f;
+                        Pp[nn * nt] = m * p0 * f;
+                        Qp[nn * nt] = t0 * f;
                     }
                     double fc[SCK_G], fs[SCK_G];
 #pragma unroll
@@ -456,7 +460,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         for (int nn = nmin + (k & 1); nn <= nmax; nn += 2) {
                             const long o_ = (long)(nn - nmin) * NM;
                             const double2 a_ = ta[o_], b_ = tb[o_];
-                            const double P = Pp[nn], Q = Qp[nn];
+                            const double P = Pp[nn * nt], Q = Qp[nn * nt];
                             e1r += a_.x * P; e1i += a_.y * P; e3r += a_.x * Q; e3i += a_.y * Q;
                             e2r += b_.x * Q; e2i += b_.y * Q; e4r += b_.x * P; e4i += b_.y * P;
                         }
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         for (int nn = nmin + ((k + 1) & 1); nn <= nmax; nn += 2) {
                             const long o_ = (long)(nn - nmin) * NM;
                             const double2 a_ = ta[o_], b_ = tb[o_];
-                            const double P = Pp[nn], Q = Qp[nn];
+                            const double P = Pp[nn * nt], Q = Qp[nn * nt];
                             o1r += a_.x * Q; o1i += a_.y * Q; o3r += a_.x * P; o3i += a_.y * P;
                             o2r += b_.x * P; o2i += b_.y * P; o4r += b_.x * Q; o4i += b_.y * Q;
                         }
@@ -500,6 +504,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         }
                     }
                 }
+                __syncthreads();  // everybody is done with the P' / Q' vectors that share the reduction rows' memory
                 // ---- per-thread epilogue: S, Z, cross sections -> weighted row in shared memory ----
                 if (active) {
                     const double dk = 2.0 * pin / lam, w = a.weight[o];

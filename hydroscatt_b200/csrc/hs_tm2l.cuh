@@ -621,7 +621,7 @@ __device__ void tm2l_particle(const T2Args &a, int p, double *smem, Ctl *ctl, do
 }
 
 #ifndef HS_HOST_EMU
-__global__ void __launch_bounds__(320, 1) k_tm2l(T2Args a, int *queue)
+__global__ void __launch_bounds__(256, 1) k_tm2l(T2Args a, int *queue)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ Ctl ctl;

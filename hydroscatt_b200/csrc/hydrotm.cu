@@ -824,7 +824,7 @@ extern "C" int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const do
     CK(cudaFuncSetAttribute(hs::k_tm2l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaMemsetAsync(ctx->d_queue + 8, 0, sizeof(int), st));
     int grid = std::min(n, ctx->sm_count);
-    hs::k_tm2l<<<grid, 320, smem, st>>>(a, ctx->d_queue + 8);
+    hs::k_tm2l<<<grid, 256, smem, st>>>(a, ctx->d_queue + 8);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -424,12 +424,43 @@ struct StGroup {
     {
         if (cudaSetDevice(ctx->device) != cudaSuccess) { rc = -1; return; }
         rc = issue();
-        while (!rc && inflight) {
-            rc = finish();
-            if (!rc) rc = issue();       // keep this group's next round ahead of its scatter work in the launch queue
-            if (!rc) rc = flush_scatter();
-        }
+        while (!rc && inflight) advance();
+        finalize();
+    }
+
+    // one controller turn: the round in flight is (or is waited to be) complete -> controller, next round, scatter
+    void advance()
+    {
+        rc = finish();
+        if (!rc) rc = issue();       // keep this group's next round ahead of its scatter work in the launch queue
+        if (!rc) rc = flush_scatter();
+    }
+    void finalize()
+    {
         if (!rc) rc = C->sp ? flush_scatter() : write_out();
+    }
+    bool round_ready() const { return cudaStreamQuery(B->stream) == cudaSuccess; }
+
+    // Several groups on ONE host thread (fewer host cores than groups, e.g. 8 ranks on a 32-core box): whichever group's
+    // round has completed gets its controller turn; the others keep the GPU busy meanwhile.
+    static void run_many(StGroup *G, int first, int step, int ng)
+    {
+        if (first + step >= ng) { G[first].run(); return; }
+        if (cudaSetDevice(G[first].ctx->device) != cudaSuccess) { for (int g = first; g < ng; g += step) G[g].rc = -1; return; }
+        for (int g = first; g < ng; g += step) G[g].rc = G[g].issue();
+        for (;;) {
+            int live = 0, last = -1;
+            bool progressed = false;
+            for (int g = first; g < ng; g += step) {
+                if (G[g].rc || !G[g].inflight) continue;
+                live++; last = g;
+                if (G[g].round_ready()) { G[g].advance(); progressed = true; }
+            }
+            if (!live) break;
+            if (live == 1 && !progressed) G[last].advance();  // nothing else to look after: block on its stream
+            else if (!progressed) std::this_thread::yield();
+        }
+        for (int g = first; g < ng; g += step) G[g].finalize();
     }
 
     // per-particle records -> device arrays
@@ -535,15 +566,18 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
     if (!ns) return 0;
     if (st_init(ctx, S)) return -1;
     CK(cudaEventRecord(S.ev_in, st));
-    // one host thread per group: leave a core for the caller's thread, and share the host between the ranks of a
-    // one-process-per-GPU job (torchrun exports LOCAL_WORLD_SIZE)
-    int ng_auto = ns >= 8192 ? 6 : (ns >= 2048 ? 4 : (ns >= 256 ? 2 : 1));
+    // Groups (concurrent rounds on the GPU) and the host threads that drive them: one thread per group when the host has
+    // the cores, else several groups per thread (leave a core for the caller's thread, and share the host between the
+    // ranks of a one-process-per-GPU job: torchrun exports LOCAL_WORLD_SIZE)
+    const int ng_auto = ns >= 8192 ? 6 : (ns >= 2048 ? 4 : (ns >= 256 ? 2 : 1));
+    const int ng = std::max(1, std::min(ST_GROUPS, getenv("HYDROTM_GROUPS") ? atoi(getenv("HYDROTM_GROUPS")) : ng_auto));
+    int nth = ng;
     {
         const int cores = (int)std::thread::hardware_concurrency();
         const int ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
-        if (cores > 0) ng_auto = std::max(1, std::min(ng_auto, cores / ranks - 1));
+        if (cores > 0) nth = std::max(1, std::min(ng, cores / ranks - 1));
+        if (getenv("HYDROTM_THREADS")) nth = std::max(1, std::min(ng, atoi(getenv("HYDROTM_THREADS"))));
     }
-    const int ng = std::max(1, std::min(ST_GROUPS, getenv("HYDROTM_GROUPS") ? atoi(getenv("HYDROTM_GROUPS")) : ng_auto));
     // deal the particles, heaviest first, round-robin: every group gets the same size mix
     std::vector<int> ord(ns);
     for (int j = 0; j < ns; j++) ord[j] = j;
@@ -569,11 +603,11 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
     auto T0 = std::chrono::steady_clock::now();
     const bool timeline = getenv("HYDROTM_TIMELINE") != nullptr;
     for (int g = 0; g < ng; g++) { G[g].timeline = timeline; G[g].t_base = T0; }
-    if (ng == 1) G[0].run();
+    if (nth == 1) StGroup::run_many(G, 0, 1, ng);
     else {
         std::thread th[ST_GROUPS];
-        for (int g = 0; g < ng; g++) th[g] = std::thread([&G, g]() { G[g].run(); });
-        for (int g = 0; g < ng; g++) th[g].join();
+        for (int t = 0; t < nth; t++) th[t] = std::thread([&G, t, nth, ng]() { StGroup::run_many(G, t, nth, ng); });
+        for (int t = 0; t < nth; t++) th[t].join();
     }
     for (int g = 0; g < ng; g++)
         for (const StP &s : G[g].P) {
@@ -602,7 +636,7 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         for (int g = 0; g < ng; g++)
             fprintf(stderr, "[hydrotm-staged] group %d: %zu particles, %d rounds: plan+issue %.2f ms, wait %.2f ms, controller %.2f ms\n", g,
                     G[g].P.size(), G[g].nround, G[g].t_plan, G[g].t_wait, G[g].t_ctl);
-        fprintf(stderr, "[hydrotm-staged] %d particles, %d groups, %.2f ms\n", ns, ng, tot);
+        fprintf(stderr, "[hydrotm-staged] %d particles, %d groups on %d host threads, %.2f ms\n", ns, ng, nth, tot);
     }
     return 0;
 }

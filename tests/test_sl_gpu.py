@@ -142,7 +142,7 @@ def test_equal_area_radius_and_large_batch_escalation(engine):
 def test_staged_pipeline_invariants(engine, monkeypatch):
     """The staged pipeline must not depend on how it is scheduled: speculation depth, number of particle groups,
     scratch budget (forces deferred particles) and an undersized arena (retry through HS_RC_ARENA_FULL) all give the
-    same (NMAX, NGAUSS, trials, status) and T-matrices; the fused one-CTA-per-particle kernel agrees too."""
+    same (NMAX, NGAUSS, trials, status) and T-matrices, also with several groups driven by one host thread; the fused one-CTA-per-particle kernel agrees too."""
     w = rain_grid("W")
     sel = slice(None, None, 3)
     args = [w[k][sel] for k in ("radius", "wavelength", "mr", "mi", "axis_ratio")]
@@ -160,6 +160,7 @@ def test_staged_pipeline_invariants(engine, monkeypatch):
     ref_meta, ref_T = run()
     assert (ref_meta[3] == 0).all()
     for env in (dict(HYDROTM_SPEC=1), dict(HYDROTM_SPEC=5), dict(HYDROTM_GROUPS=1), dict(HYDROTM_GROUPS=3, HYDROTM_SPEC=3),
+                dict(HYDROTM_GROUPS=4, HYDROTM_THREADS=2), dict(HYDROTM_GROUPS=5, HYDROTM_THREADS=1, HYDROTM_SCRATCH_GB=0.002),
                 dict(HYDROTM_SCRATCH_GB=0.002), dict(_margin=0.05), dict(HYDROTM_STAGED_MIN=1000), dict(HYDROTM_STAGED_MIN=12)):
         meta, T = run(**env)
         for a, b in zip(ref_meta, meta):

@@ -44,7 +44,13 @@ struct ScArgs {
     const int *order;       // CTA -> particle, heaviest (largest NMAX) first, or null
     const double *frames;   // [n_inc][max blocks][n_orient][SC_FR]: particle-frame directions + polarisation rotations (k_scatter_frames)
     int frame_blocks;       // geometry blocks per incident direction in `frames`
+    const double2 *wtab;    // Wigner table (k_scatter_wig): [(d, block)][1 + SCK_G directions][tri(m, n)][n_orient] pairs
+    int wig_nb;             // largest n in `wtab`
 };
+
+// triangular index of (m, n >= m) in a Wigner table that goes up to n = nb
+__host__ __device__ __forceinline__ long sc_tri(int m, int n, int nb) { return (long)m * (nb + 1) - (long)m * (m - 1) / 2 + (n - m); }
+__host__ __device__ __forceinline__ long sc_tri_size(int nb) { return (long)(nb + 1) * (nb + 2) / 2; }
 
 // Wigner pi_n = d/sin, tau_n = dd/dtheta generated in lock-step with n (VIGAMPL as a recurrence)
 struct WigRec {
@@ -284,13 +290,14 @@ struct WigTab {
         qs1 = pole ? 0.0 : 1.0 / qs;
         qspow = 1.0;
     }
-    __device__ __forceinline__ void start(int m, const double *cm)
+    // mode m (call for m = 0, 1, 2, ... in order: qspow accumulates sin^m); cm = prod_{i<=m} sqrt((2i-1)/2i)
+    __device__ __forceinline__ void start(int m, double cm)
     {
         if (m == 0) { d1 = 1.0; d2 = x; }
-        else { qspow *= qs; d1 = 0.0; d2 = cm[m] * qspow; }
+        else { qspow *= qs; d1 = 0.0; d2 = cm * qspow; }
     }
-    __device__ __forceinline__ void next(int n, int m, const double *sq, const double *rsq, const double *rn1,
-                                         const double *r2n1, double &pi_n, double &tau_n)
+    // n = max(m,1), max(m,1)+1, ... in order
+    __device__ __forceinline__ void next(int n, int m, double &pi_n, double &tau_n)
     {
         if (pole) {
             if (m != 1) { pi_n = 0.0; tau_n = 0.0; return; }
@@ -301,14 +308,16 @@ struct WigTab {
             return;
         }
         const double qn = n, qn1 = n + 1, qn2 = 2 * n + 1;
+        const double r2n1 = 1.0 / qn2;
         double d3, der;
         if (m == 0) {
-            d3 = (qn2 * x * d2 - qn * d1) * rn1[n];
-            der = qs1 * (qn1 * qn * r2n1[n]) * (-d1 + d3);
+            d3 = (qn2 * x * d2 - qn * d1) * (1.0 / qn1);
+            der = qs1 * (qn1 * qn * r2n1) * (-d1 + d3);
         } else {
-            const double qnm = sq[n], qnm1 = sq[n + 1];
-            d3 = (qn2 * x * d2 - qnm * d1) * rsq[n + 1];
-            der = qs1 * (-qn1 * qnm * d1 + qn * qnm1 * d3) * r2n1[n];
+            const double qmm = (double)(m * m);
+            const double qnm = sqrt(qn * qn - qmm), qnm1 = sqrt(qn1 * qn1 - qmm);
+            d3 = (qn2 * x * d2 - qnm * d1) * (1.0 / qnm1);
+            der = qs1 * (-qn1 * qnm * d1 + qn * qnm1 * d3) * r2n1;
         }
         pi_n = d2 * qs1;
         tau_n = der;
@@ -349,11 +358,44 @@ __global__ void k_scatter_frames(ScArgs a, double *frames)
     }
 }
 
+// Wigner table of a scatter call: the pi / tau functions of the particle-frame directions only depend on (orientation,
+// geometry, m, n), not on the particle, so they are generated ONCE per call (same recurrence, same operation order as
+// the per-thread WigTab that the orientation threads of k_scatter used to carry) instead of once per particle:
+//   direction 0 (incident):       { P'_n, Q'_n } = { sgn f_n m pi0_n, sgn f_n tau0_n },  sgn = (-1)^(n >> 1)
+//   direction 1 + g (scattered):  { f_n m pi_n, f_n tau_n }                              f_n = sqrt((2n+1) / (n(n+1)))
+// grid (orientation blocks, m, (d, block, direction)); thread = orientation.
+__global__ void __launch_bounds__(64) k_scatter_wig(ScArgs a, double2 *wtab)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y, nb = a.wig_nb;
+    const int db = blockIdx.z / (1 + SCK_G), dir = blockIdx.z - db * (1 + SCK_G);
+    const int d = db / a.frame_blocks, b = db - d * a.frame_blocks;
+    if (o >= a.n_orient) return;
+    const int gb = a.g_begin[d] + b * SCK_G, gend = a.g_begin[d + 1];
+    const int ng = max(0, min(SCK_G, gend - gb));
+    if (dir > ng || (b > 0 && ng == 0)) return;
+    const double *fr = a.frames + ((long)db * a.n_orient + o) * SC_FR;
+    WigTab w;
+    w.setup(dir == 0 ? fr[0] : fr[6 + 6 * (dir - 1)]);
+    double cm = 1.0;
+    for (int i = 0; i <= m; i++) {
+        if (i > 0) cm = cm * sqrt((double)(2 * i - 1) / (double)(2 * i));
+        w.start(i, cm);
+    }
+    const int nmin = m > 1 ? m : 1;
+    double2 *out = wtab + (((long)db * (1 + SCK_G) + dir) * sc_tri_size(nb) + sc_tri(m, nmin, nb)) * a.n_orient + o;
+    for (int n = nmin; n <= nb; n++) {
+        double pi_n, tau_n;
+        w.next(n, m, pi_n, tau_n);
+        const double f0 = sqrt((double)(2 * n + 1) / (double)(n * (n + 1)));
+        const double f = (dir == 0 && (n & 2)) ? -f0 : f0;
+        out[(long)(n - nmin) * a.n_orient] = make_double2(m * pi_n * f, tau_n * f);
+    }
+}
+
 __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
 {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double s_fn[HS_NPN1 + 2], s_cm[HS_NPN1 + 2], s_rn1[HS_NPN1 + 2], s_r2n1[HS_NPN1 + 2];
-    __shared__ double s_sq[HS_NPN1 + 3], s_rsq[HS_NPN1 + 3];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int p = a.order ? a.order[blockIdx.x] : blockIdx.x;
     const bool bad = (a.status[p] != HS_ST_OK && a.status[p] != HS_ST_NGAUSS_LIMIT && a.status[p] != HS_ST_SINGULAR) || a.toff[p] < 0;
@@ -367,16 +409,6 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
     const double2 *tg = reinterpret_cast<const double2 *>(a.tarena) + a.toff[p];
     const int nmax = a.nmax[p];
     const double lam = a.lam[p];
-    for (int n = tid; n <= nmax + 1; n += nt) {
-        s_fn[n] = (n == 0) ? 0.0 : sqrt((double)(2 * n + 1) / (double)(n * (n + 1)));
-        s_rn1[n] = 1.0 / (double)(n + 1);
-        s_r2n1[n] = 1.0 / (double)(2 * n + 1);
-    }
-    if (tid == 0) {
-        double c = 1.0;
-        s_cm[0] = 1.0;
-        for (int i = 1; i <= nmax; i++) { c = c * sqrt((double)(2 * i - 1) / (double)(2 * i)); s_cm[i] = c; }
-    }
     // dynamic smem: [T stage: 2*nmax*nmax complex][reduction rows: nt * stride][accs]
     double2 *sT = reinterpret_cast<double2 *>(sm);
     const int stride = SCK_G * 24 + 3;
@@ -396,28 +428,29 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                 const bool active = o < a.n_orient;
                 // ---- per-thread setup ----
                 double R[2][2], R1[SCK_G][2][2], dphi[SCK_G];
-                WigTab w0, ws[SCK_G];
                 double acc[SCK_G][8];
                 double acc_t = 0.0, acc_p = 0.0;
+                const long dblk = (long)d * a.frame_blocks + (gb - a.g_begin[d]) / SCK_G;
                 if (active) {
                     // orientation / geometry quantities do not depend on the particle: read them from the table built
                     // once per call by k_scatter_frames (AMPL's angle nudges and Euler rotations)
-                    const double *fr = a.frames + (((long)d * a.frame_blocks + (gb - a.g_begin[d]) / SCK_G) * a.n_orient + o) * SC_FR;
+                    const double *fr = a.frames + (dblk * a.n_orient + o) * SC_FR;
                     R[0][0] = fr[2]; R[0][1] = fr[3]; R[1][0] = fr[4]; R[1][1] = fr[5];
-                    w0.setup(fr[0]);
 #pragma unroll
                     for (int g = 0; g < SCK_G; g++) {
                         if (g < ng) {
                             const double *fg = fr + 6 + 6 * g;
                             dphi[g] = fg[1];
-                            ws[g].setup(fg[0]);
                             R1[g][0][0] = fg[2]; R1[g][0][1] = fg[3]; R1[g][1][0] = fg[4]; R1[g][1][1] = fg[5];
                         }
 #pragma unroll
                         for (int k = 0; k < 8; k++) acc[g][k] = 0.0;
                     }
                 }
-                // P' = sgn f m pi0, Q' = sgn f tau0, sgn = (-1)^(n'>>1): per-thread vectors in shared memory ([n'][thread], aliased
+                // Wigner functions of this thread's directions: table of the call (k_scatter_wig), [tri(m, n)][orientation]
+                const long tri = sc_tri_size(a.wig_nb);
+                const double2 *wt0 = a.wtab + dblk * (1 + SCK_G) * tri * a.n_orient + (active ? o : 0);
+                // P' = sgn f m pi0, Q' = sgn f tau0 of the current mode: per-thread vectors in shared memory ([n'][thread], aliased
                 // with the reduction rows, which are only written after the mode sweep).  As thread-local arrays they lived in
                 // L1-cached local memory, which the heavy class (3 CTAs x 55 KB of shared memory per SM) leaves too small.
                 double *Pp = srow + tid, *Qp = srow + (long)(a.nmax_bound + 2) * nt + tid;
@@ -426,33 +459,29 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
                     __syncthreads();
                     for (int e = tid; e < 2 * NM * NM; e += nt) sT[e] = tg[moff + e];
-                    for (int n = nmin + tid; n <= nmax + 1; n += nt) {
-                        double v = sqrt((double)n * (double)n - (double)(m * m));
-                        s_sq[n] = v;
-                        s_rsq[n] = (n > m) ? 1.0 / v : 0.0;
-                    }
                     __syncthreads();
                     moff += 2L * NM * NM;
                     if (!active) continue;
-                    w0.start(m, s_cm);
+                    const double2 *wm0 = wt0 + sc_tri(m, nmin, a.wig_nb) * a.n_orient;
                     for (int nn = nmin; nn <= nmax; nn++) {
-                        double p0, t0;
-                        w0.next(nn, m, s_sq, s_rsq, s_rn1, s_r2n1, p0, t0);
-                        const double f = (nn & 2) ? -s_fn[nn] : s_fn[nn];
-                        Pp[nn * nt] = m * p0 * f;
-                        Qp[nn * nt] = t0 * f;
+                        const double2 v = wm0[(long)(nn - nmin) * a.n_orient];
+                        Pp[nn * nt] = v.x;
+                        Qp[nn * nt] = v.y;
                     }
-                    double fc[SCK_G], fs[SCK_G];
+                    // per-mode sums over n of i^(-n-1) (f m pi +- f tau) (G1 +- G2), ... (see below)
+                    double A[SCK_G][8];
 #pragma unroll
                     for (int g = 0; g < SCK_G; g++)
-                        if (g < ng) {
-                            ws[g].start(m, s_cm);
-                            if (m == 0) { fc[g] = 1.0; fs[g] = 0.0; }
-                            else { double sn, cs; sincos(m * dphi[g], &sn, &cs); fc[g] = 2.0 * cs; fs[g] = 2.0 * sn; }
-                        }
-                    const double wm = (m == 0) ? 1.0 : 2.0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) A[g][k] = 0.0;
+                    double xt = 0.0, xp = 0.0;
+                    const double2 *wg = wt0 + (tri + sc_tri(m, nmin, a.wig_nb)) * a.n_orient;  // first scattered direction, n = nmin
                     for (int n = nmin; n <= nmax; n++) {
                         const int k = n - nmin;
+                        double2 wv[SCK_G];   // { f m pi_n, f tau_n } of the scattered directions: loaded ahead of the T sweep
+#pragma unroll
+                        for (int g = 0; g < SCK_G; g++)
+                            if (g < ng) wv[g] = wg[((long)g * tri + k) * a.n_orient];
                         const double2 *ta = sT + (long)(((n + 1) & 1) * NM) * NM + k;  // tau = 1 row, stride NM over n'
                         const double2 *tb = sT + (long)((n & 1) * NM) * NM + k;        // tau = 2 row
                         // same-parity n': T11 (ta), T22 (tb); phase i^(n&1)
@@ -481,27 +510,43 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                             g1r = e1r - o1i; g1i = e1i + o1r; g2r = e2r - o2i; g2i = e2i + o2r;
                             g3r = e3r - o3i; g3i = e3i + o3r; g4r = e4r - o4i; g4i = e4i + o4r;
                         }
-                        acc_t += wm * (g1r * g1r + g1i * g1i + g2r * g2r + g2i * g2i);
-                        acc_p += wm * (g3r * g3r + g3i * g3i + g4r * g4r + g4i * g4i);
-                        const double f = s_fn[n];
-                        const int pw = (-(n + 1)) & 3;
-                        const double ar = (pw == 0) ? f : (pw == 2) ? -f : 0.0, ai = (pw == 1) ? f : (pw == 3) ? -f : 0.0;
+                        xt += g1r * g1r + g1i * g1i + g2r * g2r + g2i * g2i;
+                        xp += g3r * g3r + g3i * g3i + g4r * g4r + g4i * g4i;
+                        // With s = f m pi, t = f tau of a scattered direction (table), u = s G1 + t G2, w = t G1 + s G2,
+                        // v = s G3 + t G4, z = t G3 + s G4:  u + w = (s + t)(G1 + G2), u - w = (s - t)(G1 - G2), same for v, z.
+                        // A accumulates i^(-n-1) times those four products; u, v, w, z are recovered per mode (they are
+                        // linear), which takes 8 FMAs per direction and n instead of 36.
+                        const double p12r = g1r + g2r, p12i = g1i + g2i, m12r = g1r - g2r, m12i = g1i - g2i;
+                        const double p34r = g3r + g4r, p34i = g3i + g4i, m34r = g3r - g4r, m34i = g3i - g4i;
+                        const bool neg = ((-(n + 1)) & 2) != 0;   // i^(-n-1) = -1 or -i
 #pragma unroll
                         for (int g = 0; g < SCK_G; g++) {
                             if (g >= ng) continue;
-                            double p_, t_;
-                            ws[g].next(n, m, s_sq, s_rsq, s_rn1, s_r2n1, p_, t_);
-                            const double mp = m * p_;
-                            const double ur = mp * g1r + t_ * g2r, ui = mp * g1i + t_ * g2i;
-                            const double vr = mp * g3r + t_ * g4r, vi = mp * g3i + t_ * g4i;
-                            const double wr = t_ * g1r + mp * g2r, wi = t_ * g1i + mp * g2i;
-                            const double zr = t_ * g3r + mp * g4r, zi = t_ * g3i + mp * g4i;
-                            const double cr = ar * fc[g], ci = ai * fc[g], sr = ar * fs[g], si = ai * fs[g];
-                            acc[g][0] += ur * cr - ui * ci; acc[g][1] += ur * ci + ui * cr;
-                            acc[g][2] += vr * sr - vi * si; acc[g][3] += vr * si + vi * sr;
-                            acc[g][4] -= wr * sr - wi * si; acc[g][5] -= wr * si + wi * sr;
-                            acc[g][6] += zr * cr - zi * ci; acc[g][7] += zr * ci + zi * cr;
+                            const double sp_ = neg ? -(wv[g].x + wv[g].y) : (wv[g].x + wv[g].y), sm_ = neg ? -(wv[g].x - wv[g].y) : (wv[g].x - wv[g].y);
+                            if ((n + 1) & 1) {  // times i
+                                A[g][0] -= sp_ * p12i; A[g][1] += sp_ * p12r; A[g][2] -= sm_ * m12i; A[g][3] += sm_ * m12r;
+                                A[g][4] -= sp_ * p34i; A[g][5] += sp_ * p34r; A[g][6] -= sm_ * m34i; A[g][7] += sm_ * m34r;
+                            } else {
+                                A[g][0] += sp_ * p12r; A[g][1] += sp_ * p12i; A[g][2] += sm_ * m12r; A[g][3] += sm_ * m12i;
+                                A[g][4] += sp_ * p34r; A[g][5] += sp_ * p34i; A[g][6] += sm_ * m34r; A[g][7] += sm_ * m34i;
+                            }
                         }
+                    }
+                    const double wm = (m == 0) ? 1.0 : 2.0;
+                    acc_t += wm * xt;
+                    acc_p += wm * xp;
+#pragma unroll
+                    for (int g = 0; g < SCK_G; g++) {
+                        if (g >= ng) continue;
+                        double fc, fs;
+                        if (m == 0) { fc = 0.5; fs = 0.0; }
+                        else { double sn, cs; sincos(m * dphi[g], &sn, &cs); fc = cs; fs = sn; }  // (2 cos, 2 sin) / 2
+                        const double ur = A[g][0] + A[g][2], ui = A[g][1] + A[g][3], wr = A[g][0] - A[g][2], wi = A[g][1] - A[g][3];
+                        const double vr = A[g][4] + A[g][6], vi = A[g][5] + A[g][7], zr = A[g][4] - A[g][6], zi = A[g][5] - A[g][7];
+                        acc[g][0] += fc * ur; acc[g][1] += fc * ui;   // VV
+                        acc[g][2] += fs * vr; acc[g][3] += fs * vi;   // VH
+                        acc[g][4] -= fs * wr; acc[g][5] -= fs * wi;   // HV
+                        acc[g][6] += fc * zr; acc[g][7] += fc * zi;   // HH
                     }
                 }
                 __syncthreads();  // everybody is done with the P' / Q' vectors that share the reduction rows' memory

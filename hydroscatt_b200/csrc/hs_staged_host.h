@@ -263,6 +263,10 @@ struct StGroup {
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
         a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res; a.fuse = (C->fuse_solve ? 1 : 0) | (getenv("HYDROTM_SOLVE2") && atoi(getenv("HYDROTM_SOLVE2")) == 0 ? 0 : 2); a.prof = C->prof;
         const int ni = (int)items.size();
+        // HYDROTM_PROF_SEL: bit mask of the kernel variants that record phase cycles (1: m>=1 wide, 2: m=0 wide, 4: m>=1 narrow,
+        // 8: m=0 narrow, 16: small modes); default all
+        static const int psel = getenv("HYDROTM_PROF_SEL") ? atoi(getenv("HYDROTM_PROF_SEL")) : 31;
+        auto pa = [&](int bit) { StArgs x = a; if (!(psel & bit)) x.prof = nullptr; return x; };
         k_st_radial<<<((int)rad.size() + 7) / 8, 128, 0, st>>>(a, (const StRadTask *)(d + o_rad), (int)rad.size());
         mark("radial");
         k_st_wigner<<<((int)mitems.size() + 7) / 8, 128, 0, st>>>(a, (int)mitems.size());
@@ -277,16 +281,16 @@ struct StGroup {
             CK(cudaEventRecord(B->ev_fork, st));
             CK(cudaStreamWaitEvent(s2, B->ev_fork, 0));
         }
-        if (!at1.empty()) { k_st_assemble<false, 32><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a1), (int)at1.size()); launches++; mark("asm m>=1"); }
-        if (!at0.empty()) { k_st_assemble<true, 32><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(a, (const StATask *)(d + o_a0), (int)at0.size()); launches++; mark("asm m=0"); }
+        if (!at1.empty()) { k_st_assemble<false, 32><<<(int)at1.size(), 256, ST_ASM_SMEM, st>>>(pa(1), (const StATask *)(d + o_a1), (int)at1.size()); launches++; mark("asm m>=1"); }
+        if (!at0.empty()) { k_st_assemble<true, 32><<<(int)at0.size(), 256, ST_ASM_SMEM, st>>>(pa(2), (const StATask *)(d + o_a0), (int)at0.size()); launches++; mark("asm m=0"); }
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
         const int gsm[4] = {16384, 36864, 65536, 200704};
         if (!gl[3].empty()) { k_st_solve<256, false><<<(int)gl[3].size(), 256, gsm[3], st>>>(a, (const int *)(d + og[3]), (int)gl[3].size()); launches++; }
         for (int c = 2; c >= 0; c--)
             if (!gl[c].empty()) { k_st_solve<256, false><<<(int)gl[c].size(), 256, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; mark("solve"); }
-        if (!as1.empty()) { k_st_assemble<false, 16><<<(int)as1.size(), 128, ST_ASM_SMEM16, s2>>>(a, (const StATask *)(d + o_s1), (int)as1.size()); launches++; }
-        if (!as0.empty()) { k_st_assemble<true, 16><<<(int)as0.size(), 128, ST_ASM_SMEM16, s2>>>(a, (const StATask *)(d + o_s0), (int)as0.size()); launches++; }
-        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, s2>>>(a, (const int *)(d + o_sm), (int)sm.size()); launches++; }
+        if (!as1.empty()) { k_st_assemble<false, 16><<<(int)as1.size(), 128, ST_ASM_SMEM16, s2>>>(pa(4), (const StATask *)(d + o_s1), (int)as1.size()); launches++; }
+        if (!as0.empty()) { k_st_assemble<true, 16><<<(int)as0.size(), 128, ST_ASM_SMEM16, s2>>>(pa(8), (const StATask *)(d + o_s0), (int)as0.size()); launches++; }
+        if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, s2>>>(pa(16), (const int *)(d + o_sm), (int)sm.size()); launches++; }
         if (two) {
             CK(cudaEventRecord(B->ev_join, s2));
             CK(cudaStreamWaitEvent(st, B->ev_join, 0));

@@ -43,6 +43,8 @@ struct hs_ctx {
     double *d_sc = nullptr;      // scatter geometry tables (device)
     double *d_frames = nullptr;  // scatter kernel: per (orientation, geometry) frames
     size_t frames_cap = 0;
+    double2 *d_scwig = nullptr;  // scatter kernel: Wigner table of the call (k_scatter_wig)
+    size_t scwig_cap = 0;
     int *d_order = nullptr;      // scatter kernel: CTA -> particle map, heaviest first
     int order_cap = 0;
     double *d_xs_tmp = nullptr;
@@ -138,7 +140,7 @@ extern "C" void hs_ctx_destroy(hs_ctx *ctx)
 {
     if (!ctx) return;
     cudaFree(ctx->d_gx); cudaFree(ctx->d_gw); cudaFree(ctx->d_queue); cudaFree(ctx->d_items);
-    cudaFree(ctx->d_ws_global); cudaFree(ctx->d_ws_fb); cudaFree(ctx->d_sc); cudaFree(ctx->d_xs_tmp); cudaFree(ctx->d_order); cudaFree(ctx->d_frames);
+    cudaFree(ctx->d_ws_global); cudaFree(ctx->d_ws_fb); cudaFree(ctx->d_sc); cudaFree(ctx->d_xs_tmp); cudaFree(ctx->d_order); cudaFree(ctx->d_frames); cudaFree(ctx->d_scwig);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int b = 0; b < 8; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -230,7 +232,7 @@ static int scatter_prepare(hs_ctx *ctx, int n, const double *d_tarena, const lon
     a.n = n; a.tarena = d_tarena; a.toff = d_toff; a.nmax = d_nmax; a.status = d_status; a.lam = d_lam;
     a.n_inc = n_inc; a.inc = dblk; a.g_begin = dib; a.gsc = dblk + 128; a.g_out = dib + 65; a.n_geom = n_geom;
     a.n_orient = n_orient; a.alpha = d_alpha; a.beta = d_beta; a.weight = d_weight; a.scale = scale;
-    a.S = d_S; a.Z = d_Z; a.xs = xs_inc;
+    a.S = d_S; a.Z = d_Z; a.xs = xs_inc; a.wtab = nullptr; a.wig_nb = 0;
     {   // orientation / geometry frames: once per call instead of once per particle
         int maxblk = 1;
         for (int d = 0; d < n_inc; d++) maxblk = std::max(maxblk, (g_begin[d + 1] - g_begin[d] + SCK_G - 1) / SCK_G);
@@ -248,6 +250,26 @@ static int scatter_prepare(hs_ctx *ctx, int n, const double *d_tarena, const lon
     }
     P.a = a; P.n_inc = n_inc; P.inc_of_geom = dib + 130; P.xs_inc = xs_inc; P.d_xs = d_xs; P.n_geom = n_geom;
     P.threads = std::min(64, std::max(32, (n_orient + 31) / 32 * 32));
+    return 0;
+}
+
+// Wigner table of a scatter call up to n = nb (the largest NMAX the launch will meet); a.frames must be in place
+static int scatter_build_wig(hs_ctx *ctx, hs::ScArgs &a, int nb, cudaStream_t st)
+{
+    nb = std::max(1, std::min(nb, HS_NPN1));
+    const int ndb = a.n_inc * a.frame_blocks;
+    const size_t need = (size_t)ndb * (1 + SCK_G) * hs::sc_tri_size(nb) * a.n_orient;
+    if (need > ctx->scwig_cap) {
+        if (ctx->d_scwig) cudaFree(ctx->d_scwig);
+        ctx->d_scwig = nullptr; ctx->scwig_cap = 0;
+        CK(cudaMalloc(&ctx->d_scwig, need * sizeof(double2)));
+        ctx->scwig_cap = need;
+    }
+    a.wtab = ctx->d_scwig; a.wig_nb = nb;
+    dim3 g((a.n_orient + 63) / 64, nb + 1, ndb * (1 + SCK_G));
+    hs::k_scatter_wig<<<g, 64, 0, st>>>(a, ctx->d_scwig);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -590,6 +612,8 @@ extern "C" int hs_calctmat_scatter_batch(hs_ctx *ctx, int n, const double *d_axi
     { int rc = scatter_prepare(ctx, n, d_tarena, d_toff, d_nmax, d_status, d_lam, n_geom, h_geom, n_orient, d_alpha, d_beta,
                                d_weight, scale, d_S, d_Z, d_xs, st, SP); if (rc) return rc; }
     CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - 8192));
+    // scatter launches that overlap the convergence rounds do not know the largest NMAX yet: table up to the limit
+    if (getenv("HYDROTM_OVERLAP_SCATTER")) { int rc = scatter_build_wig(ctx, SP.a, HS_NPN1, st); if (rc) return rc; }
     bool used = false;
     int rc = calctmat_impl(ctx, n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, np, ddelt, ndgs, rescale_ddelt, d_tarena, arena_cap, d_arena_top,
                            d_toff, d_nmax, d_ngauss, d_ntrials, d_status, stream, &SP, &used);
@@ -878,6 +902,8 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
         }
         if (max_smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
         CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        { int top = 1; for (int c = 0; c < 3; c++) if (cls_cnt[c]) top = std::max(top, cls_bound[c]);
+          int rc = scatter_build_wig(ctx, a, top, st); if (rc) return rc; }
         CK(cudaEventRecord(ctx->ev_start, st));
         for (int c = 0; c < 3; c++) {
             if (!cls_cnt[c]) continue;
@@ -898,6 +924,7 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
         size_t smem = smem_for(nmax_bound);
         if (smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
         CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { int rc = scatter_build_wig(ctx, a, nmax_bound, st); if (rc) return rc; }
         hs::k_scatter<<<n, threads, smem, st>>>(a);
         ctx->launches++;
         CK(cudaGetLastError());

@@ -409,9 +409,9 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
     const double2 *tg = reinterpret_cast<const double2 *>(a.tarena) + a.toff[p];
     const int nmax = a.nmax[p];
     const double lam = a.lam[p];
-    // dynamic smem: [T stage: 2*nmax*nmax complex][reduction rows: nt * stride][accs]
+    // dynamic smem: [T stage: 2*nmax*nmax complex][reduction rows: nt * stride][accs][per-thread amplitude sums: 8 SCK_G x nt]
     double2 *sT = reinterpret_cast<double2 *>(sm);
-    const int stride = SCK_G * 24 + 3;
+    const int stride = 24 + 3;  // one scattered direction (S 8, Z 16) + the two cross sections per reduction row
     double *srow = sm + 4L * a.nmax_bound * a.nmax_bound;
     const long vec_doubles = 2L * (a.nmax_bound + 2) * nt, row_doubles = (long)nt * stride;
     double *accs = srow + (vec_doubles > row_doubles ? vec_doubles : row_doubles);
@@ -427,26 +427,15 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                 const int o = o0 + tid;
                 const bool active = o < a.n_orient;
                 // ---- per-thread setup ----
-                double R[2][2], R1[SCK_G][2][2], dphi[SCK_G];
-                double acc[SCK_G][8];
                 double acc_t = 0.0, acc_p = 0.0;
                 const long dblk = (long)d * a.frame_blocks + (gb - a.g_begin[d]) / SCK_G;
-                if (active) {
-                    // orientation / geometry quantities do not depend on the particle: read them from the table built
-                    // once per call by k_scatter_frames (AMPL's angle nudges and Euler rotations)
-                    const double *fr = a.frames + (dblk * a.n_orient + o) * SC_FR;
-                    R[0][0] = fr[2]; R[0][1] = fr[3]; R[1][0] = fr[4]; R[1][1] = fr[5];
+                // orientation / geometry quantities do not depend on the particle: they come from the table built once per
+                // call by k_scatter_frames (AMPL's angle nudges and Euler rotations), read where they are needed
+                const double *fr = a.frames + (dblk * a.n_orient + (active ? o : 0)) * SC_FR;
+                // amplitude sums over the modes: per-thread slots in shared memory ([component][thread]), updated once per mode
+                double *sacc = accs + (SCK_G * 24 + 2) + tid;
 #pragma unroll
-                    for (int g = 0; g < SCK_G; g++) {
-                        if (g < ng) {
-                            const double *fg = fr + 6 + 6 * g;
-                            dphi[g] = fg[1];
-                            R1[g][0][0] = fg[2]; R1[g][0][1] = fg[3]; R1[g][1][0] = fg[4]; R1[g][1][1] = fg[5];
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; k++) acc[g][k] = 0.0;
-                    }
-                }
+                for (int k = 0; k < 8 * SCK_G; k++) sacc[k * nt] = 0.0;
                 // Wigner functions of this thread's directions: table of the call (k_scatter_wig), [tri(m, n)][orientation]
                 const long tri = sc_tri_size(a.wig_nb);
                 const double2 *wt0 = a.wtab + dblk * (1 + SCK_G) * tri * a.n_orient + (active ? o : 0);
@@ -540,37 +529,44 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         if (g >= ng) continue;
                         double fc, fs;
                         if (m == 0) { fc = 0.5; fs = 0.0; }
-                        else { double sn, cs; sincos(m * dphi[g], &sn, &cs); fc = cs; fs = sn; }  // (2 cos, 2 sin) / 2
+                        else { double sn, cs; sincos(m * fr[6 + 6 * g + 1], &sn, &cs); fc = cs; fs = sn; }  // (2 cos, 2 sin) / 2
                         const double ur = A[g][0] + A[g][2], ui = A[g][1] + A[g][3], wr = A[g][0] - A[g][2], wi = A[g][1] - A[g][3];
                         const double vr = A[g][4] + A[g][6], vi = A[g][5] + A[g][7], zr = A[g][4] - A[g][6], zi = A[g][5] - A[g][7];
-                        acc[g][0] += fc * ur; acc[g][1] += fc * ui;   // VV
-                        acc[g][2] += fs * vr; acc[g][3] += fs * vi;   // VH
-                        acc[g][4] -= fs * wr; acc[g][5] -= fs * wi;   // HV
-                        acc[g][6] += fc * zr; acc[g][7] += fc * zi;   // HH
+                        double *sa = sacc + 8 * g * nt;
+                        sa[0 * nt] += fc * ur; sa[1 * nt] += fc * ui;   // VV
+                        sa[2 * nt] += fs * vr; sa[3 * nt] += fs * vi;   // VH
+                        sa[4 * nt] -= fs * wr; sa[5 * nt] -= fs * wi;   // HV
+                        sa[6 * nt] += fc * zr; sa[7 * nt] += fc * zi;   // HH
                     }
                 }
                 __syncthreads();  // everybody is done with the P' / Q' vectors that share the reduction rows' memory
-                // ---- per-thread epilogue: S, Z, cross sections -> weighted row in shared memory ----
-                if (active) {
-                    const double dk = 2.0 * pin / lam, w = a.weight[o];
-                    double *row = srow + (long)tid * stride;
-                    const double c0 = 4.0 * pin / (dk * dk);
-                    row[ng * 24] = w * c0 * (R[0][1] * R[0][1] * acc_t + R[1][1] * R[1][1] * acc_p);
-                    row[ng * 24 + 1] = w * c0 * (R[0][0] * R[0][0] * acc_t + R[1][0] * R[1][0] * acc_p);
-#pragma unroll
-                    for (int g = 0; g < SCK_G; g++) {
-                        if (g >= ng) continue;
-                        double vvr = acc[g][0] / dk, vvi = acc[g][1] / dk, vhr = acc[g][2] / dk, vhi = acc[g][3] / dk;
-                        double hvr = acc[g][4] / dk, hvi = acc[g][5] / dk, hhr = acc[g][6] / dk, hhi = acc[g][7] / dk;
+                // ---- per-thread epilogue: S, Z, cross sections -> weighted row in shared memory, one scattered direction at a
+                // time (rows of 24 + 2 components; the reduction rows share their memory with the P' / Q' vectors) ----
+                for (int g = 0; g < ng; g++) {
+                    const int ncol = 24 + (g == 0 ? 2 : 0);
+                    if (active) {
+                        const double dk = 2.0 * pin / lam, w = a.weight[o];
+                        const double R[2][2] = {{fr[2], fr[3]}, {fr[4], fr[5]}};
+                        double *row = srow + (long)tid * stride;
+                        if (g == 0) {
+                            const double c0 = 4.0 * pin / (dk * dk);
+                            row[24] = w * c0 * (R[0][1] * R[0][1] * acc_t + R[1][1] * R[1][1] * acc_p);
+                            row[25] = w * c0 * (R[0][0] * R[0][0] * acc_t + R[1][0] * R[1][0] * acc_p);
+                        }
+                        const double *sa = sacc + 8 * g * nt, *fg = fr + 6 + 6 * g;
+                        const double R1[2][2] = {{fg[2], fg[3]}, {fg[4], fg[5]}};
+                        const double rdk = 1.0 / dk;
+                        double vvr = sa[0 * nt] * rdk, vvi = sa[1 * nt] * rdk, vhr = sa[2 * nt] * rdk, vhi = sa[3 * nt] * rdk;
+                        double hvr = sa[4 * nt] * rdk, hvi = sa[5 * nt] * rdk, hhr = sa[6 * nt] * rdk, hhi = sa[7 * nt] * rdk;
                         double cvvr = vvr * R[0][0] + vhr * R[1][0], cvvi = vvi * R[0][0] + vhi * R[1][0];
                         double cvhr = vvr * R[0][1] + vhr * R[1][1], cvhi = vvi * R[0][1] + vhi * R[1][1];
                         double chvr = hvr * R[0][0] + hhr * R[1][0], chvi = hvi * R[0][0] + hhi * R[1][0];
                         double chhr = hvr * R[0][1] + hhr * R[1][1], chhi = hvi * R[0][1] + hhi * R[1][1];
-                        double s11r = R1[g][0][0] * cvvr + R1[g][0][1] * chvr, s11i = R1[g][0][0] * cvvi + R1[g][0][1] * chvi;
-                        double s12r = R1[g][0][0] * cvhr + R1[g][0][1] * chhr, s12i = R1[g][0][0] * cvhi + R1[g][0][1] * chhi;
-                        double s21r = R1[g][1][0] * cvvr + R1[g][1][1] * chvr, s21i = R1[g][1][0] * cvvi + R1[g][1][1] * chvi;
-                        double s22r = R1[g][1][0] * cvhr + R1[g][1][1] * chhr, s22i = R1[g][1][0] * cvhi + R1[g][1][1] * chhi;
-                        double *o_ = row + g * 24;
+                        double s11r = R1[0][0] * cvvr + R1[0][1] * chvr, s11i = R1[0][0] * cvvi + R1[0][1] * chvi;
+                        double s12r = R1[0][0] * cvhr + R1[0][1] * chhr, s12i = R1[0][0] * cvhi + R1[0][1] * chhi;
+                        double s21r = R1[1][0] * cvvr + R1[1][1] * chvr, s21i = R1[1][0] * cvvi + R1[1][1] * chvi;
+                        double s22r = R1[1][0] * cvhr + R1[1][1] * chhr, s22i = R1[1][0] * cvhi + R1[1][1] * chhi;
+                        double *o_ = row;
                         o_[0] = w * s11r; o_[1] = w * s11i; o_[2] = w * s12r; o_[3] = w * s12i;
                         o_[4] = w * s21r; o_[5] = w * s21i; o_[6] = w * s22r; o_[7] = w * s22i;
 #define RE(a, b) (a##r * b##r + a##i * b##i)
@@ -595,15 +591,16 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
 #undef RE
 #undef IM
                     }
+                    __syncthreads();
+                    const int cnt = min(nt, a.n_orient - o0);
+                    for (int c = tid; c < ncol; c += nt) {
+                        const int ci = c < 24 ? g * 24 + c : ng * 24 + (c - 24);
+                        double acc_ = accs[ci];
+                        for (int j = 0; j < cnt; j++) acc_ += srow[(long)j * stride + c];
+                        accs[ci] = acc_;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
-                const int cnt = min(nt, a.n_orient - o0);
-                for (int c = tid; c < ncomp; c += nt) {
-                    double acc_ = accs[c];
-                    for (int j = 0; j < cnt; j++) acc_ += srow[(long)j * stride + c];
-                    accs[c] = acc_;
-                }
-                __syncthreads();
             }
             for (int c = tid; c < ncomp; c += nt) {
                 const double v = accs[c] * a.scale;

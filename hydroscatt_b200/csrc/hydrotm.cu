@@ -75,9 +75,9 @@ struct ScPrep {  // particle-independent part of a scatter call (scatter_prepare
 };
 static inline size_t sc_smem(int threads, int nmax_bound)
 {
-    // T stage + max(reduction rows, the per-thread P' / Q' vectors that alias them) + accumulators
-    const size_t rows = (size_t)threads * (SCK_G * 24 + 3), vecs = (size_t)2 * (nmax_bound + 2) * threads;
-    return ((size_t)4 * nmax_bound * nmax_bound + std::max(rows, vecs) + SCK_G * 24 + 2) * sizeof(double);
+    // T stage + max(reduction rows, the per-thread P' / Q' vectors that alias them) + accumulators + per-thread amplitude sums
+    const size_t rows = (size_t)threads * (24 + 3), vecs = (size_t)2 * (nmax_bound + 2) * threads;
+    return ((size_t)4 * nmax_bound * nmax_bound + std::max(rows, vecs) + SCK_G * 24 + 2 + (size_t)8 * SCK_G * threads) * sizeof(double);
 }
 static int ensure_gauss(hs_ctx *ctx, int gmax);
 #include "hs_staged_host.h"

@@ -393,10 +393,15 @@ __global__ void __launch_bounds__(64) k_scatter_wig(ScArgs a, double2 *wtab)
     }
 }
 
-__global__ void __launch_bounds__(64) k_scatter(ScArgs a)
+//   * SPLIT (1, 2 or 4) adjacent lanes share one orientation and take every SPLIT-th row n of a mode: more warps for the
+//     same shared memory (the heavy NMAX classes are limited by their T stage), and the lanes of a group read the same
+//     P' / Q' entries (fewer shared-memory wavefronts per FMA).
+template <int SPLIT>
+__global__ void __launch_bounds__(64 * SPLIT) k_scatter(ScArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int nto = nt / SPLIT, oi = tid / SPLIT, h = tid % SPLIT;  // orientations per pass, this thread's one, its row slice
     const int p = a.order ? a.order[blockIdx.x] : blockIdx.x;
     const bool bad = (a.status[p] != HS_ST_OK && a.status[p] != HS_ST_NGAUSS_LIMIT && a.status[p] != HS_ST_SINGULAR) || a.toff[p] < 0;
     if (bad) {
@@ -409,11 +414,11 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
     const double2 *tg = reinterpret_cast<const double2 *>(a.tarena) + a.toff[p];
     const int nmax = a.nmax[p];
     const double lam = a.lam[p];
-    // dynamic smem: [T stage: 2*nmax*nmax complex][reduction rows: nt * stride][accs][per-thread amplitude sums: 8 SCK_G x nt]
+    // dynamic smem: [T stage: 2*nmax*nmax complex][reduction rows: nto * stride][accs][per-orientation amplitude sums: 8 SCK_G x nto]
     double2 *sT = reinterpret_cast<double2 *>(sm);
     const int stride = 24 + 3;  // one scattered direction (S 8, Z 16) + the two cross sections per reduction row
     double *srow = sm + 4L * a.nmax_bound * a.nmax_bound;
-    const long vec_doubles = 2L * (a.nmax_bound + 2) * nt, row_doubles = (long)nt * stride;
+    const long vec_doubles = 2L * (a.nmax_bound + 2) * nto, row_doubles = (long)nto * stride;
     double *accs = srow + (vec_doubles > row_doubles ? vec_doubles : row_doubles);
     const double pin = 3.14159265358979323846;
 
@@ -423,9 +428,10 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
             const int ng = max(0, min(SCK_G, gend - gb));
             const int ncomp = ng * 24 + 2;
             for (int c = tid; c < ncomp; c += nt) accs[c] = 0.0;
-            for (int o0 = 0; o0 < a.n_orient; o0 += nt) {
-                const int o = o0 + tid;
+            for (int o0 = 0; o0 < a.n_orient; o0 += nto) {
+                const int o = o0 + oi;
                 const bool active = o < a.n_orient;
+                const unsigned lanes = __ballot_sync(0xffffffffu, active);  // the SPLIT lanes of an orientation are in or out together
                 // ---- per-thread setup ----
                 double acc_t = 0.0, acc_p = 0.0;
                 const long dblk = (long)d * a.frame_blocks + (gb - a.g_begin[d]) / SCK_G;
@@ -433,16 +439,18 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                 // call by k_scatter_frames (AMPL's angle nudges and Euler rotations), read where they are needed
                 const double *fr = a.frames + (dblk * a.n_orient + (active ? o : 0)) * SC_FR;
                 // amplitude sums over the modes: per-thread slots in shared memory ([component][thread]), updated once per mode
-                double *sacc = accs + (SCK_G * 24 + 2) + tid;
+                double *sacc = accs + (SCK_G * 24 + 2) + oi;
+                if (h == 0) {
 #pragma unroll
-                for (int k = 0; k < 8 * SCK_G; k++) sacc[k * nt] = 0.0;
+                    for (int k = 0; k < 8 * SCK_G; k++) sacc[k * nto] = 0.0;
+                }
                 // Wigner functions of this thread's directions: table of the call (k_scatter_wig), [tri(m, n)][orientation]
                 const long tri = sc_tri_size(a.wig_nb);
                 const double2 *wt0 = a.wtab + dblk * (1 + SCK_G) * tri * a.n_orient + (active ? o : 0);
                 // P' = sgn f m pi0, Q' = sgn f tau0 of the current mode: per-thread vectors in shared memory ([n'][thread], aliased
                 // with the reduction rows, which are only written after the mode sweep).  As thread-local arrays they lived in
                 // L1-cached local memory, which the heavy class (3 CTAs x 55 KB of shared memory per SM) leaves too small.
-                double *Pp = srow + tid, *Qp = srow + (long)(a.nmax_bound + 2) * nt + tid;
+                double *Pp = srow + oi, *Qp = srow + (long)(a.nmax_bound + 2) * nto + oi;
                 long moff = 0;
                 for (int m = 0; m <= nmax; m++) {
                     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
@@ -452,11 +460,12 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                     moff += 2L * NM * NM;
                     if (!active) continue;
                     const double2 *wm0 = wt0 + sc_tri(m, nmin, a.wig_nb) * a.n_orient;
-                    for (int nn = nmin; nn <= nmax; nn++) {
+                    for (int nn = nmin + h; nn <= nmax; nn += SPLIT) {
                         const double2 v = wm0[(long)(nn - nmin) * a.n_orient];
-                        Pp[nn * nt] = v.x;
-                        Qp[nn * nt] = v.y;
+                        Pp[nn * nto] = v.x;
+                        Qp[nn * nto] = v.y;
                     }
+                    if (SPLIT > 1) __syncwarp(lanes);
                     // per-mode sums over n of i^(-n-1) (f m pi +- f tau) (G1 +- G2), ... (see below)
                     double A[SCK_G][8];
 #pragma unroll
@@ -465,7 +474,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         for (int k = 0; k < 8; k++) A[g][k] = 0.0;
                     double xt = 0.0, xp = 0.0;
                     const double2 *wg = wt0 + (tri + sc_tri(m, nmin, a.wig_nb)) * a.n_orient;  // first scattered direction, n = nmin
-                    for (int n = nmin; n <= nmax; n++) {
+                    for (int n = nmin + h; n <= nmax; n += SPLIT) {
                         const int k = n - nmin;
                         double2 wv[SCK_G];   // { f m pi_n, f tau_n } of the scattered directions: loaded ahead of the T sweep
 #pragma unroll
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         for (int nn = nmin + (k & 1); nn <= nmax; nn += 2) {
                             const long o_ = (long)(nn - nmin) * NM;
                             const double2 a_ = ta[o_], b_ = tb[o_];
-                            const double P = Pp[nn * nt], Q = Qp[nn * nt];
+                            const double P = Pp[nn * nto], Q = Qp[nn * nto];
                             e1r += a_.x * P; e1i += a_.y * P; e3r += a_.x * Q; e3i += a_.y * Q;
                             e2r += b_.x * Q; e2i += b_.y * Q; e4r += b_.x * P; e4i += b_.y * P;
                         }
@@ -487,7 +496,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         for (int nn = nmin + ((k + 1) & 1); nn <= nmax; nn += 2) {
                             const long o_ = (long)(nn - nmin) * NM;
                             const double2 a_ = ta[o_], b_ = tb[o_];
-                            const double P = Pp[nn * nt], Q = Qp[nn * nt];
+                            const double P = Pp[nn * nto], Q = Qp[nn * nto];
                             o1r += a_.x * Q; o1i += a_.y * Q; o3r += a_.x * P; o3i += a_.y * P;
                             o2r += b_.x * P; o2i += b_.y * P; o4r += b_.x * Q; o4i += b_.y * Q;
                         }
@@ -530,13 +539,27 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                         double fc, fs;
                         if (m == 0) { fc = 0.5; fs = 0.0; }
                         else { double sn, cs; sincos(m * fr[6 + 6 * g + 1], &sn, &cs); fc = cs; fs = sn; }  // (2 cos, 2 sin) / 2
+                        if (SPLIT > 1) {  // add up the row slices of this orientation's lanes
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+#pragma unroll
+                                for (int sh = 1; sh < SPLIT; sh <<= 1) A[g][k] += __shfl_xor_sync(lanes, A[g][k], sh);
+                            if (h != 0) continue;
+                        }
                         const double ur = A[g][0] + A[g][2], ui = A[g][1] + A[g][3], wr = A[g][0] - A[g][2], wi = A[g][1] - A[g][3];
                         const double vr = A[g][4] + A[g][6], vi = A[g][5] + A[g][7], zr = A[g][4] - A[g][6], zi = A[g][5] - A[g][7];
-                        double *sa = sacc + 8 * g * nt;
-                        sa[0 * nt] += fc * ur; sa[1 * nt] += fc * ui;   // VV
-                        sa[2 * nt] += fs * vr; sa[3 * nt] += fs * vi;   // VH
-                        sa[4 * nt] -= fs * wr; sa[5 * nt] -= fs * wi;   // HV
-                        sa[6 * nt] += fc * zr; sa[7 * nt] += fc * zi;   // HH
+                        double *sa = sacc + 8 * g * nto;
+                        sa[0 * nto] += fc * ur; sa[1 * nto] += fc * ui;   // VV
+                        sa[2 * nto] += fs * vr; sa[3 * nto] += fs * vi;   // VH
+                        sa[4 * nto] -= fs * wr; sa[5 * nto] -= fs * wi;   // HV
+                        sa[6 * nto] += fc * zr; sa[7 * nto] += fc * zi;   // HH
+                    }
+                }
+                if (SPLIT > 1 && active) {
+#pragma unroll
+                    for (int sh = 1; sh < SPLIT; sh <<= 1) {
+                        acc_t += __shfl_xor_sync(lanes, acc_t, sh);
+                        acc_p += __shfl_xor_sync(lanes, acc_p, sh);
                     }
                 }
                 __syncthreads();  // everybody is done with the P' / Q' vectors that share the reduction rows' memory
@@ -544,20 +567,20 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
                 // time (rows of 24 + 2 components; the reduction rows share their memory with the P' / Q' vectors) ----
                 for (int g = 0; g < ng; g++) {
                     const int ncol = 24 + (g == 0 ? 2 : 0);
-                    if (active) {
+                    if (active && h == 0) {
                         const double dk = 2.0 * pin / lam, w = a.weight[o];
                         const double R[2][2] = {{fr[2], fr[3]}, {fr[4], fr[5]}};
-                        double *row = srow + (long)tid * stride;
+                        double *row = srow + (long)oi * stride;
                         if (g == 0) {
                             const double c0 = 4.0 * pin / (dk * dk);
                             row[24] = w * c0 * (R[0][1] * R[0][1] * acc_t + R[1][1] * R[1][1] * acc_p);
                             row[25] = w * c0 * (R[0][0] * R[0][0] * acc_t + R[1][0] * R[1][0] * acc_p);
                         }
-                        const double *sa = sacc + 8 * g * nt, *fg = fr + 6 + 6 * g;
+                        const double *sa = sacc + 8 * g * nto, *fg = fr + 6 + 6 * g;
                         const double R1[2][2] = {{fg[2], fg[3]}, {fg[4], fg[5]}};
                         const double rdk = 1.0 / dk;
-                        double vvr = sa[0 * nt] * rdk, vvi = sa[1 * nt] * rdk, vhr = sa[2 * nt] * rdk, vhi = sa[3 * nt] * rdk;
-                        double hvr = sa[4 * nt] * rdk, hvi = sa[5 * nt] * rdk, hhr = sa[6 * nt] * rdk, hhi = sa[7 * nt] * rdk;
+                        double vvr = sa[0 * nto] * rdk, vvi = sa[1 * nto] * rdk, vhr = sa[2 * nto] * rdk, vhi = sa[3 * nto] * rdk;
+                        double hvr = sa[4 * nto] * rdk, hvi = sa[5 * nto] * rdk, hhr = sa[6 * nto] * rdk, hhi = sa[7 * nto] * rdk;
                         double cvvr = vvr * R[0][0] + vhr * R[1][0], cvvi = vvi * R[0][0] + vhi * R[1][0];
                         double cvhr = vvr * R[0][1] + vhr * R[1][1], cvhi = vvi * R[0][1] + vhi * R[1][1];
                         double chvr = hvr * R[0][0] + hhr * R[1][0], chvi = hvi * R[0][0] + hhi * R[1][0];
@@ -592,7 +615,7 @@ __global__ void __launch_bounds__(64) k_scatter(ScArgs a)
 #undef IM
                     }
                     __syncthreads();
-                    const int cnt = min(nt, a.n_orient - o0);
+                    const int cnt = min(nto, a.n_orient - o0);
                     for (int c = tid; c < ncol; c += nt) {
                         const int ci = c < 24 ? g * 24 + c : ng * 24 + (c - 24);
                         double acc_ = accs[ci];

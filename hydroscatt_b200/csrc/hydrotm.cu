@@ -73,11 +73,27 @@ struct ScPrep {  // particle-independent part of a scatter call (scatter_prepare
     const int *inc_of_geom = nullptr;
     double *xs_inc = nullptr, *d_xs = nullptr;
 };
-static inline size_t sc_smem(int threads, int nmax_bound)
+static inline size_t sc_smem(int nto, int nmax_bound)
 {
-    // T stage + max(reduction rows, the per-thread P' / Q' vectors that alias them) + accumulators + per-thread amplitude sums
-    const size_t rows = (size_t)threads * (24 + 3), vecs = (size_t)2 * (nmax_bound + 2) * threads;
-    return ((size_t)4 * nmax_bound * nmax_bound + std::max(rows, vecs) + SCK_G * 24 + 2 + (size_t)8 * SCK_G * threads) * sizeof(double);
+    // nto = orientations per pass (threads / SPLIT).  T stage + max(reduction rows, the per-orientation P' / Q' vectors
+    // that alias them) + accumulators + per-orientation amplitude sums
+    const size_t rows = (size_t)nto * (24 + 3), vecs = (size_t)2 * (nmax_bound + 2) * nto;
+    return ((size_t)4 * nmax_bound * nmax_bound + std::max(rows, vecs) + SCK_G * 24 + 2 + (size_t)8 * SCK_G * nto) * sizeof(double);
+}
+// k_scatter<SPLIT> launch: `nto` orientations per pass x SPLIT lanes each
+static inline cudaError_t sc_launch(int split, int grid, int nto, size_t smem, cudaStream_t st, const hs::ScArgs &a)
+{
+    if (split == 4) hs::k_scatter<4><<<grid, nto * 4, smem, st>>>(a);
+    else if (split == 2) hs::k_scatter<2><<<grid, nto * 2, smem, st>>>(a);
+    else hs::k_scatter<1><<<grid, nto, smem, st>>>(a);
+    return cudaGetLastError();
+}
+static inline cudaError_t sc_set_smem(int bytes)
+{
+    cudaError_t e = cudaFuncSetAttribute(hs::k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hs::k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hs::k_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
 }
 static int ensure_gauss(hs_ctx *ctx, int gmax);
 #include "hs_staged_host.h"
@@ -611,7 +627,7 @@ extern "C" int hs_calctmat_scatter_batch(hs_ctx *ctx, int n, const double *d_axi
     ScPrep SP;
     { int rc = scatter_prepare(ctx, n, d_tarena, d_toff, d_nmax, d_status, d_lam, n_geom, h_geom, n_orient, d_alpha, d_beta,
                                d_weight, scale, d_S, d_Z, d_xs, st, SP); if (rc) return rc; }
-    CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - 8192));
+    CK(sc_set_smem(ctx->smem_optin - 8192));
     // scatter launches that overlap the convergence rounds do not know the largest NMAX yet: table up to the limit
     if (getenv("HYDROTM_OVERLAP_SCATTER")) { int rc = scatter_build_wig(ctx, SP.a, HS_NPN1, st); if (rc) return rc; }
     bool used = false;
@@ -875,6 +891,9 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
     // concurrent streams, each with a T stage sized for its own largest NMAX (more CTAs per SM for the small particles).
     const int threads = SP.threads;
     auto smem_for = [&](int nb) { return sc_smem(threads, nb); };
+    // lanes per orientation of the three NMAX classes (20, NPN1], (10, 20], [0, 10]: HYDROTM_SC_SPLIT="h,m,s"
+    int split[3] = {2, 1, 1};
+    if (const char *e = getenv("HYDROTM_SC_SPLIT")) sscanf(e, "%d,%d,%d", &split[0], &split[1], &split[2]);
     a.order = nullptr;
     if (n >= 1024) {
         if (n > ctx->order_cap) {
@@ -901,7 +920,7 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
             if (cnt) max_smem = std::max(max_smem, smem_for(cls_bound[c]));
         }
         if (max_smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
-        CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        CK(sc_set_smem((int)max_smem));
         { int top = 1; for (int c = 0; c < 3; c++) if (cls_cnt[c]) top = std::max(top, cls_bound[c]);
           int rc = scatter_build_wig(ctx, a, top, st); if (rc) return rc; }
         CK(cudaEventRecord(ctx->ev_start, st));
@@ -912,9 +931,8 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
             hs::ScArgs ac = a;
             ac.order = ctx->d_order + cls_start[c];
             ac.nmax_bound = cls_bound[c];
-            hs::k_scatter<<<cls_cnt[c], threads, smem_for(cls_bound[c]), bs>>>(ac);
+            CK(sc_launch(split[c], cls_cnt[c], threads, smem_for(cls_bound[c]), bs, ac));
             ctx->launches++;
-            CK(cudaGetLastError());
             CK(cudaEventRecord(ctx->ev_done[c], bs));
             CK(cudaStreamWaitEvent(st, ctx->ev_done[c], 0));
         }
@@ -923,11 +941,10 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
         a.nmax_bound = nmax_bound;
         size_t smem = smem_for(nmax_bound);
         if (smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
-        CK(cudaFuncSetAttribute(hs::k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(sc_set_smem((int)smem));
         { int rc = scatter_build_wig(ctx, a, nmax_bound, st); if (rc) return rc; }
-        hs::k_scatter<<<n, threads, smem, st>>>(a);
+        CK(sc_launch(nmax_bound > 20 ? split[0] : (nmax_bound > 10 ? split[1] : split[2]), n, threads, smem, st, a));
         ctx->launches++;
-        CK(cudaGetLastError());
     }
     if (d_xs) {
         long tot = (long)n * n_geom * 2;

@@ -1,5 +1,6 @@
 """GPU: fused scatter kernel, PSD integration, observables and the pytmatrix shim end-to-end against the oracle."""
 import numpy as np
+import torch
 import pytest
 
 import oracle
@@ -84,6 +85,29 @@ def test_psd_integration_and_observables(engine):
     # regression anchor (restatement run): D0=1.5, Nw=8000, mu=0 -> refl_h ~ 40.4 dBZ on the
     # rectangle-rule canting path; the trapz/pytmatrix path must land within a few tenths of a dB of it
     assert abs(obs[1 - 1 + 1, 2] - obs[1, 2]) == 0.0
+
+
+def test_scatter_lane_splits_agree(engine, monkeypatch):
+    """k_scatter<SPLIT>: 1, 2 or 4 lanes per orientation (row slices of a mode added up by shuffles) must give the same
+    orientation-averaged S / Z / cross sections; more than 1024 particles so that the three NMAX classes are launched."""
+    from hydroscatt_b200 import tables
+    al, be, wt, scale = tables.fixed_orientation_nodes(10.0)
+    ws = [rain_grid(b) for b in ("S", "C", "X", "Ku", "Ka", "W")]
+    cat = lambda k: np.concatenate([w[k] for w in ws] * 3)
+    tb = engine.calctmat(cat("radius"), cat("wavelength"), cat("mr"), cat("mi"), cat("axis_ratio"))
+    assert tb.n >= 1024 and int(tb.nmax.max()) > 20 and int(tb.nmax.min()) <= 10
+
+    def run(split):
+        monkeypatch.setenv("HYDROTM_SC_SPLIT", split)
+        S, Z, xs = tb.scatter([GB, GF], al, be, weight=wt, scale=scale, want_xs=True)
+        monkeypatch.delenv("HYDROTM_SC_SPLIT")
+        return [t.cpu().numpy().copy() for t in (torch.view_as_real(S), Z, xs)]
+
+    ref = run("1,1,1")
+    for split in ("2,2,2", "4,4,4", "4,2,1"):
+        for a, b in zip(ref, run(split)):
+            assert np.isfinite(b).all()
+            assert np.abs(a - b).max() <= 1e-12 * np.abs(a).max(), split
 
 
 def test_fused_psd_observables_equal_unfused(engine):
@@ -231,7 +255,7 @@ def test_calctmat_scatter_one_call_equals_two_calls(engine, monkeypatch):
     cat = lambda k: np.concatenate([np.tile(w[k], 6) for w in ws])  # 1260 particles: the ordered / class-split scatter path
     args = [cat(k) for k in ("radius", "wavelength", "mr", "mi", "axis_ratio")]
     tb = engine.calctmat(*args)
-    S0, Z0, x0 = tb.scatter([GB[:4], GF[:4]], al, be, weight=wt, scale=scale, want_xs=True)
+    S0, Z0, x0 = tb.scatter([GB, GF], al, be, weight=wt, scale=scale, want_xs=True)
     for overlap in (False, True):
         if overlap:
             monkeypatch.setenv("HYDROTM_OVERLAP_SCATTER", "1")

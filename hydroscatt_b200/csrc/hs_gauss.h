@@ -4,11 +4,10 @@
 #include <vector>
 
 namespace hs {
-// Gauss-Legendre rule of even order n on [-1,1] (Newton on P_n; same published scheme the oracle restates):
-// returns the n/2 positive nodes ascending and their weights.
-inline void gauss_positive(int n, double *xp, double *wp)
+// Gauss-Legendre rule of order n on [-1,1] (Newton on P_n; same published scheme the oracle restates, oracle/sl_oracle.c
+// hso_gauss): nodes ascending, any n >= 1.
+inline void gauss_full(int n, double *z, double *w)
 {
-    std::vector<double> z(n), w(n);
     int ind = n % 2, k = n / 2 + ind;
     double f = (double)n, x = 0.0;
     for (int i = 1; i <= k; i++) {
@@ -41,9 +40,15 @@ inline void gauss_positive(int n, double *xp, double *wp)
         w[m - 1] = 2.0 * pa * pa * (1.0 - x * x);
         if (!(i == k && ind == 1)) { z[i - 1] = -z[m - 1]; w[i - 1] = w[m - 1]; }
     }
+}
+
+// even order n: the n/2 positive nodes ascending and their weights
+inline void gauss_positive(int n, double *xp, double *wp)
+{
+    std::vector<double> z(n), w(n);
+    gauss_full(n, z.data(), w.data());
     int g = n / 2;
     for (int j = 0; j < g; j++) { xp[j] = z[g + j]; wp[j] = w[g + j]; }
 }
-
 
 }  // namespace hs

@@ -72,6 +72,18 @@ __host__ __device__ inline long long st_t_mode_off(int nmax, int m) { return 2LL
 
 #ifndef HS_HOST_EMU
 
+// Reciprocal for the dependent chains (downward ratio recurrences, Legendre recurrence, pivot inverse): the hardware seed
+// (upper 32 bits) and two Newton steps, ~60 cycles of latency and 5 instructions against ~135 cycles / ~30 instructions of
+// the IEEE division; 1-2 ulp.  Arguments are normal numbers here (a zero pivot is flagged singular before it is used).
+__device__ __forceinline__ double hs_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 // equal-volume radius of the particle (calctmat_particle: RAT != 1 -> SAREA)
 __device__ inline double st_arev(double axi, double rat, double eps)
 {
@@ -98,7 +110,7 @@ __device__ inline void st_rjb(double x, double *y, double *u, int nmax, int nnma
     const double xx = 1.0 / x;
     double zc = 1.0 / ((double)(2 * l + 1) * xx);
     for (int i1 = l - 1; i1 >= 1; i1--) {
-        zc = 1.0 / ((double)(2 * i1 + 1) * xx - zc);
+        zc = hs_rcp((double)(2 * i1 + 1) * xx - zc);
         if (i1 <= nmax) zz[i1 - 1] = zc;
     }
     const double z1 = zz[0];
@@ -148,7 +160,7 @@ __device__ inline void st_cjb(double xr, double xi, double *yr, double *yi, doub
         qf = (double)(2 * i1 + 1);
         const double ar = qf * cxxr - czr;
         const double ai = qf * cxxi - czi;
-        const double ari = 1.0 / (ar * ar + ai * ai);
+        const double ari = hs_rcp(ar * ar + ai * ai);
         czr = ar * ari;
         czi = -ai * ari;
         if (i1 <= nmax) { zr_[i1 - 1] = czr; zi_[i1 - 1] = czi; }
@@ -295,8 +307,8 @@ __global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
             double a1 = 1.0, a2 = x;
             for (int n = 1; n <= nmax; n++) {
                 const double qn = n, qn1 = n + 1, qn2 = 2 * n + 1;
-                const double a3 = (qn2 * x * a2 - qn * a1) / qn1;
-                const double der = qs1 * (qn1 * qn / qn2) * (-a1 + a3);
+                const double a3 = (qn2 * x * a2 - qn * a1) * hs_rcp(qn1);
+                const double der = qs1 * (qn1 * qn * hs_rcp(qn2)) * (-a1 + a3);
                 const double si = (n & 1) ? -1.0 : 1.0;
                 d1[(long)(n - 1) * gp + i] = a2 * si;
                 d2[(long)(n - 1) * gp + i] = -der * si;
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
                 const double qn = n, qn1 = n + 1, qn2 = 2 * n + 1;
                 const double qnm = sq[n], qnm1 = sq[n + 1];
                 const double a3 = (qn2 * x * a2 - qnm * a1) * rsq[n + 1];
-                const double der = qs1 * (-qn1 * qnm * a1 + qn * qnm1 * a3) * (1.0 / qn2);
+                const double der = qs1 * (-qn1 * qnm * a1 + qn * qnm1 * a3) * hs_rcp(qn2);
                 const double si = ((n + m) & 1) ? -1.0 : 1.0;
                 d1[(long)(n - nmin) * gp + i] = a2 * si;
                 d2[(long)(n - nmin) * gp + i] = -der * si;
@@ -404,7 +416,7 @@ __device__ __forceinline__ void solve_subs(const SysDesc d, int gl, int gw, int 
             if ((key >> 8) == 0ull && gl == 0) *sing = 1;
             const unsigned ck = b0 + 16u * (unsigned)colof(k);
             const double2 pv = st_lds128(ck + 16u * (unsigned)(p * rstep));
-            const double rden = 1.0 / (pv.x * pv.x + pv.y * pv.y);
+            const double rden = hs_rcp(pv.x * pv.x + pv.y * pv.y);
             const double2 inv = make_double2(pv.x * rden, -pv.y * rden);
             const double2 fkk = st_lds128(ck + 16u * (unsigned)(k * rstep));
             for (int j = k + 1 + gl; j < nc; j += gw) {
@@ -595,7 +607,7 @@ __device__ __forceinline__ void solve_grp2s(const SysDesc d, int t, int nl, int 
         if ((key >> 8) == 0ull && t == 0) *sing = 1;
         const unsigned ck = b0 + 16u * (d.off + d.stride * k);
         const double2 pv = st_lds128(ck + 16u * (p * rstep));
-        const double rden = 1.0 / (pv.x * pv.x + pv.y * pv.y);  // one division per step (the other variants divide twice: last-ulp differences)
+        const double rden = hs_rcp(pv.x * pv.x + pv.y * pv.y);  // one reciprocal per step (the other variants divide twice: last-ulp differences)
         const double2 inv = make_double2(pv.x * rden, -pv.y * rden);
         const double2 fkk = st_lds128(ck + 16u * (k * rstep));
         unsigned long long nkey = 0ull;
@@ -858,7 +870,7 @@ __global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs
     const double ppi = kw * kw, pir = ppi * a.mr[p], pii = ppi * a.mi[p];
     // NM <= 32: the block is the whole mode; the systems are combined in the (now free) operand area, solved here and only
     // the T block leaves the SM.  Larger modes write their part of [Q | RgQ] to global memory for k_st_solve.
-    const bool fused = NM <= KR && ((a.fuse & 1) || KR == 16);
+    const bool fused = NM <= KR && (a.fuse & 1);
     double2 *sys = fused ? reinterpret_cast<double2 *>(op) : a.sys + it.sys_off + st_sys_mode_off(nmax, m);
 #pragma unroll
     for (int r = 0; r < NTR; r++)
@@ -1000,6 +1012,12 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
             const int warp = threadIdx.x >> 5;
             const int q = (m == 0) ? (warp >> 1) : (warp >> 2);
             if (q < nsys && sd[q].n > 0) solve_grp2s(sd[q], threadIdx.x & (m == 0 ? 63 : 127), m == 0 ? 64 : 128, 1 + q, keyslot[q], &sing);
+        } else if (THREADS == 64) {
+            // NM <= 16: one warp per system (a lane pair owns up to two of the 2 n <= 32 columns); m = 0: two systems per warp, one after the other
+            __shared__ unsigned long long keyslot[4][2];
+            const int warp = threadIdx.x >> 5;
+            for (int q = warp; q < nsys; q += 2)
+                if (sd[q].n > 0) solve_grp2s(sd[q], threadIdx.x & 31, 32, 1 + warp, keyslot[q], &sing);
         } else {
             // one warp per system (m = 0: four half-size systems, m >= 1: the two parity classes)
             const int w = threadIdx.x >> 5;

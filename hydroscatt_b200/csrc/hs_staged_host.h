@@ -200,7 +200,7 @@ struct StGroup {
                     mitems.push_back(mix);
                     const int NM = it.nmax - (m > 1 ? m : 1) + 1;
                     if (NM <= ST_SMALL_NM) { sm.push_back(mix); continue; }
-                    if (NM <= 16 && C->fuse_solve && C->kr16) { (m == 0 ? as0 : as1).push_back({mix, 0, 0}); continue; }
+                    if (NM <= 16 && C->kr16) { (m == 0 ? as0 : as1).push_back({mix, 0, 0}); if (!C->fuse_solve) gl[0].push_back(mix); continue; }
                     const int nst = (NM + 31) / 32;
                     for (int sr = 0; sr < nst; sr++)
                         for (int sc = 0; sc < nst; sc++) (m == 0 ? at0 : at1).push_back({mix, (short)sr, (short)sc});
@@ -286,10 +286,21 @@ struct StGroup {
         if (!gl[4].empty()) { k_st_solve<256, true><<<(int)gl[4].size(), 256, 0, st>>>(a, (const int *)(d + o_g4), (int)gl[4].size()); launches++; }
         const int gsm[4] = {16384, 36864, 65536, 200704};
         if (!gl[3].empty()) { k_st_solve<256, false><<<(int)gl[3].size(), 256, gsm[3], st>>>(a, (const int *)(d + og[3]), (int)gl[3].size()); launches++; }
-        for (int c = 2; c >= 0; c--)
+        for (int c = 2; c >= (C->kr16 ? 1 : 0); c--)
             if (!gl[c].empty()) { k_st_solve<256, false><<<(int)gl[c].size(), 256, gsm[c], st>>>(a, (const int *)(d + og[c]), (int)gl[c].size()); launches++; mark("solve"); }
         if (!as1.empty()) { k_st_assemble<false, 16><<<(int)as1.size(), 128, ST_ASM_SMEM16, s2>>>(pa(4), (const StATask *)(d + o_s1), (int)as1.size()); launches++; }
         if (!as0.empty()) { k_st_assemble<true, 16><<<(int)as0.size(), 128, ST_ASM_SMEM16, s2>>>(pa(8), (const StATask *)(d + o_s0), (int)as0.size()); launches++; }
+        if (C->kr16 && !gl[0].empty()) {
+            // right-sized solver for NM <= 16 (64 threads, shared memory = the mode's two systems); the list is sorted by NM (descending):
+            // two launches so that the small modes are not held to the shared-memory footprint of NM = 16
+            const int *L = (const int *)(h + og[0]);
+            const int tot = (int)gl[0].size();
+            auto nm_of = [&](int x) { return items[x & 0xFFFFFF].nmax - std::max(x >> 24, 1) + 1; };
+            int cut = 0;
+            while (cut < tot && nm_of(L[cut]) > 11) cut++;
+            if (cut) { const int nm = nm_of(L[0]); k_st_solve<64, false><<<cut, 64, 64 * nm * nm, s2>>>(a, (const int *)(d + og[0]), cut); launches++; }
+            if (tot > cut) { const int nm = nm_of(L[cut]); k_st_solve<64, false><<<tot - cut, 64, 64 * nm * nm, s2>>>(a, (const int *)(d + og[0]) + cut, tot - cut); launches++; }
+        }
         if (!sm.empty()) { k_st_mode_small<<<((int)sm.size() + 7) / 8, 256, 8 * ST_SMALL_SLICE * 8, s2>>>(pa(16), (const int *)(d + o_sm), (int)sm.size()); launches++; }
         if (two) {
             CK(cudaEventRecord(B->ev_join, s2));

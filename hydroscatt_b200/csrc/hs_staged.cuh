@@ -40,6 +40,8 @@ struct StArgs {
     const double *axi, *lam, *mr, *mi, *eps;
     double rat;
     const double *gx, *gw;   // Gauss table (see TmArgs)
+    const double *gfx, *gfw; // cylinders: full n-point rules, n = 1.., rule n at offset n (n - 1) / 2, nodes ascending
+    int np;                  // shape: -1 spheroid, -2 finite circular cylinder (eps = diameter / length)
     const double *cm, *dd;   // cm[m] = prod_{i<=m} sqrt((2i-1)/2i); dd[n] = sqrt((2n+1)/(n(n+1)))
     double *tab, *wig;
     double2 *sys;
@@ -85,20 +87,70 @@ __device__ __forceinline__ double hs_rcp(double x)
 }
 
 // equal-volume radius of the particle (calctmat_particle: RAT != 1 -> SAREA)
-__device__ inline double st_arev(double axi, double rat, double eps)
+__device__ inline double st_arev(double axi, double rat, double eps, int np = -1)
 {
     if (fabs(rat - 1.0) > 1e-8) {
-        double e, r;
-        if (eps < 1.0) {
-            e = sqrt(1.0 - eps * eps);
-            r = 0.5 * (pow(eps, 2.0 / 3.0) + pow(eps, -1.0 / 3.0) * asin(e) / e);
+        if (np == -2) {  // SAREAC
+            rat = pow(1.5 / eps, 1.0 / 3.0);
+            rat = rat / sqrt((eps + 2.0) / (2.0 * eps));
         } else {
-            e = sqrt(1.0 - 1.0 / (eps * eps));
-            r = 0.25 * (2.0 * pow(eps, 2.0 / 3.0) + pow(eps, -4.0 / 3.0) * log((1.0 + e) / (1.0 - e)) / e);
+            double e, r;
+            if (eps < 1.0) {
+                e = sqrt(1.0 - eps * eps);
+                r = 0.5 * (pow(eps, 2.0 / 3.0) + pow(eps, -1.0 / 3.0) * asin(e) / e);
+            } else {
+                e = sqrt(1.0 - 1.0 / (eps * eps));
+                r = 0.25 * (2.0 * pow(eps, 2.0 / 3.0) + pow(eps, -4.0 / 3.0) * log((1.0 + e) / (1.0 - e)) / e);
+            }
+            rat = 1.0 / sqrt(r);
         }
-        rat = 1.0 / sqrt(r);
     }
     return rat * axi;
+}
+
+// Quadrature node i (0 = next to the pole) of a trial with g nodes on the half range: x = cos(theta) < 0 and its weight.
+// Spheroids: Gauss-Legendre on [-1, 0] (table of the 2g-point rule).  Cylinders (CONST, NP = -2): two Gauss segments
+// split at the edge angle, [-1, xx] with g / 2 nodes and [xx, 0] with the rest, xx = -cos(atan(eps)).
+__device__ __forceinline__ void st_node(const StArgs &a, int g, int i, double eps, double &x, double &w)
+{
+    if (a.np != -2) {
+        const long goff = (long)g * (g - 1) / 2;
+        x = -a.gx[goff + g - 1 - i];
+        w = a.gw[goff + g - 1 - i];
+        return;
+    }
+    const int ng1 = g / 2, ng2 = g - ng1;
+    const double xx = -cos(atan(eps));
+    if (i < ng1) {
+        const long o = (long)ng1 * (ng1 - 1) / 2 + i;
+        w = 0.5 * (xx + 1.0) * a.gfw[o];
+        x = 0.5 * (xx + 1.0) * a.gfx[o] + 0.5 * (xx - 1.0);
+    } else {
+        const long o = (long)ng2 * (ng2 - 1) / 2 + (i - ng1);
+        w = -0.5 * xx * a.gfw[o];
+        x = -0.5 * xx * a.gfx[o] + 0.5 * xx;
+    }
+}
+
+// surface at x = cos(theta) < 0: r^2 and (dr/dtheta) / r  (VARY: RSP1 spheroid, RSP3 cylinder); rev = equal-volume radius
+__device__ __forceinline__ void st_surface(int np, double x, double rev, double eps, double &r2, double &drr)
+{
+    if (np != -2) {
+        const double A = rev * pow(eps, 1.0 / 3.0);
+        const double aa = A * A, ee = eps * eps, ee1 = ee - 1.0;
+        const double cc = x * x, ssq = 1.0 - cc, sth = sqrt(ssq);
+        const double rq = 1.0 / (ssq + ee * cc);
+        r2 = aa * rq;
+        drr = rq * x * sth * ee1;
+        return;
+    }
+    const double h = rev * pow(2.0 / (3.0 * eps * eps), 1.0 / 3.0), ac = h * eps;
+    const double co = -x, si = sqrt(1.0 - co * co);
+    double rad, rthet;
+    if (si / co > ac / h) { rad = ac / si; rthet = -ac * co / (si * si); }
+    else { rad = h / co; rthet = h * si / (co * co); }
+    r2 = rad * rad;
+    drr = -rthet / rad;
 }
 
 // ---- S: radial functions.  Same recurrences as rjb / ryb / cjb, with the ratios parked in a thread-local array and the
@@ -231,23 +283,26 @@ __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *ta
     const double PI = 3.14159265358979323846;
     const int p = it.p;
     const double lam = a.lam[p], mrr = a.mr[p], mri = a.mi[p], eps = a.eps[p];
-    const double arev = st_arev(a.axi[p], a.rat, eps);
+    const double arev = st_arev(a.axi[p], a.rat, eps, a.np);
     const double kw = PI * 2.0 / lam;
-    const double A = arev * pow(eps, 1.0 / 3.0);
-    const double aa = A * A, ee = eps * eps, ee1 = ee - 1.0;
-    const long goff = (long)g * (g - 1) / 2;
-    const double xp = a.gx[goff + g - 1 - i], wv = a.gw[goff + g - 1 - i];
-    const double x = -xp;
-    const double cc = x * x, ssq = 1.0 - cc, sth = sqrt(ssq);
-    const double rq = 1.0 / (ssq + ee * cc);
-    const double r = aa * rq;
+    double x, wv, r, drr;
+    st_node(a, g, i, eps, x, wv);
+    st_surface(a.np, x, arev, eps, r, drr);
+    const double xp = -x;
     const double v = sqrt(r) * kw;
     double *tab = a.tab + it.tab_off;
     double *tb = tab + (long)NA_COUNT * gp;
     const long tsz = (long)nmax * gp;
-    // extra orders of the downward recurrences (VARY): from the largest k r over the nodes
-    const double r0 = st_r_of_node(a.gx[goff + g - 1], aa, ee), r1 = st_r_of_node(a.gx[goff], aa, ee);
-    const double ta = fmax(sqrt(r0) * kw, sqrt(r1) * kw);
+    // extra orders of the downward recurrences (VARY): from the largest k r over the nodes (spheroid: one of the end
+    // nodes; cylinder: one of the two nodes next to the edge)
+    double ta;
+    {
+        const int ia = a.np == -2 ? g / 2 - 1 : 0, ib = a.np == -2 ? g / 2 : g - 1;
+        double xa, xb, wa, ra, rb, da;
+        st_node(a, g, ia, eps, xa, wa); st_surface(a.np, xa, arev, eps, ra, da);
+        st_node(a, g, ib, eps, xb, wa); st_surface(a.np, xb, arev, eps, rb, da);
+        ta = fmax(sqrt(ra) * kw, sqrt(rb) * kw);
+    }
     if (kind == 0) {
         const double v0 = 1.0 / (mrr * mrr + mri * mri);
         const double prr = mrr * v0, pri = -mri * v0;
@@ -256,7 +311,7 @@ __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *ta
         tab[NA_X * gp + i] = xp;
         tab[NA_S * gp + i] = sqrt(yv);
         tab[NA_SS * gp + i] = yv;
-        tab[NA_DR * gp + i] = rq * x * sth * ee1;
+        tab[NA_DR * gp + i] = drr;
         tab[NA_DDR * gp + i] = vi;
         tab[NA_DRR * gp + i] = prr * vi;
         tab[NA_DRI * gp + i] = pri * vi;
@@ -289,7 +344,7 @@ __global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
     double *d1 = a.wig + it.wig_off + st_wig_mode_off(nmax, m, gp);
     double *d2 = d1 + (long)NM * gp;
-    const long goff = (long)g * (g - 1) / 2;
+    const double eps = a.eps[it.p];
     double *sq = sq_[hw], *rsq = rsq_[hw];
     if (live && m > 0) {
         const double qmm = (double)m * (double)m;
@@ -301,7 +356,9 @@ __global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
     }
     __syncwarp();
     for (int i = l16; i < g; i += 16) {
-        const double x = a.gx[goff + g - 1 - i];
+        double xn, wn;
+        st_node(a, g, i, eps, xn, wn);
+        const double x = -xn;
         const double qs = sqrt(1.0 - x * x), qs1 = 1.0 / qs;
         if (m == 0) {
             double a1 = 1.0, a2 = x;

@@ -93,6 +93,7 @@ __global__ void k_st_scatter_out8(int n, const int *rec, int *nmax, int *ngauss,
 struct StCall {  // arguments of one hs_calctmat_batch call
     const double *d_axi, *d_lam, *d_mr, *d_mi, *d_eps;
     double rat, ddelt;
+    int np = -1;  // shape (HS_SHAPE_*)
     int ndgs;
     double *d_tarena;
     long long arena_cap;
@@ -220,8 +221,12 @@ struct StGroup {
             std::lock_guard<std::mutex> lk(ctx->mu);
             if (ensure_gauss(ctx, std::max(gneed, 64))) return -1;
         }
-        const double *gx, *gw;
-        { std::lock_guard<std::mutex> lk(ctx->mu); gx = ctx->d_gx; gw = ctx->d_gw; }
+        if (C->np == -2 && gneed / 2 + 1 > ctx->gfmax) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            if (ensure_gauss_full(ctx, gneed / 2 + 1)) return -1;
+        }
+        const double *gx, *gw, *gfx, *gfw;
+        { std::lock_guard<std::mutex> lk(ctx->mu); gx = ctx->d_gx; gw = ctx->d_gw; gfx = ctx->d_gfx; gfw = ctx->d_gfw; }
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
         const size_t o_items = 0, o_mi = al(o_items + items.size() * sizeof(StItem)), o_rad = al(o_mi + mitems.size() * sizeof(int)),
                      o_a0 = al(o_rad + rad.size() * sizeof(StRadTask)), o_a1 = al(o_a0 + at0.size() * sizeof(StATask)),
@@ -259,7 +264,7 @@ struct StGroup {
         StArgs a;
         a.items = (const StItem *)(d + o_items); a.modes = (const int *)(d + o_mi);
         a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
-        a.gx = gx; a.gw = gw; a.cm = S->d_cm; a.dd = S->d_dd;
+        a.gx = gx; a.gw = gw; a.gfx = gfx; a.gfw = gfw; a.np = C->np; a.cm = S->d_cm; a.dd = S->d_dd;
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
         a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res; a.fuse = (C->fuse_solve ? 1 : 0) | (getenv("HYDROTM_SOLVE2") && atoi(getenv("HYDROTM_SOLVE2")) == 0 ? 0 : 2); a.prof = C->prof;
         const int ni = (int)items.size();

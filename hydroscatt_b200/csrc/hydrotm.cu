@@ -32,6 +32,8 @@ struct hs_ctx {
     // Gauss table
     int gmax = 0;
     double *d_gx = nullptr, *d_gw = nullptr;
+    int gfmax = 0;               // cylinders: full n-point Gauss rules, n = 1..gfmax
+    double *d_gfx = nullptr, *d_gfw = nullptr;
     // scratch
     int *d_queue = nullptr;      // work-queue counters (16)
     int *d_items = nullptr;      // particle index lists
@@ -96,6 +98,7 @@ static inline cudaError_t sc_set_smem(int bytes)
     return e;
 }
 static int ensure_gauss(hs_ctx *ctx, int gmax);
+static int ensure_gauss_full(hs_ctx *ctx, int nmaxrule);
 #include "hs_staged_host.h"
 struct StBufsHolder { StShared s; };
 
@@ -114,6 +117,26 @@ static int ensure_gauss(hs_ctx *ctx, int gmax)
     if (ctx->d_gx) ctx->gauss_old.push_back(ctx->d_gx);
     if (ctx->d_gw) ctx->gauss_old.push_back(ctx->d_gw);
     ctx->d_gx = nx; ctx->d_gw = nw; ctx->gmax = gmax;
+    return 0;
+}
+
+// full n-point rules for the two-segment quadrature of cylinders (same retirement scheme as ensure_gauss: kernels in
+// flight may still read the old tables)
+static int ensure_gauss_full(hs_ctx *ctx, int nmaxrule)
+{
+    if (nmaxrule <= ctx->gfmax) return 0;
+    nmaxrule = std::min(std::max(nmaxrule, 64), HS_NPNG1 / 2 + 1);
+    size_t tot = (size_t)nmaxrule * (nmaxrule + 1) / 2;
+    std::vector<double> hx(tot), hw(tot);
+    for (int n = 1; n <= nmaxrule; n++) hs::gauss_full(n, &hx[(size_t)n * (n - 1) / 2], &hw[(size_t)n * (n - 1) / 2]);
+    double *nx = nullptr, *nw = nullptr;
+    CK(cudaMalloc(&nx, tot * sizeof(double)));
+    CK(cudaMalloc(&nw, tot * sizeof(double)));
+    CK(cudaMemcpy(nx, hx.data(), tot * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(nw, hw.data(), tot * sizeof(double), cudaMemcpyHostToDevice));
+    if (ctx->d_gfx) ctx->gauss_old.push_back(ctx->d_gfx);
+    if (ctx->d_gfw) ctx->gauss_old.push_back(ctx->d_gfw);
+    ctx->d_gfx = nx; ctx->d_gfw = nw; ctx->gfmax = nmaxrule;
     return 0;
 }
 
@@ -155,7 +178,7 @@ extern "C" int hs_ctx_create(hs_ctx **out, int device)
 extern "C" void hs_ctx_destroy(hs_ctx *ctx)
 {
     if (!ctx) return;
-    cudaFree(ctx->d_gx); cudaFree(ctx->d_gw); cudaFree(ctx->d_queue); cudaFree(ctx->d_items);
+    cudaFree(ctx->d_gx); cudaFree(ctx->d_gw); cudaFree(ctx->d_gfx); cudaFree(ctx->d_gfw); cudaFree(ctx->d_queue); cudaFree(ctx->d_items);
     cudaFree(ctx->d_ws_global); cudaFree(ctx->d_ws_fb); cudaFree(ctx->d_sc); cudaFree(ctx->d_xs_tmp); cudaFree(ctx->d_order); cudaFree(ctx->d_frames); cudaFree(ctx->d_scwig);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int b = 0; b < 8; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
@@ -303,14 +326,17 @@ struct Bucket {
 // max(NMAX0 + 1, ceil(|m| k a_max + 2)) is a tight estimate on the 6-band rain sweep; particles that still outgrow
 // their shared-memory slice continue in the global-memory fall-back workspace (no re-launch).
 __global__ void k_nmax0(int n, const double *axi, const double *lam, const double *mr, const double *mi,
-                        const double *eps, double rat, int *out, int *out_n0, int *out_lb)
+                        const double *eps, double rat, int np, int *out, int *out_n0, int *out_lb)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double PI = 3.14159265358979323846;
     double r = rat;
     double e_ = eps[i];
-    if (fabs(rat - 1.0) > 1e-8) {
+    if (fabs(rat - 1.0) > 1e-8 && np == -2) {  // SAREAC
+        r = pow(1.5 / e_, 1.0 / 3.0);
+        r = r / sqrt((e_ + 2.0) / (2.0 * e_));
+    } else if (fabs(rat - 1.0) > 1e-8) {
         double e, q;
         if (e_ < 1.0) { e = sqrt(1.0 - e_ * e_); q = 0.5 * (pow(e_, 2.0 / 3.0) + pow(e_, -1.0 / 3.0) * asin(e) / e); }
         else { e = sqrt(1.0 - 1.0 / (e_ * e_)); q = 0.25 * (2.0 * pow(e_, 2.0 / 3.0) + pow(e_, -4.0 / 3.0) * log((1.0 + e) / (1.0 - e)) / e); }
@@ -321,6 +347,7 @@ __global__ void k_nmax0(int n, const double *axi, const double *lam, const doubl
     int n0 = ixxx > 4 ? ixxx : 4;
     double a = (e_ > 0.0) ? pow(e_, 1.0 / 3.0) : 1.0;
     double xa = xev * fmax(a, a / e_);
+    if (np == -2 && e_ > 0.0) xa = xev * pow(2.0 / (3.0 * e_ * e_), 1.0 / 3.0) * sqrt(1.0 + e_ * e_);  // edge of the cylinder
     double mx = sqrt(mr[i] * mr[i] + mi[i] * mi[i]) * xa;
     int pred = (mx > 0.0 && mx < 1e6) ? (int)ceil(mx + 2.0) : 0;
     out[i] = max(n0 + 1, pred);
@@ -349,7 +376,10 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
 {
     if (!ctx) return -2;
     if (n <= 0) return 0;
-    if (np != HS_SHAPE_SPHEROID) { ctx->err = "only spheroids (np=-1) are supported"; return -3; }
+    if (np != HS_SHAPE_SPHEROID && np != HS_SHAPE_CYLINDER) { ctx->err = "shapes: spheroid (np = -1) or finite circular cylinder (np = -2)"; return -3; }
+    if (np == HS_SHAPE_CYLINDER && getenv("HYDROTM_STAGED_MIN") && atoi(getenv("HYDROTM_STAGED_MIN")) > 0) {
+        ctx->err = "cylinders are only implemented in the staged pipeline (unset HYDROTM_STAGED_MIN)"; return -3;
+    }
     if (ndgs < 1) { ctx->err = "ndgs must be >= 1"; return -3; }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
@@ -417,7 +447,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     // predicted starting NMAX -> initial bucket
     // (the kernel writes straight into the pinned host block: no D2H copy that could queue behind a caller's bulk transfer)
     int *h_n0 = ctx->h_pin, *h_st = ctx->h_pin + n, *h_start = ctx->h_pin + 2 * (size_t)n, *h_lb = ctx->h_pin + 3 * (size_t)n;
-    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, h_n0, h_start, h_lb);
+    k_nmax0<<<(n + 255) / 256, 256, 0, st>>>(n, d_axi, d_lam, d_mr, d_mi, d_eps, rat, np, h_n0, h_start, h_lb);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -428,7 +458,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     if (!ctx->st) ctx->st = new StBufsHolder();
     bool staged_done = false;
     StCall SC;
-    SC.d_axi = d_axi; SC.d_lam = d_lam; SC.d_mr = d_mr; SC.d_mi = d_mi; SC.d_eps = d_eps; SC.rat = rat; SC.ddelt = ddelt; SC.ndgs = ndgs;
+    SC.d_axi = d_axi; SC.d_lam = d_lam; SC.d_mr = d_mr; SC.d_mi = d_mi; SC.d_eps = d_eps; SC.rat = rat; SC.np = np; SC.ddelt = ddelt; SC.ndgs = ndgs;
     SC.d_tarena = d_tarena; SC.arena_cap = arena_cap; SC.d_arena_top = d_arena_top; SC.d_toff = d_toff;
     SC.d_nmax = d_nmax; SC.d_ngauss = d_ngauss; SC.d_ntrials = d_ntrials; SC.d_status = d_status;
     SC.scratch_budget = (size_t)((getenv("HYDROTM_SCRATCH_GB") ? atof(getenv("HYDROTM_SCRATCH_GB")) : 4.0) * (double)(1ull << 30));

@@ -53,6 +53,7 @@ extern "C" {
 #define HS_ST_INTERNAL_GAUSS 101    /* never returned to the caller */
 
 #define HS_SHAPE_SPHEROID (-1)
+#define HS_SHAPE_CYLINDER (-2) /* finite circular cylinder, axis_ratio = diameter / length (Mishchenko NP = -2) */
 
 typedef struct hs_ctx hs_ctx;
 
@@ -77,7 +78,7 @@ long long hs_launch_count(const hs_ctx *ctx);
  *   d_axi,d_lam,d_mr,d_mi,d_eps : device [n]  radius, wavelength (same unit), Re m, Im m, axis ratio
  *                                 (horizontal/vertical, >1 oblate)
  *   rat      : 1.0 = d_axi is the equal-volume radius; other = equal-surface-area radius (SAREA)
- *   np       : HS_SHAPE_SPHEROID
+ *   np       : HS_SHAPE_SPHEROID or HS_SHAPE_CYLINDER
  *   ddelt    : convergence tolerance as the caller states it; rescale_ddelt != 0 applies
  *              Mishchenko's DDELT = 0.1*DDELT before use
  *   d_tarena : device buffer of arena_cap complex128; d_arena_top device counter (complex entries

@@ -183,6 +183,33 @@ def test_shim_end_to_end_on_gpu(engine):
     assert g["Ai"] > 0 and g["sca"] > 0
 
 
+def test_shim_cylinder_on_gpu(engine):
+    """Scatterer(shape=SHAPE_CYLINDER) through the shim: per-call S / Z and a small orientation-averaged scatter table on
+    the CUDA back-end against the oracle back-end."""
+    import hydroscatt_b200
+    hydroscatt_b200.install_shims()
+    from pytmatrix import orientation, radar, tmatrix_aux
+    from pytmatrix import tmatrix as tmod
+    from pytmatrix.tmatrix import Scatterer
+    from tests.oracle_backend import OracleBackend
+
+    def run(backend):
+        tmod.set_backend(backend)
+        tm = Scatterer(radius=1.5, wavelength=tmatrix_aux.wl_X, m=complex(1.78, 0.002), axis_ratio=0.5,
+                       shape=Scatterer.SHAPE_CYLINDER)
+        tm.set_geometry(tmatrix_aux.geom_horiz_back)
+        S, Z = tm.get_SZ()
+        out = [np.asarray(S).ravel().view(float), np.asarray(Z).ravel()]
+        tm.orient = orientation.orient_averaged_fixed
+        tm.or_pdf = orientation.gaussian_pdf(20.0)
+        out.append(np.array([radar.refl(tm), radar.Zdr(tm), radar.ldr(tm)]))
+        tmod.set_backend(None)
+        return out
+
+    for a, b in zip(run(None), run(OracleBackend())):
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+
+
 def test_golden_rain_amplitudes_through_shim(engine):
     """The amplitudes the unmodified reference script feeds to its canting formulas (fixture generated by running
     scattering_rain.py on the oracle back-end, tools/gen_golden_rain.py) reproduced by the shim on the CUDA back-end."""

@@ -4,8 +4,7 @@
 #include <vector>
 
 namespace hs {
-// Gauss-Legendre rule of order n on [-1,1] (Newton on P_n; same published scheme the oracle restates, oracle/sl_oracle.c
-// hso_gauss): nodes ascending, any n >= 1.
+// Gauss-Legendre rule of order n on [-1,1] (Newton on P_n; the published GAUSS scheme): nodes ascending, any n >= 1.
 inline void gauss_full(int n, double *z, double *w)
 {
     int ind = n % 2, k = n / 2 + ind;

@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(256) k_psd_obs_fused(int n_dsd, int n_D, int n
     extern __shared__ double psm[];
     const int ldw = n_D | 1;
     double *sW = psm;                                  // [64][ldw]
-    double *sT = sW + PSDF_RB * ldw;                   // [n_D][64] (4 tables x 16 columns)
-    double *sO = sT + (size_t)n_D * (PSDF_TB * PSDF_NC);  // [64][65] integrated values
+    double *sT = sW + PSDF_RB * ldw;                   // [n_D][64] (4 tables x 16 columns); later [64][61] staged observables
+    double *sO = sT + max((size_t)n_D * (PSDF_TB * PSDF_NC), (size_t)PSDF_RB * 61);  // [64][65] integrated values
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x * PSDF_RB;
     const int t_begin = blockIdx.y * tabs_per_cta, t_end = min(n_tab, t_begin + tabs_per_cta);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) k_psd_obs_fused(int n_dsd, int n_D, int n
                 const double wl = lam_tab[t];
                 const double xs_h = 2.0 * PI * (z0 - z1 - z4 + z5), xs_v = 2.0 * PI * (z0 + z1 + z4 + z5);
                 const double pref = wl * wl * wl * wl / (PI * PI * PI * PI * PI * kw_sqr);
-                double *o = obs + ((long)(r0 + r) * n_tab + t) * 15;
+                double *o = sT + r * 61 + tt * 15;  // staged: [64 rows][4 tables x 15] (+1 pad), sT is free until the next tile
                 const double nan = __longlong_as_double(0x7ff8000000000000LL);
                 o[0] = want_sca ? 10.0 * log10(v[14] / 1e6) : nan;
                 o[1] = want_sca ? 10.0 * log10(v[15] / 1e6) : nan;
@@ -212,6 +212,15 @@ __global__ void __launch_bounds__(256) k_psd_obs_fused(int n_dsd, int n_D, int n
                 o[12] = Ah;
                 o[13] = Av;
                 o[14] = Ah - Av;
+            }
+        }
+        __syncthreads();
+        // coalesced store: the 4 tables x 15 observables of a DSD are contiguous in obs
+        {
+            const int nt_ = min(PSDF_TB, t_end - t0), rowlen = nt_ * 15;
+            for (int e = tid; e < PSDF_RB * rowlen; e += 256) {
+                const int r = e / rowlen, k = e - r * rowlen;
+                if (r0 + r < n_dsd) obs[((long)(r0 + r) * n_tab + t0) * 15 + k] = sT[r * 61 + k];
             }
         }
     }

@@ -29,6 +29,18 @@ def test_fused_scatter_equals_ampl_and_xsect(engine):
     assert _rel(S2.cpu().numpy(), S1.cpu().numpy()) < 1e-12
     assert _rel(Z2.cpu().numpy(), Z1.cpu().numpy()) < 1e-12
     assert _rel(x2.cpu().numpy(), x1.cpu().numpy()) < 1e-12
+    # more orientations than one pass of the kernel holds (133 > 64), three scattered directions for one incidence (two
+    # geometry blocks), a second incidence with one
+    al = np.repeat(np.linspace(0, 360, 8)[:-1], 19)
+    be = np.tile(np.linspace(0.5, 179.0, 19), 7)
+    wt = np.tile(np.linspace(0.2, 0.02, 19), 7)
+    geoms = [GB, GF, (90.0, 40.0, 0.0, 65.0), (30.0, 150.0, 20.0, 200.0)]
+    S1, Z1 = tb.ampl(geoms, al, be, weight=wt, scale=0.11, reduce=True)
+    x1 = tb.xsect([(g[0], g[2]) for g in geoms], al, be, wt, 0.11)
+    S2, Z2, x2 = tb.scatter(geoms, al, be, weight=wt, scale=0.11)
+    assert _rel(S2.cpu().numpy(), S1.cpu().numpy()) < 1e-12
+    assert _rel(Z2.cpu().numpy(), Z1.cpu().numpy()) < 1e-12
+    assert _rel(x2.cpu().numpy(), x1.cpu().numpy()) < 1e-12
 
 
 def test_orientation_averaged_table_matches_oracle(engine):

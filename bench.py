@@ -228,6 +228,11 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("HS_BENCH_BIND", "1") != "0":
+        from hydroscatt_b200.dist import bind_to_gpu_cpus
+        bound = bind_to_gpu_cpus(local)  # before any pinned allocation
+        if bound is not None:
+            print("[bench] rank %d bound to CPUs %d-%d (%d)" % (rank, bound[0], bound[-1], len(bound)), file=sys.stderr)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -324,7 +329,7 @@ def run_gpu(args):
             hb["rows"].copy_(rows, non_blocking=True)
             # 274 MB of observables: in 32 pieces, so that the pipeline's small host<->device transfers of the next step are
             # not queued behind one 5 ms DMA (measured: 11.7 -> 11.3 ms per end-to-end step)
-            nch = 32
+            nch = int(os.environ.get("HS_BENCH_D2H_CHUNKS", "32"))
             for c in range(nch):
                 a_, b_ = c * n_dsd // nch, (c + 1) * n_dsd // nch
                 hb["obs"][a_:b_].copy_(obs[a_:b_], non_blocking=True)

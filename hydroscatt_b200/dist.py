@@ -72,3 +72,25 @@ def build_rows_sharded(eng, radius, wavelength, m_re, m_im, axis_ratio, geom_bac
     meta = torch.stack([tb.nmax, tb.ngauss, tb.ntrials, tb.status], dim=1).to(torch.float64)
     full = gather_rows(torch.cat([rows, meta], dim=1), idx, n, group)
     return full[:, :tables.ROW].contiguous(), full[:, tables.ROW:].to(torch.int32)
+
+
+def bind_to_gpu_cpus(device_index):
+    """One process per GPU: run this process (and the pinned host buffers it allocates afterwards) on the CPU cores NVML
+    reports as local to the GPU, so that result copies do not cross the socket interconnect.  Returns the CPU set, or
+    None if NVML is unavailable / reports no affinity / the affinity is the whole machine (nothing to do)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None

@@ -84,3 +84,15 @@ def scatter(t, nmax, lam, thet0, phi0, gsc, alpha=0.0, beta=0.0):
                       C.c_double(alpha), C.c_double(beta), _dp(out), _dp(xs))
     o = out.reshape(ng, 24)
     return o[:, :8].copy().view(np.complex128).reshape(ng, 2, 2), o[:, 8:].reshape(ng, 4, 4), xs
+
+
+def gauss_full(n):
+    z, w = np.zeros(n), np.zeros(n)
+    lib().emu_gauss_full(int(n), _dp(z), _dp(w))
+    return z, w
+
+
+def gauss_positive(n):
+    x, w = np.zeros(n // 2), np.zeros(n // 2)
+    lib().emu_gauss_positive(int(n), _dp(x), _dp(w))
+    return x, w

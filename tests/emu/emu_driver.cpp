@@ -80,3 +80,7 @@ extern "C" void emu_scatter(const double *t, int nmax, double lam, double thet0,
     for (int k = 1; k <= HS_NPN1; k++) fn[k] = sqrt((double)(2 * k + 1) / (double)(k * (k + 1)));
     hs::scatter_one(reinterpret_cast<const double2 *>(t), nmax, lam, thet0, phi0, ng, gsc, alpha, beta, fn.data(), out, xs2);
 }
+
+// hs_gauss.h: the n-point rule (any n; cylinders use odd orders too) and the positive half of an even rule
+extern "C" void emu_gauss_full(int n, double *z, double *w) { hs::gauss_full(n, z, w); }
+extern "C" void emu_gauss_positive(int n, double *xp, double *wp) { hs::gauss_positive(n, xp, wp); }

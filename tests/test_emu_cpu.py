@@ -57,3 +57,16 @@ def test_emu_xsect_equals_sphere_integral():
         sv *= 2 * np.pi / nph
         out = emu.xsect(tp, nmax, 6.5, t0, p0, a, b)
         assert abs(out[0] - sh) / sh < 1e-6 and abs(out[1] - sv) / sv < 1e-6
+
+
+def test_gauss_tables_any_order():
+    """The host-side generator of the device Gauss tables: n-point rules of any order (the two-segment quadrature of
+    cylinders needs odd ones) against numpy, and the positive half used for spheroids."""
+    for n in (1, 2, 3, 7, 8, 15, 31, 64, 125, 250):
+        z, w = emu.gauss_full(n)
+        zr, wr = np.polynomial.legendre.leggauss(n)
+        assert np.abs(z - zr).max() < 5e-15 and np.abs(w - wr).max() < 5e-15, n
+        assert (np.diff(z) > 0).all() and abs(w.sum() - 2.0) < 1e-13
+        if n % 2 == 0:
+            xp, wp = emu.gauss_positive(n)
+            assert (xp == z[n // 2:]).all() and (wp == w[n // 2:]).all()

@@ -75,3 +75,23 @@ def test_gather_single_process():
     rows = torch.tensor([[20.0], [0.0], [10.0]], dtype=torch.float64)
     full = hdist.gather_rows(rows, idx, 3)
     assert full[:, 0].tolist() == [0.0, 10.0, 20.0]
+
+
+def test_bench_reference_arm_under_torchrun_world2():
+    """bench.py --impl reference launched like the driver does for N = 2: rank 0 alone times the CPU port and prints ONE
+    JSON line with the contract's keys, the other rank exits 0 without work (bounded sample: every 64th particle)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0", "--cpu-stride", "64"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "T-matrix solves/s" and d["unit"] == "solves/s" and d["n_gpus"] == 2
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

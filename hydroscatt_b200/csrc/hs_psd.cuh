@@ -146,8 +146,10 @@ __global__ void __launch_bounds__(256) k_psd_obs_fused(int n_dsd, int n_D, int n
     extern __shared__ double psm[];
     const int ldw = n_D | 1;
     double *sW = psm;                                  // [64][ldw]
-    double *sT = sW + PSDF_RB * ldw;                   // [n_D][64] (4 tables x 16 columns); later [64][61] staged observables
-    double *sO = sT + max((size_t)n_D * (PSDF_TB * PSDF_NC), (size_t)PSDF_RB * 61);  // [64][65] integrated values
+    // one area, three uses per tile, separated by barriers: [n_D][64] table tile (4 tables x 16 columns) -> [64][65]
+    // integrated values -> [64][61] staged observables.  (Three separate areas held the kernel to two CTAs per SM.)
+    double *sT = sW + PSDF_RB * ldw;
+    double *sO = sT;
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x * PSDF_RB;
     const int t_begin = blockIdx.y * tabs_per_cta, t_end = min(n_tab, t_begin + tabs_per_cta);
@@ -179,14 +181,18 @@ __global__ void __launch_bounds__(256) k_psd_obs_fused(int n_dsd, int n_D, int n
                 acc[1][2 * q] += w1 * tv.x; acc[1][2 * q + 1] += w1 * tv.y;
             }
         }
+        __syncthreads();  // every warp is done with the table tile
 #pragma unroll
         for (int q = 0; q < 8; q++) { sO[rr * 65 + cg * 8 + q] = acc[0][q]; sO[(rr + 32) * 65 + cg * 8 + q] = acc[1][q]; }
         __syncthreads();
         // observables: thread = (row, table)
         {
             const int r = tid & 63, tt = tid >> 6, t = t0 + tt;
+            double v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = sO[r * 65 + tt * 16 + q];
+            __syncthreads();  // the staged observables overwrite the integrated values
             if (r0 + r < n_dsd && t < t_end) {
-                const double *v = sO + r * 65 + tt * 16;
                 const double z0 = v[0], z1 = v[1], z4 = v[2], z5 = v[3], z10 = v[4], z11 = v[5], z14 = v[6], z15 = v[7];
                 const double wl = lam_tab[t];
                 const double xs_h = 2.0 * PI * (z0 - z1 - z4 + z5), xs_v = 2.0 * PI * (z0 + z1 + z4 + z5);

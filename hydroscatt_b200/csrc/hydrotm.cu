@@ -772,8 +772,8 @@ extern "C" int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, co
     if (n_dsd <= 0 || n_D <= 0 || n_tab <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
-    // weights + table tile (doubles as the staging area of the coalesced observable store: at least 64 x 61) + integrated values
-    const size_t smem = ((size_t)PSDF_RB * (n_D | 1) + std::max((size_t)n_D * PSDF_TB * PSDF_NC, (size_t)PSDF_RB * 61) + PSDF_RB * 65) * sizeof(double);
+    // weights + one area that is in turn the table tile, the integrated values ([64][65]) and the staged observables
+    const size_t smem = ((size_t)PSDF_RB * (n_D | 1) + std::max((size_t)n_D * PSDF_TB * PSDF_NC, (size_t)PSDF_RB * 65)) * sizeof(double);
     if (smem > (size_t)ctx->smem_optin) { ctx->err = "hs_psd_observables: too many diameters for one shared-memory tile"; return -3; }
     CK(cudaFuncSetAttribute(hs::k_psd_obs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int rb = (n_dsd + PSDF_RB - 1) / PSDF_RB;

@@ -396,12 +396,14 @@ __global__ void __launch_bounds__(64) k_scatter_wig(ScArgs a, double2 *wtab)
 //   * SPLIT (1, 2 or 4) adjacent lanes share one orientation and take every SPLIT-th row n of a mode: more warps for the
 //     same shared memory (the heavy NMAX classes are limited by their T stage), and the lanes of a group read the same
 //     P' / Q' entries (fewer shared-memory wavefronts per FMA).
-template <int SPLIT>
+//   * NTO = orientations per pass as a compile-time constant (64, the usual case; 0 = blockDim.x / SPLIT): the [n'][thread]
+//     strides of the P' / Q' vectors become immediates of the LDS instructions instead of two integer instructions per load.
+template <int SPLIT, int NTO>
 __global__ void __launch_bounds__(64 * SPLIT) k_scatter(ScArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int nto = nt / SPLIT, oi = tid / SPLIT, h = tid % SPLIT;  // orientations per pass, this thread's one, its row slice
+    const int nto = NTO ? NTO : nt / SPLIT, oi = tid / SPLIT, h = tid % SPLIT;  // orientations per pass, this thread's one, its row slice
     const int p = a.order ? a.order[blockIdx.x] : blockIdx.x;
     const bool bad = (a.status[p] != HS_ST_OK && a.status[p] != HS_ST_NGAUSS_LIMIT && a.status[p] != HS_ST_SINGULAR) || a.toff[p] < 0;
     if (bad) {

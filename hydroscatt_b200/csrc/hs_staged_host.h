@@ -433,7 +433,7 @@ struct StGroup {
         ScArgs sa = sp->a;
         sa.order = B->d_scord + off;
         sa.nmax_bound = bound;
-        k_scatter<1><<<nnew, sp->threads, smem, ss>>>(sa);
+        CK(sc_launch(1, nnew, sp->threads, smem, ss, sa));
         launches += 2;
         CK(cudaGetLastError());
         return 0;

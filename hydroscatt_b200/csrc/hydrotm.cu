@@ -85,17 +85,26 @@ static inline size_t sc_smem(int nto, int nmax_bound)
 // k_scatter<SPLIT> launch: `nto` orientations per pass x SPLIT lanes each
 static inline cudaError_t sc_launch(int split, int grid, int nto, size_t smem, cudaStream_t st, const hs::ScArgs &a)
 {
-    if (split == 4) hs::k_scatter<4><<<grid, nto * 4, smem, st>>>(a);
-    else if (split == 2) hs::k_scatter<2><<<grid, nto * 2, smem, st>>>(a);
-    else hs::k_scatter<1><<<grid, nto, smem, st>>>(a);
+    if (nto == 64) {
+        if (split == 4) hs::k_scatter<4, 64><<<grid, nto * 4, smem, st>>>(a);
+        else if (split == 2) hs::k_scatter<2, 64><<<grid, nto * 2, smem, st>>>(a);
+        else hs::k_scatter<1, 64><<<grid, nto, smem, st>>>(a);
+    } else {
+        if (split == 4) hs::k_scatter<4, 0><<<grid, nto * 4, smem, st>>>(a);
+        else if (split == 2) hs::k_scatter<2, 0><<<grid, nto * 2, smem, st>>>(a);
+        else hs::k_scatter<1, 0><<<grid, nto, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 static inline cudaError_t sc_set_smem(int bytes)
 {
-    cudaError_t e = cudaFuncSetAttribute(hs::k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hs::k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hs::k_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    return e;
+    const void *f[6] = {(const void *)hs::k_scatter<1, 64>, (const void *)hs::k_scatter<2, 64>, (const void *)hs::k_scatter<4, 64>,
+                        (const void *)hs::k_scatter<1, 0>, (const void *)hs::k_scatter<2, 0>, (const void *)hs::k_scatter<4, 0>};
+    for (int i = 0; i < 6; i++) {
+        cudaError_t e = cudaFuncSetAttribute(f[i], cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 static int ensure_gauss(hs_ctx *ctx, int gmax);
 static int ensure_gauss_full(hs_ctx *ctx, int nmaxrule);

@@ -486,21 +486,29 @@ __global__ void __launch_bounds__(64 * SPLIT) k_scatter(ScArgs a)
                         const double2 *tb = sT + (long)((n & 1) * NM) * NM + k;        // tau = 2 row
                         // same-parity n': T11 (ta), T22 (tb); phase i^(n&1)
                         double e1r = 0, e1i = 0, e3r = 0, e3i = 0, e2r = 0, e2i = 0, e4r = 0, e4i = 0;
-                        for (int nn = nmin + (k & 1); nn <= nmax; nn += 2) {
-                            const long o_ = (long)(nn - nmin) * NM;
-                            const double2 a_ = ta[o_], b_ = tb[o_];
-                            const double P = Pp[nn * nto], Q = Qp[nn * nto];
-                            e1r += a_.x * P; e1i += a_.y * P; e3r += a_.x * Q; e3i += a_.y * Q;
-                            e2r += b_.x * Q; e2i += b_.y * Q; e4r += b_.x * P; e4i += b_.y * P;
+                        {   // running pointers: the row stride NM is a run-time value, one add per pointer and step
+                            const int nn0 = nmin + (k & 1);
+                            const double2 *pa = ta + (long)(k & 1) * NM, *pb = tb + (long)(k & 1) * NM;
+                            const double *pP = Pp + nn0 * nto, *pQ = Qp + nn0 * nto;
+                            for (int nn = nn0; nn <= nmax; nn += 2, pa += 2 * NM, pb += 2 * NM, pP += 2 * nto, pQ += 2 * nto) {
+                                const double2 a_ = *pa, b_ = *pb;
+                                const double P = *pP, Q = *pQ;
+                                e1r += a_.x * P; e1i += a_.y * P; e3r += a_.x * Q; e3i += a_.y * Q;
+                                e2r += b_.x * Q; e2i += b_.y * Q; e4r += b_.x * P; e4i += b_.y * P;
+                            }
                         }
                         // other-parity n': T12 (ta), T21 (tb); phase i^((n+1)&1)
                         double o1r = 0, o1i = 0, o3r = 0, o3i = 0, o2r = 0, o2i = 0, o4r = 0, o4i = 0;
-                        for (int nn = nmin + ((k + 1) & 1); nn <= nmax; nn += 2) {
-                            const long o_ = (long)(nn - nmin) * NM;
-                            const double2 a_ = ta[o_], b_ = tb[o_];
-                            const double P = Pp[nn * nto], Q = Qp[nn * nto];
-                            o1r += a_.x * Q; o1i += a_.y * Q; o3r += a_.x * P; o3i += a_.y * P;
-                            o2r += b_.x * P; o2i += b_.y * P; o4r += b_.x * Q; o4i += b_.y * Q;
+                        {
+                            const int nn0 = nmin + ((k + 1) & 1);
+                            const double2 *pa = ta + (long)((k + 1) & 1) * NM, *pb = tb + (long)((k + 1) & 1) * NM;
+                            const double *pP = Pp + nn0 * nto, *pQ = Qp + nn0 * nto;
+                            for (int nn = nn0; nn <= nmax; nn += 2, pa += 2 * NM, pb += 2 * NM, pP += 2 * nto, pQ += 2 * nto) {
+                                const double2 a_ = *pa, b_ = *pb;
+                                const double P = *pP, Q = *pQ;
+                                o1r += a_.x * Q; o1i += a_.y * Q; o3r += a_.x * P; o3i += a_.y * P;
+                                o2r += b_.x * P; o2i += b_.y * P; o4r += b_.x * Q; o4i += b_.y * Q;
+                            }
                         }
                         double g1r, g1i, g2r, g2i, g3r, g3i, g4r, g4i;
                         if (n & 1) {  // same-parity phase = i, other-parity phase = 1

@@ -40,14 +40,15 @@ def sl(name, w, ndgs=2):
 
 
 # W1xR: C-band 10 degC rain grid, R jittered replicas (numpy default_rng(1234), D (1 + U(-0.02, 0.02)), m (1 + N(0, 1e-3)))
-R = 1024
+import os
+R = int(os.environ.get("HS_W1_REPLICAS", "1024"))  # SURVEY 8(d) states 4096 (286 720 particles): HS_W1_REPLICAS=4096
 w = rain_grid("C")
 rng = np.random.default_rng(1234)
 jd = 1.0 + rng.uniform(-0.02, 0.02, (R, 70))
 jm = 1.0 + rng.normal(0.0, 1e-3, (R, 70))
 w1 = dict(radius=(w["radius"] * jd).ravel(), wavelength=np.tile(w["wavelength"], R), mr=(w["mr"] * jm).ravel(),
           mi=(w["mi"] * jm).ravel(), axis_ratio=np.tile(w["axis_ratio"], R))
-sl("W1xR rain C-band 10 degC, 70 D x 1024 replicas", w1)
+sl("W1xR rain C-band 10 degC, 70 D x %d replicas" % R, w1)
 ice = ice_grid(seed=11, n=7680)
 sl("W3 ice crystals X/Ka/W, ndgs 2", ice)
 ice15 = ice_grid(seed=12, n=1024)

@@ -132,26 +132,39 @@ __device__ __forceinline__ void st_node(const StArgs &a, int g, int i, double ep
     }
 }
 
-// surface at x = cos(theta) < 0: r^2 and (dr/dtheta) / r  (VARY: RSP1 spheroid, RSP3 cylinder); rev = equal-volume radius
-__device__ __forceinline__ void st_surface(int np, double x, double rev, double eps, double &r2, double &drr)
-{
-    if (np != -2) {
-        const double A = rev * pow(eps, 1.0 / 3.0);
-        const double aa = A * A, ee = eps * eps, ee1 = ee - 1.0;
-        const double cc = x * x, ssq = 1.0 - cc, sth = sqrt(ssq);
-        const double rq = 1.0 / (ssq + ee * cc);
-        r2 = aa * rq;
-        drr = rq * x * sth * ee1;
-        return;
+// surface at x = cos(theta) < 0: r^2 and (dr/dtheta) / r  (VARY: RSP1 spheroid, RSP3 cylinder); rev = equal-volume radius.
+// The particle constants (one pow) are prepared once per thread, the surface is evaluated at several nodes.
+struct StSurf {
+    int np;
+    double aa, ee, ee1;  // spheroid: a^2, eps^2, eps^2 - 1
+    double h, ac;        // cylinder: half length, radius
+    __device__ __forceinline__ void init(int np_, double rev, double eps)
+    {
+        np = np_;
+        if (np != -2) {
+            const double A = rev * pow(eps, 1.0 / 3.0);
+            aa = A * A; ee = eps * eps; ee1 = ee - 1.0; h = 0.0; ac = 0.0;
+        } else {
+            h = rev * pow(2.0 / (3.0 * eps * eps), 1.0 / 3.0); ac = h * eps; aa = 0.0; ee = 0.0; ee1 = 0.0;
+        }
     }
-    const double h = rev * pow(2.0 / (3.0 * eps * eps), 1.0 / 3.0), ac = h * eps;
-    const double co = -x, si = sqrt(1.0 - co * co);
-    double rad, rthet;
-    if (si / co > ac / h) { rad = ac / si; rthet = -ac * co / (si * si); }
-    else { rad = h / co; rthet = h * si / (co * co); }
-    r2 = rad * rad;
-    drr = -rthet / rad;
-}
+    __device__ __forceinline__ void at(double x, double &r2, double &drr) const
+    {
+        if (np != -2) {
+            const double cc = x * x, ssq = 1.0 - cc, sth = sqrt(ssq);
+            const double rq = 1.0 / (ssq + ee * cc);
+            r2 = aa * rq;
+            drr = rq * x * sth * ee1;
+            return;
+        }
+        const double co = -x, si = sqrt(1.0 - co * co);
+        double rad, rthet;
+        if (si / co > ac / h) { rad = ac / si; rthet = -ac * co / (si * si); }
+        else { rad = h / co; rthet = h * si / (co * co); }
+        r2 = rad * rad;
+        drr = -rthet / rad;
+    }
+};
 
 // ---- S: radial functions.  Same recurrences as rjb / ryb / cjb, with the ratios parked in a thread-local array and the
 // results written n-major ([n][gp], coalesced over the nodes of a warp).
@@ -246,13 +259,6 @@ __device__ inline void st_cjb(double xr, double xi, double *yr, double *yi, doub
     }
 }
 
-__device__ __forceinline__ double st_r_of_node(double xp, double aa, double ee)
-{
-    const double x = -xp;
-    const double cc = x * x, ssq = 1.0 - cc;
-    return aa * (1.0 / (ssq + ee * cc));
-}
-
 __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *tasks, int ntasks)
 {
     // one half-warp per task of 16 nodes (most trial items have 10..16 nodes); the host orders the tasks kind-major, so
@@ -286,8 +292,10 @@ __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *ta
     const double arev = st_arev(a.axi[p], a.rat, eps, a.np);
     const double kw = PI * 2.0 / lam;
     double x, wv, r, drr;
+    StSurf surf;
+    surf.init(a.np, arev, eps);
     st_node(a, g, i, eps, x, wv);
-    st_surface(a.np, x, arev, eps, r, drr);
+    surf.at(x, r, drr);
     const double xp = -x;
     const double v = sqrt(r) * kw;
     double *tab = a.tab + it.tab_off;
@@ -299,8 +307,8 @@ __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *ta
     {
         const int ia = a.np == -2 ? g / 2 - 1 : 0, ib = a.np == -2 ? g / 2 : g - 1;
         double xa, xb, wa, ra, rb, da;
-        st_node(a, g, ia, eps, xa, wa); st_surface(a.np, xa, arev, eps, ra, da);
-        st_node(a, g, ib, eps, xb, wa); st_surface(a.np, xb, arev, eps, rb, da);
+        st_node(a, g, ia, eps, xa, wa); surf.at(xa, ra, da);
+        st_node(a, g, ib, eps, xb, wa); surf.at(xb, rb, da);
         ta = fmax(sqrt(ra) * kw, sqrt(rb) * kw);
     }
     if (kind == 0) {

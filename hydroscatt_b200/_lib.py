@@ -43,6 +43,9 @@ SIGNATURES = {
                                  C.c_int, C.c_double, _dp, C.c_void_p]),
     "hs_psd_observables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int,
                                      _dp, C.c_void_p]),
+    "hs_canting_observables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_longlong, C.c_longlong, _dp, C.c_double,
+                                         C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_void_p]),
+    "hs_canting_mixture": (C.c_int, [C.c_void_p, C.c_longlong, _dp, _dp, _dp, C.c_void_p]),
     "hs_tm2l_batch": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp,
                                 C.c_void_p]),
     "hs_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),

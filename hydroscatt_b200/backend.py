@@ -25,6 +25,7 @@ class TMHandle:
         self.nmax_host = int(batch.nmax[0].item())
         self.ngauss_host = int(batch.ngauss[0].item())
         self.status_host = int(batch.status[0].item())
+        self.toff_host = int(batch.toff[0].item())
 
     @property
     def nmax(self):
@@ -58,6 +59,9 @@ class CudaBackend:
         h = TMHandle(tb)
         if h.status_host not in (_engine.ST_OK, _engine.ST_NGAUSS_LIMIT):
             raise ConvergenceError("calctmat: " + _engine.STATUS_TEXT.get(h.status_host, str(h.status_host)))
+        if h.toff_host < 0:
+            # NMAX*NDGS outran NPNG1 before the first NGAUSS trial: upstream prints and STOPs; there is no T-matrix
+            raise ConvergenceError("calctmat: NGAUSS = NMAX*NDGS exceeds NPNG1=500 before convergence (no T-matrix)")
         return h
 
     def calcampl(self, h, thet0, thet, phi0, phi, alpha, beta):
@@ -116,6 +120,10 @@ class CudaBackend:
         bad = np.nonzero((st != _engine.ST_OK) & (st != _engine.ST_NGAUSS_LIMIT))[0]
         if bad.size:
             raise ConvergenceError("calctmat: particle %d: %s" % (bad[0], _engine.STATUS_TEXT.get(int(st[bad[0]]))))
+        empty = np.nonzero(tb.toff.cpu().numpy() < 0)[0]
+        if empty.size:
+            raise ConvergenceError("calctmat: particle %d: NGAUSS = NMAX*NDGS exceeds NPNG1=500 before convergence "
+                                   "(no T-matrix)" % empty[0])
         g4 = [tuple(g[:4]) for g in geometries]
         res = {"nmax": tb.nmax.cpu().numpy(), "ngauss": tb.ngauss.cpu().numpy()}
         if angular:

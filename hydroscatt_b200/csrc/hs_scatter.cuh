@@ -48,6 +48,13 @@ struct ScArgs {
     int wig_nb;             // largest n in `wtab`
 };
 
+// the one validity predicate of the scatter stage (k_scatter, k_order_by_nmax): a particle has a usable T-matrix when the
+// controller finished it (converged, NGAUSS cap with the last T kept, or a flagged near-singular solve) and it owns an arena slot
+__host__ __device__ __forceinline__ bool sc_has_tmatrix(int status, long long toff)
+{
+    return (status == HS_ST_OK || status == HS_ST_NGAUSS_LIMIT || status == HS_ST_SINGULAR) && toff >= 0;
+}
+
 // triangular index of (m, n >= m) in a Wigner table that goes up to n = nb
 __host__ __device__ __forceinline__ long sc_tri(int m, int n, int nb) { return (long)m * (nb + 1) - (long)m * (m - 1) / 2 + (n - m); }
 __host__ __device__ __forceinline__ long sc_tri_size(int nb) { return (long)(nb + 1) * (nb + 2) / 2; }
@@ -405,7 +412,9 @@ __global__ void __launch_bounds__(64 * SPLIT) k_scatter(ScArgs a)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nto = NTO ? NTO : nt / SPLIT, oi = tid / SPLIT, h = tid % SPLIT;  // orientations per pass, this thread's one, its row slice
     const int p = a.order ? a.order[blockIdx.x] : blockIdx.x;
-    const bool bad = (a.status[p] != HS_ST_OK && a.status[p] != HS_ST_NGAUSS_LIMIT && a.status[p] != HS_ST_SINGULAR) || a.toff[p] < 0;
+    // a particle outside its launch class's bounds (cannot happen with k_order_by_nmax's predicate; checked because the T stage
+    // and the Wigner table are sized for the class) is reported as NaN instead of overrunning shared memory
+    const bool bad = !sc_has_tmatrix(a.status[p], a.toff[p]) || a.nmax[p] > a.nmax_bound || a.nmax[p] > a.wig_nb;
     if (bad) {
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
         for (int t = tid; t < a.n_geom * 8; t += nt) a.S[(long)p * a.n_geom * 8 + t] = nan;
@@ -652,14 +661,14 @@ __global__ void __launch_bounds__(64 * SPLIT) k_scatter(ScArgs a)
 }
 // CTA -> particle map with the largest NMAX first (one block; counting sort on NMAX): the heavy particles start first
 // instead of forming the tail of the launch.
-__global__ void __launch_bounds__(1024) k_order_by_nmax(int n, const int *nmax, const int *status, int *order, int *hist_out)
+__global__ void __launch_bounds__(1024) k_order_by_nmax(int n, const int *nmax, const int *status, const long long *toff, int *order, int *hist_out)
 {
     __shared__ int cnt[HS_NPN1 + 2];
     for (int t = threadIdx.x; t < HS_NPN1 + 2; t += blockDim.x) cnt[t] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int v = nmax[i];
-        v = (status[i] == HS_ST_OK && v > 0 && v <= HS_NPN1) ? v : 0;
+        v = (sc_has_tmatrix(status[i], toff[i]) && v > 0 && v <= HS_NPN1) ? v : 0;
         atomicAdd(&cnt[v], 1);
     }
     __syncthreads();
@@ -673,7 +682,7 @@ __global__ void __launch_bounds__(1024) k_order_by_nmax(int n, const int *nmax, 
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int v = nmax[i];
-        v = (status[i] == HS_ST_OK && v > 0 && v <= HS_NPN1) ? v : 0;
+        v = (sc_has_tmatrix(status[i], toff[i]) && v > 0 && v <= HS_NPN1) ? v : 0;
         order[atomicAdd(&cnt[v], 1)] = i;
     }
 }

@@ -381,7 +381,7 @@ struct StGroup {
             s.kspec = k;
         }
         nround++;
-        if (nround > 4 * HS_NPN1 + HS_NPNG1) { ctx->err = "staged controller did not terminate"; return -4; }
+        if (nround > 4 * HS_NPN1 + HS_NPNG1) { hs_set_err(ctx, "staged controller did not terminate"); return -4; }
         auto T2 = std::chrono::steady_clock::now();
         t_wait += std::chrono::duration<double, std::milli>(T1 - T0).count();
         t_ctl += std::chrono::duration<double, std::milli>(T2 - T1).count();
@@ -429,7 +429,7 @@ struct StGroup {
         CK(cudaMemcpyAsync(B->d_scord + off, B->h_scord + off, (size_t)nnew * sizeof(int), cudaMemcpyHostToDevice, ss));
         k_st_scatter_out8<<<(nnew + 255) / 256, 256, 0, ss>>>(nnew, B->d_screc + 8 * (size_t)off, C->d_nmax, C->d_ngauss, C->d_ntrials, C->d_status, C->d_toff);
         const size_t smem = sc_smem(sp->threads, bound);
-        if (smem > (size_t)ctx->smem_optin - 8192) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
+        if (smem > (size_t)ctx->smem_optin - 8192) { hs_set_err(ctx, "scatter: nmax too large for the shared-memory T stage"); return -4; }
         ScArgs sa = sp->a;
         sa.order = B->d_scord + off;
         sa.nmax_bound = bound;
@@ -634,14 +634,22 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
             if (s.done == 1 && s.nmax > C.nmax_max) C.nmax_max = s.nmax;
             if (s.status == HS_ST_ARENA_FULL) C.arena_full = true;
         }
+    // join EVERY group stream back into the caller's stream before reporting an error: the caller may drop its arena and
+    // output buffers as soon as this returns non-zero, and kernels of the healthy groups may still be running
+    int first_rc = 0;
     for (int g = 0; g < ng; g++) {
         ctx->launches += G[g].launches;
-        if (G[g].rc) return G[g].rc;
-        CK(cudaEventRecord(S.g[g].ev, S.g[g].stream));
-        CK(cudaStreamWaitEvent(st, S.g[g].ev, 0));
-        CK(cudaEventRecord(S.g[g].sc_ev, S.g[g].sc_stream));
-        CK(cudaStreamWaitEvent(st, S.g[g].sc_ev, 0));
+        if (G[g].rc && !first_rc) first_rc = G[g].rc;
+        cudaError_t e1 = cudaEventRecord(S.g[g].ev, S.g[g].stream);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(st, S.g[g].ev, 0);
+        cudaError_t e2 = cudaEventRecord(S.g[g].sc_ev, S.g[g].sc_stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, S.g[g].sc_ev, 0);
+        if ((e1 != cudaSuccess || e2 != cudaSuccess) && !first_rc) {
+            hs_set_err(ctx, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            first_rc = -1;
+        }
     }
+    if (first_rc) { cudaDeviceSynchronize(); return first_rc; }
     if (timeline) {
         cudaDeviceSynchronize();
         for (int g = 0; g < ng; g++)

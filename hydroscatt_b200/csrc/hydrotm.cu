@@ -19,6 +19,7 @@
 #include "hs_xsect.cuh"
 #include "hs_scatter.cuh"
 #include "hs_psd.cuh"
+#include "hs_cant.cuh"
 #include "hs_tm2l.cuh"
 #include "hs_staged.cuh"
 
@@ -55,16 +56,23 @@ struct hs_ctx {
     double *d_ws_fb = nullptr;   // global-memory fall-back workspace slices
     double *d_ws_global = nullptr;
     size_t ws_global_bytes = 0;
-    std::mutex mu;               // guards err / the Gauss table when the staged groups run on their own host threads
+    std::mutex mu;               // guards the Gauss table when the staged groups run on their own host threads
+    std::mutex err_mu;           // guards err (written from the group threads; separate: CK runs inside regions that hold mu)
     std::vector<double *> gauss_old;  // superseded Gauss tables (kernels in flight may still read them; freed with the context)
     struct StBufsHolder *st = nullptr;  // staged pipeline buffers (hs_staged_host.h)
 };
+
+static inline void hs_set_err(hs_ctx *ctx, const std::string &msg)
+{
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
+    hs_set_err(ctx, msg);
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) {                                                                   \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            hs_set_err(ctx, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
             return -1;                                                                             \
         }                                                                                          \
     } while (0)
@@ -228,7 +236,7 @@ static int scatter_prepare(hs_ctx *ctx, int n, const double *d_tarena, const lon
                            const double *d_alpha, const double *d_beta, const double *d_weight, double scale,
                            double *d_S, double *d_Z, double *d_xs, cudaStream_t st, ScPrep &P)
 {
-    if (n_geom > 64) { ctx->err = "at most 64 geometries per call"; return -3; }
+    if (n_geom > 64) { hs_set_err(ctx, "at most 64 geometries per call"); return -3; }
     // group geometries by incidence direction
     std::vector<double> inc;           // unique (thet0, phi0)
     std::vector<int> inc_of(n_geom);
@@ -385,11 +393,11 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
 {
     if (!ctx) return -2;
     if (n <= 0) return 0;
-    if (np != HS_SHAPE_SPHEROID && np != HS_SHAPE_CYLINDER) { ctx->err = "shapes: spheroid (np = -1) or finite circular cylinder (np = -2)"; return -3; }
+    if (np != HS_SHAPE_SPHEROID && np != HS_SHAPE_CYLINDER) { hs_set_err(ctx, "shapes: spheroid (np = -1) or finite circular cylinder (np = -2)"); return -3; }
     if (np == HS_SHAPE_CYLINDER && getenv("HYDROTM_STAGED_MIN") && atoi(getenv("HYDROTM_STAGED_MIN")) > 0) {
-        ctx->err = "cylinders are only implemented in the staged pipeline (unset HYDROTM_STAGED_MIN)"; return -3;
+        hs_set_err(ctx, "cylinders are only implemented in the staged pipeline (unset HYDROTM_STAGED_MIN)"); return -3;
     }
-    if (ndgs < 1) { ctx->err = "ndgs must be >= 1"; return -3; }
+    if (ndgs < 1) { hs_set_err(ctx, "ndgs must be >= 1"); return -3; }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
     if (rescale_ddelt) ddelt = 0.1 * ddelt;
@@ -566,7 +574,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
                                  : launch_tm<false, false, false>(a, grid, B.threads, smem, bs);
             }
             ctx->launches++;
-            if (e != cudaSuccess) { ctx->err = std::string("k_calctmat launch: ") + cudaGetErrorString(e); return -1; }
+            if (e != cudaSuccess) { hs_set_err(ctx, std::string("k_calctmat launch: ") + cudaGetErrorString(e)); return -1; }
             CK(cudaEventRecord(ctx->ev_done[b], bs));
             CK(cudaStreamWaitEvent(st, ctx->ev_done[b], 0));
         }
@@ -582,7 +590,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
             for (int i : lists[b]) {
                 if (h_st[i] == HS_ST_INTERNAL_ESCALATE) {
                     int nb = std::min(b + 1, NB - 1);
-                    if (nb == b) { ctx->err = "workspace escalation beyond the largest bucket"; return -4; }
+                    if (nb == b) { hs_set_err(ctx, "workspace escalation beyond the largest bucket"); return -4; }
                     next[nb].push_back(i);
                 } else if (h_st[i] == HS_ST_INTERNAL_GAUSS) {
                     need_gauss = true;
@@ -660,7 +668,7 @@ extern "C" int hs_calctmat_scatter_batch(hs_ctx *ctx, int n, const double *d_axi
 {
     if (!ctx) return -2;
     if (n <= 0) return 0;
-    if (n_geom <= 0 || n_orient <= 0) { ctx->err = "hs_calctmat_scatter_batch: no geometries / orientations"; return -3; }
+    if (n_geom <= 0 || n_orient <= 0) { hs_set_err(ctx, "hs_calctmat_scatter_batch: no geometries / orientations"); return -3; }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
     ScPrep SP;
@@ -734,7 +742,7 @@ extern "C" int hs_psd_weights(hs_ctx *ctx, int kind, int n_dsd, const double *d_
 {
     if (!ctx) return -2;
     if (n_dsd <= 0 || n_D <= 0) return 0;
-    if (kind < 0 || kind > 2) { ctx->err = "unknown PSD kind"; return -3; }
+    if (kind < 0 || kind > 2) { hs_set_err(ctx, "unknown PSD kind"); return -3; }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
     long tot = (long)n_dsd * n_D;
@@ -783,7 +791,7 @@ extern "C" int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, co
     CK(cudaSetDevice(ctx->device));
     // weights + one area that is in turn the table tile, the integrated values ([64][65]) and the staged observables
     const size_t smem = ((size_t)PSDF_RB * (n_D | 1) + std::max((size_t)n_D * PSDF_TB * PSDF_NC, (size_t)PSDF_RB * 65)) * sizeof(double);
-    if (smem > (size_t)ctx->smem_optin) { ctx->err = "hs_psd_observables: too many diameters for one shared-memory tile"; return -3; }
+    if (smem > (size_t)ctx->smem_optin) { hs_set_err(ctx, "hs_psd_observables: too many diameters for one shared-memory tile"); return -3; }
     CK(cudaFuncSetAttribute(hs::k_psd_obs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int rb = (n_dsd + PSDF_RB - 1) / PSDF_RB;
     // enough CTAs for two waves of the SMs: split the tables when there are few DSD tiles
@@ -792,6 +800,44 @@ extern "C" int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, co
     splits = (n_tab + per - 1) / per;
     dim3 grid(rb, splits);
     hs::k_psd_obs_fused<<<grid, 256, smem, st>>>(n_dsd, n_D, n_tab, per, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, want_sca, d_obs);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hs_canting_observables(hs_ctx *ctx, int n_tab, int n_D, const double *d_f, const double *d_mom, long long mom_stride_tab,
+                                      long long mom_stride_D, const double *d_lam_tab, double kw_sqr, int n_dsd, const double *d_W,
+                                      int n_extra, const double *d_extra, double *d_out, double *d_out_extra, void *stream)
+{
+    if (!ctx) return -2;
+    if (n_tab <= 0 || n_D <= 0) return 0;
+    if (n_extra < 0 || n_extra > CANT_NX || (n_extra > 0 && (!d_extra || !d_out_extra))) {
+        hs_set_err(ctx, "hs_canting_observables: 0..4 extra columns, with their input and output arrays"); return -3;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    if (!d_W) {
+        const long tot = (long)n_tab * n_D;
+        hs::k_canting_sp<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(n_tab, n_D, d_f, d_mom, (long)mom_stride_tab, (long)mom_stride_D,
+                                                                       d_lam_tab, kw_sqr, d_out);
+    } else {
+        if (n_dsd <= 0) return 0;
+        dim3 grid((n_dsd + CANT_RB - 1) / CANT_RB, n_tab);
+        hs::k_canting_psd<<<grid, CANT_RB * CANT_NC, 0, st>>>(n_dsd, n_D, n_tab, d_W, d_f, d_mom, (long)mom_stride_tab, (long)mom_stride_D,
+                                                             d_lam_tab, kw_sqr, n_extra, d_extra, d_out, d_out_extra);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hs_canting_mixture(hs_ctx *ctx, long long n, const double *d_a, const double *d_b, double *d_out, void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    hs::k_canting_mixture<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((long)n, d_a, d_b, d_out);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -893,7 +939,7 @@ extern "C" int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const do
 {
     if (!ctx) return -2;
     if (n <= 0) return 0;
-    if (!(wavelength_cm > 0.0)) { ctx->err = "wavelength must be positive"; return -3; }
+    if (!(wavelength_cm > 0.0)) { hs_set_err(ctx, "wavelength must be positive"); return -3; }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
     hs::T2Args a;
@@ -944,7 +990,7 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
         }
         if (ensure_pin(ctx, (HS_NPN1 + 2) * sizeof(int))) return -1;
         int *hist = ctx->h_pin;
-        hs::k_order_by_nmax<<<1, 1024, 0, st>>>(n, d_nmax, d_status, ctx->d_order, hist);
+        hs::k_order_by_nmax<<<1, 1024, 0, st>>>(n, d_nmax, d_status, d_toff, ctx->d_order, hist);
         ctx->launches++;
         CK(cudaStreamSynchronize(st));
         const int bounds[3] = {HS_NPN1, 20, 10};  // classes (20, NPN1], (10, 20], [0, 10] in the sorted (descending) order
@@ -959,7 +1005,7 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
             start += cnt;
             if (cnt) max_smem = std::max(max_smem, smem_for(cls_bound[c]));
         }
-        if (max_smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
+        if (max_smem > (size_t)ctx->smem_optin) { hs_set_err(ctx, "scatter: nmax too large for the shared-memory T stage"); return -4; }
         CK(sc_set_smem((int)max_smem));
         { int top = 1; for (int c = 0; c < 3; c++) if (cls_cnt[c]) top = std::max(top, cls_bound[c]);
           int rc = scatter_build_wig(ctx, a, top, st); if (rc) return rc; }
@@ -980,7 +1026,7 @@ extern "C" int hs_scatter_batch(hs_ctx *ctx, int n, const double *d_tarena, cons
         int nmax_bound = ctx->last_nmax_max > 0 ? ctx->last_nmax_max : HS_NPN1;
         a.nmax_bound = nmax_bound;
         size_t smem = smem_for(nmax_bound);
-        if (smem > (size_t)ctx->smem_optin) { ctx->err = "scatter: nmax too large for the shared-memory T stage"; return -4; }
+        if (smem > (size_t)ctx->smem_optin) { hs_set_err(ctx, "scatter: nmax too large for the shared-memory T stage"); return -4; }
         CK(sc_set_smem((int)smem));
         { int rc = scatter_build_wig(ctx, a, nmax_bound, st); if (rc) return rc; }
         CK(sc_launch(nmax_bound > 20 ? split[0] : (nmax_bound > 10 ? split[1] : split[2]), n, threads, smem, st, a));

@@ -95,6 +95,8 @@ class Engine:
         sizes = [np.size(a) if not torch.is_tensor(a) else a.numel()
                  for a in (radius, wavelength, m_re, m_im, axis_ratio)]
         n = max(sizes)
+        if any(k not in (1, n) for k in sizes):
+            raise ValueError("calctmat: array arguments must have one element or the batch size %d (got %s)" % (n, sizes))
         axi = self._dev(radius, n)
         lam = self._dev(wavelength, n)
         mr = self._dev(m_re, n)
@@ -277,6 +279,8 @@ class TMatrixBatch:
         if be.numel() != O:
             raise ValueError("alpha and beta must have the same length")
         w = eng._dev(weight if weight is not None else np.ones(O))
+        if w.numel() != O:
+            raise ValueError("weight must have one entry per orientation")
         if reduce:
             S = torch.empty((self.n, G, 2, 2), dtype=torch.complex128, device=dev)
             Z = torch.empty((self.n, G, 4, 4), dtype=torch.float64, device=dev)
@@ -304,6 +308,8 @@ class TMatrixBatch:
         be = eng._dev(beta)
         O = al.numel()
         w = eng._dev(weight if weight is not None else np.ones(O))
+        if be.numel() != O or w.numel() != O:
+            raise ValueError("alpha, beta and weight must have the same length")
         S = torch.empty((self.n, G, 2, 2), dtype=torch.complex128, device=dev)
         Z = torch.empty((self.n, G, 4, 4), dtype=torch.float64, device=dev)
         xs = torch.empty((self.n, G, 2), dtype=torch.float64, device=dev) if want_xs else None
@@ -325,6 +331,8 @@ class TMatrixBatch:
         be = eng._dev(beta)
         O = al.numel()
         w = eng._dev(weight if weight is not None else np.ones(O))
+        if be.numel() != O or w.numel() != O:
+            raise ValueError("alpha, beta and weight must have the same length")
         out = torch.empty((self.n, G, 2), dtype=torch.float64, device=eng.device)
         with torch.cuda.device(eng.device):
             rc = eng.lib.hs_xsect_batch(eng._h, self.n, _ptr(self.arena), _ptr(self.toff), _ptr(self.nmax),

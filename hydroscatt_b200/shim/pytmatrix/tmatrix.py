@@ -256,9 +256,30 @@ class Scatterer(object):
         if nodes is None:
             raise NotImplementedError("scatter tables need orient_single or orient_averaged_fixed")
         (alpha, beta, weight, scale) = nodes
-        return get_backend().scatter_table(radii, radius_type, self.wavelength, m, axis_ratio, self.shape,
-                                           self.ddelt, self.ndgs, geometries, alpha, beta, weight, scale,
-                                           angular)
+
+        def table(geoms, alpha, beta):
+            return get_backend().scatter_table(radii, radius_type, self.wavelength, m, axis_ratio, self.shape,
+                                               self.ddelt, self.ndgs, geoms, alpha, beta, weight, scale, angular)
+
+        if self.orient != orientation.orient_single:
+            return table(geometries, alpha, beta)
+        # orient_single: upstream init_scatter_table calls set_geometry(geom) per geometry, so the particle orientation
+        # is elements 4, 5 of EACH geometry tuple, not the Scatterer's current alpha / beta
+        groups = {}
+        for (gi, g) in enumerate(geometries):
+            groups.setdefault((float(g[4]), float(g[5])), []).append(gi)
+        res = None
+        for ((a, b), idx) in groups.items():
+            part = table([geometries[i] for i in idx], np.array([a]), np.array([b]))
+            if len(groups) == 1:
+                return part
+            if res is None:
+                res = {k: (v if v.ndim < 2 else np.empty((v.shape[0], len(geometries)) + v.shape[2:], v.dtype))
+                       for (k, v) in part.items()}
+            for (k, v) in part.items():
+                if v.ndim >= 2:
+                    res[k][:, idx] = v
+        return res
 
 
 # upstream alias

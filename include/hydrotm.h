@@ -180,6 +180,32 @@ int hs_observables(hs_ctx *ctx, int n, int stride, const double *d_in, int off_b
                    int off_sca, const double *d_lam, int lam_stride, double kw_sqr, double *d_out, void *stream);
 
 /*
+ * Canting-angle ("angular moments") observables: batched scattering.compute_scattering_canting_sp (scattering.py:182-309)
+ * and compute_scattering_canting_psd (scattering.py:312-448; looped 9 300x at scattering_rain.py:295-316 and 11 011x at
+ * scattering_hail.py:298-372).  SURVEY.md rows S4, S5.
+ *   d_f    : device [n_tab][n_D][8]  fv180, fh180, fv0, fh0 (re, im; metres) per table (species / band / temperature)
+ *   d_mom  : device angular moments a1, a2, a3, a4, a5, a7 of the canting distribution, 6 contiguous doubles at
+ *            d_mom[t * mom_stride_tab + i * mom_stride_D] (strides in doubles; 0 = shared by all tables / diameters)
+ *   d_lam_tab : device [n_tab] wavelength [mm];  kw_sqr: dielectric factor of the reflectivity
+ *   d_W    : device [n_dsd][n_D] = psd_vals * delta_d (rectangle rule), or NULL for the single-particle form
+ *   d_extra: device [n_D][n_extra] (n_extra <= 4) extra per-diameter columns summed with the same weights (e.g. D^3 and
+ *            D^3 v(D) for precip.compute_lwc / compute_rainfall_rate), or NULL;  d_out_extra: device [n_dsd][n_extra]
+ *   d_out  : d_W == NULL: [n_tab][n_D][15];  else [n_dsd][n_tab][15].  Columns (the reference's DataFrame order):
+ *            sca_xsect_h, sca_xsect_v, ext_xsect_h, ext_xsect_v, ldr_h, ldr_v, refl_h, refl_v, zdr [dB], rho_hv,
+ *            delta_hv [deg], kdp [deg/km], A_h, A_v, Adp [dB/km].
+ * Asynchronous on `stream`.
+ */
+int hs_canting_observables(hs_ctx *ctx, int n_tab, int n_D, const double *d_f, const double *d_mom, long long mom_stride_tab,
+                           long long mom_stride_D, const double *d_lam_tab, double kw_sqr, int n_dsd, const double *d_W,
+                           int n_extra, const double *d_extra, double *d_out, double *d_out_extra, void *stream);
+
+/*
+ * scattering.compute_scattering_mixture (scattering.py:590-673, row S7) on n rows of the 15 canting observables
+ * (incoherent sum of two species); the cross-section columns 0..3, which the reference's mixture does not define, are NaN.
+ */
+int hs_canting_mixture(hs_ctx *ctx, long long n, const double *d_a, const double *d_b, double *d_out, void *stream);
+
+/*
  * Two-layer (coated spheroid) T-matrix amplitudes for n particles at one wavelength: the batched equivalent of
  * tm2l.tmatrix(2) = tmatrix_py.f (fixed nrank 17, 7 azimuthal modes, 31-node Patterson rule; rows F1-F11).
  *   d_dpart,d_dcore : device [n] outer / inner equal-volume diameter [cm]   (fort.20 columns 1-2, tmatrix_py.f:580)

@@ -45,10 +45,8 @@ class OracleBackend:
         return S * scale, Z * scale
 
     def xsect(self, h, inc, alpha, beta, weight, scale, want_asym=False):
-        """cross sections through the host-emulated device function (same formula as the CUDA kernel)."""
-        r = emu.calctmat(h.tm_args[0], h.lam, h.tm_args[1].real, h.tm_args[1].imag, h.tm_args[2]) \
-            if hasattr(h, "tm_args") else None
-        raise NotImplementedError
+        raise NotImplementedError("the CPU oracle has no closed-form sca_xsect; the GPU tests check the CUDA one against "
+                                  "brute-force quadrature of oracle amplitudes (tests/test_scatter_gpu.py)")
 
     def psd_integrate(self, table, D, psd_w, rule="trapz"):
         D = np.asarray(D, dtype=np.float64)

@@ -145,6 +145,50 @@ def test_psd_integrator_table_and_trapz():
     assert radar.Kdp(tm) > 0 and radar.Ai(tm) > 0
 
 
+def test_scatter_table_save_load_round_trip(tmp_path):
+    """PSDIntegrator.save_scatter_table / load_scatter_table: upstream's pickle layout
+    (num_points, D_max, _psd_D, _S_table, _Z_table, _angular_table, _m_table, geometries) under "psd_scatter", and a loaded
+    table gives the same PSD-integrated S / Z and angular-integrated quantities without any T-matrix computation."""
+    import pickle
+    tm = Scatterer(wavelength=tmatrix_aux.wl_X, m=refractive.m_w_10C[tmatrix_aux.wl_X])
+    tm.orient = orientation.orient_averaged_fixed
+    tm.or_pdf = orientation.gaussian_pdf(7.0)
+    geoms = (tmatrix_aux.geom_horiz_back, tmatrix_aux.geom_horiz_forw)
+    pi = psd.PSDIntegrator(num_points=5, D_max=2.5, geometries=geoms,
+                           axis_ratio_func=lambda D: 1.0 / tmatrix_aux.dsr_thurai_2007(D))
+    tm.psd_integrator = pi
+    pi.init_scatter_table(tm, angular_integration=True)
+    fn = str(tmp_path / "table.pkl")
+    pi.save_scatter_table(fn, description="x band test")
+    raw = pickle.load(open(fn, "rb"))
+    assert set(raw) == {"description", "time", "psd_scatter", "version"} and len(raw["psd_scatter"]) == 8
+    assert raw["psd_scatter"][0] == 5 and raw["psd_scatter"][1] == 2.5 and raw["psd_scatter"][7] == geoms
+    tm.psd = psd.GammaPSD(D0=1.2, Nw=4e3, mu=1, D_max=2.5)
+    ref = {}
+    for g in geoms:
+        tm.set_geometry(g)
+        ref[g] = (tm.get_SZ(), scatter.sca_xsect(tm), scatter.ext_xsect(tm), scatter.asym(tm))
+
+    class NoCompute(OracleBackend):
+        def calctmat(self, *a, **k):
+            raise AssertionError("a loaded table must not trigger a T-matrix computation")
+        scatter_table = calctmat
+
+    tmod.set_backend(NoCompute())
+    tm2 = Scatterer(wavelength=tmatrix_aux.wl_X, m=refractive.m_w_10C[tmatrix_aux.wl_X])
+    tm2.psd_integrator = psd.PSDIntegrator()
+    (when, desc) = tm2.psd_integrator.load_scatter_table(fn)
+    assert desc == "x band test" and tm2.psd_integrator.num_points == 5 and tm2.psd_integrator.geometries == geoms
+    tm2.psd = psd.GammaPSD(D0=1.2, Nw=4e3, mu=1, D_max=2.5)
+    for g in geoms:
+        tm2.set_geometry(g)
+        (S, Z) = tm2.get_SZ()
+        assert np.array_equal(S, ref[g][0][0]) and np.array_equal(Z, ref[g][0][1])
+        # (the CPU oracle back-end has no sca_xsect / asym: NaN tables; the round trip must preserve them bit for bit)
+        got = (scatter.sca_xsect(tm2), scatter.ext_xsect(tm2), scatter.asym(tm2))
+        assert np.array_equal(np.array(got), np.array(ref[g][1:]), equal_nan=True) and got[1] > 0
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
 def test_reference_scattering_module_on_shim_regression_vectors():
     """The UNMODIFIED reference scattering.py on top of the shims: analytic-canting observables of single drops

@@ -82,6 +82,10 @@ def test_reference_call_sequence_on_cuda_amplitudes(engine):
     sp = canting.compute_scattering_canting_sp(wl, fv180, fh180, fv0, fh0, a, eng=engine).cpu().numpy()[0]
     gold = np.array(FX["sp"])[:, :15]
     err = np.abs(sp[FX["sp_rows"]] - gold)
+    # spheres (D < 0.7 mm, axis ratio 1): fh - fv is rounding noise, ldr = -300 dB carries no information
+    noise = gold[:, 4] < -150.0
+    assert noise.sum() == 2 and (sp[FX["sp_rows"]][noise, 4:6] < -150.0).all()
+    err[noise, 4:6] = 0.0
     # north-star bar: observables within 0.01 dB / 0.01 deg/km; measured far inside it.  ldr (a 1e-6 ratio of the amplitudes'
     # DIFFERENCE) amplifies the 1e-7 amplitude error most.
     assert err.max() < 1e-3, err.max(0)

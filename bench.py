@@ -9,8 +9,13 @@ scattering_rain.py:236-267 for each of the 246 (band, T) tables and the radar ob
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1: launched under torchrun, one rank per GPU; every rank builds its own jittered W2 replica (weak scaling, no
-data-path collective inside the solve), then the per-particle table records are all-gathered over NCCL.
+N > 1: launched under torchrun, one rank per GPU.  The global table is N W2 sweeps (weak scaling: one sweep's worth of
+particles per GPU; sweep 0 is W2, the others have jittered diameters); the GLOBAL particle list is dealt cost-sorted
+round-robin over the ranks (hydroscatt_b200.dist.ShardPlan), every rank solves and scatters its shard with no data-path
+collective, ONE all-gather over NCCL returns the complete table to every rank, and rank r integrates the PSDs of its
+own 246 tables and copies only those results to the host.  `--scaling strong --replicas R` keeps the global table at R
+sweeps for every N.  Sub-measurements in the same line: the two-layer path at W5's full size (108 150 coated spheroids,
+split over the ranks) and, at N = 1, W1 x 4096.
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, "port") on the host cores.
 """
 import argparse
@@ -218,10 +223,56 @@ def run_reference(args):
                        "ddelt_rescale": True},
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.cpu_tm2l_stride > 0:
+        n2c, t2c = cpu_tm2l_pass(args.cpu_tm2l_stride, cores)
+        line["tm2l"] = {"metric": "two-layer T-matrix particles/s", "value": n2c / t2c, "unit": "particles/s", "cores": cores, "kind": "port",
+                        "sample": f"every {args.cpu_tm2l_stride}th particle of W5 ({n2c} of 108150): oracle/tm2l_oracle.c "
+                                  f"(restated tmatrix_py.f), {t2c:.1f} s"}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+OBS_NORTH_STAR = ("refl_h", "zdr", "kdp", "rho_hv", "A_h", "Adp")   # BASELINE.json north_star: Zh, Zdr, Kdp, rhohv, Ah, Adp
+
+
+def workload_global(replicas):
+    """`replicas` W2 sweeps (replica 0 = W2 itself, the others with diameters jittered by <= 1 %) as ONE flat particle list,
+    table-major: replica r owns tables [246 r, 246 (r + 1))."""
+    ws = [workload_w2(r) for r in range(replicas)]
+    g = {k: np.concatenate([w[k] for w in ws]) for k in ("radius", "wavelength", "mr", "mi", "eps")}
+    g.update(replicas=ws, n_tab=ws[0]["n_tab"], n_D=ws[0]["n_D"], lam_tab=ws[0]["lam_tab"])
+    return g
+
+
+def workload_w5():
+    """W5: two-layer melting-hail profile, 350 D x 309 levels at C band = 108 150 coated spheroids."""
+    nD, nL = 350, 309
+    D = np.tile(np.linspace(0.02, 3.5, nD), nL)                                  # cm
+    fmw = np.repeat(np.linspace(0.02, 0.98, nL), nD)
+    rng = np.random.default_rng(7)
+    return [D, D * (1.0 - 0.5 * fmw) ** (1.0 / 3.0), 1.0 - 0.25 * rng.uniform(0, 1, D.size),
+            np.minimum(1.0, 0.8 + 0.25 * rng.uniform(0, 1, D.size)), np.full(D.size, (8.601 + 1.687j) ** 2),
+            np.full(D.size, (1.78 + 0.002j) ** 2)]
+
+
+def _cpu_tm2l_chunk(cols):
+    import oracle
+    return oracle.tm2l(*cols, 5.35).shape[0]
+
+
+def cpu_tm2l_pass(stride, cores):
+    """Two-layer oracle (restated tmatrix_py.f) on every `stride`-th particle of W5, one process per core."""
+    import multiprocessing as mp
+    w5 = workload_w5()
+    idx = np.arange(0, w5[0].size, stride)
+    nchunk = cores * 4
+    jobs = [[c[idx[k::nchunk]] for c in w5] for k in range(nchunk) if idx[k::nchunk].size]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_tm2l_chunk, jobs, chunksize=1)
+    return idx.size, time.perf_counter() - t0
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -243,36 +294,56 @@ def run_gpu(args):
         dist.barrier()
     from hydroscatt_b200.engine import Engine
     from hydroscatt_b200 import tables
+    from hydroscatt_b200 import dist as hdist
 
     eng = Engine(local)
     dev = eng.device
-    w = workload_w2(rank)
+    # weak scaling (default): the global table is `world` W2 sweeps, so every GPU owns one sweep's worth of particles;
+    # strong: a fixed global table of --replicas sweeps at every N.  Either way the GLOBAL particle list is dealt
+    # cost-sorted round-robin over the ranks (dist.ShardPlan), every rank solves and scatters its shard, ONE all-gather
+    # returns the complete table to every rank, and rank r integrates the PSDs of its own tables.
+    strong = args.scaling == "strong"
+    R = args.replicas if strong else world
+    assert R % world == 0, "--replicas must be a multiple of the number of GPUs"
+    g = workload_global(R)
+    n_glob = g["radius"].size
+    plan = hdist.ShardPlan(hdist.predicted_cost(g["radius"], g["wavelength"], g["mr"], g["mi"], g["eps"]), world, rank)
+    idx = plan.idx
+    n = idx.size
+    rep_per = R // world
+    my_reps = list(range(rank * rep_per, (rank + 1) * rep_per))
+    n_tab, n_D = g["n_tab"], g["n_D"]
     d0, nw, mu = dsd_grid()
     al, be, wt, scale = orientation_nodes()
-    n = w["radius"].size
     n_dsd = d0.size
+    cols = None if os.environ.get("HS_BENCH_OBS", "north_star") == "all" else [tables.OBS_COLUMNS.index(c) for c in OBS_NORTH_STAR]
+    n_obs = 15 if cols is None else len(cols)
 
-    # pinned host inputs (e2e path) and device-resident copies (kernel path)
-    host_in = {k: torch.from_numpy(np.ascontiguousarray(w[k])).pin_memory() for k in ("radius", "wavelength", "mr", "mi", "eps")}
+    # pinned host inputs (e2e path) and device-resident copies (kernel path): this rank's shard of the global list
+    host_in = {k: torch.from_numpy(np.ascontiguousarray(g[k][idx])).pin_memory() for k in ("radius", "wavelength", "mr", "mi", "eps")}
     host_dsd = {k: torch.from_numpy(v).pin_memory() for k, v in (("d0", d0), ("nw", nw), ("mu", mu))}
     dev_in = {k: v.to(dev) for k, v in host_in.items()}
     dev_dsd = {k: v.to(dev) for k, v in host_dsd.items()}
     dmax = torch.full((n_dsd,), 7.0, dtype=torch.float64, device=dev)
     h2d = sum(v.numel() * 8 for v in host_in.values()) + sum(v.numel() * 8 for v in host_dsd.values())
-    host_rows = torch.empty((n, tables.ROW), dtype=torch.float64).pin_memory()
-    host_obs = torch.empty((n_dsd, w["n_tab"], 15), dtype=torch.float64).pin_memory()
-    host_meta = torch.empty((4, n), dtype=torch.int32).pin_memory()
-    d2h = host_rows.numel() * 8 + host_obs.numel() * 8 + host_meta.numel() * 4
-    gathered = torch.empty((world * n, tables.ROW), dtype=torch.float64, device=dev) if world > 1 else None
+    n_rows_mine = rep_per * n_tab * n_D
+
+    def host_bufs():
+        return dict(rows=torch.empty((n_rows_mine, tables.ROW), dtype=torch.float64).pin_memory(),
+                    obs=torch.empty((rep_per, n_dsd, n_tab, n_obs), dtype=torch.float64).pin_memory(),
+                    meta=torch.empty((4, n), dtype=torch.int32).pin_memory())
+
+    host_out = [host_bufs(), host_bufs()]
+    d2h = sum(t.numel() * t.element_size() for t in host_out[0].values())
+    full_buf = torch.empty((n_glob, tables.ROW), dtype=torch.float64, device=dev) if world > 1 else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     stage_ms = {"calctmat": 0.0, "scatter": 0.0, "psd": 0.0}
     last = {}
-
     split = {"on": False}
 
     def step(inp, dsd, timed):
-        e = [ev() for _ in range(5)]
+        e = [ev() for _ in range(6)]
         e[0].record()
         if args.unfused_scatter or split["on"]:
             tb = eng.calctmat(inp["radius"], inp["wavelength"], inp["mr"], inp["mi"], inp["eps"], ddelt=DDELT, ndgs=NDGS)
@@ -286,31 +357,30 @@ def run_gpu(args):
                                                 ddelt=DDELT, ndgs=NDGS)
             e[1].record()
         e[2].record()
+        rows = eng.pack_rows(S, Z, xs, tb.lam, 0, 1)              # hs_pack_rows: the 56-double table records of the shard
         e[3].record()
-        rows = torch.empty((n, tables.ROW), dtype=torch.float64, device=dev)
-        Sr = torch.view_as_real(S).reshape(n, 2, 8)
-        rows[:, 0:8], rows[:, 8:24] = Sr[:, 0], Z[:, 0].reshape(n, 16)
-        rows[:, 24:32], rows[:, 32:48] = Sr[:, 1], Z[:, 1].reshape(n, 16)
-        rows[:, 48:50], rows[:, 50:52] = xs[:, 0], xs[:, 1]
-        ext_h, ext_v = 2.0 * tb.lam * Sr[:, 1, 7], 2.0 * tb.lam * Sr[:, 1, 1]
-        rows[:, 52], rows[:, 53], rows[:, 54], rows[:, 55] = ext_h, ext_v, ext_h, ext_v
         if world > 1:
-            dist.all_gather_into_tensor(gathered, rows)  # every rank ends up with every replica's scatter tables
-        obs, _ = tables.integrate_psd(eng, rows, w["n_tab"], w["D"], "gamma", dsd["d0"], dsd["nw"], dsd["mu"], dmax,
-                                      w["lam_tab"], rule="trapz", want_integ=False)
+            full = plan.gather(rows, eng=eng, out=full_buf)       # all_gather_into_tensor (NCCL) + hs_gather_rows
+            mine = full[rank * n_rows_mine:(rank + 1) * n_rows_mine]
+        else:
+            mine = rows                                           # one rank: the shard is the table, already in table order
         e[4].record()
+        obs = []
+        for q, r in enumerate(my_reps):
+            w = g["replicas"][r]
+            o, _ = tables.integrate_psd(eng, mine[q * n_tab * n_D:(q + 1) * n_tab * n_D], n_tab, w["D"], "gamma", dsd["d0"], dsd["nw"],
+                                        dsd["mu"], dmax, w["lam_tab"], rule="trapz", want_integ=False, columns=cols)
+            obs.append(o)
+        e[5].record()
         if timed:
             last["e"] = e
-        last.update(tb=tb, rows=rows, obs=obs)
-        return tb, rows, obs
+        last.update(tb=tb, rows=mine, obs=obs)
+        return tb, mine, obs
 
     # End-to-end step: pinned host inputs -> device -> tables + observables -> pinned host results.  The D2H copies of
     # step k run on a copy stream and overlap the compute of step k+1 (two sets of host result buffers); every step
     # still moves all of its own inputs and results inside the timed region.
     copy_stream = torch.cuda.Stream(dev)
-    host_out = [dict(rows=host_rows, obs=host_obs, meta=host_meta),
-                dict(rows=torch.empty_like(host_rows).pin_memory(), obs=torch.empty_like(host_obs).pin_memory(),
-                     meta=torch.empty_like(host_meta).pin_memory())]
     copied = [None, None]
 
     def step_e2e(k=0):
@@ -324,15 +394,16 @@ def run_gpu(args):
         ready.record()
         copy_stream.wait_event(ready)
         with torch.cuda.stream(copy_stream):
-            for t in (rows, obs, tb.nmax, tb.ngauss, tb.ntrials, tb.status):
+            for t in [rows, tb.nmax, tb.ngauss, tb.ntrials, tb.status] + obs:
                 t.record_stream(copy_stream)
             hb["rows"].copy_(rows, non_blocking=True)
-            # 274 MB of observables: in 32 pieces, so that the pipeline's small host<->device transfers of the next step are
-            # not queued behind one 5 ms DMA (measured: 11.7 -> 11.3 ms per end-to-end step)
-            nch = int(os.environ.get("HS_BENCH_D2H_CHUNKS", "32"))
-            for c in range(nch):
-                a_, b_ = c * n_dsd // nch, (c + 1) * n_dsd // nch
-                hb["obs"][a_:b_].copy_(obs[a_:b_], non_blocking=True)
+            # the observables in pieces, so that the pipeline's small host<->device transfers of the next step are not
+            # queued behind one multi-millisecond DMA
+            nch = int(os.environ.get("HS_BENCH_D2H_CHUNKS", "16"))
+            for q, o in enumerate(obs):
+                for c in range(nch):
+                    a_, b_ = c * n_dsd // nch, (c + 1) * n_dsd // nch
+                    hb["obs"][q, a_:b_].copy_(o[a_:b_], non_blocking=True)
             hb["meta"][0].copy_(tb.nmax, non_blocking=True)
             hb["meta"][1].copy_(tb.ngauss, non_blocking=True)
             hb["meta"][2].copy_(tb.ntrials, non_blocking=True)
@@ -361,6 +432,7 @@ def run_gpu(args):
         sync_all()
         ms_total = t0.elapsed_time(t1)
     launches = eng.launch_count - l0
+    coll_ms = last["e"][3].elapsed_time(last["e"][4]) if world > 1 else 0.0
     # stage split (and the roofline of the dominant stage): a short pass with the T-matrix and scatter calls issued
     # separately, so that CUDA events on the launching stream bracket each stage
     split["on"] = True
@@ -372,7 +444,7 @@ def run_gpu(args):
         step(dev_in, dev_dsd, True)
         sync_all()
         e = last["e"]
-        for k, (a, b) in zip(("calctmat", "scatter", "psd"), ((0, 1), (1, 2), (3, 4))):
+        for k, (a, b) in zip(("calctmat", "scatter", "psd"), ((0, 1), (1, 2), (4, 5))):
             acc[k] += e[a].elapsed_time(e[b]) / nsplit
     stage_ms.update(acc)
     split["on"] = False
@@ -391,46 +463,69 @@ def run_gpu(args):
     wall_e2e = (time.perf_counter() - tw0) * 1e3
     ms_e2e = max(ms_e2e, wall_e2e)  # host-side work counts for the end-to-end number
 
-    # second half of the headline metric: two-layer (tm2l) particles, W5-like synthetic coated hail
-    rng = np.random.default_rng(7 + rank)
-    n2 = 148 * 40
-    D2 = np.linspace(0.01, 3.5, n2)
-    fmw = rng.uniform(0.05, 0.95, n2)
-    t2_in = (D2, D2 * (1.0 - 0.5 * fmw) ** (1.0 / 3.0), 1.0 - 0.25 * rng.uniform(0, 1, n2),
-             np.minimum(1.0, 1.0 - 0.25 * rng.uniform(0, 1, n2) + 0.05), np.full(n2, (8.601 + 1.687j) ** 2),
-             np.full(n2, (1.78 + 0.002j) ** 2))
-    t2_dev = [torch.from_numpy(np.ascontiguousarray(np.real(a))).to(dev) for a in t2_in[:4]]
-    t2_eps = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in t2_in[4:]]
-    eng.tm2l(*t2_dev, *t2_eps, 5.35)
+    # second half of the headline metric: the two-layer (tm2l) path at W5's full size (350 D x 309 levels =
+    # 108 150 coated spheroids), the particle list split evenly over the ranks (independent particles, no collective)
+    w5 = workload_w5()
+    n5 = w5[0].size
+    sl5 = slice(rank * n5 // world, (rank + 1) * n5 // world)
+    t2_dev = [torch.from_numpy(np.ascontiguousarray(a[sl5])).to(dev) for a in w5]
+    eng.tm2l(*t2_dev, 5.35)
     sync_all()
     q0, q1 = ev(), ev()
     q0.record()
-    for _ in range(3):
-        eng.tm2l(*t2_dev, *t2_eps, 5.35)
+    for _ in range(2):
+        amp5, st5 = eng.tm2l(*t2_dev, 5.35)
     q1.record()
     sync_all()
-    ms_tm2l = q0.elapsed_time(q1) / 3.0
+    ms_tm2l = q0.elapsed_time(q1) / 2.0
+    bad5 = int((st5 != 0).sum().item())
 
-    tms = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    # W1 x 4096 (the C-band 10 degC rain grid replicated 4096 times with jitter = 286 720 spheroids), one GPU only
+    ms_w1 = None
+    if world == 1 and not args.no_sublines:
+        from tests.workloads import rain_grid
+        Rw = 4096
+        wg = rain_grid("C")
+        rng = np.random.default_rng(1234)
+        jd = 1.0 + rng.uniform(-0.02, 0.02, (Rw, 70))
+        jm = 1.0 + rng.normal(0.0, 1e-3, (Rw, 70))
+        w1 = [(wg["radius"] * jd).ravel(), np.tile(wg["wavelength"], Rw), (wg["mr"] * jm).ravel(), (wg["mi"] * jm).ravel(),
+              np.tile(wg["axis_ratio"], Rw)]
+        w1d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in w1]
+        run_w1 = lambda: eng.calctmat_scatter(*w1d, [GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, ddelt=DDELT, ndgs=NDGS)
+        run_w1()
+        torch.cuda.synchronize()
+        q0, q1 = ev(), ev()
+        q0.record()
+        for _ in range(3):
+            tb1 = run_w1()[0]
+        q1.record()
+        torch.cuda.synchronize()
+        ms_w1 = q0.elapsed_time(q1) / 3.0
+        bad1 = int((tb1.status != 0).sum().item())
+        del w1d, tb1
+
+    tms = torch.tensor([ms_total, ms_e2e, ms_tm2l, coll_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = tms.tolist()
+    ms_total, ms_e2e, ms_tm2l, coll_ms = tms.tolist()
 
     tb = last["tb"]
     nmax = tb.nmax.cpu().numpy()
     ngauss = tb.ngauss.cpu().numpy()
     status = tb.status.cpu().numpy()
-    fl_tm, fl_am = algorithmic_flops(w, nmax, ngauss)
+    wl = {"radius": g["radius"][idx], "wavelength": g["wavelength"][idx], "mr": g["mr"][idx], "mi": g["mi"][idx], "eps": g["eps"][idx]}
+    fl_tm, fl_am = algorithmic_flops(wl, nmax, ngauss)
     if rank == 0:
         ms_step = ms_total / args.steps
-        units = n * world
+        units = n_glob
         value = units / (ms_step * 1e-3)
         dom = max(stage_ms, key=stage_ms.get)
         dom_fl = {"calctmat": fl_tm.sum(), "scatter": fl_am.sum()}.get(dom, fl_tm.sum())
         dom_kernel = {"calctmat": "k_st_assemble (+k_st_radial, k_st_wigner, k_st_mode_small)", "scatter": "k_scatter", "psd": "k_psd_obs_fused"}[dom]
         ach = dom_fl / (stage_ms[dom] * 1e-3) / 1e12
         cores = os.cpu_count() or 1
-        cpu = None
+        cpu = cpu2 = None
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
@@ -438,18 +533,32 @@ def run_gpu(args):
             cpu = {"value": ncpu / tcpu, "unit": "solves/s", "cores": cores, "kind": "port",
                    "sample": f"every {args.cpu_stride}th particle of W2 ({ncpu} of 17220): calctmat + 2x50 calcampl, "
                              f"no cross sections / PSD integration, {tcpu:.1f} s"}
+            n2c, t2c = cpu_tm2l_pass(args.cpu_tm2l_stride, cores)
+            cpu2 = {"value": n2c / t2c, "unit": "particles/s", "cores": cores, "kind": "port",
+                    "sample": f"every {args.cpu_tm2l_stride}th particle of W5 ({n2c} of {n5}): oracle/tm2l_oracle.c (restated tmatrix_py.f), {t2c:.1f} s"}
+        traffic, traffic_note = None, "no ncu capture committed"
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic, traffic_note = tj.get("calctmat_stage_dram_bytes_per_step"), tj.get("note")
         line = {
             "metric": "T-matrix solves/s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": W2_NAME,
-                       "l2": "working set per step (0.35 GB T arena, 0.3-0.7 GB stage scratch, 0.27 GB observables) exceeds the 126 MB L2",
-                       "psd_output": "15 observables per (DSD, table); the integrated S/Z array is not materialised",
-                       "parallelism": f"particles sharded x{world}" if world > 1 else "single GPU",
+            "config": {"workload": W2_NAME if R == 1 else W2_NAME.replace("per GPU", "per sweep") + f"; global table = {R} sweeps "
+                       f"(sweep 0 = W2, the others with diameters jittered <= 1 %) = {n_glob} spheroids, {R * n_tab} tables",
+                       "l2": "working set per step (0.35 GB T arena, 0.3-0.7 GB stage scratch, 0.1-0.27 GB observables) exceeds the 126 MB L2",
+                       "psd_output": f"{n_obs} observables per (DSD, table)" + (" (" + ", ".join(OBS_NORTH_STAR) + ": the set BASELINE north_star names; "
+                                     "HS_BENCH_OBS=all writes the 15-column frame)" if cols is not None else "") +
+                                     "; the integrated S/Z array is not materialised",
+                       "parallelism": (f"global particle list dealt cost-sorted round-robin over {world} ranks (dist.ShardPlan), one "
+                                       f"all_gather_into_tensor of the table records per step, PSD integration sharded by table")
+                       if world > 1 else "single GPU",
                        "ddelt_rescale": True},
             "clocks": clk.summary(),
-            "e2e": {"value": units / (ms_e2e / args.steps * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": units / (ms_e2e / args.steps * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
+                    "note": "bytes summed over the ranks; every rank copies its shard's inputs in and its own tables + observables out"},
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
             "stage_ms_note": "stages timed in a separate pass with hs_calctmat_batch and hs_scatter_batch issued one after the other; "
@@ -458,7 +567,8 @@ def run_gpu(args):
             # DMMA contraction + fused solve, k_st_mode_small), timed live with CUDA events on the launching stream; its
             # kernels overlap on several streams, so the stage (not one launch) is the unit
             "roofline": {"bound": "tensor", "kernel": dom_kernel, "achieved": ach, "peak": peak_tensor_tf if dom == "calctmat" else peak_tf,
-                         "unit": "TFLOP/s", "frac": ach / (peak_tensor_tf if dom == "calctmat" else peak_tf), "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach / (peak_tensor_tf if dom == "calctmat" else peak_tf), "traffic": traffic,
+                         "traffic_note": traffic_note,
                          "pipe": "FP64 tensor core (DMMA m8n8k4) + FP64 FMA" if dom == "calctmat" else "FP64 FMA",
                          "peak_source": "measured in this run (hs_fp64_tensor_peak: DMMA m8n8k4 loop %.1f TFLOP/s; hs_fp64_peak: DFMA loop "
                                         "%.1f TFLOP/s); MEASURED_PEAKS.json has no FP64 figure" % (peak_tensor_tf, peak_tf),
@@ -468,15 +578,24 @@ def run_gpu(args):
                          "scatter_note": "the scatter figure counts SURVEY 8(d)'s per-call flops (one calcampl per orientation and "
                                          "geometry, plus the cross sections); the fused kernel shares one T-matrix sweep between "
                                          "them and executes ~12x fewer real flops, so it is a work-equivalent rate, not a pipe utilisation"},
-            "tm2l": {"metric": "two-layer T-matrix particles/s", "value": n2 * world / (ms_tm2l * 1e-3),
-                     "particles": n2, "ms": ms_tm2l, "algorithmic_flop_per_particle": 4.8e7,
-                     "achieved_tflops": 4.8e7 * n2 / (ms_tm2l * 1e-3) / 1e12,
-                     "frac_of_fp64_peak": 4.8e7 * n2 / (ms_tm2l * 1e-3) / 1e12 / peak_tf},
+            "tm2l": {"metric": "two-layer T-matrix particles/s", "workload": "W5 melting-hail profile 350 D x 309 levels, C band"
+                     + (f", split over {world} ranks" if world > 1 else ""), "value": n5 / (ms_tm2l * 1e-3),
+                     "particles": n5, "ms": ms_tm2l, "status_nonzero_rank0": bad5, "algorithmic_flop_per_particle": 4.8e7,
+                     "achieved_tflops": 4.8e7 * n5 / (ms_tm2l * 1e-3) / 1e12,
+                     "frac_of_fp64_peak": 4.8e7 * n5 / world / (ms_tm2l * 1e-3) / 1e12 / peak_tf},
             "status_counts": {str(k): int((status == k).sum()) for k in np.unique(status)},
             "nmax_range": [int(nmax.min()), int(nmax.max())],
         }
+        if world > 1:
+            line["collective"] = {"op": "all_gather_into_tensor (NCCL) + hs_gather_rows reorder", "bytes_per_rank": n * tables.ROW * 8,
+                                  "ms": coll_ms}
+        if ms_w1 is not None:
+            line["w1x4096"] = {"workload": "W1 x 4096: C-band 10 degC rain grid, 70 D x 4096 jittered replicas", "particles": 70 * 4096,
+                               "ms": ms_w1, "value": 70 * 4096 / (ms_w1 * 1e-3), "unit": "solves/s", "status_nonzero": bad1,
+                               "what": "T-matrices + 2 geometries x 50 orientations + cross sections (hs_calctmat_scatter_batch)"}
         if cpu:
             line["cpu_baseline"] = cpu
+            line["tm2l"]["cpu_baseline"] = cpu2
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -490,6 +609,11 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-stride", type=int, default=1, dest="cpu_stride")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sublines", action="store_true", dest="no_sublines", help="skip the W1 x 4096 sub-measurement")
+    ap.add_argument("--cpu-tm2l-stride", type=int, default=8, dest="cpu_tm2l_stride")
+    ap.add_argument("--scaling", default="weak", choices=("weak", "strong"),
+                    help="weak (default): one W2 sweep per GPU; strong: a fixed global table of --replicas sweeps at every N")
+    ap.add_argument("--replicas", type=int, default=8)
     ap.add_argument("--unfused-scatter", action="store_true", dest="unfused_scatter",
                     help="separate hs_calctmat_batch / hs_scatter_batch calls (per-stage timing) instead of hs_calctmat_scatter_batch")
     args = ap.parse_args()

@@ -43,6 +43,11 @@ SIGNATURES = {
                                  C.c_int, C.c_double, _dp, C.c_void_p]),
     "hs_psd_observables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int,
                                      _dp, C.c_void_p]),
+    "hs_psd_observables_sel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int), _dp, C.c_void_p]),
+    "hs_pack_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
+                               C.c_void_p]),
+    "hs_gather_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, _dp, _dp, _dp, C.c_void_p]),
     "hs_canting_observables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_longlong, C.c_longlong, _dp, C.c_double,
                                          C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_void_p]),
     "hs_canting_mixture": (C.c_int, [C.c_void_p, C.c_longlong, _dp, _dp, _dp, C.c_void_p]),

@@ -139,9 +139,12 @@ __global__ void k_observables(int n, int stride, const double *in, int ob, int o
 #define PSDF_NC 16
 __constant__ int c_psdf_col[PSDF_NC] = {8, 9, 12, 13, 18, 19, 22, 23, 24, 25, 30, 31, 54, 55, 48, 49};
 
+// caller-selected observable columns (hs_psd_observables_sel): n columns, in the caller's order
+struct PsdSel { int n; signed char col[15]; };
+
 __global__ void __launch_bounds__(256) k_psd_obs_fused(int n_dsd, int n_D, int n_tab, int tabs_per_cta, const double *__restrict__ W,
                                                         const double *__restrict__ rows, const double *__restrict__ lam_tab,
-                                                        double kw_sqr, int hpol_quirk, int want_sca, double *__restrict__ obs)
+                                                        double kw_sqr, int hpol_quirk, int want_sca, PsdSel sel, double *__restrict__ obs)
 {
     extern __shared__ double psm[];
     const int ldw = n_D | 1;
@@ -221,15 +224,58 @@ __global__ void __launch_bounds__(256) k_psd_obs_fused(int n_dsd, int n_D, int n
             }
         }
         __syncthreads();
-        // coalesced store: the 4 tables x 15 observables of a DSD are contiguous in obs
+        // coalesced store: the 4 tables x n_sel observables of a DSD are contiguous in obs
         {
-            const int nt_ = min(PSDF_TB, t_end - t0), rowlen = nt_ * 15;
-            for (int e = tid; e < PSDF_RB * rowlen; e += 256) {
-                const int r = e / rowlen, k = e - r * rowlen;
-                if (r0 + r < n_dsd) obs[((long)(r0 + r) * n_tab + t0) * 15 + k] = sT[r * 61 + k];
+            const int nt_ = min(PSDF_TB, t_end - t0), rowlen = nt_ * sel.n;
+            if (sel.n == 15) {
+                for (int e = tid; e < PSDF_RB * rowlen; e += 256) {
+                    const int r = e / rowlen, k = e - r * rowlen;
+                    if (r0 + r < n_dsd) obs[((long)(r0 + r) * n_tab + t0) * 15 + k] = sT[r * 61 + k];
+                }
+            } else {
+                for (int e = tid; e < PSDF_RB * rowlen; e += 256) {
+                    const int r = e / rowlen, k = e - r * rowlen, tt = k / sel.n, q = k - tt * sel.n;
+                    if (r0 + r < n_dsd) obs[((long)(r0 + r) * n_tab + t0) * sel.n + k] = sT[r * 61 + tt * 15 + sel.col[q]];
+                }
             }
         }
     }
+}
+
+// Table records (tables.py layout, 56 doubles) from the outputs of hs_scatter_batch: S [n][G][2][2] complex, Z [n][G][4][4],
+// xs [n][G][2]; gb / gf = geometry index of the back / forward geometry, fb / ff = index of the geometry holding the forward
+// amplitude at the back / forward geometry's incidence direction (optical theorem: ext_h = 2 lambda Im S22, ext_v = 2 lambda Im S11).
+__global__ void k_pack_rows(int n, int G, const double *__restrict__ S, const double *__restrict__ Z, const double *__restrict__ xs,
+                            const double *__restrict__ lam, int gb, int gf, int fb, int ff, double *__restrict__ rows)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n * 56) return;
+    const int i = (int)(idx / 56), c = (int)(idx - (long)i * 56);
+    double v;
+    if (c < 48) {
+        const int g = c < 24 ? gb : gf, k = c < 24 ? c : c - 24;
+        v = k < 8 ? S[((long)i * G + g) * 8 + k] : Z[((long)i * G + g) * 16 + (k - 8)];
+    } else if (c < 52) {
+        const int g = c < 50 ? gb : gf;
+        v = xs[((long)i * G + g) * 2 + (c & 1)];
+    } else {
+        const int f = c < 54 ? fb : ff;
+        v = 2.0 * lam[i] * S[((long)i * G + f) * 8 + ((c & 1) ? 1 : 7)];
+    }
+    rows[idx] = v;
+}
+
+// dst[i][:] = src[index[i]][:]  (ncol doubles per record; index < 0: record left untouched).  Puts all-gathered shard records
+// back into table order (hydroscatt_b200/dist.py).
+__global__ void k_gather_rows(long n_out, int ncol, const double *__restrict__ src, const long long *__restrict__ index,
+                              double *__restrict__ dst)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_out * ncol) return;
+    const long i = idx / ncol;
+    const int c = (int)(idx - i * ncol);
+    const long long j = index[i];
+    if (j >= 0) dst[idx] = src[j * ncol + c];
 }
 
 #endif  // HS_HOST_EMU

@@ -1,4 +1,6 @@
 // hs_tm2l.cuh -- two-layer (coated spheroid) EBCM T-matrix, one particle per CTA, everything resident in shared memory.
+// The CTA is warp-specialised: 8 assembly warps integrate the six matrices of azimuthal mode m + 1 while 4 solver warps run
+// the latency-bound chain of mode m (T2 = x^-1 y, the two products, T = Bn^-1 X, far field) out of a second matrix buffer.
 //
 // Replaces the reference's Fortran program hydroscatt/f_2l_tmatrix/tmatrix_py.f (f2py module tm2l; rows F1-F11 of
 // SURVEY.md 8(a)): rddata (:476-790), quad (:1340-1595), gener (:792-1338), genlgp (:1597-1670), genbsl/bessel
@@ -14,6 +16,9 @@
 #include "hs_compat.cuh"
 #include "hs_tmat.cuh"
 #include "hs_patterson31.h"
+#ifndef HS_HOST_EMU
+#include "hs_staged.cuh"   // solve_grp2s: the shared-space Gauss-Jordan of the single-layer pipeline
+#endif
 
 namespace hs {
 
@@ -216,6 +221,10 @@ __device__ inline void t2_genlgp(double theta, double sinth, double costh, int k
 }
 
 // shared-memory layout of one particle (offsets in doubles)
+struct T2Mat {
+    double2 *A, *B, *C, *D;  // [2][17][17] parity-class matrices of a, b, c, d
+    double2 *aug;            // [2][17][34]: [x | y] -> [. | T2] -> [Bn | X] -> [. | T]
+};
 struct T2Smem {
     // node scalars [31]
     double *sinth, *costh, *ckr, *dckr, *ckp2r, *ckp2i, *dkp2r, *dkp2i, *theta;
@@ -224,16 +233,15 @@ struct T2Smem {
     // column tables [31][17]
     double *jkr, *jki, *hkr, *hki, *j3r, *j3i, *rbkr, *rbki, *rhkr, *rhki, *rbk2r, *rbk2i;
     double *pn;       // [31][18]
-    double2 *A, *B, *C, *D;  // [2][17][17] parity-class matrices of a, b, c, d
-    double2 *aug;     // [2][17][34]: [x | y] then [b - T2 c ... ] see below
-    double2 *aug2;    // [2][17][34]
+    T2Mat mat[2];     // matrix buffers of two consecutive modes (assembly of m + 1 overlaps the solve chain of m)
 };
 #define T2_TAB (T2_NNODE * T2_NRANK)
-__host__ __device__ inline int t2_smem_doubles()
+#define T2_MAT_DOUBLES (2 * (4 * 2 * 289 + 2 * 17 * 34))
+__host__ __device__ inline int t2_smem_doubles(int nbuf = 2)
 {
-    return 9 * T2_NNODE + 25 * T2_TAB + T2_NNODE * T2_NRANKI + 2 * (4 * 2 * 289 + 2 * 2 * 17 * 34);
+    return 9 * T2_NNODE + 25 * T2_TAB + T2_NNODE * T2_NRANKI + nbuf * T2_MAT_DOUBLES;
 }
-__device__ inline void t2_carve(T2Smem &s, double *p)
+__device__ inline void t2_carve(T2Smem &s, double *p, int nbuf = 2)
 {
     s.sinth = p; p += T2_NNODE; s.costh = p; p += T2_NNODE; s.ckr = p; p += T2_NNODE; s.dckr = p; p += T2_NNODE;
     s.ckp2r = p; p += T2_NNODE; s.ckp2i = p; p += T2_NNODE; s.dkp2r = p; p += T2_NNODE; s.dkp2i = p; p += T2_NNODE;
@@ -243,12 +251,16 @@ __device__ inline void t2_carve(T2Smem &s, double *p)
                          &s.rhkr, &s.rhki, &s.rbk2r, &s.rbk2i};
     for (int i = 0; i < 25; i++) { *tabs[i] = p; p += T2_TAB; }
     s.pn = p; p += T2_NNODE * T2_NRANKI;
-    s.A = reinterpret_cast<double2 *>(p); p += 2 * 2 * 289;
-    s.B = reinterpret_cast<double2 *>(p); p += 2 * 2 * 289;
-    s.C = reinterpret_cast<double2 *>(p); p += 2 * 2 * 289;
-    s.D = reinterpret_cast<double2 *>(p); p += 2 * 2 * 289;
-    s.aug = reinterpret_cast<double2 *>(p); p += 2 * 2 * 17 * 34;
-    s.aug2 = reinterpret_cast<double2 *>(p);
+    if ((9 * T2_NNODE + 25 * T2_TAB + T2_NNODE * T2_NRANKI) & 1) p++;  // (even: 14012 doubles, double2-aligned)
+    for (int b = 0; b < 2; b++) {
+        T2Mat &m = s.mat[b];
+        if (b >= nbuf) { m = s.mat[0]; continue; }
+        m.A = reinterpret_cast<double2 *>(p); p += 2 * 2 * 289;
+        m.B = reinterpret_cast<double2 *>(p); p += 2 * 2 * 289;
+        m.C = reinterpret_cast<double2 *>(p); p += 2 * 2 * 289;
+        m.D = reinterpret_cast<double2 *>(p); p += 2 * 2 * 289;
+        m.aug = reinterpret_cast<double2 *>(p); p += 2 * 2 * 17 * 34;
+    }
 }
 
 struct T2Args {
@@ -259,29 +271,53 @@ struct T2Args {
     int *status;   // [n]
 };
 
+// a group of threads that works on one phase: lane `tid` of `nt`, synchronised by named barrier `bar` (0 = whole CTA)
+struct T2Grp {
+    int tid, nt, bar;
+};
+__device__ __forceinline__ void t2_sync(const T2Grp &g)
+{
+#ifndef HS_HOST_EMU
+    if (g.bar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(g.bar), "r"(g.nt) : "memory");
+#else
+    (void)g;
+#endif
+}
+
+// per-particle constants (rddata, tmatrix_py.f:580-620, 740), recomputed by every thread
+struct T2Par {
+    double cpi, dtr, aovrb, aovrb2, conk, conk2, sigma, rtsfct, diff;
+    cd eps1, sq1, qs1, sq2, rat12, sqrat, qsrat;
+};
+__device__ inline T2Par t2_par(const T2Args &a, int p)
+{
+    T2Par P;
+    P.cpi = 3.1415927410125732;  // 4.0*atan(1.0) in single precision (tmatrix_py.f:161)
+    P.dtr = P.cpi / 180.0;
+    const double third = 0.3333333432674408;  // the single-precision literal 1./3.
+    const double dpart = a.dpart[p], dcore = a.dcore[p], alamd = a.alamd;
+    P.aovrb = a.aovrb[p]; P.aovrb2 = a.aovrb2[p];
+    P.conk = P.cpi * dpart / (alamd * pow(P.aovrb, third));
+    P.conk2 = P.cpi * dcore / (alamd * pow(P.aovrb2, third));
+    P.sigma = 2.0 * alamd / (P.cpi * 100.0);
+    P.eps1 = mk(a.eor[p], a.eoi[p]);
+    const cd eps2 = mk(a.eir[p], a.eii[p]);
+    P.sq1 = croot(P.eps1); P.qs1 = mk(1.0, 0.0) / P.sq1; P.sq2 = croot(eps2);
+    P.rat12 = eps2 / P.eps1; P.sqrat = croot(P.rat12); P.qsrat = mk(1.0, 0.0) / P.sqrat;
+    P.rtsfct = 8.0 / P.conk;
+    P.diff = (P.cpi / 2.0) / 2.0;
+    return P;
+}
+
 __device__ __forceinline__ cd ld2(const double *re, const double *im, int i) { return mk(re[i], im[i]); }
 
-// One particle per CTA.
-__device__ void tm2l_particle(const T2Args &a, int p, double *smem, Ctl *ctl, double *s_cmx, double *s_acc,
-                              const int tid, const int nt)
+// ---- K1: node geometry + radial functions (4 task kinds x 31 nodes); ends with a group barrier ----
+__device__ void t2_tables(const T2Par &P, T2Smem &s, const T2Grp &g)
 {
-    T2Smem s;
-    t2_carve(s, smem);
-    const double cpi = 3.1415927410125732;  // 4.0*atan(1.0) in single precision (tmatrix_py.f:161)
-    const double dtr = cpi / 180.0;
-    const double third = 0.3333333432674408;  // the single-precision literal 1./3.
-    const double dpart = a.dpart[p], dcore = a.dcore[p], aovrb = a.aovrb[p], aovrb2 = a.aovrb2[p], alamd = a.alamd;
-    const double conk = cpi * dpart / (alamd * pow(aovrb, third));
-    const double conk2 = cpi * dcore / (alamd * pow(aovrb2, third));
-    const double sigma = 2.0 * alamd / (cpi * 100.0);
-    const cd eps1 = mk(a.eor[p], a.eoi[p]), eps2 = mk(a.eir[p], a.eii[p]);
-    const cd sq1 = croot(eps1), qs1 = mk(1.0, 0.0) / sq1, sq2 = croot(eps2);
-    const cd rat12 = eps2 / eps1, sqrat = croot(rat12), qsrat = mk(1.0, 0.0) / sqrat;
-    const double rtsfct = 8.0 / conk;
-    const double diff = (cpi / 2.0) / 2.0, sum0 = (cpi / 2.0) / 2.0;
-
-    // ---- K1: node geometry + radial functions (4 task kinds x 31 nodes) ----
-    for (int t = tid; t < T2_NNODE; t += nt) {
+    const double sum0 = P.diff, diff = P.diff;
+    const cd sq1 = P.sq1, sq2 = P.sq2, sqrat = P.sqrat;
+    for (int t = g.tid; t < T2_NNODE; t += g.nt) {
         double theta;
         if (t == 0) theta = sum0;
         else {
@@ -292,20 +328,20 @@ __device__ void tm2l_particle(const T2Args &a, int p, double *smem, Ctl *ctl, do
         double sn, cs;
         sincos(theta, &sn, &cs);
         s.theta[t] = theta; s.sinth[t] = sn; s.costh[t] = cs;
-        double bovra = 1.0 / aovrb;
+        double bovra = 1.0 / P.aovrb;
         double qb = 1.0 / sqrt((bovra * cs) * (bovra * cs) + sn * sn);
-        s.ckr[t] = conk * qb;
-        s.dckr[t] = conk * cs * sn * (bovra * bovra - 1.0) * qb * qb * qb;
-        double bovra2 = 1.0 / aovrb2;
+        s.ckr[t] = P.conk * qb;
+        s.dckr[t] = P.conk * cs * sn * (bovra * bovra - 1.0) * qb * qb * qb;
+        double bovra2 = 1.0 / P.aovrb2;
         double qb2 = 1.0 / sqrt((bovra2 * cs) * (bovra2 * cs) + sn * sn);
-        double ckr2 = conk2 * qb2, dckr2 = conk2 * cs * sn * (bovra2 * bovra2 - 1.0) * qb2 * qb2 * qb2;
+        double ckr2 = P.conk2 * qb2, dckr2 = P.conk2 * cs * sn * (bovra2 * bovra2 - 1.0) * qb2 * qb2 * qb2;
         s.ckp2r[t] = sq1.x * ckr2; s.ckp2i[t] = sq1.y * ckr2;
         s.dkp2r[t] = sq1.x * dckr2; s.dkp2i[t] = sq1.y * dckr2;
         // park kr2 for the iswt=3 task
         s.pn[t] = ckr2;
     }
-    __syncthreads();
-    for (int task = tid; task < 4 * T2_NNODE; task += nt) {
+    t2_sync(g);
+    for (int task = g.tid; task < 4 * T2_NNODE; task += g.nt) {
         const int kind = task / T2_NNODE, t = task - kind * T2_NNODE;
         const int o = t * T2_NRANK;
         if (kind == 0) {
@@ -348,293 +384,415 @@ __device__ void tm2l_particle(const T2Args &a, int p, double *smem, Ctl *ctl, do
             }
         }
     }
-    for (int w = tid; w < 4; w += nt) s_acc[w * 2] = s_acc[w * 2 + 1] = 0.0;  // acans: [fwd pol1, fwd pol2, back pol1, back pol2]
-    __syncthreads();
+    t2_sync(g);
+}
 
+__device__ __forceinline__ double t2_prodm(int kmv)
+{
+    double prodm = 1.0;
+    if (kmv > 0) {
+        double quanm = kmv;
+        for (int i = 1; i <= kmv; i++) { quanm += 1.0; prodm = quanm * prodm / 2.0; }
+    }
+    return prodm;
+}
+
+// The 12 complex integrand values of one (irow, icol) pair (gener, tmatrix_py.f:1000-1338) summed over the quadrature nodes
+// [step0, step1) of the 31-node Patterson rule (quad, :1340-1595: step < 30 -> node step + 1, weight PAT31_W[step / 2]; step 30
+// -> the centre node).  EVEN: irow + icol even -> sub-blocks J (acc 0..5: a b c d x y) and K (acc 6..11); else I and L.
+template <bool EVEN>
+__device__ __forceinline__ void t2_pair_nodes(const T2Par &P, const T2Smem &s, int kmv, int irow, int icol, int step0, int step1, cd *acc)
+{
+    const double cmv = kmv, em = kmv > 0 ? 2.0 : 1.0, qem = -2.0 / em, cm2 = cmv * cmv;
+    const cd eps1 = P.eps1, qs1 = P.qs1, rat12 = P.rat12, qsrat = P.qsrat;
+    const double crow = irow, ccol = icol, crow1 = crow + 1.0, ccol1 = ccol + 1.0;
+    const double crowm = cmv + crow, ccolm = cmv + ccol, crij = crow + ccol, crssij = crow * ccol;
+    for (int step = step0; step < step1; step++) {
+        const int t = (step < 30) ? step + 1 : 0;
+        const double w = (step < 30) ? PAT31_W[step >> 1] : PAT31_WC;
+        const int ro = t * T2_NRANK + irow - 1, co = t * T2_NRANK + icol - 1;
+        const double sinth = s.sinth[t], costh = s.costh[t], ckr = s.ckr[t], dckr = s.dckr[t];
+        const double *pn = s.pn + t * T2_NRANKI;
+        const double pnr0c0 = pn[irow - 1] * pn[icol - 1], pnr0c1 = pn[irow - 1] * pn[icol];
+        const double pnr1c0 = pn[irow] * pn[icol - 1], pnr1c1 = pn[irow] * pn[icol];
+        double b1a = crow * costh * pnr1c1 - crowm * pnr0c1;
+        double b1b = ccol * costh * pnr1c1 - ccolm * pnr1c0;
+        const double br = s.rb[ro];
+        const cd h = ld2(s.rhr, s.rhi, ro), h2 = ld2(s.rh2r, s.rh2i, ro), b2 = ld2(s.rb2r, s.rb2i, ro);
+        const cd bk = ld2(s.rbkr, s.rbki, co), hk = ld2(s.rhkr, s.rhki, co), bk2 = ld2(s.rbk2r, s.rbk2i, co);
+        const cd hrow = mk(s.bj[ro], s.by[ro]);
+        const cd jkc = ld2(s.jkr, s.jki, co), hkc = ld2(s.hkr, s.hki, co), j3c = ld2(s.j3r, s.j3i, co);
+        const cd hbkml = hrow * jkc, bbkml = jkc * s.bj[ro], hhkml = hrow * hkc, bhkml = hkc * s.bj[ro];
+        const cd hb2ml = ld2(s.h2r, s.h2i, ro) * j3c, bb2ml = ld2(s.j2r, s.j2i, ro) * j3c;
+        const cd ckp2 = mk(s.ckp2r[t], s.ckp2i[t]), dkp2 = mk(s.dkp2r[t], s.dkp2i[t]);
+        cd v[12];
+        if (!EVEN) {
+            const double b1 = b1a + b1b;
+            const cd htbk = h * bk, btbk = bk * br, bthk = hk * br, hthk = h * hk;
+            const double fac = 2.0 * cmv * sinth;
+            const double gs = dckr * sinth * pnr1c1, tl = crssij * (crij + 2.0) / ckr, t0 = crssij / ckr;
+            const cd suma = (bk * (crow * crow1) + h * (ccol * ccol1) - tl) * gs;
+            const cd sumb = (bk * (crow * crow1) + (ccol * ccol1 * br - tl)) * gs;
+            const cd sumc = (hk * (crow * crow1) + (ccol * ccol1 * br - tl)) * gs;
+            const cd sumd = (hk * (crow * crow1) + h * (ccol * ccol1) - tl) * gs;
+            const cd ca = ((htbk + 1.0) * ckr - h * ccol - bk * crow + t0);
+            const cd cb = ((btbk + 1.0) * ckr - (ccol * br) - bk * crow + t0);
+            const cd cc = ((bthk + 1.0) * ckr - (ccol * br) - hk * crow + t0);
+            const cd cdd = ((hthk + 1.0) * ckr - h * ccol - hk * crow + t0);
+            const double bc = b1 * ckr;
+            v[0] = ((ca * bc + suma) * hbkml) * fac;
+            v[1] = ((cb * bc + sumb) * bbkml) * fac;
+            v[2] = ((cc * bc + sumc) * bhkml) * fac;
+            v[3] = ((cdd * bc + sumd) * hhkml) * fac;
+            const cd htbk2 = h2 * bk2, btbk2 = b2 * bk2;
+            const cd tinv = mk(1.0, 0.0) / ckp2;
+            const cd sumg = ((bk2 * (crow * crow1) + h2 * (ccol * ccol1) - tinv * (crssij * (crij + 2.0))) * (pnr1c1 * sinth)) * dkp2;
+            const cd sumh = ((bk2 * (crow * crow1) + b2 * (ccol * ccol1) - tinv * (crssij * (crij + 2.0))) * (pnr1c1 * sinth)) * dkp2;
+            const cd rx = h2 * ccol + bk2 * crow - tinv * crssij;
+            const cd ry = b2 * ccol + bk2 * crow - tinv * crssij;
+            v[4] = ((sumg + (((htbk2 + 1.0) * ckp2 - rx) * b1) * ckp2) * hb2ml) * fac;
+            v[5] = ((sumh + (((btbk2 + 1.0) * ckp2 - ry) * b1) * ckp2) * bb2ml) * fac;
+            // L
+            const cd e1k = eps1 * ckr;
+            v[6] = -((((ca + e1k - ckr) * bc + suma) * (qs1 * hbkml)) * fac);
+            v[7] = -((((cb + e1k - ckr) * bc + sumb) * (qs1 * bbkml)) * fac);
+            v[8] = -((((cc + e1k - ckr) * bc + sumc) * (qs1 * bhkml)) * fac);
+            v[9] = -((((cdd + e1k - ckr) * bc + sumd) * (qs1 * hhkml)) * fac);
+            v[10] = -(((((((rat12 + htbk2) * ckp2 - rx) * b1) * ckp2) + sumg) * (qsrat * hb2ml)) * fac);
+            v[11] = -(((((((rat12 + btbk2) * ckp2 - ry) * b1) * ckp2) + sumh) * (qsrat * bb2ml)) * fac);
+        } else {
+            const double cmcrco = cm2 - qem * crssij * costh * costh;
+            const double a12 = cmcrco * pnr1c1 + qem * (crow * ccolm * costh * pnr1c0 + ccol * crowm * costh * pnr0c1 - crowm * ccolm * pnr0c0);
+            b1a = ccol * ccol1 * b1a;
+            b1b = crow * crow1 * b1b;
+            const double b1 = (b1a - b1b) * sinth, dd = -qem * dckr, fac = 2.0 * sinth;
+            const double ak = a12 * ckr;
+            const cd tail = (mk(b1a, 0.0) - eps1 * b1b) * (sinth * dd);
+            const cd e1h = eps1 * h, e1b = eps1 * br, e1r = eps1 * crow - ccol;
+            // J: a, b, c, d
+            v[0] = ((((bk - e1h) * ckr + e1r) * ak + tail) * (qs1 * hbkml)) * fac;
+            v[1] = ((((bk - e1b) * ckr + e1r) * ak + tail) * (qs1 * bbkml)) * fac;
+            v[2] = ((((hk - e1b) * ckr + e1r) * ak + tail) * (qs1 * bhkml)) * fac;
+            v[3] = ((((hk - e1h) * ckr + e1r) * ak + tail) * (qs1 * hhkml)) * fac;
+            const cd d2 = dkp2 * (-qem);
+            const cd sx = ((mk(b1a, 0.0) - rat12 * b1b) * sinth) * d2;
+            const cd r12r = rat12 * crow - ccol;
+            v[4] = ((((((bk2 - rat12 * h2) * ckp2 + r12r) * a12) * ckp2) + sx) * (qsrat * hb2ml)) * fac;
+            v[5] = ((((((bk2 - rat12 * b2) * ckp2 + r12r) * a12) * ckp2) + sx) * (qsrat * bb2ml)) * fac;
+            // K
+            const double rc = crow - ccol, bd = b1 * dd;
+            v[6] = ((((bk - h) * ckr + rc) * ak + bd) * hbkml) * fac;
+            v[7] = ((((bk - br) * ckr + rc) * ak + bd) * bbkml) * fac;
+            v[8] = ((((hk - br) * ckr + rc) * ak + bd) * bhkml) * fac;
+            v[9] = ((((hk - h) * ckr + rc) * ak + bd) * hhkml) * fac;
+            const cd sxk = d2 * b1;
+            v[10] = (((((bk2 - h2) * ckp2 + rc) * a12) * ckp2 + sxk) * hb2ml) * fac;
+            v[11] = (((((bk2 - b2) * ckp2 + rc) * a12) * ckp2 + sxk) * bb2ml) * fac;
+        }
+#pragma unroll
+        for (int q = 0; q < 12; q++) { acc[q].x = fma(v[q].x, w, acc[q].x); acc[q].y = fma(v[q].y, w, acc[q].y); }
+    }
+}
+
+// ---- K2: the six matrices of mode kmv (outer-surface a, b, c, d, inner-surface x, y) into M, as two parity-class blocks each.
+// pair (n = irow, n' = icol); even pairs first (J, K), then odd pairs (I, L).  `split` (1, 2 or 4, a power of two <= 32) lanes
+// share a pair, each summing a contiguous range of the quadrature nodes; partial sums are combined by warp shuffles (the group
+// must then consist of whole warps).  No barrier at the end.
+__device__ void t2_assemble(const T2Par &P, T2Smem &s, const T2Mat &M, int kmv, const T2Grp &g, int split)
+{
+    const double prodm = t2_prodm(kmv);
+    const int nmin = kmv > 1 ? kmv : 1, NMq = T2_NRANK - nmin + 1, ld = NMq, lda = 2 * NMq;
+    for (int t = g.tid; t < T2_NNODE; t += g.nt)
+        t2_genlgp(s.theta[t], s.sinth[t], s.costh[t], kmv, prodm, s.pn + t * T2_NRANKI);
+    t2_sync(g);
+    const int h0 = (NMq + 1) >> 1, h1 = NMq >> 1;
+    const int nE = h0 * h0 + h1 * h1, nO = (kmv == 0) ? 0 : 2 * h0 * h1;
+    // warp-aligned start of the odd pairs so that no warp mixes the two code paths
+    const int nEs = nE * split, nEpad = (nEs + 31) & ~31, tot = nEpad + nO * split;
+    const int nstep = (T2_NNODE + split - 1) / split;
+    for (int base = 0; base < tot; base += g.nt) {
+        const int item = base + g.tid;       // all lanes of a warp stay in the loop (shuffles below)
+        const bool even = item < nEpad;
+        const int u0 = even ? item : item - nEpad;
+        const int pair = u0 / split, part = u0 - pair * split;
+        const bool valid = even ? (item < nEs) : (item < tot);
+        int k1 = 0, k2 = 0;  // k1 = n - nmin (irow), k2 = n' - nmin (icol)
+        if (valid) {
+            if (even) {
+                if (pair < h0 * h0) { int q = pair / h0; k1 = 2 * q; k2 = 2 * (pair - q * h0); }
+                else { int u = pair - h0 * h0; int q = u / h1; k1 = 2 * q + 1; k2 = 2 * (u - q * h1) + 1; }
+            } else {
+                if (pair < h0 * h1) { int q = pair / h1; k1 = 2 * q; k2 = 2 * (pair - q * h1) + 1; }
+                else { int u = pair - h0 * h1; int q = u / h0; k1 = 2 * q + 1; k2 = 2 * (u - q * h0); }
+            }
+        }
+        const int irow = nmin + k1, icol = nmin + k2;
+        cd acc[12];
+#pragma unroll
+        for (int q = 0; q < 12; q++) acc[q] = mk(0.0, 0.0);
+        if (valid) {
+            const int s0 = part * nstep, s1 = (s0 + nstep < T2_NNODE) ? s0 + nstep : T2_NNODE;
+            if (even) t2_pair_nodes<true>(P, s, kmv, irow, icol, s0, s1, acc);
+            else t2_pair_nodes<false>(P, s, kmv, irow, icol, s0, s1, acc);
+        }
+        for (int o = 1; o < split; o <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 12; q++) {
+                acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+                acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+            }
+        }
+        if (!valid || part != 0) continue;
+#pragma unroll
+        for (int q = 0; q < 12; q++) acc[q] = acc[q] * P.diff;
+        // scatter into the parity-class matrices: first six -> class ca, last six -> class cb
+        // even: [0..5] = J -> (2,n')-(2,n): class n'&1 ; [6..11] = K -> (1,n')-(1,n): class (n'+1)&1
+        // odd : [0..5] = I -> (1,n')-(2,n): class (n'+1)&1 ; [6..11] = L -> (2,n')-(1,n): class n'&1
+        const int c_first = even ? (icol & 1) : ((icol + 1) & 1), c_second = c_first ^ 1;
+        const int e1 = (c_first * NMq + k2) * ld + k1, e2 = (c_second * NMq + k2) * ld + k1;
+        const int g1 = (c_first * NMq + k2) * lda + k1, g2 = (c_second * NMq + k2) * lda + k1;
+        M.A[e1] = make_double2(acc[0].x, acc[0].y); M.B[e1] = make_double2(acc[1].x, acc[1].y);
+        M.C[e1] = make_double2(acc[2].x, acc[2].y); M.D[e1] = make_double2(acc[3].x, acc[3].y);
+        M.aug[g1] = make_double2(acc[4].x, acc[4].y); M.aug[g1 + NMq] = make_double2(acc[5].x, acc[5].y);
+        M.A[e2] = make_double2(acc[6].x, acc[6].y); M.B[e2] = make_double2(acc[7].x, acc[7].y);
+        M.C[e2] = make_double2(acc[8].x, acc[8].y); M.D[e2] = make_double2(acc[9].x, acc[9].y);
+        M.aug[g2] = make_double2(acc[10].x, acc[10].y); M.aug[g2 + NMq] = make_double2(acc[11].x, acc[11].y);
+    }
+    if (kmv == 0) {
+        // odd (I, L) entries vanish for m = 0: zero them explicitly
+        for (int item = g.tid; item < 2 * h0 * h1; item += g.nt) {
+            int k1, k2, u = item;
+            if (u < h0 * h1) { int q = u / h1; k1 = 2 * q; k2 = 2 * (u - q * h1) + 1; }
+            else { u -= h0 * h1; int q = u / h0; k1 = 2 * q + 1; k2 = 2 * (u - q * h0); }
+            const double2 z = make_double2(0.0, 0.0);
+            for (int c = 0; c < 2; c++) {
+                const int e = (c * NMq + k2) * ld + k1, gg = (c * NMq + k2) * lda + k1;
+                M.A[e] = z; M.B[e] = z; M.C[e] = z; M.D[e] = z; M.aug[gg] = z; M.aug[gg + NMq] = z;
+            }
+        }
+    }
+}
+
+// both parity-class systems [2][NMq][2 NMq] of M.aug: right half <- (left half)^-1 (right half)  (prcssm, :2177-2280)
+struct T2SolveWs {
+    Ctl *ctl;                       // generic solver (host emulation): descriptors + pivot keys
+    unsigned long long *keyslot;    // [2][2] pivot ping-pong of the two class groups (device)
+    int *sing;
+};
+__device__ __forceinline__ void t2_solve(const T2Mat &M, int NMq, const T2Grp &g, const T2SolveWs &ws)
+{
+#ifdef HS_HOST_EMU
     Grp<false> grp;
-    grp.tid = tid; grp.nt = nt;
+    grp.tid = g.tid; grp.nt = g.nt;
     Carve cv;
+    cv.sys = M.aug;
+    solve(grp, cv, NMq, ws.ctl);
+    if (ws.ctl->sing) *ws.sing = 1;
+#else
+    // 64 lanes per class (two whole warps; named barriers 1 and 2), the shared-space Gauss-Jordan of the single-layer pipeline
+    const int cl = g.tid >> 6;
+    SysDesc d;
+    d.base = M.aug + cl * NMq * 2 * NMq; d.n = NMq; d.ld = 2 * NMq; d.off = 0; d.stride = 1; d.rhs = NMq;
+    solve_grp2s(d, g.tid & 63, 64, 1 + cl, ws.keyslot + 2 * cl, ws.sing);
+    t2_sync(g);
+#endif
+}
 
-    for (int kmv = 0; kmv < T2_NM; kmv++) {
-        const double cmv = kmv;
-        double prodm = 1.0, em = 1.0;
-        if (kmv > 0) {
-            em = 2.0;
-            double quanm = cmv;
-            for (int i = 1; i <= kmv; i++) { quanm += 1.0; prodm = quanm * prodm / 2.0; }
-        }
-        const double qem = -2.0 / em, cm2 = cmv * cmv;
-        const int nmin = kmv > 1 ? kmv : 1, NMq = T2_NRANK - nmin + 1, ld = NMq, lda = 2 * NMq;
-        for (int t = tid; t < T2_NNODE; t += nt)
-            t2_genlgp(s.theta[t], s.sinth[t], s.costh[t], kmv, prodm, s.pn + t * T2_NRANKI);
-        for (int n = tid + 1; n <= T2_NRANK; n += nt) {
-            double ck = n, fctki = 1.0, v;
-            if (kmv > 0 && n < kmv) v = 1.0;
-            else {
-                if (kmv > 0) {
-                    double fprod = n - kmv + 1;
-                    for (int l = n - kmv + 1; l <= n + kmv; l++) { fctki *= fprod; fprod += 1.0; }
-                }
-                v = 4.0 * ck * (ck + 1.0) * fctki / (em * (2.0 * ck + 1.0));
+// ---- K3 + addprc of mode kmv on the matrices in M: T2 = x^-1 y (class-wise), rescale, X = b - T2 c, Bn = a - T2 d, T = Bn^-1 X,
+// incident / scattered coefficients and the far field at 90 deg (forward) and 270 deg (back) accumulated into s_acc.
+// Device: g = the 128 solver lanes.  Ends with a group barrier.
+__device__ void t2_chain(const T2Par &P, const T2Mat &M, int kmv, const T2Grp &g, double *s_cmx, double *s_acc, const T2SolveWs &ws)
+{
+    const double cmv = kmv, em = kmv > 0 ? 2.0 : 1.0, prodm = t2_prodm(kmv);
+    const int nmin = kmv > 1 ? kmv : 1, NMq = T2_NRANK - nmin + 1, ld = NMq, lda = 2 * NMq;
+    for (int n = g.tid + 1; n <= T2_NRANK; n += g.nt) {
+        double ck = n, fctki = 1.0, v;
+        if (kmv > 0 && n < kmv) v = 1.0;
+        else {
+            if (kmv > 0) {
+                double fprod = n - kmv + 1;
+                for (int l = n - kmv + 1; l <= n + kmv; l++) { fctki *= fprod; fprod += 1.0; }
             }
-            s_cmx[n] = v;
+            v = 4.0 * ck * (ck + 1.0) * fctki / (em * (2.0 * ck + 1.0));
         }
-        __syncthreads();
-
-        // ---- K2: assembly.  pair (n = irow, n' = icol); even pairs first (J,K), then odd pairs (I,L) ----
-        const int h0 = (NMq + 1) >> 1, h1 = NMq >> 1;
-        const int nE = h0 * h0 + h1 * h1, nO = (kmv == 0) ? 0 : 2 * h0 * h1;
-        // warp-aligned start of the odd pairs so that no warp mixes the two code paths
-        const int nEpad = (nE + 31) & ~31;
-        for (int item = tid; item < nEpad + nO; item += nt) {
-            int k1, k2;  // k1 = n - nmin (irow), k2 = n' - nmin (icol)
-            bool even;
-            if (item < nE) {
-                even = true;
-                if (item < h0 * h0) { int q = item / h0; k1 = 2 * q; k2 = 2 * (item - q * h0); }
-                else { int u = item - h0 * h0; int q = u / h1; k1 = 2 * q + 1; k2 = 2 * (u - q * h1) + 1; }
-            } else if (item >= nEpad) {
-                even = false;
-                int u = item - nEpad;
-                if (u < h0 * h1) { int q = u / h1; k1 = 2 * q; k2 = 2 * (u - q * h1) + 1; }
-                else { u -= h0 * h1; int q = u / h0; k1 = 2 * q + 1; k2 = 2 * (u - q * h0); }
-            } else continue;
-            const int irow = nmin + k1, icol = nmin + k2;
-            const double crow = irow, ccol = icol, crow1 = crow + 1.0, ccol1 = ccol + 1.0;
-            const double crowm = cmv + crow, ccolm = cmv + ccol, crij = crow + ccol, crssij = crow * ccol;
-            cd acc[12];
-#pragma unroll
-            for (int q = 0; q < 12; q++) acc[q] = mk(0.0, 0.0);
-            cd fz[12];
-            for (int step = 0; step < T2_NNODE; step++) {
-                // evaluation order of quad: pairs j=1..15 (+x, -x) accumulate first, centre (node 0) last
-                const int t = (step < 30) ? step + 1 : 0;
-                const double w = (step < 30) ? PAT31_W[step >> 1] : PAT31_WC;
-                const int ro = t * T2_NRANK + irow - 1, co = t * T2_NRANK + icol - 1;
-                const double sinth = s.sinth[t], costh = s.costh[t], ckr = s.ckr[t], dckr = s.dckr[t];
-                const double *pn = s.pn + t * T2_NRANKI;
-                const double pnr0c0 = pn[irow - 1] * pn[icol - 1], pnr0c1 = pn[irow - 1] * pn[icol];
-                const double pnr1c0 = pn[irow] * pn[icol - 1], pnr1c1 = pn[irow] * pn[icol];
-                double b1a = crow * costh * pnr1c1 - crowm * pnr0c1;
-                double b1b = ccol * costh * pnr1c1 - ccolm * pnr1c0;
-                const double br = s.rb[ro];
-                const cd h = ld2(s.rhr, s.rhi, ro), h2 = ld2(s.rh2r, s.rh2i, ro), b2 = ld2(s.rb2r, s.rb2i, ro);
-                const cd bk = ld2(s.rbkr, s.rbki, co), hk = ld2(s.rhkr, s.rhki, co), bk2 = ld2(s.rbk2r, s.rbk2i, co);
-                const cd hrow = mk(s.bj[ro], s.by[ro]);
-                const cd jkc = ld2(s.jkr, s.jki, co), hkc = ld2(s.hkr, s.hki, co), j3c = ld2(s.j3r, s.j3i, co);
-                const cd hbkml = hrow * jkc, bbkml = jkc * s.bj[ro], hhkml = hrow * hkc, bhkml = hkc * s.bj[ro];
-                const cd hb2ml = ld2(s.h2r, s.h2i, ro) * j3c, bb2ml = ld2(s.j2r, s.j2i, ro) * j3c;
-                const cd ckp2 = mk(s.ckp2r[t], s.ckp2i[t]), dkp2 = mk(s.dkp2r[t], s.dkp2i[t]);
-                cd v[12];
-                if (!even) {
-                    const double b1 = b1a + b1b;
-                    const cd htbk = h * bk, btbk = bk * br, bthk = hk * br, hthk = h * hk;
-                    const double fac = 2.0 * cmv * sinth;
-                    const double gs = dckr * sinth * pnr1c1, tl = crssij * (crij + 2.0) / ckr, t0 = crssij / ckr;
-                    const cd suma = (bk * (crow * crow1) + h * (ccol * ccol1) - tl) * gs;
-                    const cd sumb = (bk * (crow * crow1) + (ccol * ccol1 * br - tl)) * gs;
-                    const cd sumc = (hk * (crow * crow1) + (ccol * ccol1 * br - tl)) * gs;
-                    const cd sumd = (hk * (crow * crow1) + h * (ccol * ccol1) - tl) * gs;
-                    const cd ca = ((htbk + 1.0) * ckr - h * ccol - bk * crow + t0);
-                    const cd cb = ((btbk + 1.0) * ckr - (ccol * br) - bk * crow + t0);
-                    const cd cc = ((bthk + 1.0) * ckr - (ccol * br) - hk * crow + t0);
-                    const cd cdd = ((hthk + 1.0) * ckr - h * ccol - hk * crow + t0);
-                    const double bc = b1 * ckr;
-                    v[0] = ((ca * bc + suma) * hbkml) * fac;
-                    v[1] = ((cb * bc + sumb) * bbkml) * fac;
-                    v[2] = ((cc * bc + sumc) * bhkml) * fac;
-                    v[3] = ((cdd * bc + sumd) * hhkml) * fac;
-                    const cd htbk2 = h2 * bk2, btbk2 = b2 * bk2;
-                    const cd tinv = mk(1.0, 0.0) / ckp2;
-                    const cd sumg = ((bk2 * (crow * crow1) + h2 * (ccol * ccol1) - tinv * (crssij * (crij + 2.0))) * (pnr1c1 * sinth)) * dkp2;
-                    const cd sumh = ((bk2 * (crow * crow1) + b2 * (ccol * ccol1) - tinv * (crssij * (crij + 2.0))) * (pnr1c1 * sinth)) * dkp2;
-                    const cd rx = h2 * ccol + bk2 * crow - tinv * crssij;
-                    const cd ry = b2 * ccol + bk2 * crow - tinv * crssij;
-                    v[4] = ((sumg + (((htbk2 + 1.0) * ckp2 - rx) * b1) * ckp2) * hb2ml) * fac;
-                    v[5] = ((sumh + (((btbk2 + 1.0) * ckp2 - ry) * b1) * ckp2) * bb2ml) * fac;
-                    // L
-                    const cd e1k = eps1 * ckr;
-                    v[6] = -((((ca + e1k - ckr) * bc + suma) * (qs1 * hbkml)) * fac);
-                    v[7] = -((((cb + e1k - ckr) * bc + sumb) * (qs1 * bbkml)) * fac);
-                    v[8] = -((((cc + e1k - ckr) * bc + sumc) * (qs1 * bhkml)) * fac);
-                    v[9] = -((((cdd + e1k - ckr) * bc + sumd) * (qs1 * hhkml)) * fac);
-                    v[10] = -(((((((rat12 + htbk2) * ckp2 - rx) * b1) * ckp2) + sumg) * (qsrat * hb2ml)) * fac);
-                    v[11] = -(((((((rat12 + btbk2) * ckp2 - ry) * b1) * ckp2) + sumh) * (qsrat * bb2ml)) * fac);
-                } else {
-                    const double cmcrco = cm2 - qem * crssij * costh * costh;
-                    const double a12 = cmcrco * pnr1c1 + qem * (crow * ccolm * costh * pnr1c0 + ccol * crowm * costh * pnr0c1 - crowm * ccolm * pnr0c0);
-                    b1a = ccol * ccol1 * b1a;
-                    b1b = crow * crow1 * b1b;
-                    const double b1 = (b1a - b1b) * sinth, dd = -qem * dckr, fac = 2.0 * sinth;
-                    const double ak = a12 * ckr;
-                    const cd tail = (mk(b1a, 0.0) - eps1 * b1b) * (sinth * dd);
-                    const cd e1h = eps1 * h, e1b = eps1 * br, e1r = eps1 * crow - ccol;
-                    // J: a, b, c, d
-                    v[0] = ((((bk - e1h) * ckr + e1r) * ak + tail) * (qs1 * hbkml)) * fac;
-                    v[1] = ((((bk - e1b) * ckr + e1r) * ak + tail) * (qs1 * bbkml)) * fac;
-                    v[2] = ((((hk - e1b) * ckr + e1r) * ak + tail) * (qs1 * bhkml)) * fac;
-                    v[3] = ((((hk - e1h) * ckr + e1r) * ak + tail) * (qs1 * hhkml)) * fac;
-                    const cd d2 = dkp2 * (-qem);
-                    const cd sx = ((mk(b1a, 0.0) - rat12 * b1b) * sinth) * d2;
-                    const cd r12r = rat12 * crow - ccol;
-                    v[4] = ((((((bk2 - rat12 * h2) * ckp2 + r12r) * a12) * ckp2) + sx) * (qsrat * hb2ml)) * fac;
-                    v[5] = ((((((bk2 - rat12 * b2) * ckp2 + r12r) * a12) * ckp2) + sx) * (qsrat * bb2ml)) * fac;
-                    // K
-                    const double rc = crow - ccol, bd = b1 * dd;
-                    v[6] = ((((bk - h) * ckr + rc) * ak + bd) * hbkml) * fac;
-                    v[7] = ((((bk - br) * ckr + rc) * ak + bd) * bbkml) * fac;
-                    v[8] = ((((hk - br) * ckr + rc) * ak + bd) * bhkml) * fac;
-                    v[9] = ((((hk - h) * ckr + rc) * ak + bd) * hhkml) * fac;
-                    const cd sxk = d2 * b1;
-                    v[10] = (((((bk2 - h2) * ckp2 + rc) * a12) * ckp2 + sxk) * hb2ml) * fac;
-                    v[11] = (((((bk2 - b2) * ckp2 + rc) * a12) * ckp2 + sxk) * bb2ml) * fac;
-                }
-                if (step < 30) {
-                    if ((step & 1) == 0) {
-#pragma unroll
-                        for (int q = 0; q < 12; q++) fz[q] = v[q];
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 12; q++) acc[q] = acc[q] + (fz[q] + v[q]) * w;
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 12; q++) acc[q] = (acc[q] + v[q] * w) * diff;
-                }
-            }
-            // scatter into the parity-class matrices: first six -> class ca, last six -> class cb
-            // even: [0..5] = J -> (2,n')-(2,n): class n'&1 ; [6..11] = K -> (1,n')-(1,n): class (n'+1)&1
-            // odd : [0..5] = I -> (1,n')-(2,n): class (n'+1)&1 ; [6..11] = L -> (2,n')-(1,n): class n'&1
-            const int c_first = even ? (icol & 1) : ((icol + 1) & 1), c_second = c_first ^ 1;
-            const long e1 = (long)(c_first * NMq + k2) * ld + k1, e2 = (long)(c_second * NMq + k2) * ld + k1;
-            const long g1 = (long)(c_first * NMq + k2) * lda + k1, g2 = (long)(c_second * NMq + k2) * lda + k1;
-            s.A[e1] = make_double2(acc[0].x, acc[0].y); s.B[e1] = make_double2(acc[1].x, acc[1].y);
-            s.C[e1] = make_double2(acc[2].x, acc[2].y); s.D[e1] = make_double2(acc[3].x, acc[3].y);
-            s.aug[g1] = make_double2(acc[4].x, acc[4].y); s.aug[g1 + NMq] = make_double2(acc[5].x, acc[5].y);
-            s.A[e2] = make_double2(acc[6].x, acc[6].y); s.B[e2] = make_double2(acc[7].x, acc[7].y);
-            s.C[e2] = make_double2(acc[8].x, acc[8].y); s.D[e2] = make_double2(acc[9].x, acc[9].y);
-            s.aug[g2] = make_double2(acc[10].x, acc[10].y); s.aug[g2 + NMq] = make_double2(acc[11].x, acc[11].y);
-        }
-        if (kmv == 0) {
-            // odd (I, L) entries vanish for m = 0: zero them explicitly
-            for (int item = tid; item < 2 * h0 * h1; item += nt) {
-                int k1, k2, u = item;
-                if (u < h0 * h1) { int q = u / h1; k1 = 2 * q; k2 = 2 * (u - q * h1) + 1; }
-                else { u -= h0 * h1; int q = u / h0; k1 = 2 * q + 1; k2 = 2 * (u - q * h0); }
-                const double2 z = make_double2(0.0, 0.0);
-                for (int c = 0; c < 2; c++) {
-                    const long e = (long)(c * NMq + k2) * ld + k1, g = (long)(c * NMq + k2) * lda + k1;
-                    s.A[e] = z; s.B[e] = z; s.C[e] = z; s.D[e] = z; s.aug[g] = z; s.aug[g + NMq] = z;
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- K3: T2 = x^-1 y (class-wise), rescale, X = b - T2 c, Bn = a - T2 d, T = Bn^-1 X ----
-        cv.sys = s.aug;
-        solve(grp, cv, NMq, ctl);
-        for (int e = tid; e < 2 * NMq * NMq; e += nt) {
-            int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
-            double scale = s_cmx[nmin + r] / s_cmx[nmin + q];
-            double2 &y = s.aug[(long)(c * NMq + r) * lda + NMq + q];
-            y.x *= scale; y.y *= scale;
-        }
-        __syncthreads();
-        for (int e = tid; e < 2 * NMq * NMq; e += nt) {
-            int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
-            const double2 *t2 = s.aug + (long)(c * NMq + r) * lda + NMq;
-            double xr = 0, xi = 0, br_ = 0, bi_ = 0;
-            for (int j = 0; j < NMq; j++) {
-                double2 y = t2[j];
-                double2 cc = s.C[(long)(c * NMq + j) * ld + q], dd2 = s.D[(long)(c * NMq + j) * ld + q];
-                xr += y.x * cc.x - y.y * cc.y; xi += y.y * cc.x + y.x * cc.y;
-                br_ += y.x * dd2.x - y.y * dd2.y; bi_ += y.y * dd2.x + y.x * dd2.y;
-            }
-            double2 bb = s.B[(long)(c * NMq + r) * ld + q], aa = s.A[(long)(c * NMq + r) * ld + q];
-            s.aug2[(long)(c * NMq + r) * lda + NMq + q] = make_double2(bb.x - xr, bb.y - xi);
-            s.aug2[(long)(c * NMq + r) * lda + q] = make_double2(aa.x - br_, aa.y - bi_);
-        }
-        __syncthreads();
-        cv.sys = s.aug2;
-        solve(grp, cv, NMq, ctl);
-
-        // ---- addprc: incident coefficients, scattered coefficients, far field at 90 deg (forward) and 270 deg (back) ----
-        // T_c[r][q] = aug2[c][r][NMq+q];  fg(tau_j, n_j) = sum_i ab(i) T(i, j) inside each class.
-        for (int w = tid; w < 4 * NMq; w += nt) {
-            const int pol = w & 1, idx = w >> 1, c = idx / NMq, q = idx - c * NMq;
-            double pnl[T2_NRANKI];
-            const double theta = dtr * 90.0;
-            double sn, cs;
-            sincos(theta, &sn, &cs);
-            t2_genlgp(theta, sn, cs, kmv, prodm, pnl);
-            cd sacc = mk(0.0, 0.0);
-            for (int r = 0; r < NMq; r++) {
-                const int n = nmin + r;
-                const int tau = (((n + 1) & 1) == c) ? 1 : 2;
-                const double p1 = n * cs * pnl[n] - (n + cmv) * pnl[n - 1], p2 = cmv * pnl[n];
-                const int pw = (tau == 1) ? (n & 3) : ((n + 1) & 3);
-                double mag;
-                if (pol == 0) mag = (tau == 1) ? -p2 : p1;   // ab1
-                else mag = (tau == 1) ? p1 : -p2;            // ab2
-                cd ab = (pw == 0) ? mk(mag, 0.0) : (pw == 1) ? mk(0.0, mag) : (pw == 2) ? mk(-mag, 0.0) : mk(0.0, -mag);
-                double2 tt = s.aug2[(long)(c * NMq + r) * lda + NMq + q];
-                sacc = sacc + ab * mk(tt.x, tt.y);
-            }
-            // fg[pol][c][q] parked in matrix A storage (free after the products)
-            s.A[(pol * 2 + c) * NMq + q] = make_double2(sacc.x, sacc.y);
-        }
-        __syncthreads();
-        for (int w = tid; w < 4; w += nt) {
-            const int iu = w >> 1, pol = w & 1;
-            const double theta = dtr * (iu == 0 ? 90.0 : 270.0);
-            double sn, cs;
-            sincos(theta, &sn, &cs);
-            double pnl[T2_NRANKI];
-            t2_genlgp(theta, sn, cs, kmv, prodm, pnl);
-            cd fa = mk(0.0, 0.0);
-            for (int n = nmin; n <= T2_NRANK; n++) {
-                const int k = n - nmin;
-                const double p1 = n * cs * pnl[n] - (n + cmv) * pnl[n - 1], p2 = cmv * pnl[n];
-                const int pw = (4 - ((n + 1) & 3)) & 3;  // (-i)^(n+1)
-                const cd cim = (pw == 0) ? mk(1, 0) : (pw == 1) ? mk(0, 1) : (pw == 2) ? mk(-1, 0) : mk(0, -1);
-                double2 f1 = s.A[(pol * 2 + ((n + 1) & 1)) * NMq + k];   // fg(tau=1, n)
-                double2 f2 = s.A[(pol * 2 + (n & 1)) * NMq + k];         // fg(tau=2, n)
-                const double pa = pol == 0 ? p2 : p1, pb = pol == 0 ? p1 : p2;
-                cd f = mk(f1.x * pa, f1.y * pa), g = mk(-f2.y * pb, f2.x * pb);
-                cd term = (cim * (f + g)) * (1.0 / s_cmx[n]);
-                fa = (pol == 0) ? fa + term : fa - term;
-            }
-            s_acc[w * 2] += rtsfct * fa.x;
-            s_acc[w * 2 + 1] += rtsfct * fa.y;
-        }
-        __syncthreads();
+        s_cmx[n] = v;
     }
-    for (int w = tid; w < 4; w += nt) {
-        // s_acc: [iu][pol]; output order borrp borip borrpe boripe forrp forip forpe foripe
+    t2_sync(g);
+    t2_solve(M, NMq, g, ws);
+    for (int e = g.tid; e < 2 * NMq * NMq; e += g.nt) {
+        int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
+        double scale = s_cmx[nmin + r] / s_cmx[nmin + q];
+        double2 &y = M.aug[(c * NMq + r) * lda + NMq + q];
+        y.x *= scale; y.y *= scale;
+    }
+    t2_sync(g);
+    // in place: A <- a - T2 d (= Bn), B <- b - T2 c (= X); every (c, r, q) reads only its own entries of A and B
+    for (int e = g.tid; e < 2 * NMq * NMq; e += g.nt) {
+        int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
+        const double2 *t2 = M.aug + (c * NMq + r) * lda + NMq;
+        double xr = 0, xi = 0, br_ = 0, bi_ = 0;
+        for (int j = 0; j < NMq; j++) {
+            double2 y = t2[j];
+            double2 cc = M.C[(c * NMq + j) * ld + q], dd2 = M.D[(c * NMq + j) * ld + q];
+            xr += y.x * cc.x - y.y * cc.y; xi += y.y * cc.x + y.x * cc.y;
+            br_ += y.x * dd2.x - y.y * dd2.y; bi_ += y.y * dd2.x + y.x * dd2.y;
+        }
+        double2 &bb = M.B[(c * NMq + r) * ld + q], &aa = M.A[(c * NMq + r) * ld + q];
+        bb = make_double2(bb.x - xr, bb.y - xi);
+        aa = make_double2(aa.x - br_, aa.y - bi_);
+    }
+    t2_sync(g);
+    for (int e = g.tid; e < 2 * NMq * NMq; e += g.nt) {
+        int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
+        M.aug[(c * NMq + r) * lda + q] = M.A[(c * NMq + r) * ld + q];
+        M.aug[(c * NMq + r) * lda + NMq + q] = M.B[(c * NMq + r) * ld + q];
+    }
+    t2_sync(g);
+    t2_solve(M, NMq, g, ws);
+
+    // ---- addprc: T_c[r][q] = aug[c][r][NMq+q];  fg(tau_j, n_j) = sum_i ab(i) T(i, j) inside each class.
+    for (int w = g.tid; w < 4 * NMq; w += g.nt) {
+        const int pol = w & 1, idx = w >> 1, c = idx / NMq, q = idx - c * NMq;
+        double pnl[T2_NRANKI];
+        const double theta = P.dtr * 90.0;
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        t2_genlgp(theta, sn, cs, kmv, prodm, pnl);
+        cd sacc = mk(0.0, 0.0);
+        for (int r = 0; r < NMq; r++) {
+            const int n = nmin + r;
+            const int tau = (((n + 1) & 1) == c) ? 1 : 2;
+            const double p1 = n * cs * pnl[n] - (n + cmv) * pnl[n - 1], p2 = cmv * pnl[n];
+            const int pw = (tau == 1) ? (n & 3) : ((n + 1) & 3);
+            double mag;
+            if (pol == 0) mag = (tau == 1) ? -p2 : p1;   // ab1
+            else mag = (tau == 1) ? p1 : -p2;            // ab2
+            cd ab = (pw == 0) ? mk(mag, 0.0) : (pw == 1) ? mk(0.0, mag) : (pw == 2) ? mk(-mag, 0.0) : mk(0.0, -mag);
+            double2 tt = M.aug[(c * NMq + r) * lda + NMq + q];
+            sacc = sacc + ab * mk(tt.x, tt.y);
+        }
+        // fg[pol][c][q] parked in matrix A storage (free after the products)
+        M.A[(pol * 2 + c) * NMq + q] = make_double2(sacc.x, sacc.y);
+    }
+    t2_sync(g);
+    for (int w = g.tid; w < 4; w += g.nt) {
         const int iu = w >> 1, pol = w & 1;
-        const int slot = (iu == 1 ? 0 : 4) + 2 * pol;
-        a.amp[(long)p * 8 + slot] = sigma * s_acc[w * 2] / rtsfct;
-        a.amp[(long)p * 8 + slot + 1] = sigma * s_acc[w * 2 + 1] / rtsfct;
-        if (w == 0) a.status[p] = ctl->sing ? HS_ST_SINGULAR : HS_ST_OK;
+        const double theta = P.dtr * (iu == 0 ? 90.0 : 270.0);
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        double pnl[T2_NRANKI];
+        t2_genlgp(theta, sn, cs, kmv, prodm, pnl);
+        cd fa = mk(0.0, 0.0);
+        for (int n = nmin; n <= T2_NRANK; n++) {
+            const int k = n - nmin;
+            const double p1 = n * cs * pnl[n] - (n + cmv) * pnl[n - 1], p2 = cmv * pnl[n];
+            const int pw = (4 - ((n + 1) & 3)) & 3;  // (-i)^(n+1)
+            const cd cim = (pw == 0) ? mk(1, 0) : (pw == 1) ? mk(0, 1) : (pw == 2) ? mk(-1, 0) : mk(0, -1);
+            double2 f1 = M.A[(pol * 2 + ((n + 1) & 1)) * NMq + k];   // fg(tau=1, n)
+            double2 f2 = M.A[(pol * 2 + (n & 1)) * NMq + k];         // fg(tau=2, n)
+            const double pa = pol == 0 ? p2 : p1, pb = pol == 0 ? p1 : p2;
+            cd f = mk(f1.x * pa, f1.y * pa), gg = mk(-f2.y * pb, f2.x * pb);
+            cd term = (cim * (f + gg)) * (1.0 / s_cmx[n]);
+            fa = (pol == 0) ? fa + term : fa - term;
+        }
+        s_acc[w * 2] += P.rtsfct * fa.x;
+        s_acc[w * 2 + 1] += P.rtsfct * fa.y;
     }
-    __syncthreads();
+    t2_sync(g);
+}
+
+__device__ inline void t2_store(const T2Args &a, int p, const T2Par &P, const double *s_acc, int sing, int w)
+{
+    // s_acc: [iu][pol]; output order borrp borip borrpe boripe forrp forip forpe foripe
+    const int iu = w >> 1, pol = w & 1;
+    const int slot = (iu == 1 ? 0 : 4) + 2 * pol;
+    a.amp[(long)p * 8 + slot] = P.sigma * s_acc[w * 2] / P.rtsfct;
+    a.amp[(long)p * 8 + slot + 1] = P.sigma * s_acc[w * 2 + 1] / P.rtsfct;
+    if (w == 0) a.status[p] = sing ? HS_ST_SINGULAR : HS_ST_OK;
+}
+
+// One particle by ONE group, phase after phase (the single-lane host emulation of tests/emu; smem: t2_smem_doubles(1)).
+__device__ void tm2l_particle(const T2Args &a, int p, double *smem, Ctl *ctl, double *s_cmx, double *s_acc,
+                              const int tid, const int nt)
+{
+    T2Smem s;
+    t2_carve(s, smem, 1);
+    const T2Par P = t2_par(a, p);
+    T2Grp g;
+    g.tid = tid; g.nt = nt; g.bar = 0;
+    int sing = 0;
+    unsigned long long keys[4];
+    T2SolveWs ws;
+    ws.ctl = ctl; ws.keyslot = keys; ws.sing = &sing;
+    t2_tables(P, s, g);
+    for (int w = tid; w < 8; w += nt) s_acc[w] = 0.0;  // acans: [fwd pol1, fwd pol2, back pol1, back pol2]
+    t2_sync(g);
+    for (int kmv = 0; kmv < T2_NM; kmv++) {
+        t2_assemble(P, s, s.mat[0], kmv, g, 1);
+        t2_sync(g);
+        t2_chain(P, s.mat[0], kmv, g, s_cmx, s_acc, ws);
+    }
+    for (int w = tid; w < 4; w += nt) t2_store(a, p, P, s_acc, sing, w);
+    t2_sync(g);
 }
 
 #ifndef HS_HOST_EMU
-__global__ void __launch_bounds__(256, 1) k_tm2l(T2Args a, int *queue)
+#define T2_ASM_THREADS 256
+#define T2_SOLVE_THREADS 128
+#define T2_ASM_REGS 200
+#define T2_SOLVE_REGS 96
+// Persistent CTAs pull particles from a queue.  Stage s of a particle: the assembly warps (two warpgroups, 200 registers per
+// thread after setmaxnreg) integrate mode s into buffer s & 1 while the solver warps (one warpgroup, 96 registers) run the chain
+// of mode s - 1 out of buffer (s - 1) & 1; one CTA barrier per stage.  Both roles execute the same sequence of CTA barriers.
+__global__ void __launch_bounds__(T2_ASM_THREADS + T2_SOLVE_THREADS, 1) k_tm2l(T2Args a, int *queue, int split)
 {
     extern __shared__ __align__(16) double smem[];
-    __shared__ Ctl ctl;
     __shared__ double s_cmx[T2_NRANKI];
     __shared__ double s_acc[8];
-    __shared__ int s_item;
-    while (true) {
-        if (threadIdx.x == 0) { s_item = atomicAdd(queue, 1); ctl.sing = 0; }
-        __syncthreads();
-        int it = s_item;
-        __syncthreads();
-        if (it >= a.n) break;
-        tm2l_particle(a, it, smem, &ctl, s_cmx, s_acc, threadIdx.x, blockDim.x);
+    __shared__ unsigned long long s_keys[4];
+    __shared__ int s_item, s_sing;
+    const int tid = threadIdx.x;
+    T2Smem s;
+    t2_carve(s, smem, 2);
+    if (tid >= T2_ASM_THREADS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_SOLVE_REGS));
+        T2Grp gsol;
+        gsol.tid = tid - T2_ASM_THREADS; gsol.nt = T2_SOLVE_THREADS; gsol.bar = 3;
+        T2SolveWs ws;
+        ws.ctl = nullptr; ws.keyslot = s_keys; ws.sing = &s_sing;
+        while (true) {
+            __syncthreads();                                   // (1) item fetched, accumulators cleared
+            const int it = s_item;
+            if (it >= a.n) break;
+            const T2Par P = t2_par(a, it);
+            __syncthreads();                                   // (2) node tables complete
+            __syncthreads();                                   // stage 0: assembly only
+            for (int stage = 1; stage <= T2_NM; stage++) {
+                t2_chain(P, s.mat[(stage - 1) & 1], stage - 1, gsol, s_cmx, s_acc, ws);
+                __syncthreads();
+            }
+            if (gsol.tid < 4) t2_store(a, it, P, s_acc, s_sing, gsol.tid);
+            __syncthreads();                                   // (3) results stored, s_item / s_acc free
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2_ASM_REGS));
+        T2Grp gasm;
+        gasm.tid = tid; gasm.nt = T2_ASM_THREADS; gasm.bar = 4;
+        while (true) {
+            if (tid == 0) { s_item = atomicAdd(queue, 1); s_sing = 0; }
+            if (tid < 8) s_acc[tid] = 0.0;
+            __syncthreads();                                   // (1)
+            const int it = s_item;
+            if (it >= a.n) break;
+            const T2Par P = t2_par(a, it);
+            t2_tables(P, s, gasm);
+            __syncthreads();                                   // (2)
+            for (int stage = 0; stage <= T2_NM; stage++) {
+                if (stage < T2_NM) t2_assemble(P, s, s.mat[stage & 1], stage, gasm, split);
+                __syncthreads();
+            }
+            __syncthreads();                                   // (3)
+        }
     }
 }
 #endif

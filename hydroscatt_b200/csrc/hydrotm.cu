@@ -65,7 +65,7 @@ struct hs_ctx {
 static inline void hs_set_err(hs_ctx *ctx, const std::string &msg)
 {
     std::lock_guard<std::mutex> lk(ctx->err_mu);
-    hs_set_err(ctx, msg);
+    ctx->err = msg;
 }
 
 #define CK(call)                                                                                   \
@@ -782,11 +782,21 @@ extern "C" int hs_observables(hs_ctx *ctx, int n, int stride, const double *d_in
 }
 
 
-extern "C" int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double *d_W, const double *d_rows,
-                                  const double *d_lam_tab, double kw_sqr, int hpol_quirk, int want_sca, double *d_obs, void *stream)
+static int psd_obs_impl(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double *d_W, const double *d_rows, const double *d_lam_tab,
+                        double kw_sqr, int hpol_quirk, int force_sca, int n_sel, const int *h_sel, double *d_obs, void *stream)
 {
     if (!ctx) return -2;
     if (n_dsd <= 0 || n_D <= 0 || n_tab <= 0) return 0;
+    if (n_sel < 1 || n_sel > 15 || !h_sel) { hs_set_err(ctx, "hs_psd_observables_sel: 1..15 selected columns"); return -3; }
+    hs::PsdSel sel;
+    sel.n = n_sel;
+    int want_sca = force_sca > 0;
+    for (int q = 0; q < 15; q++) sel.col[q] = 0;
+    for (int q = 0; q < n_sel; q++) {
+        if (h_sel[q] < 0 || h_sel[q] > 14) { hs_set_err(ctx, "hs_psd_observables_sel: column index outside 0..14"); return -3; }
+        sel.col[q] = (signed char)h_sel[q];
+        if (h_sel[q] < 2 && force_sca < 0) want_sca = 1;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
     // weights + one area that is in turn the table tile, the integrated values ([64][65]) and the staged observables
@@ -799,7 +809,53 @@ extern "C" int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, co
     int per = ((n_tab + splits - 1) / splits + PSDF_TB - 1) / PSDF_TB * PSDF_TB;
     splits = (n_tab + per - 1) / per;
     dim3 grid(rb, splits);
-    hs::k_psd_obs_fused<<<grid, 256, smem, st>>>(n_dsd, n_D, n_tab, per, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, want_sca, d_obs);
+    hs::k_psd_obs_fused<<<grid, 256, smem, st>>>(n_dsd, n_D, n_tab, per, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, want_sca, sel, d_obs);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double *d_W, const double *d_rows,
+                                  const double *d_lam_tab, double kw_sqr, int hpol_quirk, int want_sca, double *d_obs, void *stream)
+{
+    // all 15 columns; without want_sca the two scattering cross sections are NaN (the table build may not have them)
+    int sel[15];
+    for (int q = 0; q < 15; q++) sel[q] = q;
+    return psd_obs_impl(ctx, n_dsd, n_D, n_tab, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, want_sca ? 1 : 0, 15, sel, d_obs, stream);
+}
+
+extern "C" int hs_psd_observables_sel(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double *d_W, const double *d_rows,
+                                      const double *d_lam_tab, double kw_sqr, int hpol_quirk, int n_sel, const int *h_sel,
+                                      double *d_obs, void *stream)
+{
+    return psd_obs_impl(ctx, n_dsd, n_D, n_tab, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, -1, n_sel, h_sel, d_obs, stream);
+}
+
+extern "C" int hs_pack_rows(hs_ctx *ctx, int n, int n_geom, const double *d_S, const double *d_Z, const double *d_xs, const double *d_lam,
+                            int g_back, int g_forw, int f_back, int f_forw, double *d_rows, void *stream)
+{
+    if (!ctx) return -2;
+    if (n <= 0) return 0;
+    const int idx[4] = {g_back, g_forw, f_back, f_forw};
+    for (int q = 0; q < 4; q++)
+        if (idx[q] < 0 || idx[q] >= n_geom) { hs_set_err(ctx, "hs_pack_rows: geometry index out of range"); return -3; }
+    CK(cudaSetDevice(ctx->device));
+    const long tot = (long)n * 56;
+    hs::k_pack_rows<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, n_geom, d_S, d_Z, d_xs, d_lam, g_back, g_forw,
+                                                                                    f_back, f_forw, d_rows);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hs_gather_rows(hs_ctx *ctx, long long n_out, int ncol, const double *d_src, const long long *d_index, double *d_dst,
+                              void *stream)
+{
+    if (!ctx) return -2;
+    if (n_out <= 0 || ncol <= 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const long tot = (long)n_out * ncol;
+    hs::k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>((long)n_out, ncol, d_src, d_index, d_dst);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -946,11 +1002,12 @@ extern "C" int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const do
     a.n = n; a.dpart = d_dpart; a.dcore = d_dcore; a.aovrb = d_aovrb; a.aovrb2 = d_aovrb2;
     a.eor = d_eor; a.eoi = d_eoi; a.eir = d_eir; a.eii = d_eii; a.alamd = wavelength_cm;
     a.amp = d_amp; a.status = d_status;
-    size_t smem = (size_t)hs::t2_smem_doubles() * sizeof(double);
+    size_t smem = (size_t)hs::t2_smem_doubles(2) * sizeof(double);
     CK(cudaFuncSetAttribute(hs::k_tm2l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaMemsetAsync(ctx->d_queue + 8, 0, sizeof(int), st));
     int grid = std::min(n, ctx->sm_count);
-    hs::k_tm2l<<<grid, 256, smem, st>>>(a, ctx->d_queue + 8);
+    static const int split = getenv("HYDROTM_TM2L_SPLIT") ? std::max(1, std::min(4, atoi(getenv("HYDROTM_TM2L_SPLIT")))) : 2;
+    hs::k_tm2l<<<grid, T2_ASM_THREADS + T2_SOLVE_THREADS, smem, st>>>(a, ctx->d_queue + 8, split == 3 ? 2 : split);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

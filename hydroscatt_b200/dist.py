@@ -58,19 +58,73 @@ def allreduce_sum(t, group=None):
     return t
 
 
+class ShardPlan:
+    """Cost-sorted round-robin deal of n particles over the ranks, and the permutation that puts the all-gathered shard records
+    back into particle order.  Built once per particle list (host side, numpy); `gather` is then one collective
+    (all_gather_into_tensor) plus one reorder kernel per step."""
+
+    def __init__(self, cost, world=None, rank=None, group=None):
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        cost = np.asarray(cost, dtype=np.float64)
+        order = np.argsort(-cost, kind="stable")
+        self.world, self.rank, self.group, self.n = world, rank, group, cost.size
+        self.parts = [np.sort(order[r::world]) for r in range(world)]
+        self.idx = self.parts[rank]
+        self.n_max = max(p.size for p in self.parts) if cost.size else 0
+        inv = np.empty(cost.size, dtype=np.int64)
+        for r, part in enumerate(self.parts):
+            inv[part] = r * self.n_max + np.arange(part.size)
+        self.inv = inv                    # particle i sits at record inv[i] of the gathered (rank-major) array
+        self._inv_dev = {}
+
+    def inv_on(self, device):
+        key = str(device)
+        if key not in self._inv_dev:
+            self._inv_dev[key] = torch.from_numpy(self.inv).to(device)
+        return self._inv_dev[key]
+
+    def gather(self, local, eng=None, out=None):
+        """local [n_local, C] records of this rank's particles (in the order of self.idx) -> [n, C] records of ALL particles
+        in particle order, on every rank.  eng: hydroscatt_b200 Engine (the reorder runs as hs_gather_rows on its device);
+        None: torch index_select (CPU tensors, gloo)."""
+        C = local.shape[1]
+        if self.world == 1:
+            gathered = local
+        else:
+            if local.shape[0] != self.n_max:
+                pad = torch.zeros((self.n_max, C), dtype=local.dtype, device=local.device)
+                pad[:local.shape[0]] = local
+                local = pad
+            gathered = torch.empty((self.world * self.n_max, C), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(gathered, local.contiguous(), group=self.group)
+        inv = self.inv_on(local.device)
+        if eng is not None:
+            return eng.gather_rows(gathered, inv, out=out)
+        res = gathered.index_select(0, inv)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+
 def build_rows_sharded(eng, radius, wavelength, m_re, m_im, axis_ratio, geom_back, geom_forw, alpha, beta, weight,
-                       scale, group=None, **kw):
-    """Strong-scaling table build: every rank computes its cost-balanced shard, then all ranks hold the full table."""
+                       scale, group=None, plan=None, **kw):
+    """Sharded table build: every rank computes its cost-balanced shard (no collective inside the solve), then ONE all-gather
+    gives every rank the complete table.  Returns (rows [n, 56], meta [n, 4] int32 = nmax, ngauss, trials,
+    status) in particle order."""
     from . import tables
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     arrs = [np.asarray(a, dtype=np.float64) for a in (radius, wavelength, m_re, m_im, axis_ratio)]
     n = max(a.size for a in arrs)
     arrs = [np.broadcast_to(a, (n,)) for a in arrs]
-    idx = shard_indices(predicted_cost(*arrs), world, rank)
+    if plan is None:
+        plan = ShardPlan(predicted_cost(*arrs), group=group)
+    idx = plan.idx
     rows, tb = tables.build_rows(eng, *[a[idx] for a in arrs], geom_back, geom_forw, alpha, beta, weight, scale, **kw)
     meta = torch.stack([tb.nmax, tb.ngauss, tb.ntrials, tb.status], dim=1).to(torch.float64)
-    full = gather_rows(torch.cat([rows, meta], dim=1), idx, n, group)
+    full = plan.gather(torch.cat([rows, meta], dim=1), eng=eng)
     return full[:, :tables.ROW].contiguous(), full[:, tables.ROW:].to(torch.int32)
 
 

@@ -189,21 +189,58 @@ class Engine:
             raise EngineError(f"hs_psd_integrate rc={rc}: " + self._err())
         return out
 
-    def psd_observables(self, W, rows, n_tab, lam_tab, kw_sqr=0.93, hpol_quirk=True, want_sca=False):
+    def psd_observables(self, W, rows, n_tab, lam_tab, kw_sqr=0.93, hpol_quirk=True, want_sca=False, columns=None):
         """obs[n_dsd, n_tab, 15] straight from the weights W[n_dsd, n_D] and the table records rows[n_tab*n_D, 56]
-        (fused PSD integration + radar observables; the integrated S/Z array is never written)."""
+        (fused PSD integration + radar observables; the integrated S/Z array is never written).  columns: optional list of
+        indices into tables.OBS_COLUMNS -> obs[n_dsd, n_tab, len(columns)] holds only those, in that order."""
         W = W.contiguous()
         rows = rows.contiguous()
         nd, nD = W.shape
         assert rows.shape[0] == n_tab * nD and rows.shape[1] == 56
         lam_tab = self._dev(lam_tab, n_tab)
-        obs = torch.empty((nd, n_tab, 15), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            rc = self.lib.hs_psd_observables(self._h, nd, nD, n_tab, _ptr(W), _ptr(rows), _ptr(lam_tab), float(kw_sqr),
-                                             1 if hpol_quirk else 0, 1 if want_sca else 0, _ptr(obs), self._stream())
+            if columns is None:
+                obs = torch.empty((nd, n_tab, 15), dtype=torch.float64, device=self.device)
+                rc = self.lib.hs_psd_observables(self._h, nd, nD, n_tab, _ptr(W), _ptr(rows), _ptr(lam_tab), float(kw_sqr),
+                                                 1 if hpol_quirk else 0, 1 if want_sca else 0, _ptr(obs), self._stream())
+            else:
+                sel = (C.c_int * len(columns))(*[int(c) for c in columns])
+                obs = torch.empty((nd, n_tab, len(columns)), dtype=torch.float64, device=self.device)
+                rc = self.lib.hs_psd_observables_sel(self._h, nd, nD, n_tab, _ptr(W), _ptr(rows), _ptr(lam_tab), float(kw_sqr),
+                                                     1 if hpol_quirk else 0, len(columns), sel, _ptr(obs), self._stream())
         if rc != 0:
             raise EngineError(f"hs_psd_observables rc={rc}: " + self._err())
         return obs
+
+    def pack_rows(self, S, Z, xs, lam, g_back=0, g_forw=1, f_back=None, f_forw=None, out=None):
+        """Table records [n, 56] (tables.py layout) from hs_scatter_batch's S [n, G, 2, 2], Z [n, G, 4, 4], xs [n, G, 2]."""
+        n, G = S.shape[0], S.shape[1]
+        S, Z, xs = S.contiguous(), Z.contiguous(), xs.contiguous()
+        lam = self._dev(lam, n)
+        rows = out if out is not None else torch.empty((n, 56), dtype=torch.float64, device=self.device)
+        assert rows.is_contiguous() and rows.shape == (n, 56)
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_pack_rows(self._h, n, G, _ptr(S), _ptr(Z), _ptr(xs), _ptr(lam), int(g_back), int(g_forw),
+                                       int(g_forw if f_back is None else f_back), int(g_forw if f_forw is None else f_forw),
+                                       _ptr(rows), self._stream())
+        if rc != 0:
+            raise EngineError(f"hs_pack_rows rc={rc}: " + self._err())
+        return rows
+
+    def gather_rows(self, src, index, out=None):
+        """out[i] = src[index[i]] for records of doubles (index: int64 device tensor; negative entries leave out[i] untouched)."""
+        src = src.contiguous()
+        ncol = src.shape[1]
+        index = index.contiguous()
+        n_out = index.numel()
+        if out is None:
+            out = torch.empty((n_out, ncol), dtype=torch.float64, device=self.device)
+        assert out.is_contiguous() and out.shape == (n_out, ncol) and index.dtype == torch.int64
+        with torch.cuda.device(self.device):
+            rc = self.lib.hs_gather_rows(self._h, n_out, ncol, _ptr(src), _ptr(index), _ptr(out), self._stream())
+        if rc != 0:
+            raise EngineError(f"hs_gather_rows rc={rc}: " + self._err())
+        return out
 
     def observables(self, rows, off_back, off_forw, off_ext, off_sca, lam, kw_sqr=0.93):
         """[n,15] radar observables from rows [n, stride] (layout: include/hydrotm.h hs_observables)."""

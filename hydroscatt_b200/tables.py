@@ -34,18 +34,7 @@ def build_rows(eng, radius, wavelength, m_re, m_im, axis_ratio, geom_back, geom_
     allg = geoms + [f for f in dict.fromkeys(fw) if f not in geoms]
     tb, S, Z, xs = eng.calctmat_scatter(radius, wavelength, m_re, m_im, axis_ratio, allg, alpha, beta, weight=weight,
                                         scale=scale, want_xs=True, rat=rat, ddelt=ddelt, ndgs=ndgs, rescale_ddelt=rescale_ddelt)
-    n = tb.n
-    rows = torch.empty((n, ROW), dtype=torch.float64, device=eng.device)
-    Sr = torch.view_as_real(S).reshape(n, len(allg), 8)
-    Zr = Z.reshape(n, len(allg), 16)
-    lam = tb.lam
-    for gi in range(2):
-        rows[:, 24 * gi:24 * gi + 8] = Sr[:, gi]
-        rows[:, 24 * gi + 8:24 * gi + 24] = Zr[:, gi]
-        rows[:, 48 + 2 * gi:50 + 2 * gi] = xs[:, gi]
-        fi = allg.index(fw[gi])
-        rows[:, 52 + 2 * gi] = 2.0 * lam * Sr[:, fi, 7]   # 2 lambda Im S22
-        rows[:, 53 + 2 * gi] = 2.0 * lam * Sr[:, fi, 1]   # 2 lambda Im S11
+    rows = eng.pack_rows(S, Z, xs, tb.lam, 0, 1, allg.index(fw[0]), allg.index(fw[1]))
     return rows, tb
 
 
@@ -55,19 +44,22 @@ def sp_observables(eng, rows, lam, kw_sqr=0.93):
 
 
 def integrate_psd(eng, rows, n_tab, D, kind, p0, p1, p2, dmax, lam_tab, rule="trapz", kw_sqr=0.93,
-                  hpol_quirk=True, want_integ=True):
+                  hpol_quirk=True, want_integ=True, columns=None):
     """PSD-integrate n_tab tables (rows [n_tab*n_D, 56], table-major) over n_dsd size distributions and derive the
     observables of compute_scattering_psd_tm (scattering.py:530-587).
 
     Returns (obs [n_dsd, n_tab, 15], integ [n_dsd, n_tab, 56]) on the device.  want_integ=False runs the fused kernel
-    (hs_psd_observables): only the integrals the observables read are formed, on chip, and integ is None.
+    (hs_psd_observables): only the integrals the observables read are formed, on chip, and integ is None; columns
+    (names or indices of OBS_COLUMNS) then selects which observables are written: obs [n_dsd, n_tab, len(columns)].
     """
     D = np.asarray(D, dtype=np.float64)
     n_D = D.size
     wq = trapz_weights(D) if rule == "trapz" else rect_weights(D)
     W = eng.psd_weights(kind, p0, p1, p2, dmax, D, wq)                       # [n_dsd, n_D]
     if not want_integ:
-        return eng.psd_observables(W, rows, n_tab, lam_tab, kw_sqr, hpol_quirk, want_sca=False), None
+        if columns is not None:
+            columns = [OBS_COLUMNS.index(c) if isinstance(c, str) else int(c) for c in columns]
+        return eng.psd_observables(W, rows, n_tab, lam_tab, kw_sqr, hpol_quirk, want_sca=False, columns=columns), None
     Tt = rows.reshape(n_tab, n_D, ROW).permute(1, 0, 2).reshape(n_D, n_tab * ROW).contiguous()
     integ = eng.psd_integrate(W, Tt)                                          # [n_dsd, n_tab*56]
     n_dsd = integ.shape[0]

@@ -169,6 +169,33 @@ int hs_psd_observables(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double 
                        const double *d_lam_tab, double kw_sqr, int hpol_quirk, int want_sca, double *d_obs, void *stream);
 
 /*
+ * Same, writing only the n_sel (1..15) observable columns the caller names, in the caller's order: d_obs [n_dsd][n_tab][n_sel],
+ * h_sel = HOST array of column indices into the 15-column list of hs_observables (e.g. {2, 4, 11, 7, 12, 14} = Zh, Zdr, Kdp,
+ * rhohv, Ah, Adp, the columns scattering_rain.py:296-316 keeps per DSD).  The scattering cross sections (columns 0, 1) are
+ * integrated only when selected.
+ */
+int hs_psd_observables_sel(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double *d_W, const double *d_rows,
+                           const double *d_lam_tab, double kw_sqr, int hpol_quirk, int n_sel, const int *h_sel, double *d_obs,
+                           void *stream);
+
+/*
+ * Table records (56 doubles per particle, layout in hydroscatt_b200/tables.py: what PSDIntegrator.init_scatter_table keeps per
+ * diameter as _S_table / _Z_table / _angular_table) from the outputs of hs_scatter_batch: d_S [n][n_geom][2][2] complex,
+ * d_Z [n][n_geom][4][4], d_xs [n][n_geom][2], d_lam [n].  g_back / g_forw: index of the back / forward geometry; f_back /
+ * f_forw: index of the geometry whose S is the forward amplitude at that geometry's incidence direction (ext_xsect by the
+ * optical theorem, scatter.ext_xsect).  d_rows: [n][56].
+ */
+int hs_pack_rows(hs_ctx *ctx, int n, int n_geom, const double *d_S, const double *d_Z, const double *d_xs, const double *d_lam,
+                 int g_back, int g_forw, int f_back, int f_forw, double *d_rows, void *stream);
+
+/*
+ * d_dst[i][0..ncol) = d_src[d_index[i]][0..ncol) for i < n_out (records of ncol doubles; d_index: device int64, negative = leave
+ * d_dst[i] untouched).  Used by the multi-GPU table build to put all-gathered shard records back into table order.
+ */
+int hs_gather_rows(hs_ctx *ctx, long long n_out, int ncol, const double *d_src, const long long *d_index, double *d_dst,
+                   void *stream);
+
+/*
  * Radar observables per row (radar.refl/Zdr/ldr/rho_hv/delta_hv/Kdp/Ai, scatter.sca_xsect/ext_xsect as combined
  * by scattering.py:451-587).  d_in: [n][stride]; column offsets: off_back / off_forw -> S(8 doubles) Z(16 doubles)
  * of the back / forward geometry, off_ext -> ext_xsect_h, ext_xsect_v (or -1: optical theorem on the forward S),

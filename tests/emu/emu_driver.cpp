@@ -66,7 +66,7 @@ extern "C" void emu_tm2l(int n, const double *p8, double alamd, double *amp, int
     a.n = n; a.dpart = col[0].data(); a.dcore = col[1].data(); a.aovrb = col[2].data(); a.aovrb2 = col[3].data();
     a.eor = col[4].data(); a.eoi = col[5].data(); a.eir = col[6].data(); a.eii = col[7].data();
     a.alamd = alamd; a.amp = amp; a.status = status;
-    std::vector<double> smem(hs::t2_smem_doubles() + 16);
+    std::vector<double> smem(hs::t2_smem_doubles(1) + 16);
     hs::Ctl ctl;
     double cmx[T2_NRANKI], acc[8];
     for (int i = 0; i < n; i++) { ctl.sing = 0; hs::tm2l_particle(a, i, smem.data(), &ctl, cmx, acc, 0, 1); }

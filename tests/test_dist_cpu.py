@@ -31,6 +31,11 @@ def _worker(rank, world, port, n, q):
         full = hdist.gather_rows(local, idx, n)
         ok = bool(torch.equal(full[:, 0], torch.arange(n, dtype=torch.float64))) and \
             bool(torch.allclose(full[:, 2], torch.from_numpy(cost)))
+        # ShardPlan: same deal, one all_gather_into_tensor + reorder (uneven shards: n is odd, the short one is padded)
+        plan = hdist.ShardPlan(cost)
+        ok = ok and np.array_equal(plan.idx, idx) and plan.world == world and plan.rank == rank
+        full2 = plan.gather(local)
+        ok = ok and bool(torch.equal(full2, full))
         part = torch.full((4, 3), float(rank + 1), dtype=torch.float64)
         hdist.allreduce_sum(part)
         ok = ok and bool((part == 3.0).all())
@@ -86,7 +91,7 @@ def test_bench_reference_arm_under_torchrun_world2():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29631", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-           "--warmup", "0", "--cpu-stride", "64"]
+           "--warmup", "0", "--cpu-stride", "64", "--cpu-tm2l-stride", "1024"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
@@ -94,4 +99,5 @@ def test_bench_reference_arm_under_torchrun_world2():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "T-matrix solves/s" and d["unit"] == "solves/s" and d["n_gpus"] == 2
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["tm2l"]["value"] > 0 and d["tm2l"]["kind"] == "port"
     assert d["e2e"] == {"value": d["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -227,7 +227,7 @@ struct T2Mat {
 };
 struct T2Smem {
     // node scalars [31]
-    double *sinth, *costh, *ckr, *dckr, *ckp2r, *ckp2i, *dkp2r, *dkp2i, *theta;
+    double *sinth, *costh, *ckr, *dckr, *ckp2r, *ckp2i, *dkp2r, *dkp2i, *theta, *rckr, *tinvr, *tinvi;
     // row tables [31][17] (index n-1)
     double *bj, *by, *j2r, *j2i, *h2r, *h2i, *rb, *rhr, *rhi, *rb2r, *rb2i, *rh2r, *rh2i;
     // column tables [31][17]
@@ -239,19 +239,19 @@ struct T2Smem {
 #define T2_MAT_DOUBLES (2 * (4 * 2 * 289 + 2 * 17 * 34))
 __host__ __device__ inline int t2_smem_doubles(int nbuf = 2)
 {
-    return 9 * T2_NNODE + 25 * T2_TAB + T2_NNODE * T2_NRANKI + nbuf * T2_MAT_DOUBLES;
+    return 12 * T2_NNODE + 25 * T2_TAB + T2_NNODE * T2_NRANKI + nbuf * T2_MAT_DOUBLES;
 }
 __device__ inline void t2_carve(T2Smem &s, double *p, int nbuf = 2)
 {
     s.sinth = p; p += T2_NNODE; s.costh = p; p += T2_NNODE; s.ckr = p; p += T2_NNODE; s.dckr = p; p += T2_NNODE;
     s.ckp2r = p; p += T2_NNODE; s.ckp2i = p; p += T2_NNODE; s.dkp2r = p; p += T2_NNODE; s.dkp2i = p; p += T2_NNODE;
-    s.theta = p; p += T2_NNODE;
+    s.theta = p; p += T2_NNODE; s.rckr = p; p += T2_NNODE; s.tinvr = p; p += T2_NNODE; s.tinvi = p; p += T2_NNODE;
     double **tabs[25] = {&s.bj, &s.by, &s.j2r, &s.j2i, &s.h2r, &s.h2i, &s.rb, &s.rhr, &s.rhi, &s.rb2r, &s.rb2i,
                          &s.rh2r, &s.rh2i, &s.jkr, &s.jki, &s.hkr, &s.hki, &s.j3r, &s.j3i, &s.rbkr, &s.rbki,
                          &s.rhkr, &s.rhki, &s.rbk2r, &s.rbk2i};
     for (int i = 0; i < 25; i++) { *tabs[i] = p; p += T2_TAB; }
     s.pn = p; p += T2_NNODE * T2_NRANKI;
-    if ((9 * T2_NNODE + 25 * T2_TAB + T2_NNODE * T2_NRANKI) & 1) p++;  // (even: 14012 doubles, double2-aligned)
+    if ((12 * T2_NNODE + 25 * T2_TAB + T2_NNODE * T2_NRANKI) & 1) p++;  // double2 alignment (14105 doubles before the matrices)
     for (int b = 0; b < 2; b++) {
         T2Mat &m = s.mat[b];
         if (b >= nbuf) { m = s.mat[0]; continue; }
@@ -269,7 +269,21 @@ struct T2Args {
     double alamd;
     double *amp;   // [n][8]
     int *status;   // [n]
+    unsigned long long *prof;  // HYDROTM_PROF: cycles per phase, summed over particles (slots: T2P_*) or null
 };
+enum { T2P_TABLES = 0, T2P_ASM, T2P_ASM_WAIT, T2P_CHAIN, T2P_CHAIN_WAIT, T2P_SOLVE1, T2P_PRODUCTS, T2P_SOLVE2, T2P_ADDPRC, T2P_PARTICLES, T2P_N };
+#ifdef HS_HOST_EMU
+#define T2_PROF(cond, slot)
+#define T2_PROF_T0
+#else
+#define T2_PROF_T0 long long tprof_ = clock64();
+#define T2_PROF(cond, slot)                                                                              \
+    if (prof_ && (cond)) {                                                                               \
+        const long long now_ = clock64();                                                                \
+        atomicAdd(&prof_[slot], (unsigned long long)(now_ - tprof_));                                    \
+        tprof_ = now_;                                                                                   \
+    }
+#endif
 
 // a group of threads that works on one phase: lane `tid` of `nt`, synchronised by named barrier `bar` (0 = whole CTA)
 struct T2Grp {
@@ -337,6 +351,9 @@ __device__ void t2_tables(const T2Par &P, T2Smem &s, const T2Grp &g)
         double ckr2 = P.conk2 * qb2, dckr2 = P.conk2 * cs * sn * (bovra2 * bovra2 - 1.0) * qb2 * qb2 * qb2;
         s.ckp2r[t] = sq1.x * ckr2; s.ckp2i[t] = sq1.y * ckr2;
         s.dkp2r[t] = sq1.x * dckr2; s.dkp2i[t] = sq1.y * dckr2;
+        // reciprocals the integrand would otherwise form for every (pair, node): 1 / kr and 1 / (k' r2)
+        s.rckr[t] = 1.0 / s.ckr[t];
+        { const cd ti = mk(1.0, 0.0) / mk(s.ckp2r[t], s.ckp2i[t]); s.tinvr[t] = ti.x; s.tinvi[t] = ti.y; }
         // park kr2 for the iswt=3 task
         s.pn[t] = ckr2;
     }
@@ -430,7 +447,8 @@ __device__ __forceinline__ void t2_pair_nodes(const T2Par &P, const T2Smem &s, i
             const double b1 = b1a + b1b;
             const cd htbk = h * bk, btbk = bk * br, bthk = hk * br, hthk = h * hk;
             const double fac = 2.0 * cmv * sinth;
-            const double gs = dckr * sinth * pnr1c1, tl = crssij * (crij + 2.0) / ckr, t0 = crssij / ckr;
+            const double rckr = s.rckr[t];
+            const double gs = dckr * sinth * pnr1c1, tl = crssij * (crij + 2.0) * rckr, t0 = crssij * rckr;
             const cd suma = (bk * (crow * crow1) + h * (ccol * ccol1) - tl) * gs;
             const cd sumb = (bk * (crow * crow1) + (ccol * ccol1 * br - tl)) * gs;
             const cd sumc = (hk * (crow * crow1) + (ccol * ccol1 * br - tl)) * gs;
@@ -445,7 +463,7 @@ __device__ __forceinline__ void t2_pair_nodes(const T2Par &P, const T2Smem &s, i
             v[2] = ((cc * bc + sumc) * bhkml) * fac;
             v[3] = ((cdd * bc + sumd) * hhkml) * fac;
             const cd htbk2 = h2 * bk2, btbk2 = b2 * bk2;
-            const cd tinv = mk(1.0, 0.0) / ckp2;
+            const cd tinv = mk(s.tinvr[t], s.tinvi[t]);
             const cd sumg = ((bk2 * (crow * crow1) + h2 * (ccol * ccol1) - tinv * (crssij * (crij + 2.0))) * (pnr1c1 * sinth)) * dkp2;
             const cd sumh = ((bk2 * (crow * crow1) + b2 * (ccol * ccol1) - tinv * (crssij * (crij + 2.0))) * (pnr1c1 * sinth)) * dkp2;
             const cd rx = h2 * ccol + bk2 * crow - tinv * crssij;
@@ -573,39 +591,161 @@ __device__ void t2_assemble(const T2Par &P, T2Smem &s, const T2Mat &M, int kmv, 
     }
 }
 
-// both parity-class systems [2][NMq][2 NMq] of M.aug: right half <- (left half)^-1 (right half)  (prcssm, :2177-2280)
+#ifndef HS_HOST_EMU
+// One parity-class system  L X = R  (L, R: [NMq][NMq] row-major with row strides ldl, ldr) eliminated by TWO warps out of
+// registers: warp `part` 0 owns L, warp 1 owns R; lane r < 17 keeps ROW r of its part in registers, padded to order 17 with
+// identity rows / columns (a padded row is the only candidate of its own column, so the real rows are eliminated exactly as in the
+// unpadded system).  A step: the L lanes publish their entries of pivot column k (one STS each, double-buffered, one 64-lane named
+// barrier per step); every warp finds the pivot row with two warp reductions (same rule as prcssm / solve_multi: largest
+// |re| + |im| among the rows not used yet, low 8 mantissa bits dropped, ties to the lowest row); the lane that holds the pivot row
+// scales it and publishes it to its own warp; every lane updates its row.  Rows are never moved: `vp` is the position the row would
+// have after the reference's row swaps, so the lane ends up holding solution row vp, which it writes to out[vp][.] (row stride ldo).
+// No LDS -> DFMA -> STS round trip per row update, ~300 instructions per step and warp.
+__device__ __forceinline__ void t2_solve_rows(const double2 *L, int ldl, const double2 *R, int ldr, double2 *out, int ldo, int NMq,
+                                              int part, int lane, int barid, double2 *colbuf, double2 *rowbuf, int *sing,
+                                              const double *rowscale = nullptr, const double *colscale = nullptr)
+{
+    const unsigned FULL = 0xffffffffu;
+    double2 v[T2_NRANK];
+    const bool realr = lane < NMq;
+    const double2 *src = part ? R + lane * ldr : L + lane * ldl;
+#pragma unroll
+    for (int j = 0; j < T2_NRANK; j++) {
+        double2 x = make_double2(0.0, 0.0);
+        if (realr && j < NMq) x = src[j];
+        else if (part == 0 && j == lane) x.x = 1.0;
+        v[j] = x;
+    }
+    int vp = lane;
+    double2 f = v[0];                             // this row's entry of the pivot column (L part)
+    double2 sc = make_double2(1.0, 0.0);          // pending scale of this row: true row = sc * v (set when the row is the pivot)
+    // NMq steps: the padded rows / columns (identity) never interact with the real ones
+    for (int k = 0; k < NMq; k++) {
+        double2 *cb = colbuf + (k & 1) * T2_NRANK;
+        if (part == 0 && lane < T2_NRANK) cb[lane] = f;
+        asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(64) : "memory");
+        double2 c = make_double2(0.0, 0.0);
+        if (lane < T2_NRANK) c = cb[lane];
+        // pivot row: only rows not used yet are candidates, and their pending scale is still 1
+        const bool cand = lane < T2_NRANK && vp >= k;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(c.x) + fabs(c.y));
+        const unsigned hi = (unsigned)(bits >> 32) + 1u, lo = ((unsigned)bits & 0xFFFFFF00u) | (unsigned)(255 - vp);
+        const unsigned m1 = __reduce_max_sync(FULL, cand ? hi : 0u);
+        const bool top = cand && hi == m1;
+        const unsigned m2 = __reduce_max_sync(FULL, top ? lo : 0u);
+        const int P = __ffs(__ballot_sync(FULL, top && lo == m2)) - 1;
+        if (m1 == 1u && (m2 >> 8) == 0u && part == 0 && lane == 0) *sing = 1;
+        // the pivot lane hands its row to the warp as it is (no arithmetic in a one-lane branch: FP64 issue slots are charged per
+        // warp instruction).  With W = sc * V the true rows, the step  W_r -= W_r[k] (W_P / pivot)  reads  V_r -= (V_r[k] / pivot) V_P
+        // for every row r != P whatever its pending scale, and the pivot row only records sc_P = 1 / pivot.
+        if (lane == P) {
+#pragma unroll
+            for (int j = 0; j < T2_NRANK; j++) rowbuf[j] = v[j];
+        }
+        const double pvx = __shfl_sync(FULL, c.x, P), pvy = __shfl_sync(FULL, c.y, P);
+        const int vpP = __shfl_sync(FULL, vp, P);
+        const double rden = hs_rcp(pvx * pvx + pvy * pvy);
+        const double2 inv = make_double2(pvx * rden, -pvy * rden);
+        double2 cs = make_double2(-(c.x * inv.x - c.y * inv.y), -(c.x * inv.y + c.y * inv.x));
+        if (lane == P) { cs = make_double2(0.0, 0.0); sc = inv; }
+        __syncwarp();
+        double2 fn = f;
+#pragma unroll
+        for (int j0 = 0; j0 < T2_NRANK; j0 += 4) {
+            double2 rw[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (j0 + q < T2_NRANK) rw[q] = rowbuf[j0 + q];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + q;
+                if (j < T2_NRANK) {
+                    double2 u = v[j];
+                    u.x = fma(-cs.y, rw[q].y, fma(cs.x, rw[q].x, u.x));
+                    u.y = fma(cs.y, rw[q].x, fma(cs.x, rw[q].y, u.y));
+                    v[j] = u;
+                    if (j == k + 1) fn = u;
+                }
+            }
+        }
+        f = fn;
+        if (vp == k) vp = vpP;
+        if (lane == P) vp = k;
+        __syncwarp();  // rowbuf is rewritten by the next step's pivot lane
+    }
+    if (part == 1 && realr) {
+        // solution row vp = sc * v, times the caller's row / column factors (cmxnrm rescaling of T2, tmatrix_py.f:387-399)
+        const double rs = rowscale ? rowscale[vp] : 1.0;
+        const double2 s2 = make_double2(sc.x * rs, sc.y * rs);
+#pragma unroll
+        for (int j = 0; j < T2_NRANK; j++)
+            if (j < NMq) {
+                const double cj = colscale ? colscale[j] : 1.0;
+                out[vp * ldo + j] = make_double2((v[j].x * s2.x - v[j].y * s2.y) * cj, (v[j].x * s2.y + v[j].y * s2.x) * cj);
+            }
+    }
+}
+#endif
+
 struct T2SolveWs {
-    Ctl *ctl;                       // generic solver (host emulation): descriptors + pivot keys
-    unsigned long long *keyslot;    // [2][2] pivot ping-pong of the two class groups (device)
+    Ctl *ctl;            // generic solver (host emulation): descriptors + pivot keys
+    double2 *colbuf;     // [2 classes][2][17] published pivot columns (device)
+    double2 *rowbuf;     // [4 warps][17] published pivot rows (device)
     int *sing;
 };
-__device__ __forceinline__ void t2_solve(const T2Mat &M, int NMq, const T2Grp &g, const T2SolveWs &ws)
+// both parity classes: M.aug right half <- L^-1 R with [L | R] = M.aug (which = 0: x, y) or L = M.A, R = M.B (which = 1: Bn, X)
+// (prcssm, tmatrix_py.f:2177-2280).  Ends with a group barrier.
+__device__ __forceinline__ void t2_solve(const T2Mat &M, int NMq, const T2Grp &g, const T2SolveWs &ws, int which,
+                                         const double *rowscale = nullptr, const double *colscale = nullptr)
 {
+    const int lda = 2 * NMq;
 #ifdef HS_HOST_EMU
+    if (which) {
+        for (int e = g.tid; e < 2 * NMq * NMq; e += g.nt) {
+            int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
+            M.aug[(c * NMq + r) * lda + q] = M.A[(c * NMq + r) * NMq + q];
+            M.aug[(c * NMq + r) * lda + NMq + q] = M.B[(c * NMq + r) * NMq + q];
+        }
+        t2_sync(g);
+    }
     Grp<false> grp;
     grp.tid = g.tid; grp.nt = g.nt;
     Carve cv;
     cv.sys = M.aug;
     solve(grp, cv, NMq, ws.ctl);
     if (ws.ctl->sing) *ws.sing = 1;
+    if (rowscale) {
+        for (int e = g.tid; e < 2 * NMq * NMq; e += g.nt) {
+            int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
+            double2 &y = M.aug[(c * NMq + r) * lda + NMq + q];
+            const double sc = rowscale[r] * colscale[q];
+            y.x *= sc; y.y *= sc;
+        }
+        t2_sync(g);
+    }
 #else
-    // 64 lanes per class (two whole warps; named barriers 1 and 2), the shared-space Gauss-Jordan of the single-layer pipeline
-    const int cl = g.tid >> 6;
-    SysDesc d;
-    d.base = M.aug + cl * NMq * 2 * NMq; d.n = NMq; d.ld = 2 * NMq; d.off = 0; d.stride = 1; d.rhs = NMq;
-    solve_grp2s(d, g.tid & 63, 64, 1 + cl, ws.keyslot + 2 * cl, ws.sing);
+    // 64 lanes per class (two whole warps; named barriers 1 and 2)
+    const int cl = g.tid >> 6, warp = g.tid >> 5;
+    double2 *aug = M.aug + cl * NMq * lda;
+    if (which) t2_solve_rows(M.A + cl * NMq * NMq, NMq, M.B + cl * NMq * NMq, NMq, aug + NMq, lda, NMq, warp & 1, g.tid & 31, 1 + cl,
+                             ws.colbuf + cl * 2 * T2_NRANK, ws.rowbuf + warp * T2_NRANK, ws.sing);
+    else t2_solve_rows(aug, lda, aug + NMq, lda, aug + NMq, lda, NMq, warp & 1, g.tid & 31, 1 + cl, ws.colbuf + cl * 2 * T2_NRANK,
+                       ws.rowbuf + warp * T2_NRANK, ws.sing, rowscale, colscale);
     t2_sync(g);
 #endif
 }
 
-// ---- K3 + addprc of mode kmv on the matrices in M: T2 = x^-1 y (class-wise), rescale, X = b - T2 c, Bn = a - T2 d, T = Bn^-1 X,
-// incident / scattered coefficients and the far field at 90 deg (forward) and 270 deg (back) accumulated into s_acc.
-// Device: g = the 128 solver lanes.  Ends with a group barrier.
-__device__ void t2_chain(const T2Par &P, const T2Mat &M, int kmv, const T2Grp &g, double *s_cmx, double *s_acc, const T2SolveWs &ws)
+// Per-mode constants of the solve chain: cmxnrm (:345-368) and its reciprocal, and for the two far-field angles (90 deg forward,
+// 270 deg back, :175) the angular factors p1 = n cos pn(n) - (n + m) pn(n - 1), p2 = m pn(n) of addprc (:2282-2523).
+struct T2Prep {
+    double cmx[T2_NRANKI], icmx[T2_NRANKI];
+    double2 pp[2][T2_NRANKI];
+};
+// items of t2_prep: n = 1..17 (cmx) and the two angles; any subset of lanes may run them (item = lane index, stride nl)
+__device__ inline void t2_prep(const T2Par &P, int kmv, T2Prep &pr, int item)
 {
-    const double cmv = kmv, em = kmv > 0 ? 2.0 : 1.0, prodm = t2_prodm(kmv);
-    const int nmin = kmv > 1 ? kmv : 1, NMq = T2_NRANK - nmin + 1, ld = NMq, lda = 2 * NMq;
-    for (int n = g.tid + 1; n <= T2_NRANK; n += g.nt) {
+    const double cmv = kmv, em = kmv > 0 ? 2.0 : 1.0;
+    if (item >= 1 && item <= T2_NRANK) {
+        const int n = item;
         double ck = n, fctki = 1.0, v;
         if (kmv > 0 && n < kmv) v = 1.0;
         else {
@@ -615,25 +755,38 @@ __device__ void t2_chain(const T2Par &P, const T2Mat &M, int kmv, const T2Grp &g
             }
             v = 4.0 * ck * (ck + 1.0) * fctki / (em * (2.0 * ck + 1.0));
         }
-        s_cmx[n] = v;
+        pr.cmx[n] = v;
+        pr.icmx[n] = 1.0 / v;
+    } else if (item == T2_NRANK + 1 || item == T2_NRANK + 2) {
+        const int q = item - (T2_NRANK + 1);
+        const double theta = P.dtr * (q == 0 ? 90.0 : 270.0);
+        double sn, cs, pnl[T2_NRANKI];
+        sincos(theta, &sn, &cs);
+        t2_genlgp(theta, sn, cs, kmv, t2_prodm(kmv), pnl);
+        pr.pp[q][0] = make_double2(0.0, 0.0);
+        for (int n = 1; n <= T2_NRANK; n++) pr.pp[q][n] = make_double2(n * cs * pnl[n] - (n + cmv) * pnl[n - 1], cmv * pnl[n]);
     }
-    t2_sync(g);
-    t2_solve(M, NMq, g, ws);
-    for (int e = g.tid; e < 2 * NMq * NMq; e += g.nt) {
-        int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
-        double scale = s_cmx[nmin + r] / s_cmx[nmin + q];
-        double2 &y = M.aug[(c * NMq + r) * lda + NMq + q];
-        y.x *= scale; y.y *= scale;
-    }
-    t2_sync(g);
+}
+#define T2_PREP_ITEMS (T2_NRANK + 3)
+
+// ---- K3 + addprc of mode kmv on the matrices in M: T2 = x^-1 y (class-wise), rescaled by cmxnrm; X = b - T2 c, Bn = a - T2 d (in
+// place of b and a); T = Bn^-1 X; incident / scattered coefficients and the far field at 90 deg (forward) and 270 deg (back)
+// accumulated into s_acc.  pr = t2_prep of this mode.  Device: g = the 128 solver lanes.  Ends with a group barrier.
+__device__ void t2_chain(const T2Par &P, const T2Mat &M, int kmv, const T2Grp &g, const T2Prep &pr, double *s_acc, const T2SolveWs &ws,
+                         unsigned long long *prof_ = nullptr)
+{
+    T2_PROF_T0
+    const int nmin = kmv > 1 ? kmv : 1, NMq = T2_NRANK - nmin + 1, ld = NMq, lda = 2 * NMq;
+    t2_solve(M, NMq, g, ws, 0, pr.cmx + nmin, pr.icmx + nmin);  // T2, rescaled by cmxnrm(row) / cmxnrm(column) (:387-399)
+    T2_PROF(g.tid == 0, T2P_SOLVE1)
     // in place: A <- a - T2 d (= Bn), B <- b - T2 c (= X); every (c, r, q) reads only its own entries of A and B
     for (int e = g.tid; e < 2 * NMq * NMq; e += g.nt) {
         int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
         const double2 *t2 = M.aug + (c * NMq + r) * lda + NMq;
+        const double2 *pc = M.C + c * NMq * ld + q, *pd = M.D + c * NMq * ld + q;
         double xr = 0, xi = 0, br_ = 0, bi_ = 0;
         for (int j = 0; j < NMq; j++) {
-            double2 y = t2[j];
-            double2 cc = M.C[(c * NMq + j) * ld + q], dd2 = M.D[(c * NMq + j) * ld + q];
+            const double2 y = t2[j], cc = pc[j * ld], dd2 = pd[j * ld];
             xr += y.x * cc.x - y.y * cc.y; xi += y.y * cc.x + y.x * cc.y;
             br_ += y.x * dd2.x - y.y * dd2.y; bi_ += y.y * dd2.x + y.x * dd2.y;
         }
@@ -642,63 +795,50 @@ __device__ void t2_chain(const T2Par &P, const T2Mat &M, int kmv, const T2Grp &g
         aa = make_double2(aa.x - br_, aa.y - bi_);
     }
     t2_sync(g);
-    for (int e = g.tid; e < 2 * NMq * NMq; e += g.nt) {
-        int c = e / (NMq * NMq), r = (e / NMq) % NMq, q = e % NMq;
-        M.aug[(c * NMq + r) * lda + q] = M.A[(c * NMq + r) * ld + q];
-        M.aug[(c * NMq + r) * lda + NMq + q] = M.B[(c * NMq + r) * ld + q];
-    }
-    t2_sync(g);
-    t2_solve(M, NMq, g, ws);
+    T2_PROF(g.tid == 0, T2P_PRODUCTS)
+    t2_solve(M, NMq, g, ws, 1);
+    T2_PROF(g.tid == 0, T2P_SOLVE2)
 
     // ---- addprc: T_c[r][q] = aug[c][r][NMq+q];  fg(tau_j, n_j) = sum_i ab(i) T(i, j) inside each class.
     for (int w = g.tid; w < 4 * NMq; w += g.nt) {
         const int pol = w & 1, idx = w >> 1, c = idx / NMq, q = idx - c * NMq;
-        double pnl[T2_NRANKI];
-        const double theta = P.dtr * 90.0;
-        double sn, cs;
-        sincos(theta, &sn, &cs);
-        t2_genlgp(theta, sn, cs, kmv, prodm, pnl);
         cd sacc = mk(0.0, 0.0);
         for (int r = 0; r < NMq; r++) {
             const int n = nmin + r;
             const int tau = (((n + 1) & 1) == c) ? 1 : 2;
-            const double p1 = n * cs * pnl[n] - (n + cmv) * pnl[n - 1], p2 = cmv * pnl[n];
+            const double2 pq = pr.pp[0][n];                     // incidence at 90 deg
             const int pw = (tau == 1) ? (n & 3) : ((n + 1) & 3);
             double mag;
-            if (pol == 0) mag = (tau == 1) ? -p2 : p1;   // ab1
-            else mag = (tau == 1) ? p1 : -p2;            // ab2
+            if (pol == 0) mag = (tau == 1) ? -pq.y : pq.x;   // ab1
+            else mag = (tau == 1) ? pq.x : -pq.y;            // ab2
             cd ab = (pw == 0) ? mk(mag, 0.0) : (pw == 1) ? mk(0.0, mag) : (pw == 2) ? mk(-mag, 0.0) : mk(0.0, -mag);
             double2 tt = M.aug[(c * NMq + r) * lda + NMq + q];
             sacc = sacc + ab * mk(tt.x, tt.y);
         }
-        // fg[pol][c][q] parked in matrix A storage (free after the products)
-        M.A[(pol * 2 + c) * NMq + q] = make_double2(sacc.x, sacc.y);
+        // fg[pol][c][q] parked in matrix C storage (free after the products)
+        M.C[(pol * 2 + c) * NMq + q] = make_double2(sacc.x, sacc.y);
     }
     t2_sync(g);
     for (int w = g.tid; w < 4; w += g.nt) {
         const int iu = w >> 1, pol = w & 1;
-        const double theta = P.dtr * (iu == 0 ? 90.0 : 270.0);
-        double sn, cs;
-        sincos(theta, &sn, &cs);
-        double pnl[T2_NRANKI];
-        t2_genlgp(theta, sn, cs, kmv, prodm, pnl);
         cd fa = mk(0.0, 0.0);
         for (int n = nmin; n <= T2_NRANK; n++) {
             const int k = n - nmin;
-            const double p1 = n * cs * pnl[n] - (n + cmv) * pnl[n - 1], p2 = cmv * pnl[n];
+            const double2 pq = pr.pp[iu][n];
             const int pw = (4 - ((n + 1) & 3)) & 3;  // (-i)^(n+1)
             const cd cim = (pw == 0) ? mk(1, 0) : (pw == 1) ? mk(0, 1) : (pw == 2) ? mk(-1, 0) : mk(0, -1);
-            double2 f1 = M.A[(pol * 2 + ((n + 1) & 1)) * NMq + k];   // fg(tau=1, n)
-            double2 f2 = M.A[(pol * 2 + (n & 1)) * NMq + k];         // fg(tau=2, n)
-            const double pa = pol == 0 ? p2 : p1, pb = pol == 0 ? p1 : p2;
+            double2 f1 = M.C[(pol * 2 + ((n + 1) & 1)) * NMq + k];   // fg(tau=1, n)
+            double2 f2 = M.C[(pol * 2 + (n & 1)) * NMq + k];         // fg(tau=2, n)
+            const double pa = pol == 0 ? pq.y : pq.x, pb = pol == 0 ? pq.x : pq.y;
             cd f = mk(f1.x * pa, f1.y * pa), gg = mk(-f2.y * pb, f2.x * pb);
-            cd term = (cim * (f + gg)) * (1.0 / s_cmx[n]);
+            cd term = (cim * (f + gg)) * pr.icmx[n];
             fa = (pol == 0) ? fa + term : fa - term;
         }
         s_acc[w * 2] += P.rtsfct * fa.x;
         s_acc[w * 2 + 1] += P.rtsfct * fa.y;
     }
     t2_sync(g);
+    T2_PROF(g.tid == 0, T2P_ADDPRC)
 }
 
 __device__ inline void t2_store(const T2Args &a, int p, const T2Par &P, const double *s_acc, int sing, int w)
@@ -721,16 +861,17 @@ __device__ void tm2l_particle(const T2Args &a, int p, double *smem, Ctl *ctl, do
     T2Grp g;
     g.tid = tid; g.nt = nt; g.bar = 0;
     int sing = 0;
-    unsigned long long keys[4];
+    T2Prep *pr = reinterpret_cast<T2Prep *>(s_cmx);   // caller's scratch: at least sizeof(T2Prep)
     T2SolveWs ws;
-    ws.ctl = ctl; ws.keyslot = keys; ws.sing = &sing;
+    ws.ctl = ctl; ws.colbuf = nullptr; ws.rowbuf = nullptr; ws.sing = &sing;
     t2_tables(P, s, g);
     for (int w = tid; w < 8; w += nt) s_acc[w] = 0.0;  // acans: [fwd pol1, fwd pol2, back pol1, back pol2]
     t2_sync(g);
     for (int kmv = 0; kmv < T2_NM; kmv++) {
         t2_assemble(P, s, s.mat[0], kmv, g, 1);
+        for (int it = tid; it < T2_PREP_ITEMS; it += nt) t2_prep(P, kmv, *pr, it);
         t2_sync(g);
-        t2_chain(P, s.mat[0], kmv, g, s_cmx, s_acc, ws);
+        t2_chain(P, s.mat[0], kmv, g, *pr, s_acc, ws);
     }
     for (int w = tid; w < 4; w += nt) t2_store(a, p, P, s_acc, sing, w);
     t2_sync(g);
@@ -739,17 +880,17 @@ __device__ void tm2l_particle(const T2Args &a, int p, double *smem, Ctl *ctl, do
 #ifndef HS_HOST_EMU
 #define T2_ASM_THREADS 256
 #define T2_SOLVE_THREADS 128
-#define T2_ASM_REGS 200
-#define T2_SOLVE_REGS 96
-// Persistent CTAs pull particles from a queue.  Stage s of a particle: the assembly warps (two warpgroups, 200 registers per
-// thread after setmaxnreg) integrate mode s into buffer s & 1 while the solver warps (one warpgroup, 96 registers) run the chain
+#define T2_ASM_REGS 192
+#define T2_SOLVE_REGS 112
+// Persistent CTAs pull particles from a queue.  Stage s of a particle: the assembly warps (two warpgroups, 192 registers per
+// thread after setmaxnreg) integrate mode s into buffer s & 1 while the solver warps (one warpgroup, 112 registers) run the chain
 // of mode s - 1 out of buffer (s - 1) & 1; one CTA barrier per stage.  Both roles execute the same sequence of CTA barriers.
 __global__ void __launch_bounds__(T2_ASM_THREADS + T2_SOLVE_THREADS, 1) k_tm2l(T2Args a, int *queue, int split)
 {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double s_cmx[T2_NRANKI];
+    __shared__ T2Prep s_prep[T2_NM];
     __shared__ double s_acc[8];
-    __shared__ unsigned long long s_keys[4];
+    __shared__ double2 s_colbuf[2 * 2 * T2_NRANK], s_rowbuf[4 * T2_NRANK];
     __shared__ int s_item, s_sing;
     const int tid = threadIdx.x;
     T2Smem s;
@@ -759,17 +900,26 @@ __global__ void __launch_bounds__(T2_ASM_THREADS + T2_SOLVE_THREADS, 1) k_tm2l(T
         T2Grp gsol;
         gsol.tid = tid - T2_ASM_THREADS; gsol.nt = T2_SOLVE_THREADS; gsol.bar = 3;
         T2SolveWs ws;
-        ws.ctl = nullptr; ws.keyslot = s_keys; ws.sing = &s_sing;
+        ws.ctl = nullptr; ws.colbuf = s_colbuf; ws.rowbuf = s_rowbuf; ws.sing = &s_sing;
         while (true) {
             __syncthreads();                                   // (1) item fetched, accumulators cleared
             const int it = s_item;
             if (it >= a.n) break;
             const T2Par P = t2_par(a, it);
+            // while the assembly warps build the node tables: the per-mode constants of all seven chains
+            for (int w = gsol.tid; w < T2_NM * 32; w += T2_SOLVE_THREADS) {
+                const int kmv = w >> 5, item = w & 31;
+                if (item < T2_PREP_ITEMS) t2_prep(P, kmv, s_prep[kmv], item);
+            }
             __syncthreads();                                   // (2) node tables complete
             __syncthreads();                                   // stage 0: assembly only
+            unsigned long long *prof_ = a.prof;
+            T2_PROF_T0
             for (int stage = 1; stage <= T2_NM; stage++) {
-                t2_chain(P, s.mat[(stage - 1) & 1], stage - 1, gsol, s_cmx, s_acc, ws);
+                t2_chain(P, s.mat[(stage - 1) & 1], stage - 1, gsol, s_prep[stage - 1], s_acc, ws, a.prof);
+                T2_PROF(gsol.tid == 0, T2P_CHAIN)
                 __syncthreads();
+                T2_PROF(gsol.tid == 0, T2P_CHAIN_WAIT)
             }
             if (gsol.tid < 4) t2_store(a, it, P, s_acc, s_sing, gsol.tid);
             __syncthreads();                                   // (3) results stored, s_item / s_acc free
@@ -785,12 +935,18 @@ __global__ void __launch_bounds__(T2_ASM_THREADS + T2_SOLVE_THREADS, 1) k_tm2l(T
             const int it = s_item;
             if (it >= a.n) break;
             const T2Par P = t2_par(a, it);
+            unsigned long long *prof_ = a.prof;
+            T2_PROF_T0
             t2_tables(P, s, gasm);
             __syncthreads();                                   // (2)
+            T2_PROF(tid == 0, T2P_TABLES)
             for (int stage = 0; stage <= T2_NM; stage++) {
                 if (stage < T2_NM) t2_assemble(P, s, s.mat[stage & 1], stage, gasm, split);
+                T2_PROF(tid == 0, T2P_ASM)
                 __syncthreads();
+                T2_PROF(tid == 0, T2P_ASM_WAIT)
             }
+            if (prof_ && tid == 0) atomicAdd(&prof_[T2P_PARTICLES], 1ull);
             __syncthreads();                                   // (3)
         }
     }

@@ -1001,15 +1001,31 @@ extern "C" int hs_tm2l_batch(hs_ctx *ctx, int n, const double *d_dpart, const do
     hs::T2Args a;
     a.n = n; a.dpart = d_dpart; a.dcore = d_dcore; a.aovrb = d_aovrb; a.aovrb2 = d_aovrb2;
     a.eor = d_eor; a.eoi = d_eoi; a.eir = d_eir; a.eii = d_eii; a.alamd = wavelength_cm;
-    a.amp = d_amp; a.status = d_status;
+    a.amp = d_amp; a.status = d_status; a.prof = nullptr;
+    const bool prof = getenv("HYDROTM_PROF") != nullptr;
+    if (prof) {
+        if (!ctx->d_prof) CK(cudaMalloc(&ctx->d_prof, 24 * sizeof(long long)));
+        CK(cudaMemsetAsync(ctx->d_prof, 0, 24 * sizeof(long long), st));
+        a.prof = (unsigned long long *)ctx->d_prof;
+    }
     size_t smem = (size_t)hs::t2_smem_doubles(2) * sizeof(double);
     CK(cudaFuncSetAttribute(hs::k_tm2l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaMemsetAsync(ctx->d_queue + 8, 0, sizeof(int), st));
     int grid = std::min(n, ctx->sm_count);
-    static const int split = getenv("HYDROTM_TM2L_SPLIT") ? std::max(1, std::min(4, atoi(getenv("HYDROTM_TM2L_SPLIT")))) : 2;
+    static const int split = getenv("HYDROTM_TM2L_SPLIT") ? std::max(1, std::min(4, atoi(getenv("HYDROTM_TM2L_SPLIT")))) : 1;
     hs::k_tm2l<<<grid, T2_ASM_THREADS + T2_SOLVE_THREADS, smem, st>>>(a, ctx->d_queue + 8, split == 3 ? 2 : split);
     ctx->launches++;
     CK(cudaGetLastError());
+    if (prof) {
+        unsigned long long h[24];
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(h, ctx->d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        const char *nm[] = {"tables", "assemble", "asm wait", "chain", "chain wait", "solve1", "products", "solve2", "addprc"};
+        const double np_ = (double)std::max<unsigned long long>(1, h[hs::T2P_PARTICLES]);
+        fprintf(stderr, "[hydrotm-tm2l] %llu particles, kcycles per particle:", h[hs::T2P_PARTICLES]);
+        for (int q = 0; q < hs::T2P_PARTICLES; q++) fprintf(stderr, " %s %.1f", nm[q], h[q] / np_ / 1e3);
+        fprintf(stderr, "\n");
+    }
     return 0;
 }
 

@@ -68,7 +68,7 @@ extern "C" void emu_tm2l(int n, const double *p8, double alamd, double *amp, int
     a.alamd = alamd; a.amp = amp; a.status = status;
     std::vector<double> smem(hs::t2_smem_doubles(1) + 16);
     hs::Ctl ctl;
-    double cmx[T2_NRANKI], acc[8];
+    double cmx[sizeof(hs::T2Prep) / sizeof(double) + 2], acc[8];
     for (int i = 0; i < n; i++) { ctl.sing = 0; hs::tm2l_particle(a, i, smem.data(), &ctl, cmx, acc, 0, 1); }
 }
 

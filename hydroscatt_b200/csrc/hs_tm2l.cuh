@@ -145,9 +145,10 @@ __device__ inline void t2_genbkr(cd z, cd *bs, cd *cn, bool want_y)
     sincos(z.x, &sn, &cs);
     cd ar = mk(sn * ex1, -cs * ex2) / z;
     int k = 0;
+    const cd zi = mk(1.0, 0.0) / z;  // one reciprocal instead of a complex division per recurrence step
     for (int ij = nval; ij >= 2; ij--) {
         double f = (double)(2 * ij - 1);
-        cd cf = mk(f, 0.0) / z;
+        cd cf = zi * f;
         cd c = b * cf - a;  // rj(ij-1)
         if (!(fabs(c.x) <= alarge && fabs(c.y) <= alarge)) {
             if (ij + 1 > T2_NRANKI) {
@@ -179,7 +180,7 @@ __device__ inline void t2_genbkr(cd z, cd *bs, cd *cn, bool want_y)
     cn[0] = c0; cn[1] = c1;
     for (int i = 3; i <= T2_NRANKI; i++) {
         double f = (double)(2 * i - 3);
-        cd cf = mk(f, 0.0) / z;
+        cd cf = zi * f;
         cd c2 = c1 * cf - c0;
         cn[i - 1] = c2;
         c0 = c1; c1 = c2;
@@ -882,72 +883,78 @@ __device__ void tm2l_particle(const T2Args &a, int p, double *smem, Ctl *ctl, do
 #define T2_SOLVE_THREADS 128
 #define T2_ASM_REGS 192
 #define T2_SOLVE_REGS 112
-// Persistent CTAs pull particles from a queue.  Stage s of a particle: the assembly warps (two warpgroups, 192 registers per
-// thread after setmaxnreg) integrate mode s into buffer s & 1 while the solver warps (one warpgroup, 112 registers) run the chain
-// of mode s - 1 out of buffer (s - 1) & 1; one CTA barrier per stage.  Both roles execute the same sequence of CTA barriers.
+// Persistent CTAs pull particles from a queue and run ONE continuous software pipeline over the (particle, mode) items they
+// draw: at stage t the assembly warps (two warpgroups, 192 registers per thread after setmaxnreg) integrate item t into matrix
+// buffer t & 1 -- building the node tables first when the item opens a new particle -- while the solver warps (one warpgroup, 112
+// registers) run the chain of item t - 1 out of buffer (t - 1) & 1 (the chain never reads the node tables, so the last mode of
+// particle p overlaps the tables and the first mode of particle p + 1); one CTA barrier per stage.
 __global__ void __launch_bounds__(T2_ASM_THREADS + T2_SOLVE_THREADS, 1) k_tm2l(T2Args a, int *queue, int split)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ T2Prep s_prep[T2_NM];
     __shared__ double s_acc[8];
     __shared__ double2 s_colbuf[2 * 2 * T2_NRANK], s_rowbuf[4 * T2_NRANK];
-    __shared__ int s_item, s_sing;
+    __shared__ int s_pid[2], s_sing;
     const int tid = threadIdx.x;
     T2Smem s;
     t2_carve(s, smem, 2);
+    unsigned long long *prof_ = a.prof;
     if (tid >= T2_ASM_THREADS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_SOLVE_REGS));
         T2Grp gsol;
         gsol.tid = tid - T2_ASM_THREADS; gsol.nt = T2_SOLVE_THREADS; gsol.bar = 3;
         T2SolveWs ws;
         ws.ctl = nullptr; ws.colbuf = s_colbuf; ws.rowbuf = s_rowbuf; ws.sing = &s_sing;
-        while (true) {
-            __syncthreads();                                   // (1) item fetched, accumulators cleared
-            const int it = s_item;
-            if (it >= a.n) break;
-            const T2Par P = t2_par(a, it);
-            // while the assembly warps build the node tables: the per-mode constants of all seven chains
-            for (int w = gsol.tid; w < T2_NM * 32; w += T2_SOLVE_THREADS) {
-                const int kmv = w >> 5, item = w & 31;
-                if (item < T2_PREP_ITEMS) t2_prep(P, kmv, s_prep[kmv], item);
+        __syncthreads();                                       // stage 0: nothing to solve yet
+        T2Par P;
+        T2_PROF_T0
+        for (int t = 1;; t++) {
+            const int it = s_pid[(t - 1) & 1], kmv = (t - 1) % T2_NM;
+            if (it < 0) break;
+            if (kmv == 0) {
+                // a new particle: constants of its seven chains, accumulators, singular flag
+                P = t2_par(a, it);
+                for (int w = gsol.tid; w < T2_NM * 32; w += T2_SOLVE_THREADS) {
+                    const int m = w >> 5, item = w & 31;
+                    if (item < T2_PREP_ITEMS) t2_prep(P, m, s_prep[m], item);
+                }
+                if (gsol.tid < 8) s_acc[gsol.tid] = 0.0;
+                if (gsol.tid == 8) s_sing = 0;
+                t2_sync(gsol);
             }
-            __syncthreads();                                   // (2) node tables complete
-            __syncthreads();                                   // stage 0: assembly only
-            unsigned long long *prof_ = a.prof;
-            T2_PROF_T0
-            for (int stage = 1; stage <= T2_NM; stage++) {
-                t2_chain(P, s.mat[(stage - 1) & 1], stage - 1, gsol, s_prep[stage - 1], s_acc, ws, a.prof);
-                T2_PROF(gsol.tid == 0, T2P_CHAIN)
-                __syncthreads();
-                T2_PROF(gsol.tid == 0, T2P_CHAIN_WAIT)
-            }
-            if (gsol.tid < 4) t2_store(a, it, P, s_acc, s_sing, gsol.tid);
-            __syncthreads();                                   // (3) results stored, s_item / s_acc free
+            t2_chain(P, s.mat[(t - 1) & 1], kmv, gsol, s_prep[kmv], s_acc, ws, a.prof);
+            if (kmv == T2_NM - 1 && gsol.tid < 4) t2_store(a, it, P, s_acc, s_sing, gsol.tid);
+            T2_PROF(gsol.tid == 0, T2P_CHAIN)
+            __syncthreads();
+            T2_PROF(gsol.tid == 0, T2P_CHAIN_WAIT)
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2_ASM_REGS));
         T2Grp gasm;
         gasm.tid = tid; gasm.nt = T2_ASM_THREADS; gasm.bar = 4;
-        while (true) {
-            if (tid == 0) { s_item = atomicAdd(queue, 1); s_sing = 0; }
-            if (tid < 8) s_acc[tid] = 0.0;
-            __syncthreads();                                   // (1)
-            const int it = s_item;
-            if (it >= a.n) break;
-            const T2Par P = t2_par(a, it);
-            unsigned long long *prof_ = a.prof;
-            T2_PROF_T0
-            t2_tables(P, s, gasm);
-            __syncthreads();                                   // (2)
-            T2_PROF(tid == 0, T2P_TABLES)
-            for (int stage = 0; stage <= T2_NM; stage++) {
-                if (stage < T2_NM) t2_assemble(P, s, s.mat[stage & 1], stage, gasm, split);
-                T2_PROF(tid == 0, T2P_ASM)
-                __syncthreads();
-                T2_PROF(tid == 0, T2P_ASM_WAIT)
+        T2Par P;
+        int it = -1;
+        T2_PROF_T0
+        for (int t = 0;; t++) {
+            const int kmv = t % T2_NM;
+            if (kmv == 0) {
+                if (tid == 0) s_pid[t & 1] = atomicAdd(queue, 1);
+                t2_sync(gasm);
+                it = s_pid[t & 1];
+                if (it >= a.n) it = -1;
+                if (it >= 0) {
+                    P = t2_par(a, it);
+                    t2_tables(P, s, gasm);
+                    T2_PROF(tid == 0, T2P_TABLES)
+                }
             }
-            if (prof_ && tid == 0) atomicAdd(&prof_[T2P_PARTICLES], 1ull);
-            __syncthreads();                                   // (3)
+            if (tid == 0) s_pid[t & 1] = it;
+            if (it >= 0) t2_assemble(P, s, s.mat[t & 1], kmv, gasm, split);
+            T2_PROF(tid == 0, T2P_ASM)
+            __syncthreads();
+            T2_PROF(tid == 0, T2P_ASM_WAIT)
+            if (it < 0) break;
+            if (prof_ && tid == 0 && kmv == T2_NM - 1) atomicAdd(&prof_[T2P_PARTICLES], 1ull);
         }
     }
 }

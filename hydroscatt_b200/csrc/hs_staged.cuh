@@ -730,6 +730,96 @@ __device__ __forceinline__ void solve_grp2s(const SysDesc d, int t, int nl, int 
 }
 
 
+// ---- The same elimination out of REGISTERS (used by the fused solve of k_st_assemble; the two-layer kernel has a 17-row copy).
+// Lane r keeps ROW r of the system (n <= 32); the 2 n columns of [A | B] are dealt in blocks of 16 to the W = 1, 2 or 4 warps of the
+// group (2 n <= 16 W).  A step: the warp that owns pivot column k publishes it (one STS per lane, double-buffered, one named barrier
+// of the group per step); every warp finds the pivot row with two warp reductions (same rule as solve_multi: largest |re| + |im|
+// among the rows not used yet, low 8 mantissa bits dropped, ties to the lowest row); the pivot lane hands its 16 entries to its warp
+// through shared memory and every lane updates its row:  V_r -= (V_r[k] / pivot) V_P.  Rows are neither moved nor scaled: `vp` is the
+// position the row would have after the reference's row swaps and `sc` = 1 / pivot the pending scale of a used row (with W = sc V
+// the true rows, the update of row r != P reads the same for every pending scale), so lane r ends up with solution row vp = sc V_r,
+// which it writes back over the right-hand side.  No LDS -> DFMA -> STS round trip per row update, no arithmetic in one-lane
+// branches: ~250 instructions per step and warp against ~2 000-3 000 cycles per step of the shared-memory variant.
+__device__ __forceinline__ void solve_rows16(const SysDesc d, int w, int W, int lane, int barid, double2 *colbuf, double2 *rowbuf, int *sing)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int n = d.n, nc = 2 * n;
+    const unsigned b0 = (unsigned)__cvta_generic_to_shared(d.base);
+    // byte offset of element (r, j): row (off + stride r), column off + stride j (j < n) or rhs + off + stride (j - n)
+    const unsigned rowoff = 16u * (unsigned)((d.off + d.stride * lane) * d.ld);
+    double2 v[16];
+    const bool realr = lane < n;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int jg = 16 * w + j;
+        double2 x = make_double2(0.0, 0.0);
+        if (realr && jg < nc) x = st_lds128(b0 + rowoff + 16u * (unsigned)(jg < n ? d.off + d.stride * jg : d.rhs + d.off + d.stride * (jg - n)));
+        v[j] = x;
+    }
+    int vp = lane;
+    double2 f = v[0];                             // this row's entry of the next pivot column, if this warp owns it
+    double2 sc = make_double2(1.0, 0.0);
+    for (int k = 0; k < n; k++) {
+        double2 *cb = colbuf + (k & 1) * 32;
+        if (w == (k >> 4)) cb[lane] = f;
+        asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(32 * W) : "memory");
+        const double2 c = cb[lane];
+        const bool cand = realr && vp >= k;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(c.x) + fabs(c.y));
+        const unsigned hi = (unsigned)(bits >> 32) + 1u, lo = ((unsigned)bits & 0xFFFFFF00u) | (unsigned)(255 - vp);
+        const unsigned m1 = __reduce_max_sync(FULL, cand ? hi : 0u);
+        const bool top = cand && hi == m1;
+        const unsigned m2 = __reduce_max_sync(FULL, top ? lo : 0u);
+        const int P = __ffs(__ballot_sync(FULL, top && lo == m2)) - 1;
+        if (m1 == 1u && (m2 >> 8) == 0u && w == 0 && lane == 0) *sing = 1;
+        if (lane == P) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) rowbuf[j] = v[j];
+        }
+        const double pvx = __shfl_sync(FULL, c.x, P), pvy = __shfl_sync(FULL, c.y, P);
+        const int vpP = __shfl_sync(FULL, vp, P);
+        const double rden = hs_rcp(pvx * pvx + pvy * pvy);
+        const double2 inv = make_double2(pvx * rden, -pvy * rden);
+        double2 cs = make_double2(-(c.x * inv.x - c.y * inv.y), -(c.x * inv.y + c.y * inv.x));
+        if (lane == P) { cs = make_double2(0.0, 0.0); sc = inv; }
+        if (!realr) cs = make_double2(0.0, 0.0);
+        __syncwarp();
+        double2 fn = f;
+        const int jn = k + 1 - 16 * w;            // local index of the next pivot column (if 0 <= jn < 16)
+#pragma unroll
+        for (int j0 = 0; j0 < 16; j0 += 4) {
+            double2 rw[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) rw[q] = rowbuf[j0 + q];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + q;
+                double2 u = v[j];
+                u.x = fma(-cs.y, rw[q].y, fma(cs.x, rw[q].x, u.x));
+                u.y = fma(cs.y, rw[q].x, fma(cs.x, rw[q].y, u.y));
+                v[j] = u;
+                if (j == jn) fn = u;
+            }
+        }
+        f = fn;
+        if (vp == k) vp = vpP;
+        if (lane == P) vp = k;
+        __syncwarp();  // rowbuf is rewritten by the next step's pivot lane
+    }
+    // every warp is past its last read of the system before solution rows overwrite right-hand sides (row vp != row lane)
+    asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(32 * W) : "memory");
+    if (realr) {
+        const unsigned outrow = 16u * (unsigned)((d.off + d.stride * vp) * d.ld);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int jg = 16 * w + j;
+            if (jg >= n && jg < nc)
+                st_sts128(b0 + outrow + 16u * (unsigned)(d.rhs + d.off + d.stride * (jg - n)),
+                          make_double2(v[j].x * sc.x - v[j].y * sc.y, v[j].x * sc.y + v[j].y * sc.x));
+        }
+    }
+}
+
 // ---- A: Q / RgQ integrals of one 32 x 32 block of (k1, k2) = (n1 - nmin, n2 - nmin) as DMMA contractions ----
 // See assemble_tiled (hs_tmat.cuh) for the factorisation: X = sum over nodes of (left factor of (n1, node)) x (right
 // factor of (n2, node)).  Left operand tables L_t[(k1, F)][node], F in {j, y}: P1 = d1 dF, P2 = d2 dF, P3 = d1 F,
@@ -970,6 +1060,7 @@ __global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs
     }
     if (!fused) return;
     __shared__ unsigned long long keyslot[4][2];
+    __shared__ double2 s_colbuf[4][2 * 32], s_rowbuf[THREADS / 32][16];  // register solver: published pivot columns / rows
     __shared__ int sing;
     if (tid == 0) sing = 0;
     __syncthreads();
@@ -981,13 +1072,21 @@ __global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs
         const int q = tid / LM0;
         SysDesc d;
         d.base = sys + (long)(q >> 1) * NM * ldc; d.ld = ldc; d.off = q & 1; d.stride = 2; d.rhs = NM; d.n = (NM + 1 - (q & 1)) >> 1;
-        if (d.n > 0) { if (a.fuse & 2) solve_grp2s(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing); else solve_grp(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing); }
+        if (d.n > 0) {
+            if ((a.fuse & 8) && KR == 32) solve_rows16(d, (tid % LM0) >> 5, LM0 / 32, lane, 1 + q, s_colbuf[q], s_rowbuf[tid >> 5], &sing);
+            else if (a.fuse & 2) solve_grp2s(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing);
+            else solve_grp(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing);
+        }
     } else {
         // the two parity classes
         const int q = tid / LM1;
         SysDesc d;
         d.base = sys + (long)q * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
-        if (a.fuse & 2) solve_grp2s(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing); else solve_grp(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
+        // measured per elimination step inside the pipeline (W2): wide modes (NM 17..32, four warps per system) 2 940 -> 2 260 cycles;
+        // no gain for the narrow variant and the m = 0 half systems, which therefore keep the shared-memory elimination
+        if ((a.fuse & 4) && (KR == 32 || (a.fuse & 8))) solve_rows16(d, (tid % LM1) >> 5, LM1 / 32, lane, 1 + q, s_colbuf[q], s_rowbuf[tid >> 5], &sing);
+        else if (a.fuse & 2) solve_grp2s(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
+        else solve_grp(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
     }
     __syncthreads();
     ST_PROF(3)

@@ -201,3 +201,27 @@ def rayleigh_confocal(a_h_out, ar_vh_out, a_h_in, eps1, eps2, k0):
         den = ea * (1.0 + (eps1 - 1.0) * L2) + frac * L2 * eps1 * (eps2 - eps1)
         res.append(k0**2 * vol * num / den / (4.0 * np.pi))
     return res[0], res[1], ar_in
+
+
+# ---- single-layer use of the same blocks -------------------------------------------------------------------------
+def spheroid_amplitudes(radius_mm, wavelength_mm, m, axis_ratio, n_max, n_gauss=96):
+    """Homogeneous spheroid (pytmatrix conventions: equal-volume radius, axis_ratio = horizontal / vertical) through the
+    generalised Q blocks above: T = -Q[j, j] Q[h, j]^-1 per azimuthal mode at a GIVEN truncation n_max, then the far field at
+    horizontal incidence.  Returns (S_vv back, S_hh back, S_vv forward, S_hh forward) in mm, the units of pytmatrix's S --
+    an independent check of the single-layer oracle's numerics at its own converged order; the
+    convergence controller (row P2) is not involved."""
+    k0 = 2.0 * np.pi / wavelength_mm
+    ar_vh = 1.0 / axis_ratio
+    a_h = radius_mm * axis_ratio ** (1.0 / 3.0)
+    xg, wg = np.polynomial.legendre.leggauss(n_gauss)
+    x = 0.5 * xg + 0.5
+    w = wg  # half range, doubled
+    s2 = 1.0 - x * x
+    q = 1.0 / np.sqrt((x / ar_vh)**2 + s2)
+    r, u = a_h * q, x * np.sqrt(s2) * (1.0 / ar_vh**2 - 1.0) * q * q
+    Tm = []
+    for mm in range(n_max + 1):
+        qh = _q_matrix(mm, n_max, k0, complex(m), r, u, x, w, "h", "j")
+        qj = _q_matrix(mm, n_max, k0, complex(m), r, u, x, w, "j", "j")
+        Tm.append(-np.linalg.solve(qh.T, qj.T).T)
+    return amplitudes_horizontal(Tm, k0, n_max)

@@ -92,3 +92,23 @@ def test_strongly_oblate_confocal_truncation_converges():
         a = _c(ti.tm2l(D, d_int, 0.7, ar_in, eps1, eps2, lam_cm, quirks=False, n_max=nmax, m_max=min(6, nmax), n_gauss=ng))
         errs.append(abs(a[2] - svv) / abs(svv))
     assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-3, errs
+
+
+def test_single_layer_oracle_matches_independent_formulation():
+    """oracle/sl_oracle.c (restated Mishchenko / pytmatrix calctmat + calcampl) against the independent blocks of
+    oracle/tm2l_indep.py (scipy Bessel functions, Gauss-Legendre with 96+ nodes, LAPACK) at the oracle's own converged NMAX:
+    rain drops at C, X and W band, an oblate ice plate and a prolate column.  The amplitudes are converged to ~ddelt, so the two
+    must agree far inside 1e-6 once the oracle is run with a tight ddelt."""
+    cases = [(0.5, 53.5, 8.601 + 1.687j, 1.0 / 0.9707), (2.0, 53.5, 8.601 + 1.687j, 1.0 / 0.79), (3.5, 33.3, 7.942 + 2.332j, 1.0 / 0.5577),
+             (1.5, 3.19, 3.117 + 1.665j, 1.0 / 0.85), (0.4, 8.43, 1.78 + 0.0024j, 3.0), (0.3, 33.3, 1.78 + 0.0024j, 1.0 / 2.5)]
+    worst = 0.0
+    for (rad, lam, m, eps) in cases:
+        tm = oracle.TMatrix(rad, lam, m, eps, ddelt=1e-9)
+        Sb, _ = tm.ampl(90.0, 90.0, 0.0, 180.0)
+        Sf, _ = tm.ampl(90.0, 90.0, 0.0, 0.0)
+        ref = np.array(ti.spheroid_amplitudes(rad, lam, m, eps, n_max=tm.nmax + 2, n_gauss=max(96, 4 * tm.ngauss)))
+        got = np.array([Sb[0, 0], Sb[1, 1], Sf[0, 0], Sf[1, 1]])
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        worst = max(worst, err)
+        assert err < 1e-6, ((rad, lam, m, eps), tm.nmax, tm.ngauss, err, got, ref)
+    print("single-layer oracle vs independent formulation, worst relative difference:", worst)

@@ -50,6 +50,9 @@ SIGNATURES = {
     "hs_gather_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, _dp, _dp, _dp, C.c_void_p]),
     "hs_canting_observables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_longlong, C.c_longlong, _dp, C.c_double,
                                          C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_void_p]),
+    "hs_canting_mc_scratch_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_double]),
+    "hs_canting_moments_mc": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_double, C.c_int, C.POINTER(C.c_ulonglong), C.c_double, _dp,
+                                        C.c_longlong, _dp, C.c_void_p]),
     "hs_canting_mixture": (C.c_int, [C.c_void_p, C.c_longlong, _dp, _dp, _dp, C.c_void_p]),
     "hs_tm2l_batch": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp,
                                 C.c_void_p]),

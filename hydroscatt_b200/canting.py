@@ -34,6 +34,38 @@ def compute_angular_moments_analytical(canting_angle):
             "a5": 1.0 / 8.0 * p * (1.0 - np.power(r, 4.0)), "a7": 0.5 * r * (1 + r)}
 
 
+def compute_angular_moments(canting_angle, ele=0.0, n_part=500000, seed=0, eng=None):
+    """scattering.compute_angular_moments (scattering.py:70-133) on the device, consuming the same numpy random stream
+    (default_rng(seed): one uniform alpha vector, then n_part normal betas per canting angle).  Returns the reference's dict of
+    numpy arrays a1, a2, a3, a4, a5, a7; agreement with the reference is at rounding level (libm vs CUDA sin / cos, summation
+    order), not at Monte-Carlo level."""
+    eng = eng if eng is not None else _engine.default_engine()
+    sig = np.atleast_1d(np.asarray(canting_angle, dtype=np.float64)).ravel()
+    st = np.random.default_rng(seed=seed).bit_generator.state
+    if st["bit_generator"] != "PCG64":
+        raise RuntimeError("numpy's default generator is not PCG64")
+    s, inc = st["state"]["state"], st["state"]["inc"]
+    m64 = (1 << 64) - 1
+    state = (C.c_ulonglong * 4)(s >> 64, s & m64, inc >> 64, inc & m64)
+    d_sig = eng._dev(sig)
+    out = torch.empty((sig.size, 6), dtype=torch.float64, device=eng.device)
+    slack = 1.03
+    while True:
+        nbytes = int(eng.lib.hs_canting_mc_scratch_bytes(sig.size, int(n_part), slack))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=eng.device)
+        with torch.cuda.device(eng.device):
+            rc = eng.lib.hs_canting_moments_mc(eng._h, sig.size, _ptr(d_sig), float(ele), int(n_part), state, slack, _ptr(scratch),
+                                               nbytes, _ptr(out), eng._stream())
+        if rc == 2 and slack < 2.0:
+            slack *= 1.5
+            continue
+        if rc != 0:
+            raise _engine.EngineError(f"hs_canting_moments_mc rc={rc}: " + eng._err())
+        break
+    o = out.cpu().numpy()
+    return {k: o[:, i].copy() for i, k in enumerate(MOMENT_KEYS)}
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 

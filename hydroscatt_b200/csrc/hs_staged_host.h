@@ -35,8 +35,17 @@ struct StBufs {
     int *d_scord = nullptr, *h_scord = nullptr; size_t d_scord_cap = 0, h_scord_cap = 0;
 };
 
+// host-side planning vectors of a group, kept between calls so that steady-state calls do not reallocate them
+struct StHostVecs {
+    std::vector<hs::StItem> items;
+    std::vector<int> mitems, gl[5], sm, order;
+    std::vector<hs::StRadTask> rad;
+    std::vector<hs::StATask> at0, at1, as0, as1;
+};
+
 struct StShared {
     StBufs g[ST_GROUPS];
+    StHostVecs hv[ST_GROUPS];
     double *d_cm = nullptr, *d_dd = nullptr;
     cudaEvent_t ev_in = nullptr;
 };
@@ -140,6 +149,13 @@ struct StGroup {
         TL e; e.what = what; e.round = nround;
         e.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_base).count();
         cudaEventCreate(&e.ev); cudaEventRecord(e.ev, B->stream); tl.push_back(e);
+    }
+
+    void swap_vecs(StHostVecs &h)
+    {
+        items.swap(h.items); mitems.swap(h.mitems); sm.swap(h.sm); order.swap(h.order); rad.swap(h.rad);
+        at0.swap(h.at0); at1.swap(h.at1); as0.swap(h.as0); as1.swap(h.as1);
+        for (int c = 0; c < 5; c++) gl[c].swap(h.gl[c]);
     }
 
     bool active() const
@@ -605,6 +621,7 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
     StGroup G[ST_GROUPS];
     for (int g = 0; g < ng; g++) {
         G[g].ctx = ctx; G[g].S = &S; G[g].B = &S.g[g]; G[g].C = &C; G[g].id = g;
+        G[g].swap_vecs(S.hv[g]);  // capacity of the previous call
         CK(cudaStreamWaitEvent(S.g[g].stream, S.ev_in, 0));
         CK(cudaStreamWaitEvent(S.g[g].sc_stream, S.ev_in, 0));
     }
@@ -629,6 +646,7 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         for (int t = 0; t < nth; t++) th[t] = std::thread([&G, t, nth, ng]() { StGroup::run_many(G, t, nth, ng); });
         for (int t = 0; t < nth; t++) th[t].join();
     }
+    for (int g = 0; g < ng; g++) G[g].swap_vecs(S.hv[g]);
     for (int g = 0; g < ng; g++)
         for (const StP &s : G[g].P) {
             if (s.done == 1 && s.nmax > C.nmax_max) C.nmax_max = s.nmax;

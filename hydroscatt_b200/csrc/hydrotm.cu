@@ -20,6 +20,7 @@
 #include "hs_scatter.cuh"
 #include "hs_psd.cuh"
 #include "hs_cant.cuh"
+#include "hs_cantmc.cuh"
 #include "hs_tm2l.cuh"
 #include "hs_staged.cuh"
 
@@ -858,6 +859,71 @@ extern "C" int hs_gather_rows(hs_ctx *ctx, long long n_out, int ncol, const doub
     hs::k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>((long)n_out, ncol, d_src, d_index, d_dst);
     ctx->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- Monte-Carlo canting moments on numpy's random stream (hs_cantmc.cuh) ----
+static long long cmc_nblocks(int n_cant, int n_part, double slack)
+{
+    return (long long)std::ceil((double)n_cant * (double)n_part * slack / CMC_B) + 8;
+}
+static size_t cmc_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" long long hs_canting_mc_scratch_bytes(int n_cant, int n_part, double slack)
+{
+    if (n_cant <= 0 || n_part <= 0) return 0;
+    const long long nb = cmc_nblocks(n_cant, n_part, slack);
+    size_t tot = 2 * cmc_align((size_t)n_part * 8) + cmc_align((size_t)nb * CMC_WORDS * 4) + 4 * cmc_align((size_t)nb * 4) +
+                 cmc_align((size_t)nb * 8) + cmc_align((size_t)nb * 12 * 8) + 256;
+    return (long long)tot;
+}
+
+extern "C" int hs_canting_moments_mc(hs_ctx *ctx, int n_cant, const double *d_sigma_deg, double ele_deg, int n_part,
+                                     const unsigned long long *h_pcg_state, double slack, void *d_scratch, long long scratch_bytes,
+                                     double *d_out, void *stream)
+{
+    if (!ctx) return -2;
+    if (n_cant <= 0) return 0;
+    if (n_part < CMC_B) { hs_set_err(ctx, "hs_canting_moments_mc: n_part must be at least 1024"); return -3; }
+    if (!h_pcg_state || !d_scratch || scratch_bytes < hs_canting_mc_scratch_bytes(n_cant, n_part, slack)) {
+        hs_set_err(ctx, "hs_canting_moments_mc: generator state missing or scratch smaller than hs_canting_mc_scratch_bytes"); return -3;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    hs::CmcArgs a;
+    a.g0.s = hs::u128(h_pcg_state[0], h_pcg_state[1]);
+    a.g0.inc = hs::u128(h_pcg_state[2], h_pcg_state[3]);
+    a.n_part = n_part; a.n_cant = n_cant; a.nblocks = cmc_nblocks(n_cant, n_part, slack);
+    a.sigma = d_sigma_deg;
+    const double thet0 = 3.141592653589793 / 2.0 - ele_deg * 3.141592653589793 / 180.0;
+    a.sin_t0 = sin(thet0); a.cos_t0 = cos(thet0);
+    char *p = (char *)d_scratch;
+    const long long nb = a.nblocks;
+    a.ca = (double *)p; p += cmc_align((size_t)n_part * 8);
+    a.sa = (double *)p; p += cmc_align((size_t)n_part * 8);
+    a.bitmap = (unsigned *)p; p += cmc_align((size_t)nb * CMC_WORDS * 4);
+    a.count0 = (int *)p; p += cmc_align((size_t)nb * 4);
+    a.exit0 = (int *)p; p += cmc_align((size_t)nb * 4);
+    a.entry = (int *)p; p += cmc_align((size_t)nb * 4);
+    a.cnt = (int *)p; p += cmc_align((size_t)nb * 4);
+    a.first = (long long *)p; p += cmc_align((size_t)nb * 8);
+    a.partial = (double *)p; p += cmc_align((size_t)nb * 12 * 8);
+    a.flag = (int *)p;
+    CK(cudaMemsetAsync(a.flag, 0, sizeof(int), st));
+    const unsigned gb = (unsigned)((nb + 127) / 128);
+    hs::k_cmc_alpha<<<(n_part + 127) / 128, 128, 0, st>>>(a);
+    hs::k_cmc_walk<<<gb, 128, 0, st>>>(a);
+    hs::k_cmc_fix<<<gb, 128, 0, st>>>(a);
+    hs::k_cmc_scan<<<1, 1024, 0, st>>>(a);
+    hs::k_cmc_emit<<<gb, 128, 0, st>>>(a);
+    hs::k_cmc_reduce<<<n_cant, 32, 0, st>>>(a, d_out);
+    ctx->launches += 6;
+    CK(cudaGetLastError());
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, a.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flag == 2) return 2;   // not enough of the stream covered: call again with a larger slack
+    if (flag) { hs_set_err(ctx, "hs_canting_moments_mc: sample orbits did not merge inside a block"); return -4; }
     return 0;
 }
 

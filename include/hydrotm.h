@@ -227,6 +227,23 @@ int hs_canting_observables(hs_ctx *ctx, int n_tab, int n_D, const double *d_f, c
                            int n_extra, const double *d_extra, double *d_out, double *d_out_extra, void *stream);
 
 /*
+ * Monte-Carlo angular moments of the canting-angle distribution, scattering.compute_angular_moments (scattering.py:70-133, SURVEY.md
+ * row S2 / 8(f)3), on the SAME random stream as the reference: numpy.random.default_rng(seed) -> one uniform(0, 360) vector of
+ * n_part alphas, then n_part normal(scale = sigma) betas per canting angle, in order (PCG64 + numpy's 256-layer ziggurat).
+ *   d_sigma_deg : device [n_cant] canting angles (deg);  ele_deg: elevation angle;  n_part >= 1024 (reference default 500 000)
+ *   h_pcg_state : HOST {state_hi, state_lo, inc_hi, inc_lo} of the PCG64 generator before its first draw
+ *                 (numpy.random.default_rng(seed).bit_generator.state["state"])
+ *   slack       : stream positions provided per sample (>= 1; the ziggurat consumes ~1.013 draws per normal: pass 1.03)
+ *   d_scratch   : device scratch of hs_canting_mc_scratch_bytes(n_cant, n_part, slack) bytes
+ *   d_out       : device [n_cant][6] = a1, a2, a3, a4, a5, a7 (means over the n_part samples)
+ * Returns 0, or 2 if `slack` was too small (call again with a larger one); synchronises `stream`.
+ */
+long long hs_canting_mc_scratch_bytes(int n_cant, int n_part, double slack);
+int hs_canting_moments_mc(hs_ctx *ctx, int n_cant, const double *d_sigma_deg, double ele_deg, int n_part,
+                          const unsigned long long *h_pcg_state, double slack, void *d_scratch, long long scratch_bytes,
+                          double *d_out, void *stream);
+
+/*
  * scattering.compute_scattering_mixture (scattering.py:590-673, row S7) on n rows of the 15 canting observables
  * (incoherent sum of two species); the cross-section columns 0..3, which the reference's mixture does not define, are NaN.
  */

@@ -96,3 +96,19 @@ def golden_rain_amplitudes(fx):
     Sb, Sf = np.array(fx["S_back_vv_hh"]), np.array(fx["S_forw_vv_hh"])
     return (1e-3 * (Sb[:, 0] + 1j * Sb[:, 1]), -1e-3 * (Sb[:, 2] + 1j * Sb[:, 3]),
             1e-3 * (Sf[:, 0] + 1j * Sf[:, 1]), 1e-3 * (Sf[:, 2] + 1j * Sf[:, 3]))
+
+
+def moments_mc(canting_angle, ele=0.0, n_part=500000, seed=0):
+    """scattering.py:70-133 (compute_angular_moments): numpy default_rng stream, one alpha vector, one beta vector per sigma."""
+    rng = np.random.default_rng(seed=seed)
+    thet0 = np.pi / 2 - ele * np.pi / 180.0
+    canting_angle = np.atleast_1d(np.asarray(canting_angle, dtype=float))
+    out = {k: np.zeros(canting_angle.size) for k in ("a1", "a2", "a3", "a4", "a5", "a7")}
+    alpha = rng.uniform(low=0.0, high=360.0, size=n_part) * np.pi / 180.0
+    for ind, cant_angle in enumerate(canting_angle):
+        beta = rng.normal(scale=cant_angle, size=n_part) * np.pi / 180.0
+        a1 = np.power(np.cos(beta) * np.sin(thet0) - np.sin(beta) * np.cos(thet0) * np.cos(alpha), 2.0)
+        a2 = np.sin(beta) * np.sin(beta) * np.sin(alpha) * np.sin(alpha)
+        for k, v in (("a1", a1), ("a2", a2), ("a3", a1 * a1), ("a4", a2 * a2), ("a5", a1 * a2), ("a7", a1 - a2)):
+            out[k][ind] = np.mean(v)
+    return out

@@ -91,3 +91,24 @@ def test_host_moments_equal_restatement():
     a, b = compute_angular_moments_analytical(s), cr.moments_analytical(s)
     for k in b:
         assert np.allclose(a[k], b[k], rtol=1e-15)
+
+
+def test_ziggurat_tables_and_stream_restatement_match_numpy():
+    """tools/gen_ziggurat.py: the tables in hydroscatt_b200/csrc/hs_ziggurat.h are the ones of the installed numpy, and the pure-Python
+    restatement of PCG64 + random_standard_normal that the device code (hs_cantmc.cuh) follows reproduces numpy draw for draw."""
+    import importlib.util
+    import os
+    import re
+    import struct
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ziggurat", os.path.join(root, "tools", "gen_ziggurat.py"))
+    gz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gz)
+    ki, wi, fi = gz.tables()
+    gz.check(ki, wi, fi, n=30000)
+    hdr = open(os.path.join(root, "hydroscatt_b200", "csrc", "hs_ziggurat.h")).read()
+    arrays = re.findall(r"(ZIG_\w+)\[256\] = \{([^}]*)\}", hdr)
+    got = {name: [int(x.strip().rstrip("UL"), 16) for x in body.split(",")] for name, body in arrays}
+    assert got["ZIG_KI"] == list(ki)
+    assert got["ZIG_WI_BITS"] == list(struct.unpack("<256Q", struct.pack("<256d", *wi)))
+    assert got["ZIG_FI_BITS"] == list(struct.unpack("<256Q", struct.pack("<256d", *fi)))

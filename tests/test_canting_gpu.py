@@ -229,3 +229,36 @@ def test_scatter_classes_keep_flagged_particles_in_bounds(engine):
     keep = torch.ones(tb.n, dtype=torch.bool, device=S2.device)
     keep[heavy] = False
     assert torch.equal(torch.view_as_real(S2[keep]), torch.view_as_real(S0[keep]))
+
+
+def test_mc_angular_moments_on_numpy_stream(engine):
+    """hs_canting_moments_mc against the numpy restatement of scattering.compute_angular_moments
+    (scattering.py:70-133): the device consumes the same PCG64 + ziggurat stream, so the moments agree at ROUNDING level
+    (libm vs CUDA sin / cos, summation order), far below the Monte-Carlo noise (~1e-3 at 500 000 samples)."""
+    import time
+    from hydroscatt_b200 import canting
+    sig = np.array([0.5, 1.0, 10.0, 25.0, 40.0, 63.0])
+    for ele, n_part, seed in ((0.0, 20000, 0), (30.0, 50001, 7), (0.0, 500000, 0)):
+        ref = cr.moments_mc(sig, ele=ele, n_part=n_part, seed=seed)
+        got = canting.compute_angular_moments(sig, ele=ele, n_part=n_part, seed=seed, eng=engine)
+        for k in canting.MOMENT_KEYS:
+            assert np.abs(got[k] - ref[k]).max() < 1e-12, (ele, n_part, k, got[k], ref[k])
+    # a different seed or a swapped sigma order changes the stream: the agreement above is not a coincidence of the means
+    other = canting.compute_angular_moments(sig, n_part=20000, seed=1, eng=engine)
+    ref0 = cr.moments_mc(sig, n_part=20000, seed=0)
+    assert np.abs(other["a2"] - ref0["a2"]).max() > 1e-6
+    # the hail scripts' size: 800 canting angles x 500 000 samples (scattering_hail.py) in one call; the stream is consumed in
+    # order, so the first angles of the long run must equal a short reference run, and the late ones must still be sane
+    sig800 = np.linspace(1.0, 60.0, 800)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    big = canting.compute_angular_moments(sig800, eng=engine)
+    dt = time.perf_counter() - t0
+    print("800 sigmas x 500 000 samples: %.1f ms" % (dt * 1e3))
+    ref3 = cr.moments_mc(sig800[:3])
+    for k in canting.MOMENT_KEYS:
+        assert np.abs(big[k][:3] - ref3[k]).max() < 1e-12, k
+        assert np.isfinite(big[k]).all()
+    assert (np.diff(big["a1"]) < 2e-3).all() and 0.5 < big["a1"][-1] < big["a1"][0] <= 1.0   # <cos^2 beta>-like: decreasing in sigma
+    with pytest.raises(Exception):
+        canting.compute_angular_moments(sig, n_part=100, eng=engine)

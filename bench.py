@@ -481,7 +481,7 @@ def run_gpu(args):
     bad5 = int((st5 != 0).sum().item())
 
     # W1 x 4096 (the C-band 10 degC rain grid replicated 4096 times with jitter = 286 720 spheroids), one GPU only
-    ms_w1 = None
+    ms_w1, other = None, {}
     if world == 1 and not args.no_sublines:
         from tests.workloads import rain_grid
         Rw = 4096
@@ -504,6 +504,63 @@ def run_gpu(args):
         ms_w1 = q0.elapsed_time(q1) / 3.0
         bad1 = int((tb1.status != 0).sum().item())
         del w1d, tb1
+        # W3 (ice crystals: plates / columns at X / Ka / W, ndgs 2 and 15) and W4 (single-layer hail, D 2..50 mm: NMAX up to ~55,
+        # multi-block assembly + separate solve kernel): BASELINE configs[2], [3]; same call, same outputs
+        from tests.workloads import ice_grid, hail_grid
+        other = {}
+        for name, wk, ndgs_ in (("w3_ice_ndgs2", ice_grid(seed=11, n=7680), 2), ("w3_ice_ndgs15", ice_grid(seed=12, n=1024), 15),
+                                ("w4_hail_single_layer", hail_grid(seed=13, n=1600), 2)):
+            wd = [torch.from_numpy(np.ascontiguousarray(wk[k])).to(dev) for k in ("radius", "wavelength", "mr", "mi", "axis_ratio")]
+            run_o = lambda: eng.calctmat_scatter(*wd, [GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, ddelt=DDELT, ndgs=ndgs_)
+            run_o()
+            torch.cuda.synchronize()
+            q0, q1 = ev(), ev()
+            q0.record()
+            for _ in range(5):
+                tbo = run_o()[0]
+            q1.record()
+            torch.cuda.synchronize()
+            ms_o = q0.elapsed_time(q1) / 5.0
+            nm_o, st_o = tbo.nmax.cpu().numpy(), tbo.status.cpu().numpy()
+            other[name] = {"particles": int(st_o.size), "ms": ms_o, "value": st_o.size / (ms_o * 1e-3), "unit": "solves/s", "ndgs": ndgs_,
+                           "nmax_range": [int(nm_o[st_o == 0].min()), int(nm_o[st_o == 0].max())],
+                           "status_counts": {str(k): int((st_o == k).sum()) for k in np.unique(st_o)}}
+
+    # Throughput with two table builds in flight (N = 1 only, a sub-line: the headline times one build at a time): two
+    # contexts, two streams, two host threads; one build's latency-bound convergence rounds overlap the other's scatter / PSD kernels
+    piped = None
+    if world == 1 and not args.no_sublines and (os.cpu_count() or 1) >= 12:
+        import threading as _th
+        engs2 = [eng, Engine(local)]
+        streams2 = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        w0 = g["replicas"][0]
+
+        def build_on(i, nsteps):
+            with torch.cuda.stream(streams2[i]):
+                for _ in range(nsteps):
+                    tb_, S_, Z_, xs_ = engs2[i].calctmat_scatter(dev_in["radius"], dev_in["wavelength"], dev_in["mr"], dev_in["mi"], dev_in["eps"],
+                                                                 [GEOM_BACK, GEOM_FORW], al, be, weight=wt, scale=scale, want_xs=True,
+                                                                 ddelt=DDELT, ndgs=NDGS)
+                    rows_ = engs2[i].pack_rows(S_, Z_, xs_, tb_.lam, 0, 1)
+                    tables.integrate_psd(engs2[i], rows_, n_tab, w0["D"], "gamma", dev_dsd["d0"], dev_dsd["nw"], dev_dsd["mu"], dmax,
+                                         w0["lam_tab"], rule="trapz", want_integ=False, columns=cols)
+
+        torch.cuda.synchronize()
+        for i in range(2):
+            build_on(i, 2)
+        torch.cuda.synchronize()
+        kp = max(2, (args.steps // 2) * 2)
+        tp0 = time.perf_counter()
+        ths = [_th.Thread(target=build_on, args=(i, kp // 2)) for i in range(2)]
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+        torch.cuda.synchronize()
+        dtp = time.perf_counter() - tp0
+        piped = {"builds_in_flight": 2, "steps": kp, "ms_per_step": dtp * 1e3 / kp, "value": n * kp / dtp, "unit": "solves/s",
+                 "timing": "host wall clock around both threads, device synchronised on both sides"}
+        del engs2
 
     tms = torch.tensor([ms_total, ms_e2e, ms_tm2l, coll_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -593,6 +650,10 @@ def run_gpu(args):
             line["w1x4096"] = {"workload": "W1 x 4096: C-band 10 degC rain grid, 70 D x 4096 jittered replicas", "particles": 70 * 4096,
                                "ms": ms_w1, "value": 70 * 4096 / (ms_w1 * 1e-3), "unit": "solves/s", "status_nonzero": bad1,
                                "what": "T-matrices + 2 geometries x 50 orientations + cross sections (hs_calctmat_scatter_batch)"}
+        if ms_w1 is not None:
+            line["other_workloads"] = other
+        if piped is not None:
+            line["pipelined_builds"] = piped
         if cpu:
             line["cpu_baseline"] = cpu
             line["tm2l"]["cpu_baseline"] = cpu2

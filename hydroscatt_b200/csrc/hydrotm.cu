@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <mutex>
 #include <thread>
+#include <condition_variable>
+#include <functional>
 
 #include "../../include/hydrotm.h"
 #include "hs_gauss.h"

@@ -664,9 +664,16 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         if (getenv("HYDROTM_THREADS")) nth = std::max(1, std::min(ng, atoi(getenv("HYDROTM_THREADS"))));
     }
     // deal the particles, heaviest first, round-robin: every group gets the same size mix
+    // (stable counting sort on the starting order: a comparison sort of 17 220 keys cost 0.3 ms before the first kernel)
     std::vector<int> ord(ns);
-    for (int j = 0; j < ns; j++) ord[j] = j;
-    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return n0_of[x] > n0_of[y]; });
+    {
+        int cnt[HS_NPN1 + 3] = {0};
+        auto key = [&](int j) { return std::min(std::max(n0_of[j], -1), HS_NPN1) + 1; };
+        for (int j = 0; j < ns; j++) cnt[key(j)]++;
+        int acc = 0;
+        for (int v = HS_NPN1 + 1; v >= 0; v--) { const int c = cnt[v]; cnt[v] = acc; acc += c; }
+        for (int j = 0; j < ns; j++) ord[cnt[key(j)]++] = j;
+    }
     StGroup G[ST_GROUPS];
     for (int g = 0; g < ng; g++) {
         G[g].ctx = ctx; G[g].S = &S; G[g].B = &S.g[g]; G[g].C = &C; G[g].id = g;
@@ -674,6 +681,7 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         CK(cudaStreamWaitEvent(S.g[g].stream, S.ev_in, 0));
         CK(cudaStreamWaitEvent(S.g[g].sc_stream, S.ev_in, 0));
     }
+    for (int g = 0; g < ng; g++) G[g].P.reserve((size_t)ns / ng + 1);
     for (int r = 0; r < ns; r++) {
         const int j = ord[r];
         StP s;
@@ -681,7 +689,8 @@ static int calctmat_staged(hs_ctx *ctx, StShared &S, cudaStream_t st, const std:
         s.q1s = 0.0; s.q1e = 0.0; s.t_off = -1; s.first_item = 0; s.n_items = 0; s.scattered = 0;
         // every trial from the starting order to the converged one is needed, so a lower bound of the converged order is free
         // parallelism: the first round runs them all at once
-        s.kspec = std::max(2, std::min(12, lb_of[j] - n0_of[j] + 1)); s.dprev = 0.0; s.dlast = 0.0;
+        static const int spec0 = getenv("HYDROTM_SPEC0") ? atoi(getenv("HYDROTM_SPEC0")) : 0;  // extra speculative trials in round 0
+        s.kspec = std::max(2, std::min(12 + spec0, lb_of[j] - n0_of[j] + 1 + spec0)); s.dprev = 0.0; s.dlast = 0.0;
         if (s.nmax < 0) { s.done = 2; s.status = HS_ST_BAD_INPUT; s.nmax = 0; }
         else if (s.nmax >= HS_NPN1) { s.done = 2; s.status = HS_ST_NMAX_LIMIT; }
         G[r % ng].P.push_back(s);

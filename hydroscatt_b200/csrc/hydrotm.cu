@@ -475,6 +475,7 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     // trials and modes as independent work items); the small ones stay on the fused one-particle-per-group kernel.
     const int staged_min = getenv("HYDROTM_STAGED_MIN") ? atoi(getenv("HYDROTM_STAGED_MIN")) : 0;
     std::vector<int> st_sel, st_n0, st_lb;
+    st_sel.reserve(n); st_n0.reserve(n); st_lb.reserve(n);
     if (!ctx->st) ctx->st = new StBufsHolder();
     bool staged_done = false;
     StCall SC;

@@ -51,6 +51,7 @@ struct StArgs {
     long long *toff;
     StResult *res;
     int fuse;                // solve modes with NM <= 32 inside k_st_assemble (default) or in k_st_solve
+#define ST_FUSE_RESERVED 16  // bit of `fuse`: result records cleared and arena slots reserved by the planner (device-driven rounds)
     unsigned long long *prof;  // HYDROTM_PROF=1: phase cycle counters of k_st_assemble [prologue, chunks, epilogue, solve, T write, #CTAs, sum NM, sum g]
 };
 
@@ -259,17 +260,13 @@ __device__ inline void st_cjb(double xr, double xi, double *yr, double *yi, doub
     }
 }
 
-__global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *tasks, int ntasks)
+// one radial task (16 nodes of one function kind of one item) on a half-warp; l16 = lane within the half-warp
+__device__ __forceinline__ void st_radial_task(const StArgs &a, const StRadTask t, int l16)
 {
-    // one half-warp per task of 16 nodes (most trial items have 10..16 nodes); the host orders the tasks kind-major, so
-    // the two halves of a warp run the same recurrence on items of similar size
-    const int wt = blockIdx.x * 8 + (threadIdx.x >> 4);
-    if (wt >= ntasks) return;
-    const StRadTask t = tasks[wt];
     const StItem it = a.items[t.item];
-    const int kind = t.kn & 3, i = (t.kn >> 2) + (threadIdx.x & 15);
+    const int kind = t.kn & 3, i = (t.kn >> 2) + l16;
     const int g = it.g, nmax = it.nmax, gp = it.gp;
-    if (t.kn == 2 && (threadIdx.x & 15) == 0) {
+    if (t.kn == 2 && l16 == 0 && !(a.fuse & ST_FUSE_RESERVED)) {
         // first task of the item: clear its result record and, for a final item, reserve the packed T in the caller's arena
         // (same bump allocator as the fused kernel; a retried final trial keeps its slot)
         long long o = -1;
@@ -338,14 +335,37 @@ __global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *ta
     }
 }
 
-// ---- W: Wigner functions of one (item, mode); rows k = n - nmin, n-major ----
-__global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
+__global__ void __launch_bounds__(128) k_st_radial(StArgs a, const StRadTask *tasks, int ntasks)
 {
-    // one half-warp per (item, mode): most modes have 10..16 nodes; larger ones loop over node chunks
-    __shared__ double sq_[8][HS_NPN1 + 2], rsq_[8][HS_NPN1 + 2];
-    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
-    const int idx = blockIdx.x * 8 + hw;
-    const bool live = idx < n_mi;
+    // one half-warp per task of 16 nodes (most trial items have 10..16 nodes); the host orders the tasks kind-major, so
+    // the two halves of a warp run the same recurrence on items of similar size
+    const int wt = blockIdx.x * 8 + (threadIdx.x >> 4);
+    if (wt >= ntasks) return;
+    st_radial_task(a, tasks[wt], threadIdx.x & 15);
+}
+
+// Device-driven rounds (hs_staged_dev.h): the task lists and their lengths are produced on the device, so the stage
+// kernels are launched with a fixed grid of resident CTAs that fetch tasks from a cursor until the list is empty.
+struct StQueue { int count, cursor; };
+__global__ void __launch_bounds__(128) k_st_radial_q(StArgs a, const StRadTask *tasks, StQueue *q)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = q->count;
+    for (;;) {
+        int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(&q->cursor, 2);
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        if (t0 >= n) return;
+        const int wt = t0 + (lane >> 4);
+        if (wt < n) st_radial_task(a, tasks[wt], lane & 15);
+        __syncwarp();
+    }
+}
+
+// ---- W: Wigner functions of one (item, mode); rows k = n - nmin, n-major ----
+// one half-warp per (item, mode): most modes have 10..16 nodes; larger ones loop over node chunks
+__device__ __forceinline__ void st_wigner_task(const StArgs &a, int idx, bool live, double *sq, double *rsq, int l16)
+{
     const StModeItem mi = st_unpack_mode(live ? a.modes[idx] : 0);
     const StItem it = a.items[mi.item];
     const int m = live ? mi.m : 0, nmax = it.nmax, g = live ? it.g : 0, gp = it.gp;
@@ -353,7 +373,6 @@ __global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
     double *d1 = a.wig + it.wig_off + st_wig_mode_off(nmax, m, gp);
     double *d2 = d1 + (long)NM * gp;
     const double eps = a.eps[it.p];
-    double *sq = sq_[hw], *rsq = rsq_[hw];
     if (live && m > 0) {
         const double qmm = (double)m * (double)m;
         for (int n = m + l16; n <= nmax + 1; n += 16) {
@@ -394,6 +413,30 @@ __global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
                 a1 = a2; a2 = a3;
             }
         }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_st_wigner(StArgs a, int n_mi)
+{
+    __shared__ double sq_[8][HS_NPN1 + 2], rsq_[8][HS_NPN1 + 2];
+    const int hw = threadIdx.x >> 4;
+    const int idx = blockIdx.x * 8 + hw;
+    st_wigner_task(a, idx, idx < n_mi, sq_[hw], rsq_[hw], threadIdx.x & 15);
+}
+
+__global__ void __launch_bounds__(128) k_st_wigner_q(StArgs a, StQueue *q)
+{
+    __shared__ double sq_[8][HS_NPN1 + 2], rsq_[8][HS_NPN1 + 2];
+    const int hw = threadIdx.x >> 4, lane = threadIdx.x & 31;
+    const int n = q->count;
+    for (;;) {
+        int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(&q->cursor, 2);
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        if (t0 >= n) return;
+        const int idx = t0 + (lane >> 4);
+        st_wigner_task(a, idx, idx < n, sq_[hw], rsq_[hw], lane & 15);
+        __syncwarp();
     }
 }
 
@@ -842,14 +885,11 @@ __device__ __forceinline__ void st_dmma(double *c, double a, double b)
 // NM <= 16 only: half the registers and a quarter of the shared memory per CTA, so twice as many CTAs per SM for the
 // majority of the modes).
 template <bool M0, int KR>
-__global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs a, const StATask *tasks, int ntasks)
+__device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask tk, double *op)
 {
     constexpr int THREADS = 8 * KR, TSTR = 16 * KR, TC = KR / 8, HMAX = KR / 2;  // table stride (doubles), tile columns, rows per parity
-    extern __shared__ __align__(16) double op[];
-    if ((int)blockIdx.x >= ntasks) return;
     long long tprof = a.prof ? clock64() : 0;
 #define ST_PROF(slot) if (a.prof && threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&a.prof[slot], (unsigned long long)(now_ - tprof)); tprof = now_; }
-    const StATask tk = tasks[blockIdx.x];
     const StModeItem mi = st_unpack_mode(tk.mi);
     const StItem it = a.items[mi.item];
     const int m = M0 ? 0 : mi.m;
@@ -1119,16 +1159,37 @@ __global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs
 #undef ST_PROF
 }
 
+template <bool M0, int KR>
+__global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs a, const StATask *tasks, int ntasks)
+{
+    extern __shared__ __align__(16) double op[];
+    if ((int)blockIdx.x >= ntasks) return;
+    st_assemble_task<M0, KR>(a, tasks[blockIdx.x], op);
+}
+
+// resident CTAs fetching tasks from the device-built list (see k_st_radial_q)
+template <bool M0, int KR>
+__global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble_q(StArgs a, const StATask *tasks, StQueue *q)
+{
+    extern __shared__ __align__(16) double op[];
+    __shared__ int s_next;
+    for (;;) {
+        if (threadIdx.x == 0) { const int t_ = atomicAdd(&q->cursor, 1); s_next = t_ < q->count ? t_ : -1; }
+        __syncthreads();
+        const int t = s_next;
+        if (t < 0) return;
+        st_assemble_task<M0, KR>(a, tasks[t], op);
+        __syncthreads();  // the operand area / fused systems and s_next are re-used by the next task
+    }
+}
+
 // ---- G: parity-class systems of one (item, mode): T = -RgQ Q^-1 by the lock-step Gauss-Jordan of hs_tmat.cuh ----
 template <int THREADS, bool GLOBAL>
-__global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist, int n)
+__device__ __forceinline__ void st_solve_task(const StArgs &a, const int mix, double2 *ssys)
 {
-    extern __shared__ __align__(16) double2 ssys[];
     __shared__ SysDesc sd[HS_MAXSYS];
     __shared__ SolveCtl sc;
     __shared__ int sing;
-    if ((int)blockIdx.x >= n) return;
-    const int mix = mlist[blockIdx.x];
     const StModeItem mi = st_unpack_mode(mix);
     const StItem it = a.items[mi.item];
     const int m = mi.m, nmax = it.nmax;
@@ -1215,6 +1276,29 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
     }
 }
 
+template <int THREADS, bool GLOBAL>
+__global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist, int n)
+{
+    extern __shared__ __align__(16) double2 ssys[];
+    if ((int)blockIdx.x >= n) return;
+    st_solve_task<THREADS, GLOBAL>(a, mlist[blockIdx.x], ssys);
+}
+
+template <int THREADS, bool GLOBAL>
+__global__ void __launch_bounds__(THREADS) k_st_solve_q(StArgs a, const int *mlist, StQueue *q)
+{
+    extern __shared__ __align__(16) double2 ssys[];
+    __shared__ int s_next;
+    const int n = q->count;
+    for (;;) {
+        if (threadIdx.x == 0) s_next = atomicAdd(&q->cursor, 1);
+        __syncthreads();
+        const int t = s_next;
+        if (t >= n) return;
+        st_solve_task<THREADS, GLOBAL>(a, mlist[t], ssys);
+        __syncthreads();
+    }
+}
 
 
 // ---- A + G for small blocks (NM <= 8): one warp per (item, mode) ----
@@ -1228,18 +1312,12 @@ __global__ void __launch_bounds__(THREADS) k_st_solve(StArgs a, const int *mlist
 #endif
 #define ST_SMALL_SLICE (15 * 16 * 4)  // doubles per warp
 
-__global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small(StArgs a, const int *mlist, int n)
+// one (item, mode) with NM <= 8 on one warp; op = the warp's private slice, sd / sing = its descriptor slots
+__device__ __forceinline__ void st_small_task(const StArgs &a, const int mix, double *op, SysDesc *sd, int *sing, int lane)
 {
-    extern __shared__ __align__(16) double smraw[];
-    __shared__ SysDesc sds[8][4];
-    __shared__ int sings[8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wi = blockIdx.x * 8 + warp;
-    if (wi >= n) return;
     long long tprof = a.prof ? clock64() : 0;
 #define SM_PROF(slot) if (a.prof && lane == 0) { const long long now_ = clock64(); atomicAdd(&a.prof[slot], (unsigned long long)(now_ - tprof)); tprof = now_; }
-    double *op = smraw + warp * ST_SMALL_SLICE;
-    const StModeItem mi = st_unpack_mode(mlist[wi]);
+    const StModeItem mi = st_unpack_mode(mix);
     const StItem it = a.items[mi.item];
     const int m = mi.m, nmax = it.nmax, g = it.g, gp = it.gp;
     const int nmin = m > 1 ? m : 1, NM = nmax - nmin + 1;
@@ -1377,7 +1455,6 @@ __global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small(StArgs a, 
     }
     // solve
     SM_PROF(18)
-    SysDesc *sd = sds[warp];
     int nsys;
     if (m == 0) {
         nsys = 0;
@@ -1401,7 +1478,7 @@ __global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small(StArgs a, 
             sd[lane] = d;
         }
     }
-    if (lane == 0) sings[warp] = 0;
+    if (lane == 0) *sing = 0;
     __syncwarp();
     {
         // m = 0: four half-size systems on 8 lanes each; m >= 1: the two parity classes on 16 lanes each
@@ -1409,7 +1486,7 @@ __global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small(StArgs a, 
         SysDesc d;
         if (grp_ < nsys) d = sd[grp_];
         else { d = sd[0]; d.n = 0; }
-        solve_subs(d, gl, gw, m == 0 ? ((NM + 1) >> 1) : NM, &sings[warp]);
+        solve_subs(d, gl, gw, m == 0 ? ((NM + 1) >> 1) : NM, sing);
     }
     SM_PROF(19)
     const long long toff = it.t_off;
@@ -1434,11 +1511,40 @@ __global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small(StArgs a, 
             a.res[mi.item].qsca = qsca;
             a.res[mi.item].qext = qext;
         }
-        if (sings[warp]) a.res[mi.item].sing = 1;
+        if (*sing) a.res[mi.item].sing = 1;
     }
     SM_PROF(20)
     if (a.prof && lane == 0) { atomicAdd(&a.prof[21], 1ull); atomicAdd(&a.prof[22], (unsigned long long)NM); atomicAdd(&a.prof[23], (unsigned long long)g); }
 #undef SM_PROF
+}
+
+__global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small(StArgs a, const int *mlist, int n)
+{
+    extern __shared__ __align__(16) double smraw[];
+    __shared__ SysDesc sds[8][4];
+    __shared__ int sings[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = blockIdx.x * 8 + warp;
+    if (wi >= n) return;
+    st_small_task(a, mlist[wi], smraw + warp * ST_SMALL_SLICE, sds[warp], &sings[warp], lane);
+}
+
+// resident warps fetching (item, mode) pairs from the device-built list (see k_st_radial_q)
+__global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small_q(StArgs a, const int *mlist, StQueue *q)
+{
+    extern __shared__ __align__(16) double smraw[];
+    __shared__ SysDesc sds[8][4];
+    __shared__ int sings[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = q->count;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&q->cursor, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n) return;
+        st_small_task(a, mlist[t], smraw + warp * ST_SMALL_SLICE, sds[warp], &sings[warp], lane);
+        __syncwarp();
+    }
 }
 
 #endif  // HS_HOST_EMU

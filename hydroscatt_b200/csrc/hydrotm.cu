@@ -120,7 +120,8 @@ static inline cudaError_t sc_set_smem(int bytes)
 static int ensure_gauss(hs_ctx *ctx, int gmax);
 static int ensure_gauss_full(hs_ctx *ctx, int nmaxrule);
 #include "hs_staged_host.h"
-struct StBufsHolder { StShared s; };
+#include "hs_staged_dev.h"
+struct StBufsHolder { StShared s; DvShared d; };
 
 static int ensure_gauss(hs_ctx *ctx, int gmax)
 {
@@ -203,7 +204,7 @@ extern "C" void hs_ctx_destroy(hs_ctx *ctx)
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int b = 0; b < 8; b++) { if (ctx->bstream[b]) cudaStreamDestroy(ctx->bstream[b]); if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
-    if (ctx->st) { st_destroy(ctx->st->s); delete ctx->st; }
+    if (ctx->st) { st_destroy(ctx->st->s); dv_destroy(ctx->st->d); delete ctx->st; }
     for (double *q : ctx->gauss_old) cudaFree(q);
     delete ctx;
 }
@@ -378,6 +379,30 @@ __global__ void k_nmax0(int n, const double *axi, const double *lam, const doubl
     out_lb[i] = (mx > 0.0 && mx < 1e6) ? max(n0 + 1, (int)floor(0.6035 * mx + 4.49) - 2) : n0 + 1;
 }
 
+static int print_staged_prof(hs_ctx *ctx)
+{
+    long long hp[24];
+    CK(cudaMemcpy(hp, ctx->d_prof, sizeof(hp), cudaMemcpyDeviceToHost));
+    {
+            // staged pipeline: phases of k_st_assemble (thread 0 of every CTA)
+            const char *nm[5] = {"prologue", "chunk loop", "epilogue", "solve", "T write"};
+            double t5 = 0; for (int i = 0; i < 5; i++) t5 += (double)hp[i];
+            const double ncta = (double)hp[5] > 0 ? (double)hp[5] : 1.0;
+            for (int i = 0; i < 5; i++)
+                fprintf(stderr, "[hydrotm-prof] k_st_assemble %-10s %6.2f%%  %8.0f cycles / CTA\n", nm[i], 100.0 * hp[i] / t5, (double)hp[i] / ncta);
+            fprintf(stderr, "[hydrotm-prof] k_st_assemble chunk loop split: build %.0f, barrier %.0f, contraction %.0f, barrier %.0f cycles / CTA\n",
+                    (double)hp[8] / ncta, (double)hp[9] / ncta, (double)hp[10] / ncta, (double)hp[11] / ncta);
+            fprintf(stderr, "[hydrotm-prof] k_st_assemble solve: %.1f elimination steps / CTA -> %.0f cycles / step\n", (double)hp[12] / ncta, (double)hp[3] / std::max(1.0, (double)hp[12]));
+            {
+                const double nw = (double)hp[21] > 0 ? (double)hp[21] : 1.0;
+                fprintf(stderr, "[hydrotm-prof] k_st_mode_small %.0f warps (mean NM %.1f, g %.1f): prologue %.0f, node loop %.0f, combine %.0f, solve %.0f, T write %.0f cycles / warp\n",
+                        nw, (double)hp[22] / nw, (double)hp[23] / nw, (double)hp[16] / nw, (double)hp[17] / nw, (double)hp[18] / nw, (double)hp[19] / nw, (double)hp[20] / nw);
+            }
+            fprintf(stderr, "[hydrotm-prof] k_st_assemble %.0f CTAs, mean NM %.1f, mean g %.1f, %.0f cycles / CTA\n", ncta, (double)hp[6] / ncta, (double)hp[7] / ncta, t5 / ncta);
+    }
+    return 0;
+}
+
 template <bool WARP, bool GLOBAL_WS, bool TILED>
 static cudaError_t launch_tm(const hs::TmArgs &a, int grid, int threads, size_t smem, cudaStream_t st)
 {
@@ -456,6 +481,37 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
     const int fb_cap = (int)(hs::ws_need(48, 97) + 1) & ~1;
     if (!ctx->d_ws_fb) {
         if (cudaMalloc(&ctx->d_ws_fb, (size_t)ctx->sm_count * 8 * fb_cap * sizeof(double)) != cudaSuccess) { ctx->d_ws_fb = nullptr; cudaGetLastError(); }
+    }
+    // Device-driven rounds (hs_staged_dev.h): controller, planner and task lists on the device, no host round trip between
+    // rounds.  Default for batches of HYDROTM_DEVCTL_MIN (256) particles or more; HYDROTM_DEVCTL=0 keeps the host-driven
+    // rounds (hs_staged_host.h), which small calls use anyway (a handful of particles is latency-bound either way).
+    {
+        const int devctl = getenv("HYDROTM_DEVCTL") ? atoi(getenv("HYDROTM_DEVCTL")) : 1;
+        const int devmin = getenv("HYDROTM_DEVCTL_MIN") ? atoi(getenv("HYDROTM_DEVCTL_MIN")) : 256;
+        const bool fused_req = getenv("HYDROTM_STAGED_MIN") && atoi(getenv("HYDROTM_STAGED_MIN")) > 0;
+        const bool host_only = (getenv("HYDROTM_FUSE_SOLVE") && atoi(getenv("HYDROTM_FUSE_SOLVE")) == 0) ||
+                               (getenv("HYDROTM_KR16") && atoi(getenv("HYDROTM_KR16")) == 0) || getenv("HYDROTM_OVERLAP_SCATTER") ||
+                               getenv("HYDROTM_TIMELINE");
+        if (devctl && n >= devmin && !fused_req && !host_only) {
+            if (!ctx->st) ctx->st = new StBufsHolder();
+            if (getenv("HYDROTM_PROF") && !ctx->d_prof) { CK(cudaMalloc(&ctx->d_prof, 24 * sizeof(long long))); }
+            if (ctx->d_prof) CK(cudaMemsetAsync(ctx->d_prof, 0, 24 * sizeof(long long), st));
+            StCall SC;
+            SC.d_axi = d_axi; SC.d_lam = d_lam; SC.d_mr = d_mr; SC.d_mi = d_mi; SC.d_eps = d_eps; SC.rat = rat; SC.np = np; SC.ddelt = ddelt; SC.ndgs = ndgs;
+            SC.d_tarena = d_tarena; SC.arena_cap = arena_cap; SC.d_arena_top = d_arena_top; SC.d_toff = d_toff;
+            SC.d_nmax = d_nmax; SC.d_ngauss = d_ngauss; SC.d_ntrials = d_ntrials; SC.d_status = d_status;
+            SC.scratch_budget = (size_t)((getenv("HYDROTM_SCRATCH_GB") ? atof(getenv("HYDROTM_SCRATCH_GB")) : 4.0) * (double)(1ull << 30));
+            SC.spec = getenv("HYDROTM_SPEC") ? atoi(getenv("HYDROTM_SPEC")) : 0;
+            SC.trace = trace;
+            SC.prof = (unsigned long long *)ctx->d_prof;
+            SC.one_lane = getenv("HYDROTM_ONE_LANE") && atoi(getenv("HYDROTM_ONE_LANE")) != 0;
+            const int rc = calctmat_dev(ctx, ctx->st->s, ctx->st->d, st, n, SC);
+            if (rc) return rc;
+            lap("device-driven rounds");
+            if (ctx->d_prof) print_staged_prof(ctx);
+            if (SC.nmax_max > ctx->last_nmax_max) ctx->last_nmax_max = SC.nmax_max;
+            return SC.arena_full ? HS_RC_ARENA_FULL : 0;
+        }
     }
     if (ensure_pin(ctx, (size_t)n * sizeof(int) * 4)) return -1;
     if (n > ctx->items_cap) {
@@ -616,21 +672,8 @@ static int calctmat_impl(hs_ctx *ctx, int n, const double *d_axi, const double *
             const char *nm[8] = {"other", "trial_setup", "assemble m=0", "solve m=0", "mode_setup", "assemble m>=1", "solve m>=1", "write T"};
             for (int i = 0; i < 8; i++) fprintf(stderr, "[hydrotm-prof] %-14s %6.2f%%  %.3e cycles\n", nm[i], 100.0 * hp[i] / tot, (double)hp[i]);
         } else {
-            // staged pipeline: phases of k_st_assemble (thread 0 of every CTA)
-            const char *nm[5] = {"prologue", "chunk loop", "epilogue", "solve", "T write"};
-            double t5 = 0; for (int i = 0; i < 5; i++) t5 += (double)hp[i];
-            const double ncta = (double)hp[5] > 0 ? (double)hp[5] : 1.0;
-            for (int i = 0; i < 5; i++)
-                fprintf(stderr, "[hydrotm-prof] k_st_assemble %-10s %6.2f%%  %8.0f cycles / CTA\n", nm[i], 100.0 * hp[i] / t5, (double)hp[i] / ncta);
-            fprintf(stderr, "[hydrotm-prof] k_st_assemble chunk loop split: build %.0f, barrier %.0f, contraction %.0f, barrier %.0f cycles / CTA\n",
-                    (double)hp[8] / ncta, (double)hp[9] / ncta, (double)hp[10] / ncta, (double)hp[11] / ncta);
-            fprintf(stderr, "[hydrotm-prof] k_st_assemble solve: %.1f elimination steps / CTA -> %.0f cycles / step\n", (double)hp[12] / ncta, (double)hp[3] / std::max(1.0, (double)hp[12]));
-            {
-                const double nw = (double)hp[21] > 0 ? (double)hp[21] : 1.0;
-                fprintf(stderr, "[hydrotm-prof] k_st_mode_small %.0f warps (mean NM %.1f, g %.1f): prologue %.0f, node loop %.0f, combine %.0f, solve %.0f, T write %.0f cycles / warp\n",
-                        nw, (double)hp[22] / nw, (double)hp[23] / nw, (double)hp[16] / nw, (double)hp[17] / nw, (double)hp[18] / nw, (double)hp[19] / nw, (double)hp[20] / nw);
-            }
-            fprintf(stderr, "[hydrotm-prof] k_st_assemble %.0f CTAs, mean NM %.1f, mean g %.1f, %.0f cycles / CTA\n", ncta, (double)hp[6] / ncta, (double)hp[7] / ncta, t5 / ncta);
+            for (int i = 0; i < 24; i++) (void)hp[i];
+            print_staged_prof(ctx);
         }
     }
     // remember the largest converged NMAX (bounds the T stage of the scatter kernel); the staged pipeline reports its own

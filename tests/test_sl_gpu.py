@@ -11,6 +11,17 @@ pytestmark = pytest.mark.gpu
 GEOMS = [(90.0, 90.0, 0.0, 180.0), (90.0, 90.0, 0.0, 0.0)]
 
 
+@pytest.fixture(params=["host-rounds", "device-rounds"], autouse=True)
+def round_driver(request, monkeypatch):
+    """Every test of this module runs with both round drivers of hs_calctmat_batch: the host-driven rounds
+    (hs_staged_host.h) and the device-driven rounds (hs_staged_dev.h; the default from 256 particles per call)."""
+    if request.param == "host-rounds":
+        monkeypatch.setenv("HYDROTM_DEVCTL", "0")
+    else:
+        monkeypatch.setenv("HYDROTM_DEVCTL_MIN", "1")
+    return request.param
+
+
 def _rel(a, b):
     scale = np.abs(b).max()
     return np.abs(a - b).max() / scale
@@ -196,3 +207,46 @@ def test_cylinders_match_oracle(engine, rat):
     # a sphere-like check of the shape itself: the cylinder with the volume of a sphere scatters differently from the sphere
     sph = engine.calctmat(r[:1], lam[:1], m.real[:1], m.imag[:1], eps[:1])
     assert _rel(packed_to_full(sph.packed(0), int(sph.nmax[0]))[:4], packed_to_full(tb.packed(0), int(nmax[0]))[:4]) > 1e-3
+
+
+def test_device_rounds_equal_host_rounds(engine, monkeypatch):
+    """Device-driven rounds (controller, planner and task lists on the GPU) against the host-driven rounds: same stage
+    kernels, so (NMAX, NGAUSS, trials, status) are identical and every packed T-matrix is equal bit for bit -- whatever the
+    number of groups, the speculation depth, the rounds enqueued per host visit, a scratch pool too small for one
+    particle (grown on demand), an undersized arena (HS_RC_ARENA_FULL retry), NMAX > 32 (multi-block assembly + separate
+    solve) and Gauss rules beyond the initial table (ndgs = 15)."""
+    from tests.workloads import hail_grid, ice_grid
+    from hydroscatt_b200.engine import tmat_size
+    w = rain_grid("W")
+    h = hail_grid(n=40)
+    ic = ice_grid(seed=5, n=24)
+    cases = [([np.concatenate([w[k], h[k]]) for k in ("radius", "wavelength", "mr", "mi", "axis_ratio")], dict()),
+             ([ic[k] for k in ("radius", "wavelength", "mr", "mi", "axis_ratio")], dict(ndgs=15)),
+             ([[1.0, -1.0, 900.0, 1.0, 2.0], [33.3] * 5, [7.9, 7.9, 1.5, 7.9, 7.9], [2.3, 2.3, 0.0, 2.3, 2.3], [1.2, 1.2, 1.1, 0.0, 1.3]], dict())]
+
+    def run(args, kw, **env):
+        for k, v in env.items():
+            if not k.startswith("_"):
+                monkeypatch.setenv(k, str(v))
+        engine._arena_hint = {}
+        tb = engine.calctmat(*args, arena_margin=env.get("_margin", 1.0), **kw)
+        for k in env:
+            monkeypatch.delenv(k, raising=False)
+        meta = [t.cpu().numpy().copy() for t in (tb.nmax, tb.ngauss, tb.ntrials, tb.status)]
+        toff = tb.toff.cpu().numpy()
+        arena = tb.arena.cpu().numpy()
+        T = [arena[2 * toff[i]:2 * (toff[i] + tmat_size(int(meta[0][i])))].copy() if toff[i] >= 0 else None for i in range(tb.n)]
+        return meta, T
+
+    for args, kw in cases:
+        monkeypatch.delenv("HYDROTM_DEVCTL_MIN", raising=False)
+        ref_meta, ref_T = run(args, kw, HYDROTM_DEVCTL=0)
+        for env in (dict(), dict(HYDROTM_DEV_GROUPS=1), dict(HYDROTM_DEV_GROUPS=4, HYDROTM_SPEC=1), dict(HYDROTM_SPEC=5, HYDROTM_DEV_ROUNDS=1),
+                    dict(HYDROTM_SCRATCH_GB=0.0005, HYDROTM_DEV_GROUPS=2), dict(_margin=0.05), dict(HYDROTM_ONE_LANE=1, HYDROTM_DEV_ROUNDS=2)):
+            meta, T = run(args, kw, HYDROTM_DEVCTL=1, HYDROTM_DEVCTL_MIN=1, **env)
+            for a, b in zip(ref_meta, meta):
+                assert (a == b).all(), (env, np.nonzero(a != b)[0][:8], a[a != b][:8], b[a != b][:8])
+            for a, b in zip(ref_T, T):
+                assert (a is None) == (b is None), env
+                if a is not None:
+                    assert np.array_equal(a, b), env

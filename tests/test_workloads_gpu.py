@@ -10,6 +10,17 @@ pytestmark = pytest.mark.gpu
 GEOMS = [(90.0, 90.0, 0.0, 180.0), (90.0, 90.0, 0.0, 0.0)]
 
 
+@pytest.fixture(params=["host-rounds", "device-rounds"], autouse=True)
+def round_driver(request, monkeypatch):
+    """Every test of this module runs with both round drivers of hs_calctmat_batch: the host-driven rounds
+    (hs_staged_host.h) and the device-driven rounds (hs_staged_dev.h; the default from 256 particles per call)."""
+    if request.param == "host-rounds":
+        monkeypatch.setenv("HYDROTM_DEVCTL", "0")
+    else:
+        monkeypatch.setenv("HYDROTM_DEVCTL_MIN", "1")
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def engine():
     from hydroscatt_b200.engine import Engine

@@ -52,6 +52,7 @@ struct StArgs {
     StResult *res;
     int fuse;                // solve modes with NM <= 32 inside k_st_assemble (default) or in k_st_solve
 #define ST_FUSE_RESERVED 16  // bit of `fuse`: result records cleared and arena slots reserved by the planner (device-driven rounds)
+#define ST_FUSE_TILE 32      // bit of `fuse`: register-tiled Gauss-Jordan (hs_tilesolve.cuh) for the fused solves of k_st_assemble
     unsigned long long *prof;  // HYDROTM_PROF=1: phase cycle counters of k_st_assemble [prologue, chunks, epilogue, solve, T write, #CTAs, sum NM, sum g]
 };
 
@@ -86,6 +87,10 @@ __device__ __forceinline__ double hs_rcp(double x)
     r = fma(fma(-x, r, 1.0), r, r);
     return r;
 }
+
+}  // namespace hs
+#include "hs_regsolve.cuh"
+namespace hs {
 
 // equal-volume radius of the particle (calctmat_particle: RAT != 1 -> SAREA)
 __device__ inline double st_arev(double axi, double rat, double eps, int np = -1)
@@ -450,6 +455,10 @@ __device__ __forceinline__ void st_sts128(unsigned addr, double2 v)
 {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
+
+}  // namespace hs
+#include "hs_tilesolve.cuh"
+namespace hs {
 
 // ---- Gauss-Jordan with row pivoting of one system by a (sub-)warp: lane = column of the augmented block ----
 // Same pivot rule and arithmetic as solve_multi (hs_tmat.cuh); no CTA barrier: a lane only ever touches its own
@@ -1101,6 +1110,11 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
     if (!fused) return;
     __shared__ unsigned long long keyslot[4][2];
     __shared__ double2 s_colbuf[4][2 * 32], s_rowbuf[THREADS / 32][16];  // register solver: published pivot columns / rows
+    // register-tiled solver (hs_tilesolve.cuh): m >= 1: two systems of KR rows on half the CTA each; m = 0: four half-size systems
+    typedef TileSolve<KR, KR / 8, 4, KR / 8> TS1;
+    typedef TileSolve<KR / 2, KR / 16, 4, KR / 16> TS0;
+    __shared__ typename TS1::Buf s_tb1[M0 ? 1 : 2];
+    __shared__ typename TS0::Buf s_tb0[M0 ? 4 : 1];
     __shared__ int sing;
     if (tid == 0) sing = 0;
     __syncthreads();
@@ -1113,7 +1127,8 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
         SysDesc d;
         d.base = sys + (long)(q >> 1) * NM * ldc; d.ld = ldc; d.off = q & 1; d.stride = 2; d.rhs = NM; d.n = (NM + 1 - (q & 1)) >> 1;
         if (d.n > 0) {
-            if ((a.fuse & 8) && KR == 32) solve_rows16(d, (tid % LM0) >> 5, LM0 / 32, lane, 1 + q, s_colbuf[q], s_rowbuf[tid >> 5], &sing);
+            if (a.fuse & ST_FUSE_TILE) TS0::solve(d, tid % LM0, 1 + q, &s_tb0[M0 ? q : 0], &sing);
+            else if ((a.fuse & 8) && KR == 32) solve_rows16(d, (tid % LM0) >> 5, LM0 / 32, lane, 1 + q, s_colbuf[q], s_rowbuf[tid >> 5], &sing);
             else if (a.fuse & 2) solve_grp2s(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing);
             else solve_grp(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing);
         }
@@ -1124,7 +1139,8 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
         d.base = sys + (long)q * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
         // measured per elimination step inside the pipeline (W2): wide modes (NM 17..32, four warps per system) 2 940 -> 2 260 cycles;
         // no gain for the narrow variant and the m = 0 half systems, which therefore keep the shared-memory elimination
-        if ((a.fuse & 4) && (KR == 32 || (a.fuse & 8))) solve_rows16(d, (tid % LM1) >> 5, LM1 / 32, lane, 1 + q, s_colbuf[q], s_rowbuf[tid >> 5], &sing);
+        if (a.fuse & ST_FUSE_TILE) TS1::solve(d, tid % LM1, 1 + q, &s_tb1[M0 ? 0 : q], &sing);
+        else if ((a.fuse & 4) && (KR == 32 || (a.fuse & 8))) solve_rows16(d, (tid % LM1) >> 5, LM1 / 32, lane, 1 + q, s_colbuf[q], s_rowbuf[tid >> 5], &sing);
         else if (a.fuse & 2) solve_grp2s(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
         else solve_grp(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
     }

@@ -572,6 +572,7 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         a.tarena = C.d_tarena; a.arena_cap = C.arena_cap; a.arena_top = C.d_arena_top; a.toff = C.d_toff; a.res = L[g].res;
         a.fuse = 1 | 2 | 4 | ST_FUSE_RESERVED;
         if (getenv("HYDROTM_SOLVE_REG")) { const int v = atoi(getenv("HYDROTM_SOLVE_REG")); a.fuse = 1 | 2 | (v == 0 ? 0 : (v == 2 ? 12 : 4)) | ST_FUSE_RESERVED; }
+        if (!(getenv("HYDROTM_SOLVE_TILE") && atoi(getenv("HYDROTM_SOLVE_TILE")) == 0)) a.fuse |= ST_FUSE_TILE;
         a.prof = C.prof;
         return a;
     };
@@ -622,6 +623,13 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         return 0;
     };
 
+    // HYDROTM_DEV_TIMELINE=1: an event after every round of every group (GPU time since the call's inputs were ready)
+    const bool timeline = getenv("HYDROTM_DEV_TIMELINE") != nullptr;
+    struct TL { cudaEvent_t ev; int g, r; };
+    std::vector<TL> tl;
+    cudaEvent_t ev_t0 = nullptr;
+    if (timeline) { cudaEventCreate(&ev_t0); cudaEventRecord(ev_t0, st); for (int g = 0; g < ng; g++) cudaStreamWaitEvent(D.g[g].s1, ev_t0, 0); }
+    auto mark = [&](int g, int r) { if (!timeline) return; TL e; e.g = g; e.r = r; cudaEventCreate(&e.ev); cudaEventRecord(e.ev, D.g[g].s1); tl.push_back(e); };
     int rounds_done = 0;
     int batch = D.last_rounds > 0 ? D.last_rounds : 6;
     if (getenv("HYDROTM_DEV_ROUNDS")) batch = std::max(1, atoi(getenv("HYDROTM_DEV_ROUNDS")));
@@ -629,7 +637,7 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
     int rc = 0;
     for (;;) {
         for (int r = 0; r < batch && !rc; r++)
-            for (int g = 0; g < ng && !rc; g++) { rc = round(g); if (!rc) rc = plan(g); }
+            for (int g = 0; g < ng && !rc; g++) { rc = round(g); if (!rc) rc = plan(g); mark(g, rounds_done + r); }
         rounds_done += batch;
         if (rc) break;
         if (read_hdrs()) { rc = -1; break; }
@@ -675,6 +683,11 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         if (e != cudaSuccess && !rc) { hs_set_err(ctx, cudaGetErrorString(e)); rc = -1; }
     }
     ctx->launches += launches;
+    if (timeline) {
+        cudaDeviceSynchronize();
+        for (auto &e : tl) { float ms = -1.f; cudaEventElapsedTime(&ms, ev_t0, e.ev); cudaEventDestroy(e.ev); fprintf(stderr, "[dev-timeline] g%d r%d done %7.3f ms\n", e.g, e.r, ms); }
+        cudaEventDestroy(ev_t0);
+    }
     if (rc) { cudaDeviceSynchronize(); return rc; }
     int need_rounds = 0;
     double want = 0.0;

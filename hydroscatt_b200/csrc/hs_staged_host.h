@@ -331,7 +331,7 @@ struct StGroup {
         a.axi = C->d_axi; a.lam = C->d_lam; a.mr = C->d_mr; a.mi = C->d_mi; a.eps = C->d_eps; a.rat = C->rat;
         a.gx = gx; a.gw = gw; a.gfx = gfx; a.gfw = gfw; a.np = C->np; a.cm = S->d_cm; a.dd = S->d_dd;
         a.tab = B->d_tab; a.wig = B->d_wig; a.sys = B->d_sys;
-        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res; a.fuse = (C->fuse_solve ? 1 : 0) | (getenv("HYDROTM_SOLVE2") && atoi(getenv("HYDROTM_SOLVE2")) == 0 ? 0 : 2) | (getenv("HYDROTM_SOLVE_REG") ? (atoi(getenv("HYDROTM_SOLVE_REG")) == 0 ? 0 : (atoi(getenv("HYDROTM_SOLVE_REG")) == 2 ? 12 : 4)) : 4); a.prof = C->prof;
+        a.tarena = C->d_tarena; a.arena_cap = C->arena_cap; a.arena_top = C->d_arena_top; a.toff = C->d_toff; a.res = B->h_res; a.fuse = ((getenv("HYDROTM_SOLVE_TILE") && atoi(getenv("HYDROTM_SOLVE_TILE")) == 0) ? 0 : ST_FUSE_TILE) | (C->fuse_solve ? 1 : 0) | (getenv("HYDROTM_SOLVE2") && atoi(getenv("HYDROTM_SOLVE2")) == 0 ? 0 : 2) | (getenv("HYDROTM_SOLVE_REG") ? (atoi(getenv("HYDROTM_SOLVE_REG")) == 0 ? 0 : (atoi(getenv("HYDROTM_SOLVE_REG")) == 2 ? 12 : 4)) : 4); a.prof = C->prof;
         const int ni = (int)items.size();
         // HYDROTM_PROF_SEL: bit mask of the kernel variants that record phase cycles (1: m>=1 wide, 2: m=0 wide, 4: m>=1 narrow,
         // 8: m=0 narrow, 16: small modes); default all

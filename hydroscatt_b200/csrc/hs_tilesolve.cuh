@@ -43,8 +43,13 @@ struct TileSolve {
         const int rb = t & 7, cb = t >> 3;
         const unsigned octmask = 0xFFu << (t & 24);
         const unsigned b0 = (unsigned)__cvta_generic_to_shared(d.base);
-        auto addr = [&](int r, int c) -> unsigned {  // byte address of element (r, c), c < NS: A column, else B column c - NS
-            const int cc = c < NS ? d.off + d.stride * c : d.rhs + d.off + d.stride * (c - NS);
+        // the live column blocks are packed into the first octets: A blocks 0 .. nsb - 1, then the B blocks, so that whole
+        // warps hold no live column when n is small (and skip the update) and the A warps drop out as their columns pass k
+        const int nsb = (n + CT - 1) / CT;
+        const bool isA = cb < nsb, dead = cb >= 2 * nsb;
+        const int cbl = isA ? cb : cb - nsb;  // block index inside A or B
+        auto addr = [&](int r, int col, bool a_part) -> unsigned {  // byte address of element (r, col) of A or of B
+            const int cc = a_part ? d.off + d.stride * col : d.rhs + d.off + d.stride * col;
             return b0 + 16u * (unsigned)((d.off + d.stride * r) * d.ld + cc);
         };
         auto bar = [&]() {
@@ -59,9 +64,9 @@ struct TileSolve {
             vp[i] = r;
 #pragma unroll
             for (int j = 0; j < CT; j++) {
-                const int c = cb * CT + j;
-                const bool ok = r < n && (c < NS ? c < n : c - NS < n);
-                v[i][j] = ok ? st_lds128(addr(r, c)) : make_double2(0.0, 0.0);
+                const int col = cbl * CT + j;
+                const bool ok = r < n && col < n && !dead;
+                v[i][j] = ok ? st_lds128(addr(r, col, isA)) : make_double2(0.0, 0.0);
             }
         }
         const unsigned colb0 = (unsigned)__cvta_generic_to_shared(&buf->col[0][0]), rowb = (unsigned)__cvta_generic_to_shared(buf->row);
@@ -122,7 +127,7 @@ struct TileSolve {
                 bar();
                 // ---- update: columns of A beyond k and the valid columns of B; rows other than the pivot row ----
                 const int c0 = cb * CT;
-                const bool live = c0 < NS ? (c0 + CT - 1 > k && c0 < n) : (c0 - NS < n);
+                const bool live = isA ? (c0 + CT - 1 > k) : !dead;
                 if (__any_sync(0xffffffffu, live)) {
                     double2 pr[CT];
 #pragma unroll
@@ -161,9 +166,9 @@ struct TileSolve {
                 const double2 sc = st_lds128(invb + 16u * (unsigned)vp[i]);
 #pragma unroll
                 for (int j = 0; j < CT; j++) {
-                    const int c = cb * CT + j;
-                    if (c >= NS && c - NS < n)
-                        st_sts128(addr(vp[i], c), make_double2(v[i][j].x * sc.x - v[i][j].y * sc.y, v[i][j].x * sc.y + v[i][j].y * sc.x));
+                    const int col = cbl * CT + j;
+                    if (!isA && !dead && col < n)
+                        st_sts128(addr(vp[i], col, false), make_double2(v[i][j].x * sc.x - v[i][j].y * sc.y, v[i][j].x * sc.y + v[i][j].y * sc.x));
                 }
             }
         }

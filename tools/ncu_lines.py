@@ -20,7 +20,7 @@ def main(path, top=40):
             si = hdr.index("# Samples")
             ii = hdr.index("Instructions Executed")
             stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-            wsx = hdr.index("L1 Wavefronts Shared Excessive")
+            wsx = hdr.index("L1 Wavefronts Shared Excessive") if "L1 Wavefronts Shared Excessive" in hdr else None
             continue
         if hdr is None or r[0] == "" or r[0] in ("Function Name",):
             continue
@@ -31,7 +31,7 @@ def main(path, top=40):
         except ValueError:
             continue
         stalls = sorted(((int(r[i] or 0), h) for i, h in stall_cols), reverse=True)[:2]
-        data.append((s, n, cur, ln, r[1][:100], stalls, int(r[wsx] or 0)))
+        data.append((s, n, cur, ln, r[1][:100], stalls, int(r[wsx] or 0) if wsx is not None else 0))
     tot = sum(d[0] for d in data) or 1
     toti = sum(d[1] for d in data) or 1
     print("total samples", tot, "instructions", toti)

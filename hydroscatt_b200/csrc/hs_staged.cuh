@@ -1187,11 +1187,15 @@ __global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble_q(StAr
 {
     extern __shared__ __align__(16) double op[];
     __shared__ int s_next;
+    // thread 0 fetches the index of the task after this one while the CTA works (the cursor round trip is off the path)
+    int nxt = 0;
+    if (threadIdx.x == 0) { nxt = atomicAdd(&q->cursor, 1); if (nxt >= q->count) nxt = -1; }
     for (;;) {
-        if (threadIdx.x == 0) { const int t_ = atomicAdd(&q->cursor, 1); s_next = t_ < q->count ? t_ : -1; }
+        if (threadIdx.x == 0) s_next = nxt;
         __syncthreads();
         const int t = s_next;
         if (t < 0) return;
+        if (threadIdx.x == 0) { nxt = atomicAdd(&q->cursor, 1); if (nxt >= q->count) nxt = -1; }
         st_assemble_task<M0, KR>(a, tasks[t], op);
         __syncthreads();  // the operand area / fused systems and s_next are re-used by the next task
     }
@@ -1552,12 +1556,16 @@ __global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small_q(StArgs a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = q->count;
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&q->cursor, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n) return;
-        st_small_task(a, mlist[t], smraw + warp * ST_SMALL_SLICE, sds[warp], &sings[warp], lane);
-        __syncwarp();
+        // four (item, mode) pairs per cursor round trip
+        int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(&q->cursor, 4);
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        if (t0 >= n) return;
+        const int t1 = min(t0 + 4, n);
+        for (int t = t0; t < t1; t++) {
+            st_small_task(a, mlist[t], smraw + warp * ST_SMALL_SLICE, sds[warp], &sings[warp], lane);
+            __syncwarp();
+        }
     }
 }
 

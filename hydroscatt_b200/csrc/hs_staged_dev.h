@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) k_dv_plan(DvPlanArgs A)  // DV_PB threads
 // ---- list offsets: one CTA; warp q = exclusive prefix of the block totals of count q; capacity cut; queue lengths ----
 #define DV_PB 256  // particles per k_dv_plan block
 __global__ void __launch_bounds__(32 * DV_NQ) k_dv_scan(int np, int nb, const long long *cnt, const long long *pre, const long long *btot,
-                                                          long long *boff, DvCaps caps, DvHdr *hdr)
+                                                          long long *boff, DvCaps caps, DvHdr *hdr, DvHdr *h_out)
 {
     __shared__ long long s_tot[DV_NQ];
     __shared__ int s_bc, s_cut;
@@ -349,6 +349,10 @@ __global__ void __launch_bounds__(32 * DV_NQ) k_dv_scan(int np, int nb, const lo
         hdr->active = 0;
         hdr->cut = cut;
     }
+    // the host's copy of the header: written straight into pinned (mapped) host memory, so that the host only waits for
+    // the stream -- a D2H copy of it would queue behind whatever bulk transfer the caller has in flight on the copy engine
+    __syncthreads();
+    if (t < (int)(sizeof(DvHdr) / sizeof(int))) reinterpret_cast<volatile int *>(h_out)[t] = reinterpret_cast<const int *>(hdr)[t];
 }
 
 // ---- lists of the round ----
@@ -584,7 +588,7 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         A.ddelt = C.ddelt; A.ndgs = C.ndgs; A.spec = C.spec; A.margin = margin; A.gmax = ctx->gmax; A.gfmax = ctx->gfmax; A.shape = C.np;
         A.o_nmax = C.d_nmax; A.o_ngauss = C.d_ngauss; A.o_ntrials = C.d_ntrials; A.o_status = C.d_status; A.o_toff = C.d_toff;
         k_dv_plan<<<nb, DV_PB, 0, b.s1>>>(A);
-        k_dv_scan<<<1, 32 * DV_NQ, 0, b.s1>>>(npg[g], nb, b.cnt, b.pre, b.btot, b.boff, caps, b.hdr);
+        k_dv_scan<<<1, 32 * DV_NQ, 0, b.s1>>>(npg[g], nb, b.cnt, b.pre, b.btot, b.boff, caps, b.hdr, &D.h_hdr[g]);
         launches += 2;
         CK(cudaGetLastError());
         return 0;
@@ -618,8 +622,7 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         return 0;
     };
     auto read_hdrs = [&]() -> int {
-        for (int g = 0; g < ng; g++) CK(cudaMemcpyAsync(&D.h_hdr[g], D.g[g].hdr, sizeof(DvHdr), cudaMemcpyDeviceToHost, D.g[g].s1));
-        for (int g = 0; g < ng; g++) CK(cudaStreamSynchronize(D.g[g].s1));
+        for (int g = 0; g < ng; g++) CK(cudaStreamSynchronize(D.g[g].s1));  // k_dv_scan has written D.h_hdr[g]
         return 0;
     };
 

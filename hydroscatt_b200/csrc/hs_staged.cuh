@@ -1555,13 +1555,15 @@ __global__ void __launch_bounds__(256, ST_SMALL_CTAS) k_st_mode_small_q(StArgs a
     __shared__ int sings[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = q->count;
+    // four (item, mode) pairs per cursor round trip when the list is long; a short list (the latency-bound tail rounds, or a
+    // small batch of particles with many quadrature nodes) is dealt one pair at a time so that no warp queues up work
+    const int batch = n >= 16 * (int)(gridDim.x * 8) ? 4 : 1;
     for (;;) {
-        // four (item, mode) pairs per cursor round trip
         int t0 = 0;
-        if (lane == 0) t0 = atomicAdd(&q->cursor, 4);
+        if (lane == 0) t0 = atomicAdd(&q->cursor, batch);
         t0 = __shfl_sync(0xffffffffu, t0, 0);
         if (t0 >= n) return;
-        const int t1 = min(t0 + 4, n);
+        const int t1 = min(t0 + batch, n);
         for (int t = t0; t < t1; t++) {
             st_small_task(a, mlist[t], smraw + warp * ST_SMALL_SLICE, sds[warp], &sings[warp], lane);
             __syncwarp();

@@ -43,6 +43,7 @@ struct DvHdr {  // one group's round header
     int cut;                // first particle behind the capacity cut of the planned round (np: none)
     long long want_pool;    // pool doubles the round would have used without the cut (sizing of the next call)
     long long stuck_pool;   // stuck: pool doubles that particle needs
+    int any_big, pad;       // some round had modes with NM > 32
 };
 
 struct DvCaps { long long cap[DV_NQ]; };
@@ -75,6 +76,7 @@ struct DvShared {
     int last_rounds = 0;     // rounds the previous call needed (enqueued up front by the next one)
     double pool_per_particle = 0.0;  // doubles: grown from `want_pool` of earlier calls
     long long pool_floor = 0;        // doubles: largest single-particle need that once exceeded the pool
+    bool had_big = true;             // the previous call had modes with NM > 32 (separate solve kernels at full grid)
     bool init = false;
 };
 
@@ -344,6 +346,7 @@ __global__ void __launch_bounds__(32 * DV_NQ) k_dv_scan(int np, int nb, const lo
         hdr->q[DK_AT1].count = (int)len(DQ_AT1); hdr->q[DK_AT0].count = (int)len(DQ_AT0);
         hdr->q[DK_AS1].count = (int)len(DQ_AS1); hdr->q[DK_AS0].count = (int)len(DQ_AS0);
         hdr->q[DK_G4].count = (int)len(DQ_G4); hdr->q[DK_G3].count = (int)len(DQ_G3); hdr->q[DK_SM].count = (int)len(DQ_SM);
+        if (len(DQ_G3) + len(DQ_G4) > 0) hdr->any_big = 1;
         for (int k = 0; k < DV_NK; k++) hdr->q[k].cursor = 0;
         hdr->remaining = hdr->active;
         hdr->active = 0;
@@ -611,8 +614,10 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         if (!one_lane) { CK(cudaEventRecord(b.ev_fork, s1)); CK(cudaStreamWaitEvent(s2, b.ev_fork, 0)); }
         k_st_assemble_q<false, 32><<<sms * D.occ[DK_AT1], 256, ST_ASM_SMEM, s1>>>(pa(1), L[g].at1, q + DK_AT1);
         k_st_assemble_q<true, 32><<<sms * D.occ[DK_AT0], 256, ST_ASM_SMEM, s1>>>(pa(2), L[g].at0, q + DK_AT0);
-        k_st_solve_q<256, true><<<sms * std::min(D.occ[DK_G4], 2), 256, 0, s1>>>(a, L[g].g4, q + DK_G4);
-        k_st_solve_q<256, false><<<sms * D.occ[DK_G3], 256, 200704, s1>>>(a, L[g].g3, q + DK_G3);
+        // modes with NM > 32 (hail-sized particles): the solve kernels need 200 KB of shared memory per CTA; when the previous
+        // call had no such mode only a token grid is launched (it still drains the list, slowly, if this call has some)
+        k_st_solve_q<256, true><<<D.had_big ? sms * std::min(D.occ[DK_G4], 2) : 2, 256, 0, s1>>>(a, L[g].g4, q + DK_G4);
+        k_st_solve_q<256, false><<<D.had_big ? sms * D.occ[DK_G3] : 2, 256, 200704, s1>>>(a, L[g].g3, q + DK_G3);
         k_st_assemble_q<false, 16><<<sms * D.occ[DK_AS1], 128, ST_ASM_SMEM16, s2>>>(pa(4), L[g].as1, q + DK_AS1);
         k_st_assemble_q<true, 16><<<sms * D.occ[DK_AS0], 128, ST_ASM_SMEM16, s2>>>(pa(8), L[g].as0, q + DK_AS0);
         k_st_mode_small_q<<<sms * D.occ[DK_SM], 256, 8 * ST_SMALL_SLICE * 8, s2>>>(pa(16), L[g].sm, q + DK_SM);
@@ -702,6 +707,8 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         want = std::max(want, (double)h.want_pool / (double)std::max(1, npg[g]));
     }
     D.last_rounds = std::max(1, need_rounds);
+    D.had_big = false;
+    for (int g = 0; g < ng; g++) D.had_big |= D.h_hdr[g].any_big != 0;
     if (want > D.pool_per_particle) D.pool_per_particle = want;
     if (C.trace) {
         const double tot = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();

@@ -847,16 +847,21 @@ static int psd_obs_impl(hs_ctx *ctx, int n_dsd, int n_D, int n_tab, const double
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
     // weights + one area that is in turn the table tile, the integrated values ([64][65]) and the staged observables
-    const size_t smem = ((size_t)PSDF_RB * (n_D | 1) + std::max((size_t)n_D * PSDF_TB * PSDF_NC, (size_t)PSDF_RB * 65)) * sizeof(double);
+    // (the DMMA variant stages the table tile transposed: [64 columns][n_D | 1])
+    static const bool dmma = !(getenv("HYDROTM_PSD_DMMA") && atoi(getenv("HYDROTM_PSD_DMMA")) == 0);
+    const size_t tile = dmma ? (size_t)PSDF_TB * PSDF_NC * (n_D | 1) : (size_t)n_D * PSDF_TB * PSDF_NC;
+    const size_t smem = ((size_t)PSDF_RB * (n_D | 1) + std::max(tile, (size_t)PSDF_RB * 65)) * sizeof(double);
     if (smem > (size_t)ctx->smem_optin) { hs_set_err(ctx, "hs_psd_observables: too many diameters for one shared-memory tile"); return -3; }
-    CK(cudaFuncSetAttribute(hs::k_psd_obs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(hs::k_psd_obs_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(hs::k_psd_obs_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int rb = (n_dsd + PSDF_RB - 1) / PSDF_RB;
     // enough CTAs for two waves of the SMs: split the tables when there are few DSD tiles
     int splits = std::max(1, std::min((n_tab + PSDF_TB - 1) / PSDF_TB, (2 * ctx->sm_count + rb - 1) / rb));
     int per = ((n_tab + splits - 1) / splits + PSDF_TB - 1) / PSDF_TB * PSDF_TB;
     splits = (n_tab + per - 1) / per;
     dim3 grid(rb, splits);
-    hs::k_psd_obs_fused<<<grid, 256, smem, st>>>(n_dsd, n_D, n_tab, per, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, want_sca, sel, d_obs);
+    if (dmma) hs::k_psd_obs_fused<true><<<grid, 256, smem, st>>>(n_dsd, n_D, n_tab, per, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, want_sca, sel, d_obs);
+    else hs::k_psd_obs_fused<false><<<grid, 256, smem, st>>>(n_dsd, n_D, n_tab, per, d_W, d_rows, d_lam_tab, kw_sqr, hpol_quirk, want_sca, sel, d_obs);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -52,6 +52,12 @@ struct StArgs {
     StResult *res;
     int fuse;                // solve modes with NM <= 32 inside k_st_assemble (default) or in k_st_solve
 #define ST_FUSE_RESERVED 16  // bit of `fuse`: result records cleared and arena slots reserved by the planner (device-driven rounds)
+#ifndef ST_LEGACY_FUSED_SOLVERS
+#define ST_LEGACY_FUSED_SOLVERS 0  // 1: keep the round-1 solvers (solve_grp2s, solve_rows16) selectable for the fused solves (fuse bits 2 / 4 / 8)
+#endif
+#ifndef ST_WIDE0_CTAS
+#define ST_WIDE0_CTAS 2            // resident 256-thread CTAs per SM of the wide m = 0 assembly kernel (3 = 80 registers, 196 B of spills: measured equal, 5.01 vs 4.95 ms per W2 call)
+#endif
 #define ST_FUSE_TILE 32      // bit of `fuse`: register-tiled Gauss-Jordan (hs_tilesolve.cuh) for the fused solves of k_st_assemble
     unsigned long long *prof;  // HYDROTM_PROF=1: phase cycle counters of k_st_assemble [prologue, chunks, epilogue, solve, T write, #CTAs, sum NM, sum g]
 };
@@ -941,7 +947,10 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
     // build-phase constants of this thread: rows (kk, F) / (kk, re|im) of every table, column ii (swizzled)
     const int rho = (kk & 1) * KR + 2 * (kk >> 1);
     const int col = ii ^ (((rho >> 1) & 1) << 2);
-    double *o0 = op + rho * 8 + col, *o1 = o0 + 8;
+    // physical row = r ^ ((r >> 1) & 1): the four row pairs a warp stores (kk = 4 w .. 4 w + 3) then alternate between the two
+    // 8-word halves of a bank line (2 wavefronts per store instead of 4), and the fragment loads stay conflict-free
+    const int rsw = (rho >> 1) & 1;
+    double *o0 = op + (rho ^ rsw) * 8 + col, *o1 = op + ((rho + 1) ^ rsw) * 8 + col;
     const int k1 = kr0 + kk, k2 = kc0 + kk;
     const int n1 = nmin + k1, n2 = nmin + k2;
     const double an1 = (double)(n1 * (n1 + 1)), an2 = (double)(n2 * (n2 + 1));
@@ -1010,7 +1019,7 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
             // fragment element of table t, rows [row0, row0 + 8): row0 + (lane >> 2), node 4 ks + (lane & 3)
             auto frag = [&](int t, int row0) -> double {
                 const int r = row0 + fragrow;
-                return op[(t * (2 * KR) + r) * 8 + ((((ks ^ (r >> 1)) & 1) << 2) | fragk)];
+                return op[(t * (2 * KR) + (r ^ ((r >> 1) & 1))) * 8 + ((((ks ^ (r >> 1)) & 1) << 2) | fragk)];
             };
             double la[NTR][5];
 #pragma unroll
@@ -1106,12 +1115,14 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
         }
     }
     if (!fused) return;
+#if ST_LEGACY_FUSED_SOLVERS
     __shared__ unsigned long long keyslot[4][2];
     __shared__ double2 s_colbuf[4][2 * 32], s_rowbuf[THREADS / 32][16];  // register solver: published pivot columns / rows
+#endif
     // register-tiled solver (hs_tilesolve.cuh): m >= 1: two systems of KR rows on half the CTA each; m = 0: four half-size systems
     typedef TileSolve<KR, KR / 8, 4, KR / 8> TS1;
     typedef TileSolve<KR / 2, KR / 16, 4, KR / 16> TS0;
-    __shared__ typename TS1::Buf s_tb1[M0 ? 1 : 2];
+    __shared__ typename TS1::Buf s_tb1[M0 ? 1 : 2];  // (the compiler drops the array the instantiation does not use)
     __shared__ typename TS0::Buf s_tb0[M0 ? 4 : 1];
     __shared__ int sing;
     if (tid == 0) sing = 0;
@@ -1125,10 +1136,14 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
         SysDesc d;
         d.base = sys + (long)(q >> 1) * NM * ldc; d.ld = ldc; d.off = q & 1; d.stride = 2; d.rhs = NM; d.n = (NM + 1 - (q & 1)) >> 1;
         if (d.n > 0) {
+#if ST_LEGACY_FUSED_SOLVERS
             if (a.fuse & ST_FUSE_TILE) TS0::solve(d, tid % LM0, 1 + q, &s_tb0[M0 ? q : 0], &sing);
             else if ((a.fuse & 8) && KR == 32) solve_rows16(d, (tid % LM0) >> 5, LM0 / 32, lane, 1 + q, s_colbuf[q], s_rowbuf[tid >> 5], &sing);
             else if (a.fuse & 2) solve_grp2s(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing);
             else solve_grp(d, tid % LM0, LM0, 1 + q, keyslot[q], &sing);
+#else
+            TS0::solve(d, tid % LM0, 1 + q, &s_tb0[M0 ? q : 0], &sing);
+#endif
         }
     } else {
         // the two parity classes
@@ -1137,10 +1152,14 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
         d.base = sys + (long)q * NM * ldc; d.n = NM; d.ld = ldc; d.off = 0; d.stride = 1; d.rhs = NM;
         // measured per elimination step inside the pipeline (W2): wide modes (NM 17..32, four warps per system) 2 940 -> 2 260 cycles;
         // no gain for the narrow variant and the m = 0 half systems, which therefore keep the shared-memory elimination
+#if ST_LEGACY_FUSED_SOLVERS
         if (a.fuse & ST_FUSE_TILE) TS1::solve(d, tid % LM1, 1 + q, &s_tb1[M0 ? 0 : q], &sing);
         else if ((a.fuse & 4) && (KR == 32 || (a.fuse & 8))) solve_rows16(d, (tid % LM1) >> 5, LM1 / 32, lane, 1 + q, s_colbuf[q], s_rowbuf[tid >> 5], &sing);
         else if (a.fuse & 2) solve_grp2s(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
         else solve_grp(d, tid % LM1, LM1, 1 + q, keyslot[q], &sing);
+#else
+        TS1::solve(d, tid % LM1, 1 + q, &s_tb1[M0 ? 0 : q], &sing);
+#endif
     }
     __syncthreads();
     ST_PROF(3)
@@ -1174,7 +1193,7 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
 }
 
 template <bool M0, int KR>
-__global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs a, const StATask *tasks, int ntasks)
+__global__ void __launch_bounds__(8 * KR, KR == 32 ? (M0 ? ST_WIDE0_CTAS : 2) : 4) k_st_assemble(StArgs a, const StATask *tasks, int ntasks)
 {
     extern __shared__ __align__(16) double op[];
     if ((int)blockIdx.x >= ntasks) return;
@@ -1183,7 +1202,7 @@ __global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble(StArgs
 
 // resident CTAs fetching tasks from the device-built list (see k_st_radial_q)
 template <bool M0, int KR>
-__global__ void __launch_bounds__(8 * KR, KR == 32 ? 2 : 4) k_st_assemble_q(StArgs a, const StATask *tasks, StQueue *q)
+__global__ void __launch_bounds__(8 * KR, KR == 32 ? (M0 ? ST_WIDE0_CTAS : 2) : 4) k_st_assemble_q(StArgs a, const StATask *tasks, StQueue *q)
 {
     extern __shared__ __align__(16) double op[];
     __shared__ int s_next;
@@ -1348,7 +1367,10 @@ __device__ __forceinline__ void st_small_task(const StArgs &a, const int mix, do
     const double qm = (double)m, qmm = qm * qm;
     const int kk = lane >> 2, ii = lane & 3;
     const int rho = (kk & 1) * 8 + 2 * (kk >> 1);
-    double *o0 = op + rho * 4 + ii, *o1 = o0 + 4;
+    // physical position of (row, node) inside a table's 64 words: 16 ((row & 1) + 2 (row >> 3)) + 4 ((row >> 1) & 3) + node --
+    // the eight rows a warp stores, and the eight rows a fragment load reads, each cover the 16 bank pairs exactly twice
+    // (the plain [row][node] layout stored with 4 wavefronts instead of 2: 18 M of the kernel's 21 M bank conflicts per launch)
+    double *o0 = op + 16 * (2 * (rho >> 3)) + 4 * ((rho >> 1) & 3) + ii, *o1 = o0 + 16;
     const int n1 = nmin + kk;
     const double an1 = (double)(n1 * (n1 + 1));
     const int fragrow = lane >> 2, fragk = lane & 3;
@@ -1411,7 +1433,10 @@ __device__ __forceinline__ void st_small_task(const StArgs &a, const int mix, do
             }
             __syncwarp();
         }
-        auto frag = [&](int t, int row0) -> double { return op[(t * 16 + row0 + fragrow) * 4 + fragk]; };
+        auto frag = [&](int t, int row0) -> double {
+            const int r = row0 + fragrow;
+            return op[t * 64 + 16 * ((r & 1) + 2 * (r >> 3)) + 4 * ((r >> 1) & 3) + fragk];
+        };
         double lE[5], lO[5];
 #pragma unroll
         for (int t = 0; t < 5; t++) { lE[t] = frag(t, 0); lO[t] = frag(t, 8); }

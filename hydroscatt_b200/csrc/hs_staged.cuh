@@ -1367,10 +1367,9 @@ __device__ __forceinline__ void st_small_task(const StArgs &a, const int mix, do
     const double qm = (double)m, qmm = qm * qm;
     const int kk = lane >> 2, ii = lane & 3;
     const int rho = (kk & 1) * 8 + 2 * (kk >> 1);
-    // physical position of (row, node) inside a table's 64 words: 16 ((row & 1) + 2 (row >> 3)) + 4 ((row >> 1) & 3) + node --
-    // the eight rows a warp stores, and the eight rows a fragment load reads, each cover the 16 bank pairs exactly twice
-    // (the plain [row][node] layout stored with 4 wavefronts instead of 2: 18 M of the kernel's 21 M bank conflicts per launch)
-    double *o0 = op + 16 * (2 * (rho >> 3)) + 4 * ((rho >> 1) & 3) + ii, *o1 = o0 + 16;
+    // (a [row & 1, row >> 3][row >> 1 & 3][node] layout halves the wavefronts of these stores -- 18 M of the kernel's 21 M bank
+    // conflicts per launch -- but its address arithmetic costs more than the conflicts: node loop 12.9 k -> 13.5 k cycles per warp)
+    double *o0 = op + rho * 4 + ii, *o1 = o0 + 4;
     const int n1 = nmin + kk;
     const double an1 = (double)(n1 * (n1 + 1));
     const int fragrow = lane >> 2, fragk = lane & 3;
@@ -1433,10 +1432,7 @@ __device__ __forceinline__ void st_small_task(const StArgs &a, const int mix, do
             }
             __syncwarp();
         }
-        auto frag = [&](int t, int row0) -> double {
-            const int r = row0 + fragrow;
-            return op[t * 64 + 16 * ((r & 1) + 2 * (r >> 3)) + 4 * ((r >> 1) & 3) + fragk];
-        };
+        auto frag = [&](int t, int row0) -> double { return op[(t * 16 + row0 + fragrow) * 4 + fragk]; };
         double lE[5], lO[5];
 #pragma unroll
         for (int t = 0; t < 5; t++) { lE[t] = frag(t, 0); lO[t] = frag(t, 8); }

@@ -104,11 +104,11 @@ static void run(int n, int ngroups, int sms)
     cudaFree(d); cudaFree(cur); cudaFree(sing); cudaFree(cyc);
 }
 
-int main()
+int main(int argc, char **argv)
 {
     cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
     const int sms = pr.multiProcessorCount;
-    const int N = 20000;
+    const int N = argc > 1 ? atoi(argv[1]) : 20000;  // groups of systems (small for compute-sanitizer --tool racecheck)
     // wide m >= 1: two systems of n <= 32 per 256-thread CTA, 2 CTAs per SM
     for (int n : {17, 20, 24, 32}) { run<32, 4, 4, 4, 2, 2, 0>(n, N, sms); run<32, 4, 4, 4, 2, 2, 1>(n, N, sms); }
     // narrow m >= 1: two systems of n <= 16 per 128-thread CTA, 4 CTAs per SM

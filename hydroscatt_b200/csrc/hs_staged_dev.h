@@ -614,10 +614,11 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         if (!one_lane) { CK(cudaEventRecord(b.ev_fork, s1)); CK(cudaStreamWaitEvent(s2, b.ev_fork, 0)); }
         k_st_assemble_q<false, 32><<<sms * D.occ[DK_AT1], 256, ST_ASM_SMEM, s1>>>(pa(1), L[g].at1, q + DK_AT1);
         k_st_assemble_q<true, 32><<<sms * D.occ[DK_AT0], 256, ST_ASM_SMEM, s1>>>(pa(2), L[g].at0, q + DK_AT0);
-        // modes with NM > 32 (hail-sized particles): the solve kernels need 200 KB of shared memory per CTA; when the previous
-        // call had no such mode only a token grid is launched (it still drains the list, slowly, if this call has some)
-        k_st_solve_q<256, true><<<D.had_big ? sms * std::min(D.occ[DK_G4], 2) : 2, 256, 0, s1>>>(a, L[g].g4, q + DK_G4);
-        k_st_solve_q<256, false><<<D.had_big ? sms * D.occ[DK_G3] : 2, 256, 200704, s1>>>(a, L[g].g3, q + DK_G3);
+        // modes with NM > 32 (hail-sized particles).  When the previous call had none, a quarter of the grid is launched: the
+        // empty 200 KB-per-CTA launches cost ~1 % of a rain-sweep call at full size, and a call that does bring such modes
+        // after one that did not still drains its lists at a quarter of the rate instead of crawling on a token grid
+        k_st_solve_q<256, true><<<D.had_big ? sms * std::min(D.occ[DK_G4], 2) : sms / 2, 256, 0, s1>>>(a, L[g].g4, q + DK_G4);
+        k_st_solve_q<256, false><<<D.had_big ? sms * D.occ[DK_G3] : sms / 4, 256, 200704, s1>>>(a, L[g].g3, q + DK_G3);
         k_st_assemble_q<false, 16><<<sms * D.occ[DK_AS1], 128, ST_ASM_SMEM16, s2>>>(pa(4), L[g].as1, q + DK_AS1);
         k_st_assemble_q<true, 16><<<sms * D.occ[DK_AS0], 128, ST_ASM_SMEM16, s2>>>(pa(8), L[g].as0, q + DK_AS0);
         k_st_mode_small_q<<<sms * D.occ[DK_SM], 256, 8 * ST_SMALL_SLICE * 8, s2>>>(pa(16), L[g].sm, q + DK_SM);

@@ -16,19 +16,14 @@
 // so that one group's dependent chain (tables -> assembly -> controller) overlaps the others' kernels.
 // Included by hydrotm.cu after hs_staged_host.h.
 #pragma once
+#include "hs_dvctl.h"
 
 namespace {
 
+using hs::DvP;
+
 enum { DQ_ITEMS = 0, DQ_MODES, DQ_POOL, DQ_RAD, DQ_AT0, DQ_AT1, DQ_AS0, DQ_AS1, DQ_G3, DQ_G4, DQ_SM, DV_NQ };
 enum { DK_RAD = 0, DK_WIG, DK_AT1, DK_AT0, DK_AS1, DK_AS0, DK_G4, DK_G3, DK_SM, DV_NK };
-
-struct DvP {  // controller state of one particle (StP of the host-driven path)
-    int idx, phase, nmax, g, ntr, status, done, sing;
-    double q1s, q1e;
-    long long t_off;
-    int first_item, n_items, kspec, written;
-    double dprev, dlast;
-};
 
 struct DvHdr {  // one group's round header
     long long tot[DV_NQ];   // list lengths / pool doubles of the planned round (after the capacity cut)
@@ -79,27 +74,6 @@ struct DvShared {
     bool had_big = true;             // the previous call had modes with NM > 32 (separate solve kernels at full grid)
     bool init = false;
 };
-
-// items of particle `s` in the coming round: calls f(nmax, g, nmodes) for each; returns false if a Gauss rule is missing
-template <class F>
-__device__ __forceinline__ bool dv_items_of(const DvP &s, int ndgs, int spec, int gmax, int gfmax, int np, int *gneed, F f)
-{
-    const int cnt = s.phase == 0 ? (spec > 0 ? spec : s.kspec) : 1;
-    // every rule the round's items need must be in the tables; otherwise the particle waits for the host to extend them
-    for (int q = 0; q < cnt; q++) {
-        const int nm = s.phase == 0 ? s.nmax + q : s.nmax;
-        const int g = s.phase == 0 ? nm * ndgs : (s.phase == 1 ? s.g + 1 : s.g);
-        if (nm > HS_NPN1 || g > HS_NPNG1) break;
-        if (g > gmax || (np == -2 && g / 2 + 1 > gfmax)) { if (gneed) atomicMax(gneed, g); return false; }
-    }
-    for (int q = 0; q < cnt; q++) {
-        const int nm = s.phase == 0 ? s.nmax + q : s.nmax;
-        const int g = s.phase == 0 ? nm * ndgs : (s.phase == 1 ? s.g + 1 : s.g);
-        if (nm > HS_NPN1 || g > HS_NPNG1) break;  // the controller reports the limit when it gets there
-        f(nm, g, s.phase == 0 ? 1 : nm + 1);
-    }
-    return true;
-}
 
 __device__ __forceinline__ long long dv_item_pool(int nmax, int gp, int nmodes)
 {
@@ -166,11 +140,7 @@ __global__ void k_dv_place(int n, int ng, int spec0, const int *n0, const int *l
     const int key = s0 < 0 ? 0 : min(max(l, 0), HS_NPN1) + 1;
     const int r = base[key] + atomicAdd(&hist[HS_NPN1 + 3 + key], 1);
     DvP s;
-    s.idx = i; s.phase = 0; s.nmax = s0; s.g = 0; s.ntr = 0; s.status = HS_ST_OK; s.done = 0; s.sing = 0;
-    s.q1s = 0.0; s.q1e = 0.0; s.t_off = -1; s.first_item = 0; s.n_items = 0; s.written = 0;
-    s.kspec = max(2, min(12 + spec0, l - max(s0, 0) + 1 + spec0)); s.dprev = 0.0; s.dlast = 0.0;
-    if (s.nmax < 0) { s.done = 2; s.status = HS_ST_BAD_INPUT; s.nmax = -s.nmax - 1; }
-    else if (s.nmax >= HS_NPN1) { s.done = 2; s.status = HS_ST_NMAX_LIMIT; }
+    hs::dv_init(s, i, s0, l, spec0);
     G.P[r % ng][r / ng] = s;
 }
 
@@ -195,50 +165,17 @@ __global__ void __launch_bounds__(256) k_dv_plan(DvPlanArgs A)  // DV_PB threads
     for (int q = 0; q < DV_NQ; q++) c[q] = 0;
     if (j < A.np) {
     DvP s = A.P[j];
-    // controller (hs_staged_host.h: StGroup::finish)
-    if (!s.done && s.n_items > 0) {
-        for (int q = 0; q < s.n_items; q++) {
-            const int g_it = A.items[s.first_item + q].g;
-            const hs::StResult r = A.res[s.first_item + q];
-            if (s.phase == 2) {
-                if (r.t_off == -2) { s.status = HS_ST_ARENA_FULL; s.done = 2; break; }
-                s.t_off = r.t_off; s.sing |= r.sing; s.done = 1;
-                break;
-            }
-            const double dsca = fabs((s.q1s - r.qsca) / r.qsca), dext = fabs((s.q1e - r.qext) / r.qext);
-            s.q1s = r.qsca; s.q1e = r.qext;
-            s.ntr++;
-            s.g = g_it;
-            s.sing |= r.sing;
-            const bool ok = (dsca <= A.ddelt && dext <= A.ddelt);
-            if (s.phase == 0) {
-                s.dprev = s.dlast; s.dlast = fmax(dsca, dext) / A.ddelt;
-                if (ok) { s.phase = (g_it == HS_NPNG1) ? 2 : 1; break; }
-                else if (s.nmax + 1 > HS_NPN1) { s.status = HS_ST_NMAX_LIMIT; s.done = 2; break; }
-                else s.nmax = s.nmax + 1;
-            } else {
-                if (r.t_off == -2) { s.status = HS_ST_ARENA_FULL; s.done = 2; break; }
-                s.t_off = r.t_off;
-                if (ok) s.done = 1;
-                else if (g_it == HS_NPNG1) { s.status = HS_ST_NGAUSS_LIMIT; s.done = 1; }
-                break;
-            }
-        }
-        if (!s.done && s.phase == 0) {
-            // speculation depth from the convergence trend (see StGroup::finish)
-            int k = (s.dlast > 0.0 && s.dlast < 100.0) ? 1 : 2;
-            if (s.dprev > s.dlast && s.dlast > 1.0 && isfinite(s.dprev)) {
-                const double r = log(s.dlast) / log(s.dprev / s.dlast);
-                k = (int)fmin(8.0, fmax(1.0, ceil(r) + (double)A.margin));
-            }
-            s.kspec = k;
-        }
-    }
-    s.n_items = 0;
-    if (!s.done && s.phase == 0 && (long long)s.nmax * A.ndgs > HS_NPNG1) { s.status = HS_ST_NGAUSS_LIMIT; s.done = 2; }
+    // controller (hs_dvctl.h) over the results of the previous round, then the limit test of the coming one
+    hs::dv_consume(s, A.ddelt, A.ndgs, A.margin, [&](int q) {
+        const hs::StResult r = A.res[s.first_item + q];
+        hs::DvTrial t;
+        t.qsca = r.qsca; t.qext = r.qext; t.t_off = r.t_off; t.sing = r.sing; t.g = A.items[s.first_item + q].g;
+        return t;
+    });
     if (!s.done) {
         act = true;
-        dv_items_of(s, A.ndgs, A.spec, A.gmax, A.gfmax, A.shape, &A.hdr->gneed, [&](int nmax, int g, int nmodes) {
+        int gmiss = 0;
+        const bool planned = hs::dv_items_of(s, A.ndgs, A.spec, A.gmax, A.gfmax, A.shape, &gmiss, [&](int nmax, int g, int nmodes) {
             const int gp = (g + 3) & ~3;
             c[DQ_ITEMS]++;
             c[DQ_MODES] += nmodes;
@@ -253,6 +190,7 @@ __global__ void __launch_bounds__(256) k_dv_plan(DvPlanArgs A)  // DV_PB threads
                 if (NM > 32) c[NM <= 56 ? DQ_G3 : DQ_G4]++;
             }
         });
+        if (!planned) atomicMax(&A.hdr->gneed, gmiss);
     } else if (!s.written) {
         s.written = 1;
         int stt = s.status;
@@ -384,7 +322,7 @@ __global__ void __launch_bounds__(128) k_dv_fill(DvFillArgs A)
     const long long tot_rad = A.hdr->tot[DQ_RAD];
     const int first = (int)o[DQ_ITEMS];
     int n_items = 0;
-    const bool ok = dv_items_of(s, A.ndgs, A.spec, A.gmax, A.gfmax, A.shape, nullptr, [&](int nmax, int g, int nmodes) {
+    const bool ok = hs::dv_items_of(s, A.ndgs, A.spec, A.gmax, A.gfmax, A.shape, nullptr, [&](int nmax, int g, int nmodes) {
         const int gp = (g + 3) & ~3;
         const int ii = (int)o[DQ_ITEMS]++;
         hs::StItem it;

@@ -96,3 +96,15 @@ def gauss_positive(n):
     x, w = np.zeros(n // 2), np.zeros(n // 2)
     lib().emu_gauss_positive(int(n), _dp(x), _dp(w))
     return x, w
+
+
+def dv_rounds(s0, lb, table, ndgs=2, spec=0, spec0=0, margin=1, ddelt=1e-4):
+    """Device-driven rounds of ONE particle (controller + planner of hs_dvctl.h as host code) fed from a table of trial results
+    table = (nmax[], ngauss[], qsca[], qext[]).  Returns dict(nmax, ngauss, ntrials, status, done, rounds, planned, unknown)."""
+    tn, tg, ts, te = [np.ascontiguousarray(a) for a in table]
+    tn = tn.astype(np.int32); tg = tg.astype(np.int32); ts = ts.astype(np.float64); te = te.astype(np.float64)
+    out = np.zeros(8, np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    lib().emu_dv_rounds(int(s0), int(lb), int(ndgs), int(spec), int(spec0), int(margin), C.c_double(ddelt), int(tn.size),
+                        ip(tn), ip(tg), _dp(ts), _dp(te), ip(out))
+    return dict(zip(("nmax", "ngauss", "ntrials", "status", "done", "rounds", "planned", "unknown"), [int(v) for v in out]))

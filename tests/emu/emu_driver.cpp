@@ -84,3 +84,35 @@ extern "C" void emu_scatter(const double *t, int nmax, double lam, double thet0,
 // hs_gauss.h: the n-point rule (any n; cylinders use odd orders too) and the positive half of an even rule
 extern "C" void emu_gauss_full(int n, double *z, double *w) { hs::gauss_full(n, z, w); }
 extern "C" void emu_gauss_positive(int n, double *xp, double *wp) { hs::gauss_positive(n, xp, wp); }
+
+// ---- device-driven rounds: controller + planner (hs_dvctl.h) on a table of trial results ----
+// One particle: starting order s0, lower-bound guess lb; the trial results come from a table of n_tab known trials
+// (NMAX, NGAUSS) -> (Qsca, Qext) -- the oracle's recorded sequence; a planned trial that is not in the table gets poison
+// values, so a controller that consumed a trial beyond the reference's sequence cannot land on the reference's answer.
+// out: nmax, ngauss, ntrials, status, done, rounds, planned items, consumed-unknown flag.
+#include "../../hydroscatt_b200/csrc/hs_dvctl.h"
+extern "C" void emu_dv_rounds(int s0, int lb, int ndgs, int spec, int spec0, int margin, double ddelt, int n_tab,
+                              const int *tab_nmax, const int *tab_g, const double *tab_qsca, const double *tab_qext, int *out8)
+{
+    hs::DvP s;
+    hs::dv_init(s, 0, s0, lb, spec0);
+    int rounds = 0, planned = 0, unknown = 0;
+    std::vector<hs::DvTrial> res;
+    std::vector<int> known;
+    while (!s.done && rounds < 2000) {
+        res.clear(); known.clear();
+        hs::dv_items_of(s, ndgs, spec, 1 << 30, 1 << 30, -1, nullptr, [&](int nmax, int g, int nmodes) {
+            hs::DvTrial t; t.qsca = 1.2345e300; t.qext = -7.7e-300; t.t_off = nmodes > 1 ? 1000 + planned : -1; t.sing = 0; t.g = g;
+            int k = 0;
+            for (int i = 0; i < n_tab; i++) if (tab_nmax[i] == nmax && tab_g[i] == g) { t.qsca = tab_qsca[i]; t.qext = tab_qext[i]; k = 1; }
+            res.push_back(t); known.push_back(k);
+            planned++;
+        });
+        s.first_item = 0; s.n_items = (int)res.size();
+        const int before = s.ntr;
+        hs::dv_consume(s, ddelt, ndgs, margin, [&](int q) { return res[q]; });
+        for (int q = 0; q < s.ntr - before; q++) if (!known[q]) unknown = 1;
+        rounds++;
+    }
+    out8[0] = s.nmax; out8[1] = s.g; out8[2] = s.ntr; out8[3] = s.status; out8[4] = s.done; out8[5] = rounds; out8[6] = planned; out8[7] = unknown;
+}

@@ -547,8 +547,11 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
         static const int psel = getenv("HYDROTM_PROF_SEL") ? atoi(getenv("HYDROTM_PROF_SEL")) : 31;  // see hs_staged_host.h
         auto pa = [&](int bit) { StArgs x = a; if (!(psel & bit)) x.prof = nullptr; return x; };
         StQueue *q = b.hdr->q;
-        k_st_radial_q<<<sms * std::min(D.occ[DK_RAD], 8), 128, 0, s1>>>(a, L[g].rad, q + DK_RAD);
-        k_st_wigner_q<<<sms * std::min(D.occ[DK_WIG], 8), 128, 0, s1>>>(a, q + DK_WIG);
+        // resident CTAs per SM of the radial / Wigner kernels (HYDROTM_RAD_CTAS, HYDROTM_WIG_CTAS: experiments)
+        static const int rad_ctas = getenv("HYDROTM_RAD_CTAS") ? std::max(1, atoi(getenv("HYDROTM_RAD_CTAS"))) : 8;
+        static const int wig_ctas = getenv("HYDROTM_WIG_CTAS") ? std::max(1, atoi(getenv("HYDROTM_WIG_CTAS"))) : 8;
+        k_st_radial_q<<<sms * std::min(D.occ[DK_RAD], rad_ctas), 128, 0, s1>>>(a, L[g].rad, q + DK_RAD);
+        k_st_wigner_q<<<sms * std::min(D.occ[DK_WIG], wig_ctas), 128, 0, s1>>>(a, q + DK_WIG);
         if (!one_lane) { CK(cudaEventRecord(b.ev_fork, s1)); CK(cudaStreamWaitEvent(s2, b.ev_fork, 0)); }
         k_st_assemble_q<false, 32><<<sms * D.occ[DK_AT1], 256, ST_ASM_SMEM, s1>>>(pa(1), L[g].at1, q + DK_AT1);
         k_st_assemble_q<true, 32><<<sms * D.occ[DK_AT0], 256, ST_ASM_SMEM, s1>>>(pa(2), L[g].at0, q + DK_AT0);

@@ -947,9 +947,10 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
     // build-phase constants of this thread: rows (kk, F) / (kk, re|im) of every table, column ii (swizzled)
     const int rho = (kk & 1) * KR + 2 * (kk >> 1);
     const int col = ii ^ (((rho >> 1) & 1) << 2);
-    // physical row = r ^ ((r >> 1) & 1): the four row pairs a warp stores (kk = 4 w .. 4 w + 3) then alternate between the two
-    // 8-word halves of a bank line (2 wavefronts per store instead of 4), and the fragment loads stay conflict-free
-    const int rsw = (rho >> 1) & 1;
+    // physical row = r ^ (r >= KR): 64-bit shared-memory accesses are served per half-warp, and a half-warp stores the row
+    // pairs of one even and one odd k (kk = 2 h, 2 h + 1: rows r and KR + r), which fell into the same 8-word half of a bank
+    // line; with the odd-parity block's row pairs swapped they alternate, and the fragment loads stay conflict-free
+    const int rsw = (kk & 1);
     double *o0 = op + (rho ^ rsw) * 8 + col, *o1 = op + ((rho + 1) ^ rsw) * 8 + col;
     const int k1 = kr0 + kk, k2 = kc0 + kk;
     const int n1 = nmin + k1, n2 = nmin + k2;
@@ -1019,7 +1020,7 @@ __device__ __forceinline__ void st_assemble_task(const StArgs &a, const StATask 
             // fragment element of table t, rows [row0, row0 + 8): row0 + (lane >> 2), node 4 ks + (lane & 3)
             auto frag = [&](int t, int row0) -> double {
                 const int r = row0 + fragrow;
-                return op[(t * (2 * KR) + (r ^ ((r >> 1) & 1))) * 8 + ((((ks ^ (r >> 1)) & 1) << 2) | fragk)];
+                return op[(t * (2 * KR) + (r ^ (r >= KR ? 1 : 0))) * 8 + ((((ks ^ (r >> 1)) & 1) << 2) | fragk)];
             };
             double la[NTR][5];
 #pragma unroll
@@ -1367,9 +1368,10 @@ __device__ __forceinline__ void st_small_task(const StArgs &a, const int mix, do
     const double qm = (double)m, qmm = qm * qm;
     const int kk = lane >> 2, ii = lane & 3;
     const int rho = (kk & 1) * 8 + 2 * (kk >> 1);
-    // (a [row & 1, row >> 3][row >> 1 & 3][node] layout halves the wavefronts of these stores -- 18 M of the kernel's 21 M bank
-    // conflicts per launch -- but its address arithmetic costs more than the conflicts: node loop 12.9 k -> 13.5 k cycles per warp)
-    double *o0 = op + rho * 4 + ii, *o1 = o0 + 4;
+    // physical row = r ^ (r >= 8): a half-warp stores the row pairs of two even and two odd k; with the odd block's pairs
+    // swapped its 16 lanes cover the 16 bank pairs once (see k_st_assemble)
+    const int rsw = kk & 1;
+    double *o0 = op + (rho ^ rsw) * 4 + ii, *o1 = op + ((rho + 1) ^ rsw) * 4 + ii;
     const int n1 = nmin + kk;
     const double an1 = (double)(n1 * (n1 + 1));
     const int fragrow = lane >> 2, fragk = lane & 3;
@@ -1432,7 +1434,7 @@ __device__ __forceinline__ void st_small_task(const StArgs &a, const int mix, do
             }
             __syncwarp();
         }
-        auto frag = [&](int t, int row0) -> double { return op[(t * 16 + row0 + fragrow) * 4 + fragk]; };
+        auto frag = [&](int t, int row0) -> double { return op[(t * 16 + ((row0 + fragrow) ^ (row0 >> 3))) * 4 + fragk]; };
         double lE[5], lO[5];
 #pragma unroll
         for (int t = 0; t < 5; t++) { lE[t] = frag(t, 0); lO[t] = frag(t, 8); }

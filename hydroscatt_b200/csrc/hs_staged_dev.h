@@ -583,9 +583,9 @@ static int calctmat_dev(hs_ctx *ctx, StShared &S, DvShared &D, cudaStream_t st, 
     int rounds_done = 0;
     int batch = D.last_rounds > 0 ? D.last_rounds : 6;
     if (getenv("HYDROTM_DEV_ROUNDS")) batch = std::max(1, atoi(getenv("HYDROTM_DEV_ROUNDS")));
-    for (int g = 0; g < ng; g++) if (plan(g)) return -1;
     int rc = 0;
-    for (;;) {
+    for (int g = 0; g < ng && !rc; g++) rc = plan(g);
+    for (; !rc;) {
         for (int r = 0; r < batch && !rc; r++)
             for (int g = 0; g < ng && !rc; g++) { rc = round(g); if (!rc) rc = plan(g); mark(g, rounds_done + r); }
         rounds_done += batch;

@@ -529,7 +529,7 @@ def run_gpu(args):
     # Throughput with two table builds in flight (N = 1 only, a sub-line: the headline times one build at a time): two
     # contexts, two streams, two host threads; one build's latency-bound convergence rounds overlap the other's scatter / PSD kernels
     piped = None
-    if world == 1 and not args.no_sublines and (os.cpu_count() or 1) >= 12:
+    if world == 1 and rep_per == 1 and not args.no_sublines and (os.cpu_count() or 1) >= 12:  # (one sweep per GPU: the shard is one table set)
         import threading as _th
         engs2 = [eng, Engine(local)]
         streams2 = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]

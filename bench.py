@@ -322,6 +322,9 @@ def run_gpu(args):
     # pinned host inputs (e2e path) and device-resident copies (kernel path): this rank's shard of the global list
     host_in = {k: torch.from_numpy(np.ascontiguousarray(g[k][idx])).pin_memory() for k in ("radius", "wavelength", "mr", "mi", "eps")}
     host_dsd = {k: torch.from_numpy(v).pin_memory() for k, v in (("d0", d0), ("nw", nw), ("mu", mu))}
+    IN_KEYS, DSD_KEYS = ("radius", "wavelength", "mr", "mi", "eps"), ("d0", "nw", "mu")
+    host_in_all = torch.stack([host_in[k] for k in IN_KEYS]).pin_memory()
+    host_dsd_all = torch.stack([host_dsd[k] for k in DSD_KEYS]).pin_memory()
     dev_in = {k: v.to(dev) for k, v in host_in.items()}
     dev_dsd = {k: v.to(dev) for k, v in host_dsd.items()}
     dmax = torch.full((n_dsd,), 7.0, dtype=torch.float64, device=dev)
@@ -387,27 +390,28 @@ def run_gpu(args):
         hb = host_out[k & 1]
         if copied[k & 1] is not None:
             copied[k & 1].synchronize()  # the consumer of step k-2's results is done with this buffer
-        inp = {k_: v.to(dev, non_blocking=True) for k_, v in host_in.items()}
-        dsd = {k_: v.to(dev, non_blocking=True) for k_, v in host_dsd.items()}
+        # one H2D copy per input block (the five particle columns, the three DSD parameter columns), not one per column
+        inp_all = host_in_all.to(dev, non_blocking=True)
+        dsd_all = host_dsd_all.to(dev, non_blocking=True)
+        inp = {k_: inp_all[i_] for i_, k_ in enumerate(IN_KEYS)}
+        dsd = {k_: dsd_all[i_] for i_, k_ in enumerate(DSD_KEYS)}
         tb, rows, obs = step(inp, dsd, False)
+        meta_dev = torch.stack([tb.nmax, tb.ngauss, tb.ntrials, tb.status])  # one D2H copy for the four per-particle records
         ready = torch.cuda.Event()
         ready.record()
         copy_stream.wait_event(ready)
         with torch.cuda.stream(copy_stream):
-            for t in [rows, tb.nmax, tb.ngauss, tb.ntrials, tb.status] + obs:
+            for t in [rows, meta_dev] + obs:
                 t.record_stream(copy_stream)
             hb["rows"].copy_(rows, non_blocking=True)
             # the observables in pieces, so that the pipeline's small host<->device transfers of the next step are not
             # queued behind one multi-millisecond DMA
-            nch = int(os.environ.get("HS_BENCH_D2H_CHUNKS", "16"))
+            nch = int(os.environ.get("HS_BENCH_D2H_CHUNKS", "64"))
             for q, o in enumerate(obs):
                 for c in range(nch):
                     a_, b_ = c * n_dsd // nch, (c + 1) * n_dsd // nch
                     hb["obs"][q, a_:b_].copy_(o[a_:b_], non_blocking=True)
-            hb["meta"][0].copy_(tb.nmax, non_blocking=True)
-            hb["meta"][1].copy_(tb.ngauss, non_blocking=True)
-            hb["meta"][2].copy_(tb.ntrials, non_blocking=True)
-            hb["meta"][3].copy_(tb.status, non_blocking=True)
+            hb["meta"].copy_(meta_dev, non_blocking=True)
             done = torch.cuda.Event()
             done.record()
         copied[k & 1] = done

@@ -6,14 +6,20 @@
 //
 //   round r of a group = k_dv_fill   thread = particle: items, (item, mode) list, radial / assembly / solve task lists,
 //                                    arena slots of final items, cleared result records
-//                        S, W, A, G  k_st_*_q: resident CTAs / warps fetch tasks from the device-built lists
-//                        k_dv_plan   thread = particle: controller over the results of round r (the reference's order),
-//                                    finished particles write their output record, the others count the work of round r + 1
-//                        k_dv_scan   one CTA: exclusive prefix sums of the counts = list offsets, capacity cut, queue lengths
+//                        S, W        k_st_radial_q, k_st_wigner_q: resident warps, static stride over the device-built lists
+//                        A, G        k_st_assemble_q, k_st_mode_small_q, k_st_solve_q: resident CTAs / warps fetch tasks from a
+//                                    cursor (the next index is fetched while the current task runs)
+//                        k_dv_plan   thread = particle: controller over the results of round r (hs_dvctl.h: the reference's
+//                                    order), finished particles write their output record, the others count the work of
+//                                    round r + 1; block-wide prefix of the counts
+//                        k_dv_scan   one CTA: prefix over the block totals = list offsets, capacity cut, queue lengths;
+//                                    the header also goes to pinned host memory
 //
-// The host enqueues the rounds of every group up front (the number the previous call needed), reads one small header and
-// adds rounds only if particles are left.  Particles are dealt heaviest-first round-robin into groups on their own streams
-// so that one group's dependent chain (tables -> assembly -> controller) overlaps the others' kernels.
+// The host enqueues the rounds of every group up front (the number the previous call needed), waits once, looks at the
+// headers and adds rounds only if particles are left (Gauss tables / scratch pool grow there).  Particles are dealt
+// heaviest-first round-robin into groups on their own streams so that one group's dependent chain (tables -> assembly ->
+// controller) overlaps the others' kernels.  The controller and the per-particle planner are plain functions (hs_dvctl.h)
+// that the CPU test suite runs against the oracle's recorded trial sequences (tests/test_emu_cpu.py).
 // Included by hydrotm.cu after hs_staged_host.h.
 #pragma once
 #include "hs_dvctl.h"
